@@ -1,0 +1,160 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes bindings for the two CPU oracles (oracle/oracle_abi.h).
+
+  RefDecoder  -> oracle/_ref/libhabdec_ref.so  (the unmodified reference Decoder<float>)
+  PortDecoder -> oracle/libhabdec_oracle.so    (our CPU restatement)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+STAGE_DECIMATED, STAGE_FILTERED, STAGE_DEMOD, STAGE_FFT, STAGE_POWER, STAGE_LPTAPS, STAGE_PENDING, STAGE_BITS, STAGE_RAWCHARS = range(9)
+
+
+class Config(C.Structure):
+    _fields_ = [("baud", C.c_double), ("rtty_bits", C.c_int), ("rtty_stops", C.c_float),
+                ("lowpass_bw", C.c_float), ("lowpass_trans", C.c_float), ("dec_factor", C.c_int),
+                ("dc_remove", C.c_int), ("record", C.c_int)]
+
+
+class AfcInfo(C.Structure):
+    _fields_ = [("frequency_correction", C.c_double), ("shift_hz", C.c_double), ("noise_floor", C.c_double),
+                ("noise_variance", C.c_double), ("peak_left", C.c_int), ("peak_right", C.c_int)]
+
+
+def make_config(baud=300.0, rtty_bits=8, rtty_stops=2.0, lowpass_bw=1500.0, lowpass_trans=0.025,
+                dec_factor=256, dc_remove=False, record=True) -> Config:
+    return Config(float(baud), int(rtty_bits), float(rtty_stops), float(lowpass_bw), float(lowpass_trans),
+                  int(dec_factor), int(bool(dc_remove)), int(bool(record)))
+
+
+def _bind(lib, p):
+    f = lambda name: getattr(lib, p + "_" + name)
+    f("create").restype = C.c_void_p
+    f("create").argtypes = [C.POINTER(Config)]
+    f("destroy").argtypes = [C.c_void_p]
+    f("push_process").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double]
+    for name in ("chars", "rtty", "last_sentence", "sentences"):
+        f(name).restype = C.c_size_t
+        f(name).argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    f("stage").restype = C.c_size_t
+    f("stage").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    f("afc").argtypes = [C.c_void_p, C.POINTER(AfcInfo)]
+    f("reset_frequency_correction").argtypes = [C.c_void_p, C.c_double]
+    f("bench").restype = C.c_double
+    f("bench").argtypes = [C.POINTER(Config), C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                           C.c_double, C.c_int, C.POINTER(C.c_uint64)]
+
+
+_libs = {}
+
+
+def _load(kind):
+    if kind in _libs:
+        return _libs[kind]
+    path = os.path.join(_HERE, "_ref", "libhabdec_ref.so") if kind == "ref" else os.path.join(_HERE, "libhabdec_oracle.so")
+    if not os.path.exists(path):
+        raise FileNotFoundError(path + " (run `make -C oracle` / __graft_entry__.build())")
+    lib = C.CDLL(path)
+    _bind(lib, kind)
+    _libs[kind] = lib
+    return lib
+
+
+def available(kind: str) -> bool:
+    try:
+        _load(kind)
+        return True
+    except (OSError, FileNotFoundError):
+        return False
+
+
+class _Decoder:
+    kind = ""
+
+    def __init__(self, cfg: Config | None = None, **kw):
+        self._lib = _load(self.kind)
+        self.cfg = cfg if cfg is not None else make_config(**kw)
+        self._f = lambda name: getattr(self._lib, self.kind + "_" + name)
+        self._h = self._f("create")(C.byref(self.cfg))
+
+    def close(self):
+        if self._h:
+            self._f("destroy")(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def push_process(self, iq: np.ndarray, fs: float):
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        self._f("push_process")(self._h, iq.ctypes.data, iq.size, float(fs))
+
+    def run(self, iq: np.ndarray, fs: float, chunk: int = 65536):
+        for o in range(0, len(iq), chunk):
+            self.push_process(iq[o:o + chunk], fs)
+        return self
+
+    def _str(self, name) -> bytes:
+        n = self._f(name)(self._h, None, 0)
+        buf = C.create_string_buffer(max(n, 1))
+        self._f(name)(self._h, buf, n)
+        return buf.raw[:n]
+
+    def chars(self) -> bytes:
+        return self._str("chars")
+
+    def rtty(self) -> bytes:
+        return self._str("rtty")
+
+    def last_sentence(self) -> bytes:
+        return self._str("last_sentence")
+
+    def sentences(self) -> list[bytes]:
+        s = self._str("sentences")
+        return [x for x in s.split(b"\n") if x]
+
+    def stage(self, which: int) -> np.ndarray:
+        n = self._f("stage")(self._h, which, None, 0)
+        out = np.empty(n, dtype=np.float32)
+        if n:
+            self._f("stage")(self._h, which, out.ctypes.data, n)
+        if which in (STAGE_DECIMATED, STAGE_FILTERED, STAGE_FFT):
+            return out.view(np.complex64)
+        return out
+
+    def afc(self) -> AfcInfo:
+        a = AfcInfo()
+        self._f("afc")(self._h, C.byref(a))
+        return a
+
+    def reset_frequency_correction(self, corr: float):
+        self._f("reset_frequency_correction")(self._h, float(corr))
+
+
+class RefDecoder(_Decoder):
+    kind = "ref"
+
+
+class PortDecoder(_Decoder):
+    kind = "orc"
+
+
+def bench(kind: str, cfg: Config, iq: np.ndarray, n_threads: int, fs: float, chunk: int = 65536,
+          reps: int = 1, stride: int = 0):
+    """Returns (seconds, total_chars). iq: complex64[n] (stride 0: shared) or [n_threads, n]."""
+    lib = _load(kind)
+    iq = np.ascontiguousarray(iq, dtype=np.complex64)
+    n = iq.shape[-1]
+    if iq.ndim == 2:
+        stride = n
+    chars = C.c_uint64(0)
+    secs = getattr(lib, kind + "_bench")(C.byref(cfg), n_threads, iq.ctypes.data, n, stride, chunk, float(fs), reps,
+                                         C.byref(chars))
+    return secs, chars.value

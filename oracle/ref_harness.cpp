@@ -1,0 +1,299 @@
+// TEST INFRASTRUCTURE ONLY -- wraps the UNMODIFIED reference habdec::Decoder<float>
+// (compiled from /root/reference/code by oracle/Makefile into
+// oracle/_ref/libhabdec_ref.so) behind the oracle C ABI (oracle/oracle_abi.h).
+// No reference source is copied or edited: private members are reached with the
+// usual "#define private public" test trick so per-stage arrays can be compared.
+//
+// Reference usage rules honoured here:
+//  * ONE OS THREAD PER DECODER for its whole life -- FSK2_Demod keeps its carry in
+//    a `thread_local static` (code/Decoder/FSK2_Demod.h:35) and so does the
+//    character-callback timer (code/Decoder/Decoder.h:617).
+//  * livePrint(false); stdout of the reference is discarded.
+//  * characters = concat(character_callback_) + the still unflushed
+//    chr_callback_stream_ (the callback is paced by wall-clock, Decoder.h:617-629).
+//  * configuration order mirrors code/websocketServer/main.cpp:544-553.
+
+#include <atomic>
+#include <chrono>
+#include <complex>
+#include <condition_variable>
+#include <cstring>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <regex>
+#include <set>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+#include <array>
+#include <memory>
+#include <numeric>
+#include <algorithm>
+#include <future>
+#include <cmath>
+
+#define private public
+#include "Decoder/Decoder.h"
+#undef private
+
+#include "oracle_abi.h"
+
+namespace {
+
+struct NullBuf : std::streambuf { int overflow(int c) override { return c; } };
+struct Silencer {
+    NullBuf nb; std::streambuf* old = nullptr;
+    Silencer() { if (!getenv("HBD_REF_VERBOSE")) old = std::cout.rdbuf(&nb); }
+    ~Silencer() { if (old) std::cout.rdbuf(old); }
+};
+Silencer g_silencer;
+
+// a dedicated thread that executes closures in order; run() blocks until done
+class Worker {
+public:
+    Worker() : th_([this] { loop(); }) {}
+    ~Worker() {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+        cv_.notify_all();
+        th_.join();
+    }
+    void run(std::function<void()> f) {
+        std::unique_lock<std::mutex> l(m_);
+        job_ = std::move(f); has_job_ = true; done_ = false;
+        cv_.notify_all();
+        cv_.wait(l, [this] { return done_; });
+    }
+private:
+    void loop() {
+        std::unique_lock<std::mutex> l(m_);
+        for (;;) {
+            cv_.wait(l, [this] { return has_job_ || stop_; });
+            if (stop_) return;
+            auto f = std::move(job_); has_job_ = false;
+            l.unlock(); f(); l.lock();
+            done_ = true; cv_.notify_all();
+        }
+    }
+    std::mutex m_; std::condition_variable cv_;
+    std::function<void()> job_; bool has_job_ = false, done_ = true, stop_ = false;
+    std::thread th_;
+};
+
+void configure(habdec::Decoder<float>& D, const hbo_config& c)
+{
+    D.baud(c.baud);
+    D.rtty_bits(size_t(c.rtty_bits));
+    D.rtty_stops(c.rtty_stops);
+    D.livePrint(false);
+    D.dc_remove(c.dc_remove != 0);
+    D.lowpass_bw(c.lowpass_bw);
+    D.lowpass_trans(c.lowpass_trans);
+    D.setupDecimationStagesFactor(size_t(c.dec_factor));
+}
+
+struct Ref {
+    hbo_config cfg;
+    std::unique_ptr<Worker> w;
+    std::unique_ptr<habdec::Decoder<float>> D;
+    std::string chars_cb, sentences;
+    std::vector<float> decimated, filtered, demod;
+    size_t q_in = 0, dec_pending = 0;
+};
+
+size_t copy_str(const std::string& s, char* out, size_t cap)
+{
+    if (out && cap) memcpy(out, s.data(), std::min(cap, s.size()));
+    return s.size();
+}
+
+size_t copy_floats(const float* src, size_t n, float* out, size_t cap)
+{
+    if (out && cap && n) memcpy(out, src, std::min(cap, n) * sizeof(float));
+    return n;
+}
+
+} // namespace
+
+extern "C" {
+
+void* ref_create(const hbo_config* cfg)
+{
+    Ref* r = new Ref;
+    r->cfg = *cfg;
+    r->w.reset(new Worker);
+    r->w->run([r] {
+        r->D.reset(new habdec::Decoder<float>);
+        configure(*r->D, r->cfg);
+        r->D->character_callback_ = [r](std::string s) { r->chars_cb += s; };
+        r->D->sentence_callback_ = [r](std::string cs, std::string data, std::string crc) {
+            r->sentences += cs + "," + data + "*" + crc + "\n";
+        };
+    });
+    return r;
+}
+
+void ref_destroy(void* h)
+{
+    Ref* r = static_cast<Ref*>(h);
+    if (!r) return;
+    r->w->run([r] { r->D.reset(); });
+    delete r;
+}
+
+void ref_push_process(void* h, const float* iq, size_t n, double fs)
+{
+    Ref* r = static_cast<Ref*>(h);
+    r->w->run([=] {
+        habdec::IQVector<float> v;
+        v.resize(n);
+        v.samplingRate(fs);
+        if (n) memcpy(v.data(), iq, n * sizeof(std::complex<float>));
+        auto& D = *r->D;
+        D.pushSamples(v);
+        D();
+        if (!r->cfg.record) return;
+        // mirror the buffer bookkeeping of Decoder.h:429-435,461,492-495,522-542
+        const size_t dec = size_t(D.getDecimationFactor());
+        r->q_in += n;
+        if (r->q_in < dec) return;
+        const size_t consumed = r->q_in - r->q_in % dec;
+        r->q_in -= consumed;
+        const size_t ndec = consumed / dec;
+        const bool too_fast = D.getDecimatedSamplingRate() > 4 * D.max_decimated_sampling_rate_;
+        if (D.iq_samples_temp_.size() == ndec && ndec)
+            r->decimated.insert(r->decimated.end(), (const float*)D.iq_samples_temp_.data(),
+                                (const float*)D.iq_samples_temp_.data() + 2 * ndec);
+        r->dec_pending += ndec;
+        if (r->dec_pending < 256) return;
+        if (too_fast) { r->dec_pending = 0; return; }
+        const size_t nf = r->dec_pending - r->dec_pending % 256;
+        r->dec_pending -= nf;
+        if (D.iq_samples_filtered_.size() == nf) {
+            r->filtered.insert(r->filtered.end(), (const float*)D.iq_samples_filtered_.data(),
+                               (const float*)D.iq_samples_filtered_.data() + 2 * nf);
+            r->demod.insert(r->demod.end(), D.demodulated_.begin(), D.demodulated_.end());
+        }
+    });
+}
+
+size_t ref_chars(void* h, char* out, size_t cap)
+{
+    Ref* r = static_cast<Ref*>(h);
+    std::string s;
+    r->w->run([&] { s = r->chars_cb + r->D->chr_callback_stream_; });
+    return copy_str(s, out, cap);
+}
+
+size_t ref_rtty(void* h, char* out, size_t cap)
+{
+    Ref* r = static_cast<Ref*>(h);
+    std::string s;
+    r->w->run([&] { s = r->D->getRTTY(); });
+    return copy_str(s, out, cap);
+}
+
+size_t ref_last_sentence(void* h, char* out, size_t cap)
+{
+    Ref* r = static_cast<Ref*>(h);
+    std::string s;
+    r->w->run([&] { s = r->D->getLastSentence(); });
+    return copy_str(s, out, cap);
+}
+
+size_t ref_sentences(void* h, char* out, size_t cap)
+{
+    Ref* r = static_cast<Ref*>(h);
+    std::string s;
+    r->w->run([&] { s = r->sentences; });
+    return copy_str(s, out, cap);
+}
+
+size_t ref_stage(void* h, int stage, float* out, size_t cap)
+{
+    Ref* r = static_cast<Ref*>(h);
+    size_t n = 0;
+    r->w->run([&] {
+        auto& D = *r->D;
+        switch (stage) {
+        case HBO_STAGE_DECIMATED: n = copy_floats(r->decimated.data(), r->decimated.size(), out, cap); break;
+        case HBO_STAGE_FILTERED:  n = copy_floats(r->filtered.data(), r->filtered.size(), out, cap); break;
+        case HBO_STAGE_DEMOD:     n = copy_floats(r->demod.data(), r->demod.size(), out, cap); break;
+        case HBO_STAGE_FFT: {
+            auto f = D.getFFT();
+            n = copy_floats((const float*)f.data(), 2 * f.size(), out, cap); break;
+        }
+        case HBO_STAGE_POWER: {
+            auto p = D.getPowerSpectrum();
+            n = copy_floats(p.data(), p.size(), out, cap); break;
+        }
+        case HBO_STAGE_LPTAPS:
+            n = copy_floats(D.lowpass_fir_.taps_.data(), D.lowpass_fir_.taps_.size(), out, cap); break;
+        case HBO_STAGE_PENDING:
+            n = copy_floats(D.symbol_extractor_.samples_.data(), D.symbol_extractor_.samples_.size(), out, cap); break;
+        default: n = 0;
+        }
+    });
+    return n;
+}
+
+void ref_afc(void* h, hbo_afc_info* o)
+{
+    Ref* r = static_cast<Ref*>(h);
+    r->w->run([&] {
+        auto& D = *r->D;
+        o->frequency_correction = D.getFrequencyCorrection();
+        o->shift_hz = D.getShift();
+        D.getNoiseFloor(o->noise_floor, o->noise_variance);
+        D.getPeaks(o->peak_left, o->peak_right);
+    });
+}
+
+void ref_reset_frequency_correction(void* h, double corr)
+{
+    Ref* r = static_cast<Ref*>(h);
+    r->w->run([&] { r->D->resetFrequencyCorrection(corr); });
+}
+
+double ref_bench(const hbo_config* cfg, int n_threads, const float* iq, size_t n, size_t stride,
+                 size_t chunk, double fs, int reps, uint64_t* o_chars)
+{
+    std::atomic<int> ready{0};
+    std::atomic<bool> go{false};
+    std::atomic<uint64_t> chars{0};
+    std::vector<double> secs(n_threads, 0.0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back([&, t] {
+            habdec::Decoder<float> D;
+            configure(D, *cfg);
+            uint64_t my_chars = 0;
+            D.character_callback_ = [&](std::string s) { my_chars += s.size(); };
+            habdec::IQVector<float> v;
+            v.samplingRate(fs);
+            const std::complex<float>* src = reinterpret_cast<const std::complex<float>*>(iq) + size_t(t) * stride;
+            ready++;
+            while (!go.load()) std::this_thread::yield();
+            auto t0 = std::chrono::steady_clock::now();
+            for (int rep = 0; rep < reps; ++rep)
+                for (size_t o = 0; o < n; o += chunk) {
+                    const size_t c = std::min(chunk, n - o);
+                    v.resize(c);
+                    memcpy(v.data(), src + o, c * sizeof(std::complex<float>)); // what IQSource::get does
+                    D.pushSamples(v);
+                    D();
+                }
+            secs[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            my_chars += D.chr_callback_stream_.size();
+            chars += my_chars;
+        });
+    while (ready.load() < n_threads) std::this_thread::yield();
+    go = true;
+    for (auto& x : th) x.join();
+    if (o_chars) *o_chars = chars.load();
+    return *std::max_element(secs.begin(), secs.end());
+}
+
+} // extern "C"
