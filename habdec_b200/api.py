@@ -1,0 +1,264 @@
+"""ctypes binding of libhabdec_b200.so (include/habdec_b200.h) plus a thin Python mirror of the
+reference Decoder interface (code/Decoder/Decoder.h:65-141) used by tests and bench.
+
+The library is CUDA only: importing works anywhere (so the CPU test tier can check the exported
+symbols), creating a decoder without a B200-class device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhabdec_b200.so")
+
+HBD_OK, HBD_ERR_ARG, HBD_ERR_CUDA, HBD_ERR_STATE, HBD_ERR_NOMEM = 0, -1, -2, -3, -4
+STAGE_DECIMATED, STAGE_FILTERED, STAGE_DEMOD, STAGE_LPTAPS, STAGE_PENDING, STAGE_BITS = 0, 1, 2, 5, 6, 7
+
+
+class SpectrumInfo(C.Structure):
+    _fields_ = [("min_", C.c_float), ("max_", C.c_float), ("noise_floor_", C.c_double), ("noise_variance_", C.c_double),
+                ("sampling_rate_", C.c_double), ("shift_", C.c_double), ("peak_left_", C.c_int), ("peak_right_", C.c_int),
+                ("peak_left_valid_", C.c_int), ("peak_right_valid_", C.c_int)]
+
+
+SENTENCE_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p)
+CHARS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_char), C.c_size_t)
+
+# name -> (restype, argtypes); this table is also what the CPU test tier checks against the header
+_H = C.c_void_p
+SIGNATURES = {
+    "hbd_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_H)]),
+    "hbd_destroy": (None, [_H]),
+    "hbd_last_error": (C.c_char_p, [_H]),
+    "hbd_set_stream": (C.c_int, [_H, C.c_void_p]),
+    "hbd_set_record": (C.c_int, [_H, C.c_int]),
+    "hbd_set_baud": (C.c_int, [_H, C.c_int, C.c_double]),
+    "hbd_get_baud": (C.c_double, [_H, C.c_int]),
+    "hbd_set_rtty_bits": (C.c_int, [_H, C.c_int, C.c_size_t]),
+    "hbd_get_rtty_bits": (C.c_size_t, [_H, C.c_int]),
+    "hbd_set_rtty_stops": (C.c_int, [_H, C.c_int, C.c_float]),
+    "hbd_get_rtty_stops": (C.c_float, [_H, C.c_int]),
+    "hbd_set_lowpass_bw": (C.c_int, [_H, C.c_int, C.c_float]),
+    "hbd_get_lowpass_bw": (C.c_float, [_H, C.c_int]),
+    "hbd_set_lowpass_trans": (C.c_int, [_H, C.c_int, C.c_float]),
+    "hbd_get_lowpass_trans": (C.c_float, [_H, C.c_int]),
+    "hbd_set_dc_remove": (C.c_int, [_H, C.c_int, C.c_int]),
+    "hbd_get_dc_remove": (C.c_int, [_H, C.c_int]),
+    "hbd_setup_decimation_factor": (C.c_size_t, [_H, C.c_size_t]),
+    "hbd_setup_decimation_bw": (C.c_size_t, [_H, C.c_double]),
+    "hbd_push_samples": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_size_t, C.c_double]),
+    "hbd_push_samples_batch": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t, C.c_double]),
+    "hbd_push_samples_device": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t, C.c_double]),
+    "hbd_process": (C.c_int, [_H]),
+    "hbd_process_async": (C.c_int, [_H]),
+    "hbd_collect": (C.c_int, [_H]),
+    "hbd_synchronize": (C.c_int, [_H]),
+    "hbd_kernel_launches": (C.c_ulonglong, [_H]),
+    "hbd_get_rtty": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_get_last_sentence": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_poll_chars": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_poll_sentences": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_poll_raw_chars": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_set_sentence_callback": (C.c_int, [_H, SENTENCE_CB, C.c_void_p]),
+    "hbd_set_chars_callback": (C.c_int, [_H, CHARS_CB, C.c_void_p]),
+    "hbd_get_decimation_factor": (C.c_int, [_H]),
+    "hbd_get_input_sampling_rate": (C.c_double, [_H]),
+    "hbd_get_decimated_sampling_rate": (C.c_double, [_H]),
+    "hbd_get_symbol_rate": (C.c_double, [_H, C.c_int]),
+    "hbd_n_channels": (C.c_int, [_H]),
+    "hbd_get_bins_count": (C.c_size_t, [_H]),
+    "hbd_get_fft": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_get_demodulated": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_get_power_spectrum": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_get_peaks": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hbd_get_noise_floor": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "hbd_get_shift": (C.c_double, [_H, C.c_int]),
+    "hbd_get_frequency_correction": (C.c_double, [_H, C.c_int]),
+    "hbd_reset_frequency_correction": (C.c_int, [_H, C.c_int, C.c_double]),
+    "hbd_get_spectrum_info": (C.c_size_t, [_H, C.c_int, C.POINTER(SpectrumInfo), C.c_void_p, C.c_size_t]),
+    "hbd_debug_stage": (C.c_size_t, [_H, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_design_lowpass": (C.c_size_t, [C.c_float, C.c_float, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "hbd_extract_sentence": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "hbd_crc16": (None, [C.c_char_p, C.c_size_t, C.c_char_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (raises if it was not built: there is no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(habdec_b200 has no CPU or pure-Python compute path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class HbdError(RuntimeError):
+    pass
+
+
+def design_lowpass(rel_width: float, trans: float, input_size: int, current_taps: int = 0) -> np.ndarray:
+    lib = load()
+    out = np.zeros(4096, dtype=np.float32)
+    n = lib.hbd_design_lowpass(rel_width, trans, input_size, current_taps, out.ctypes.data, out.size)
+    return out[:n] if n != current_taps else out[:0]
+
+
+def extract_sentence(stream: bytes):
+    lib = load()
+    cs, data, crc = (C.create_string_buffer(len(stream) + 8) for _ in range(3))
+    rest = C.c_size_t(0)
+    ok = lib.hbd_extract_sentence(stream, len(stream), cs, data, crc, len(stream) + 8, C.byref(rest))
+    if not ok:
+        return None
+    return cs.value, data.value, crc.value, rest.value
+
+
+def crc16(s: bytes) -> bytes:
+    lib = load()
+    out = C.create_string_buffer(5)
+    lib.hbd_crc16(s, len(s), out)
+    return out.value
+
+
+class BatchDecoder:
+    """N independent channels on one GPU; method names follow habdec::Decoder (Decoder.h:65-141)."""
+
+    def __init__(self, n_channels: int, device: int = 0, baud: float = 300.0, rtty_bits: int = 8, rtty_stops: float = 2.0,
+                 lowpass_bw: float = 1500.0, lowpass_trans: float = 0.025, dec_factor: int = 256, dc_remove: bool = False,
+                 record: bool = False):
+        self._lib = load()
+        h = _H()
+        rc = self._lib.hbd_create(n_channels, device, C.byref(h))
+        if rc != HBD_OK:
+            raise HbdError(f"hbd_create failed ({rc}): a CUDA device (B200, sm_100a) is required, there is no CPU fallback")
+        self._h = h
+        self.n_channels = n_channels
+        self._cbs = []
+        # same order as code/websocketServer/main.cpp:544-553
+        self.baud(baud); self.rtty_bits(rtty_bits); self.rtty_stops(rtty_stops); self.dc_remove(dc_remove)
+        self.lowpass_bw(lowpass_bw); self.lowpass_trans(lowpass_trans)
+        if record:
+            self._chk(self._lib.hbd_set_record(self._h, 1))
+        if self.setupDecimationStagesFactor(dec_factor) != dec_factor:
+            raise HbdError("unsupported decimation factor %r" % dec_factor)
+
+    # ---- plumbing
+    def _chk(self, rc):
+        if rc != HBD_OK:
+            raise HbdError("habdec_b200 error %d: %s" % (rc, (self._lib.hbd_last_error(self._h) or b"").decode()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hbd_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._chk(self._lib.hbd_set_stream(self._h, cuda_stream_ptr))
+
+    # ---- configuration
+    def baud(self, v, ch=-1): self._chk(self._lib.hbd_set_baud(self._h, ch, float(v)))
+    def rtty_bits(self, v, ch=-1): self._chk(self._lib.hbd_set_rtty_bits(self._h, ch, int(v)))
+    def rtty_stops(self, v, ch=-1): self._chk(self._lib.hbd_set_rtty_stops(self._h, ch, float(v)))
+    def lowpass_bw(self, v, ch=-1): self._chk(self._lib.hbd_set_lowpass_bw(self._h, ch, float(v)))
+    def lowpass_trans(self, v, ch=-1): self._chk(self._lib.hbd_set_lowpass_trans(self._h, ch, float(v)))
+    def dc_remove(self, v, ch=-1): self._chk(self._lib.hbd_set_dc_remove(self._h, ch, int(bool(v))))
+    def setupDecimationStagesFactor(self, factor: int) -> int: return self._lib.hbd_setup_decimation_factor(self._h, int(factor))
+    def setupDecimationStagesBW(self, max_rate: float) -> int: return self._lib.hbd_setup_decimation_bw(self._h, float(max_rate))
+    def getDecimationFactor(self): return self._lib.hbd_get_decimation_factor(self._h)
+    def getInputSamplingRate(self): return self._lib.hbd_get_input_sampling_rate(self._h)
+    def getDecimatedSamplingRate(self): return self._lib.hbd_get_decimated_sampling_rate(self._h)
+
+    # ---- feed
+    def pushSamples(self, ch: int, iq: np.ndarray, fs: float):
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        self._chk(self._lib.hbd_push_samples(self._h, ch, iq.ctypes.data, iq.size, float(fs)))
+
+    def pushSamplesBatch(self, iq: np.ndarray, fs: float):
+        """iq: complex64 [n_channels, n]"""
+        assert iq.ndim == 2 and iq.shape[0] == self.n_channels and iq.dtype == np.complex64
+        pitch = iq.strides[0] // 8
+        assert iq.strides[1] == 8
+        self._chk(self._lib.hbd_push_samples_batch(self._h, iq.ctypes.data, iq.shape[1], pitch, float(fs)))
+
+    def pushSamplesDevice(self, ptr: int, n: int, pitch: int, fs: float):
+        self._chk(self._lib.hbd_push_samples_device(self._h, ptr, n, pitch, float(fs)))
+
+    # ---- run
+    def process(self): self._chk(self._lib.hbd_process(self._h))
+    __call__ = process
+    def process_async(self): self._chk(self._lib.hbd_process_async(self._h))
+    def collect(self): self._chk(self._lib.hbd_collect(self._h))
+    def synchronize(self): self._chk(self._lib.hbd_synchronize(self._h))
+    def kernel_launches(self) -> int: return int(self._lib.hbd_kernel_launches(self._h))
+
+    # ---- results
+    def _bytes(self, fn, ch) -> bytes:
+        n = fn(self._h, ch, None, 0)
+        if not n:
+            return b""
+        buf = C.create_string_buffer(n)
+        fn(self._h, ch, buf, n)
+        return buf.raw[:n]
+
+    def getRTTY(self, ch=0) -> bytes: return self._bytes(self._lib.hbd_get_rtty, ch)
+    def getLastSentence(self, ch=0) -> bytes: return self._bytes(self._lib.hbd_get_last_sentence, ch)
+    def poll_chars(self, ch=0) -> bytes: return self._bytes(self._lib.hbd_poll_chars, ch)
+    def poll_raw_chars(self, ch=0) -> bytes: return self._bytes(self._lib.hbd_poll_raw_chars, ch)
+    def poll_sentences(self, ch=0) -> list[bytes]:
+        return [s for s in self._bytes(self._lib.hbd_poll_sentences, ch).split(b"\n") if s]
+
+    def set_sentence_callback(self, fn):
+        cb = SENTENCE_CB(lambda user, ch, cs, data, crc: fn(ch, cs, data, crc))
+        self._cbs.append(cb)
+        self._chk(self._lib.hbd_set_sentence_callback(self._h, cb, None))
+
+    def set_chars_callback(self, fn):
+        cb = CHARS_CB(lambda user, ch, p, n: fn(ch, C.string_at(p, n)))
+        self._cbs.append(cb)
+        self._chk(self._lib.hbd_set_chars_callback(self._h, cb, None))
+
+    # ---- GUI data
+    def _floats(self, fn, ch, *extra, complex_=False) -> np.ndarray:
+        n = fn(self._h, ch, *extra, None, 0)
+        out = np.empty(n, dtype=np.float32)
+        if n:
+            fn(self._h, ch, *extra, out.ctypes.data, n)
+        return out.view(np.complex64) if complex_ else out
+
+    def getBinsCount(self): return self._lib.hbd_get_bins_count(self._h)
+    def getFFT(self, ch=0): return self._floats(self._lib.hbd_get_fft, ch, complex_=True)
+    def getDemodulated(self, ch=0): return self._floats(self._lib.hbd_get_demodulated, ch)
+    def getPowerSpectrum(self, ch=0): return self._floats(self._lib.hbd_get_power_spectrum, ch)
+    def getPeaks(self, ch=0):
+        pl, pr = C.c_int(0), C.c_int(0)
+        self._chk(self._lib.hbd_get_peaks(self._h, ch, C.byref(pl), C.byref(pr)))
+        return pl.value, pr.value
+    def getNoiseFloor(self, ch=0):
+        nf, nv = C.c_double(0), C.c_double(0)
+        self._chk(self._lib.hbd_get_noise_floor(self._h, ch, C.byref(nf), C.byref(nv)))
+        return nf.value, nv.value
+    def getShift(self, ch=0): return self._lib.hbd_get_shift(self._h, ch)
+    def getFrequencyCorrection(self, ch=0): return self._lib.hbd_get_frequency_correction(self._h, ch)
+    def resetFrequencyCorrection(self, corr, ch=0): self._chk(self._lib.hbd_reset_frequency_correction(self._h, ch, float(corr)))
+    def getSpectrumInfo(self, ch=0):
+        info = SpectrumInfo()
+        power = np.empty(4096, dtype=np.float32)
+        n = self._lib.hbd_get_spectrum_info(self._h, ch, C.byref(info), power.ctypes.data, power.size)
+        return info, power[:n]
+
+    def debug_stage(self, ch, stage) -> np.ndarray:
+        return self._floats(self._lib.hbd_debug_stage, ch, stage, complex_=stage in (STAGE_DECIMATED, STAGE_FILTERED))

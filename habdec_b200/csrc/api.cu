@@ -1,0 +1,928 @@
+// C ABI of libhabdec_b200.so (include/habdec_b200.h): handle, HBM state, per-call planning
+// (the host mirror of the reference's buffer bookkeeping, Decoder.h:426-436,492-542), kernel
+// sequencing and the host sentence layer.  There is no CPU compute path in here: every
+// process call launches K1..K4 or fails.
+#include "../../include/habdec_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "decim1.cuh"
+#include "decim_taps.inc"
+#include "fft_afc.cuh"
+#include "hbd_common.cuh"
+#include "host_tail.h"
+#include "slicer.cuh"
+#include "tail.cuh"
+
+using namespace hbd;
+
+namespace {
+
+struct TapTable { int M; const uint32_t* bits; int len; };
+#define HBD_TT(M, name) TapTable{M, hbd_taps_bits_##name, int(sizeof(hbd_taps_bits_##name) / 4)}
+
+// factor -> stage list, Decoder.h:286-320
+bool plan_for_factor(size_t factor, std::vector<TapTable>& st)
+{
+    st.clear();
+    switch (factor) {
+    case 256: st = {HBD_TT(64, d256_m64), HBD_TT(4, d4_m4)}; return true;
+    case 128: st = {HBD_TT(32, d128_m32), HBD_TT(4, d4_m4)}; return true;
+    case 64:  st = {HBD_TT(32, d64_m32), HBD_TT(2, d2_m2)}; return true;
+    case 32:  st = {HBD_TT(16, d32_m16), HBD_TT(2, d2_m2)}; return true;
+    case 16:  st = {HBD_TT(8, d16_m8), HBD_TT(2, d2_m2)}; return true;
+    case 8:   st = {HBD_TT(8, d8_m8)}; return true;
+    case 4:   st = {HBD_TT(4, d4_m4)}; return true;
+    case 2:   st = {HBD_TT(2, d2_m2)}; return true;
+    case 1:   return true;
+    default:  return false;
+    }
+}
+
+// host mirror of one channel
+struct HostChan {
+    double baud = 1;         // SymbolExtractor default symbol_rate_ = 1
+    size_t rtty_bits = 0;
+    float rtty_stops = 0;
+    float lp_bw = 1500, lp_trans = 0.025f;
+    bool dc_remove = false;
+    // mirrors of device counters that are pure functions of the push sizes
+    unsigned in_r = 0, dec_pending = 0;
+    size_t grown1 = 0, grown2 = 0, grown_lp = 0;
+    size_t lp_input_size = 0, lp_ntaps = 0;
+    unsigned pushed = 0;     // samples waiting in the staging row
+    unsigned last_nf = 0, last_n2 = 0;
+    bool cfg_dirty = true;
+    TextChannel text;
+};
+
+constexpr int kMarkSlots = 64; // async calls that may be outstanding between two collects
+
+__global__ void pack_raw_kernel(const unsigned char* raw, const unsigned* raw_n, const unsigned* offsets, unsigned char* packed, int n_ch)
+{
+    const int ch = blockIdx.x;
+    if (ch >= n_ch) return;
+    const unsigned n = min(raw_n[ch], unsigned(kRawCap));
+    const unsigned char* src = raw + (size_t)ch * kRawCap;
+    unsigned char* dst = packed + offsets[ch];
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void mark_kernel(const unsigned* raw_n, unsigned* mark, int n_ch)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < n_ch) mark[ch] = raw_n[ch];
+}
+
+__global__ void init_cfg_kernel(ChanState* st, const double* baud, const float* stops, const int* bits, const int* dc, const int* ntaps,
+                                const unsigned char* dirty, int n_ch)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_ch || !dirty[ch]) return;
+    st[ch].baud = baud[ch];
+    st[ch].rtty_stops = stops[ch];
+    st[ch].rtty_bits = bits[ch];
+    st[ch].dc_remove = dc[ch];
+    st[ch].lp_ntaps = ntaps[ch];
+}
+
+} // namespace
+
+struct hbd_decoder {
+    std::mutex mtx;
+    std::string err;
+    int n_ch = 0, device = 0, n_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool record = false;
+    unsigned long long launches = 0;
+
+    double fs_in = 0;
+    int factor = 1;
+    int M1 = 1, T1 = 1, M2 = 1, T2 = 1;
+    std::vector<HostChan> hc;
+
+    // device state
+    ChanState* d_state = nullptr;
+    ChanPlan* d_plan = nullptr;
+    std::vector<ChanPlan> h_plan, h_plan_uploaded;
+    float2* d_carry = nullptr;
+    float2* d_s1 = nullptr;      size_t s1_pitch = 0;
+    float2* d_decq = nullptr;    size_t dq_pitch = 0;
+    float2* d_fftbuf = nullptr;
+    float2* d_spectrum = nullptr;
+    float* d_power = nullptr;
+    float* d_lptaps = nullptr;
+    float* d_slicer = nullptr;   size_t slicer_pitch = 0;
+    float* d_demod = nullptr;    size_t demod_pitch = 0;
+    unsigned char* d_raw = nullptr;
+    unsigned* d_raw_n = nullptr;
+    unsigned* d_mark = nullptr;          // [kMarkSlots][n_ch]
+    unsigned* d_offsets = nullptr;
+    unsigned char* d_packed = nullptr;   size_t packed_cap = 0;
+    float* d_taps1 = nullptr; float* d_taps2 = nullptr;
+    float2* d_twiddle = nullptr;
+    // config upload scratch
+    double* d_cfg_baud = nullptr; float* d_cfg_stops = nullptr; int* d_cfg_bits = nullptr; int* d_cfg_dc = nullptr;
+    int* d_cfg_ntaps = nullptr; unsigned char* d_cfg_dirty = nullptr;
+    // recordings
+    float2* d_rec_dec = nullptr; float2* d_rec_filt = nullptr; size_t rec_pitch = 0;
+    unsigned char* d_rec_bits = nullptr; unsigned* d_rec_bits_n = nullptr; unsigned rec_bits_pitch = 0;
+
+    // input
+    float2* d_stage = nullptr; size_t stage_pitch = 0;   // host pushes land here
+    const float2* ext = nullptr; size_t ext_pitch = 0; size_t ext_n = 0; // zero-copy device push
+    float* h_pinned = nullptr; size_t pinned_bytes = 0;  // staging for pageable host memory
+
+    int pending_marks = 0;   // async calls since the last collect
+    size_t cap_n_in = 0;     // largest (r + n) the per-call buffers are sized for
+
+    hbd_sentence_cb sentence_cb = nullptr; void* sentence_user = nullptr;
+    hbd_chars_cb chars_cb = nullptr; void* chars_user = nullptr;
+
+    void set_error(const std::string& e) { err = e; }
+    int ensure_call_capacity(size_t n_in_max);
+    int alloc_fixed();
+    int upload_taps();
+    int process_async_locked();
+    int collect_locked();
+    void free_all();
+};
+
+#define HBD_CHECK_H(h)  if (!(h)) return HBD_ERR_ARG
+#define HBD_CHECK_CH(h, ch) if (!(h) || (ch) < 0 || (ch) >= (h)->n_ch) return HBD_ERR_ARG
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)); }
+
+// grow a [rows][pitch] device matrix, keeping the first `keep` elements of every row
+template <typename T>
+static cudaError_t grow_rows(T** p, size_t* pitch, size_t new_pitch, size_t rows, size_t keep, cudaStream_t s)
+{
+    if (new_pitch <= *pitch && *p) return cudaSuccess;
+    T* np = nullptr;
+    cudaError_t e = cudaMalloc((void**)&np, rows * new_pitch * sizeof(T));
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(np, 0, rows * new_pitch * sizeof(T), s);
+    if (e != cudaSuccess) return e;
+    if (*p && keep) {
+        e = cudaMemcpy2DAsync(np, new_pitch * sizeof(T), *p, *pitch * sizeof(T), std::min(keep, *pitch) * sizeof(T), rows,
+                              cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return e;
+    }
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return e;
+    if (*p) cudaFree(*p);
+    *p = np;
+    *pitch = new_pitch;
+    return cudaSuccess;
+}
+
+int hbd_decoder::alloc_fixed()
+{
+    const size_t n = size_t(n_ch);
+    HBD_CUDA_CHECK(dalloc(&d_state, n));
+    {
+        // Average<T>'s constructor add()s one 0: count starts at 1 (Average.h:34-37)
+        ChanState init;
+        memset(&init, 0, sizeof(init));
+        init.baud = 1; // SymbolExtractor.h:96
+        init.nf_cnt = init.nv_cnt = init.pl_cnt = init.pr_cnt = 1;
+        std::vector<ChanState> all(n, init);
+        HBD_CUDA_CHECK(cudaMemcpy(d_state, all.data(), n * sizeof(ChanState), cudaMemcpyHostToDevice));
+    }
+    HBD_CUDA_CHECK(dalloc(&d_plan, n));
+    HBD_CUDA_CHECK(dalloc(&d_carry, n * kCarryCap));
+    HBD_CUDA_CHECK(cudaMemset(d_carry, 0, n * kCarryCap * sizeof(float2)));
+    HBD_CUDA_CHECK(dalloc(&d_fftbuf, n * kFftN));
+    HBD_CUDA_CHECK(cudaMemset(d_fftbuf, 0, n * kFftN * sizeof(float2)));
+    HBD_CUDA_CHECK(dalloc(&d_spectrum, n * kFftN));
+    HBD_CUDA_CHECK(cudaMemset(d_spectrum, 0, n * kFftN * sizeof(float2)));
+    HBD_CUDA_CHECK(dalloc(&d_power, n * kFftN));
+    HBD_CUDA_CHECK(cudaMemset(d_power, 0, n * kFftN * sizeof(float)));
+    HBD_CUDA_CHECK(dalloc(&d_lptaps, n * kLpMaxTaps));
+    HBD_CUDA_CHECK(cudaMemset(d_lptaps, 0, n * kLpMaxTaps * sizeof(float)));
+    HBD_CUDA_CHECK(dalloc(&d_raw, n * kRawCap));
+    HBD_CUDA_CHECK(dalloc(&d_raw_n, n));
+    HBD_CUDA_CHECK(cudaMemset(d_raw_n, 0, n * sizeof(unsigned)));
+    HBD_CUDA_CHECK(dalloc(&d_mark, n * kMarkSlots));
+    HBD_CUDA_CHECK(dalloc(&d_offsets, n));
+    HBD_CUDA_CHECK(dalloc(&d_taps1, 512));
+    HBD_CUDA_CHECK(dalloc(&d_taps2, 512));
+    HBD_CUDA_CHECK(dalloc(&d_twiddle, kFftN));
+    HBD_CUDA_CHECK(dalloc(&d_cfg_baud, n));
+    HBD_CUDA_CHECK(dalloc(&d_cfg_stops, n));
+    HBD_CUDA_CHECK(dalloc(&d_cfg_bits, n));
+    HBD_CUDA_CHECK(dalloc(&d_cfg_dc, n));
+    HBD_CUDA_CHECK(dalloc(&d_cfg_ntaps, n));
+    HBD_CUDA_CHECK(dalloc(&d_cfg_dirty, n));
+    std::vector<float2> tw(kFftN);
+    for (int e = 0; e < kFftN; ++e) {
+        const double ang = -2.0 * M_PI * double(e) / double(kFftN);
+        tw[e] = make_float2(float(std::cos(ang)), float(std::sin(ang)));
+    }
+    HBD_CUDA_CHECK(cudaMemcpy(d_twiddle, tw.data(), sizeof(float2) * kFftN, cudaMemcpyHostToDevice));
+    return HBD_OK;
+}
+
+int hbd_decoder::upload_taps()
+{
+    std::vector<TapTable> st;
+    plan_for_factor(size_t(factor), st);
+    M1 = T1 = M2 = T2 = 1;
+    if (st.size() >= 1) {
+        M1 = st[0].M; T1 = st[0].len;
+        HBD_CUDA_CHECK(cudaMemcpy(d_taps1, st[0].bits, 4 * size_t(T1), cudaMemcpyHostToDevice));
+    }
+    if (st.size() >= 2) {
+        M2 = st[1].M; T2 = st[1].len;
+        HBD_CUDA_CHECK(cudaMemcpy(d_taps2, st[1].bits, 4 * size_t(T2), cudaMemcpyHostToDevice));
+    }
+    return HBD_OK;
+}
+
+void hbd_decoder::free_all()
+{
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    void* ptrs[] = {d_state, d_plan, d_carry, d_s1, d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_raw, d_raw_n,
+                    d_mark, d_offsets, d_packed, d_taps1, d_taps2, d_twiddle, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps,
+                    d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h_pinned) cudaFreeHost(h_pinned);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+// size the per-call buffers for pushes of up to n_in_max (carried + new) samples per channel
+int hbd_decoder::ensure_call_capacity(size_t n_in_max)
+{
+    if (n_in_max <= cap_n_in && d_s1) return HBD_OK;
+    const size_t n = size_t(n_ch);
+    const size_t grow_to = std::max(n_in_max, cap_n_in);
+    const size_t n1_max = grow_to / size_t(M1) + 2, n2_max = grow_to / size_t(factor) + 2;
+    HBD_CUDA_CHECK(grow_rows(&d_s1, &s1_pitch, (kS1Hist + n1_max + 15) & ~size_t(15), n, kS1Hist, stream));
+    HBD_CUDA_CHECK(grow_rows(&d_decq, &dq_pitch, (kLpHist + kLpBatch + n2_max + 15) & ~size_t(15), n, kLpHist + kLpBatch, stream));
+    HBD_CUDA_CHECK(grow_rows(&d_slicer, &slicer_pitch, (size_t(kSlicerVent) + 1 + kLpBatch + n2_max + 15) & ~size_t(15), n,
+                             slicer_pitch, stream));
+    HBD_CUDA_CHECK(grow_rows(&d_demod, &demod_pitch, (kLpBatch + n2_max + 15) & ~size_t(15), n, 0, stream));
+    if (record) {
+        HBD_CUDA_CHECK(grow_rows(&d_rec_dec, &rec_pitch, (kLpBatch + n2_max + 15) & ~size_t(15), n, 0, stream));
+        size_t p2 = 0;
+        if (d_rec_filt) { cudaFree(d_rec_filt); d_rec_filt = nullptr; }
+        HBD_CUDA_CHECK(grow_rows(&d_rec_filt, &p2, rec_pitch, n, 0, stream));
+        if (!d_rec_bits) {
+            rec_bits_pitch = 1u << 16;
+            HBD_CUDA_CHECK(dalloc(&d_rec_bits, n * rec_bits_pitch));
+            HBD_CUDA_CHECK(dalloc(&d_rec_bits_n, n));
+            HBD_CUDA_CHECK(cudaMemset(d_rec_bits_n, 0, n * sizeof(unsigned)));
+        }
+    }
+    cap_n_in = grow_to;
+    return HBD_OK;
+}
+
+int hbd_decoder::process_async_locked()
+{
+    if (!fs_in) return HBD_OK; // Decoder.h:418-419: uninitialised -> silently nothing
+    HBD_CUDA_CHECK(cudaSetDevice(device));
+    if (pending_marks >= kMarkSlots) { const int rc = collect_locked(); if (rc) return rc; }
+    const size_t n = size_t(n_ch);
+    const double fs_dec = fs_in / factor;
+
+    // ---- plan: the reference's buffer arithmetic, per channel ------------------------------------------
+    h_plan.resize(n);
+    size_t max_total = 0; unsigned max_n1 = 0;
+    bool any_work = false;
+    for (size_t c = 0; c < n; ++c) {
+        HostChan& x = hc[c];
+        const unsigned pushed = ext ? unsigned(ext_n) : x.pushed;
+        ChanPlan& p = h_plan[c];
+        p.r = x.in_r; p.n = pushed;
+        const unsigned total = x.in_r + pushed;
+        max_total = std::max<size_t>(max_total, total);
+        if (int(total) < factor) { p.consumed = 0; p.n1 = p.n2 = 0; p.flags = 1; }
+        else {
+            p.consumed = total - total % unsigned(factor);
+            p.n1 = p.consumed / unsigned(M1);
+            p.n2 = p.consumed / unsigned(factor);
+            p.flags = 0;
+            any_work = true;
+        }
+        max_n1 = std::max(max_n1, p.n1);
+    }
+    { const int rc = ensure_call_capacity(max_total); if (rc) return rc; }
+
+    bool cfg_dirty_any = false;
+    std::vector<float> new_taps;
+    for (size_t c = 0; c < n; ++c) {
+        HostChan& x = hc[c];
+        const ChanPlan& p = h_plan[c];
+        x.in_r = p.r + p.n - p.consumed;
+        x.pushed = 0;
+        x.last_n2 = p.n2; x.last_nf = 0;
+        if (p.flags & 1u) { cfg_dirty_any |= x.cfg_dirty; continue; }
+        // history re-zeroing when the reference's work buffers grow (Decimator.h:74-79)
+        if (M1 > 1) {
+            const size_t need = size_t(p.consumed) + size_t(T1) + size_t(M1);
+            if (x.grown1 < need) {
+                x.grown1 = need;
+                HBD_CUDA_CHECK(cudaMemsetAsync(d_carry + c * kCarryCap + (kCarryCap - (T1 - 1) - p.r), 0, sizeof(float2) * size_t(T1 - 1), stream));
+            }
+        }
+        if (M2 > 1) {
+            const size_t need = size_t(p.n1) + size_t(T2) + size_t(M2);
+            if (x.grown2 < need) {
+                x.grown2 = need;
+                HBD_CUDA_CHECK(cudaMemsetAsync(d_s1 + c * s1_pitch, 0, sizeof(float2) * kS1Hist, stream));
+            }
+        }
+        const unsigned total_dec = x.dec_pending + p.n2;
+        if (total_dec < unsigned(kLpBatch)) { x.dec_pending = total_dec; cfg_dirty_any |= x.cfg_dirty; continue; }
+        if (fs_dec > 4 * 40e3) { x.dec_pending = 0; cfg_dirty_any |= x.cfg_dirty; continue; }
+        const unsigned nf = total_dec - total_dec % unsigned(kLpBatch);
+        x.dec_pending = total_dec - nf;
+        x.last_nf = nf;
+        // low-pass design, Decoder.h:536-538
+        x.lp_input_size = nf;
+        const size_t T = design_lowpass(float(x.lp_bw / fs_dec), x.lp_trans, x.lp_input_size, x.lp_ntaps, new_taps);
+        if (T != x.lp_ntaps) {
+            if (T > size_t(kLpMaxTaps)) { set_error("low-pass needs more than kLpMaxTaps taps"); return HBD_ERR_ARG; }
+            x.lp_ntaps = T;
+            x.cfg_dirty = true;
+            HBD_CUDA_CHECK(cudaMemcpyAsync(d_lptaps + c * kLpMaxTaps, new_taps.data(), 4 * T, cudaMemcpyHostToDevice, stream));
+            HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // new_taps is reused
+        }
+        const size_t need = size_t(nf) + x.lp_ntaps;
+        if (x.grown_lp < need) { // FirFilter.h:141-147
+            x.grown_lp = need;
+            HBD_CUDA_CHECK(cudaMemsetAsync(d_decq + c * dq_pitch, 0, sizeof(float2) * kLpHist, stream));
+        }
+        cfg_dirty_any |= x.cfg_dirty;
+    }
+    if (cfg_dirty_any) {
+        std::vector<double> b(n); std::vector<float> s(n); std::vector<int> bi(n), dc(n), nt(n); std::vector<unsigned char> d(n);
+        for (size_t c = 0; c < n; ++c) {
+            b[c] = hc[c].baud; s[c] = hc[c].rtty_stops; bi[c] = int(hc[c].rtty_bits); dc[c] = hc[c].dc_remove; nt[c] = int(hc[c].lp_ntaps);
+            d[c] = hc[c].cfg_dirty; hc[c].cfg_dirty = false;
+        }
+        HBD_CUDA_CHECK(cudaMemcpyAsync(d_cfg_baud, b.data(), 8 * n, cudaMemcpyHostToDevice, stream));
+        HBD_CUDA_CHECK(cudaMemcpyAsync(d_cfg_stops, s.data(), 4 * n, cudaMemcpyHostToDevice, stream));
+        HBD_CUDA_CHECK(cudaMemcpyAsync(d_cfg_bits, bi.data(), 4 * n, cudaMemcpyHostToDevice, stream));
+        HBD_CUDA_CHECK(cudaMemcpyAsync(d_cfg_dc, dc.data(), 4 * n, cudaMemcpyHostToDevice, stream));
+        HBD_CUDA_CHECK(cudaMemcpyAsync(d_cfg_ntaps, nt.data(), 4 * n, cudaMemcpyHostToDevice, stream));
+        HBD_CUDA_CHECK(cudaMemcpyAsync(d_cfg_dirty, d.data(), n, cudaMemcpyHostToDevice, stream));
+        init_cfg_kernel<<<(n_ch + 127) / 128, 128, 0, stream>>>(d_state, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps, d_cfg_dirty, n_ch);
+        ++launches;
+        HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // host vectors go out of scope
+    }
+    if (h_plan_uploaded.size() != n || memcmp(h_plan.data(), h_plan_uploaded.data(), n * sizeof(ChanPlan)) != 0) {
+        HBD_CUDA_CHECK(cudaMemcpyAsync(d_plan, h_plan.data(), n * sizeof(ChanPlan), cudaMemcpyHostToDevice, stream));
+        HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
+        h_plan_uploaded = h_plan;
+    }
+
+    const float2* chunk = ext ? ext : d_stage;
+    const size_t chunk_pitch = ext ? ext_pitch : stage_pitch;
+    int nl = 0;
+    if (any_work) {
+        DecimArgs da{};
+        da.chunk = chunk; da.chunk_pitch = chunk_pitch; da.carry = d_carry;
+        da.s1 = d_s1; da.s1_pitch = s1_pitch; da.s1_hist = kS1Hist;
+        da.plan = d_plan; da.taps = d_taps1; da.n_channels = n_ch;
+        da.sb_per_stretch = decim1_sb_per_stretch(M1);
+        const unsigned n_sb = (M1 > 1) ? (max_n1 * unsigned(M1) + 63) / 64 + 2 : 1;
+        da.stretches_per_channel = int((n_sb + da.sb_per_stretch - 1) / da.sb_per_stretch);
+        HBD_CUDA_CHECK(launch_decim1(da, M1, T1, max_n1, n_sms, stream, &nl));
+    }
+    {
+        TailArgs ta{};
+        ta.plan = d_plan; ta.state = d_state; ta.chunk = chunk; ta.chunk_pitch = chunk_pitch; ta.carry = d_carry; ta.T1 = T1;
+        ta.s1 = d_s1; ta.s1_pitch = s1_pitch; ta.taps2 = d_taps2; ta.M2 = M2; ta.T2 = T2;
+        ta.decq = d_decq; ta.dq_pitch = dq_pitch; ta.fs_dec = fs_dec; ta.fftbuf = d_fftbuf; ta.lptaps = d_lptaps;
+        ta.slicer = d_slicer; ta.slicer_pitch = slicer_pitch; ta.demod_last = d_demod; ta.demod_pitch = demod_pitch;
+        ta.rec_decimated = record ? d_rec_dec : nullptr; ta.rec_filtered = record ? d_rec_filt : nullptr; ta.rec_pitch = rec_pitch;
+        ta.smem_window = tail_smem_window(M2, T2);
+        HBD_CUDA_CHECK(launch_tail(ta, n_ch, stream, &nl));
+    }
+    if (any_work) {
+        FftArgs fa{};
+        fa.state = d_state; fa.fftbuf = d_fftbuf; fa.spectrum = d_spectrum; fa.power = d_power; fa.twiddle = d_twiddle; fa.fs_dec = fs_dec;
+        HBD_CUDA_CHECK(launch_fft_afc(fa, n_ch, stream, &nl));
+        SlicerArgs sa{};
+        sa.state = d_state; sa.slicer = d_slicer; sa.slicer_pitch = slicer_pitch; sa.raw = d_raw; sa.raw_n = d_raw_n;
+        sa.rec_bits = record ? d_rec_bits : nullptr; sa.rec_bits_n = d_rec_bits_n; sa.rec_bits_pitch = rec_bits_pitch;
+        sa.fs_dec = fs_dec; sa.n_channels = n_ch;
+        HBD_CUDA_CHECK(launch_slicer(sa, stream, &nl));
+    }
+    mark_kernel<<<(n_ch + 255) / 256, 256, 0, stream>>>(d_raw_n, d_mark + size_t(pending_marks) * n, n_ch);
+    ++nl;
+    HBD_CUDA_CHECK(cudaGetLastError());
+    launches += unsigned(nl);
+    ++pending_marks;
+    ext = nullptr; ext_n = 0;
+    return HBD_OK;
+}
+
+int hbd_decoder::collect_locked()
+{
+    HBD_CUDA_CHECK(cudaSetDevice(device));
+    HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (!pending_marks) return HBD_OK;
+    const size_t n = size_t(n_ch);
+    std::vector<unsigned> marks(size_t(pending_marks) * n);
+    HBD_CUDA_CHECK(cudaMemcpyAsync(marks.data(), d_mark, marks.size() * 4, cudaMemcpyDeviceToHost, stream));
+    HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
+    const unsigned* final_n = marks.data() + size_t(pending_marks - 1) * n;
+    std::vector<unsigned> offs(n);
+    size_t total = 0;
+    for (size_t c = 0; c < n; ++c) { offs[c] = unsigned(total); total += std::min(final_n[c], unsigned(kRawCap)); }
+    std::vector<unsigned char> packed(total);
+    if (total) {
+        if (packed_cap < total) {
+            if (d_packed) cudaFree(d_packed);
+            packed_cap = std::max<size_t>(total * 2, 1 << 16);
+            HBD_CUDA_CHECK(dalloc(&d_packed, packed_cap));
+        }
+        HBD_CUDA_CHECK(cudaMemcpyAsync(d_offsets, offs.data(), 4 * n, cudaMemcpyHostToDevice, stream));
+        pack_raw_kernel<<<n_ch, 64, 0, stream>>>(d_raw, d_raw_n, d_offsets, d_packed, n_ch);
+        ++launches;
+        HBD_CUDA_CHECK(cudaMemcpyAsync(packed.data(), d_packed, total, cudaMemcpyDeviceToHost, stream));
+    }
+    HBD_CUDA_CHECK(cudaMemsetAsync(d_raw_n, 0, 4 * n, stream));
+    HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
+    // sentence layer, call by call like Decoder::process()
+    SentenceSink sink;
+    if (sentence_cb) {
+        hbd_sentence_cb cb = sentence_cb; void* user = sentence_user;
+        sink = [cb, user](int ch, const std::string& cs, const std::string& d, const std::string& crc) { cb(user, ch, cs.c_str(), d.c_str(), crc.c_str()); };
+    }
+    for (size_t c = 0; c < n; ++c) {
+        if (!final_n[c]) continue;
+        unsigned prev = 0;
+        const size_t before = hc[c].text.chars_pending.size();
+        for (int s = 0; s < pending_marks; ++s) {
+            const unsigned upto = std::min(marks[size_t(s) * n + c], unsigned(kRawCap));
+            if (upto > prev) hc[c].text.feed(packed.data() + offs[c] + prev, upto - prev, int(c), sink);
+            prev = std::max(prev, upto);
+        }
+        if (chars_cb && hc[c].text.chars_pending.size() > before)
+            chars_cb(chars_user, int(c), hc[c].text.chars_pending.data() + before, hc[c].text.chars_pending.size() - before);
+    }
+    pending_marks = 0;
+    return HBD_OK;
+}
+
+// =====================================================================================================
+extern "C" {
+
+int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
+{
+    if (!out || n_channels < 1) return HBD_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || cuda_device < 0 || cuda_device >= count) return HBD_ERR_CUDA;
+    if (cudaSetDevice(cuda_device) != cudaSuccess) return HBD_ERR_CUDA;
+    hbd_decoder* h = new (std::nothrow) hbd_decoder;
+    if (!h) return HBD_ERR_NOMEM;
+    h->n_ch = n_channels; h->device = cuda_device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) h->n_sms = prop.multiProcessorCount;
+    h->hc.resize(size_t(n_channels));
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return HBD_ERR_CUDA; }
+    h->own_stream = true;
+    const int rc = h->alloc_fixed();
+    if (rc) { h->free_all(); delete h; return rc; }
+    *out = h;
+    return HBD_OK;
+}
+
+void hbd_destroy(hbd_decoder* h)
+{
+    if (!h) return;
+    h->free_all();
+    delete h;
+}
+
+const char* hbd_last_error(hbd_decoder* h) { return h ? h->err.c_str() : "null handle"; }
+
+int hbd_set_stream(hbd_decoder* h, void* s)
+{
+    HBD_CHECK_H(h);
+    std::lock_guard<std::mutex> l(h->mtx);
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)s; h->own_stream = false;
+    return HBD_OK;
+}
+
+int hbd_set_record(hbd_decoder* h, int on)
+{
+    HBD_CHECK_H(h);
+    std::lock_guard<std::mutex> l(h->mtx);
+    h->record = on != 0;
+    h->cap_n_in = 0; // force (re)allocation of the recording buffers on the next call
+    return HBD_OK;
+}
+
+#define HBD_SETTER(NAME, TYPE, FIELD, DIRTY)                                         \
+    int hbd_set_##NAME(hbd_decoder* h, int ch, TYPE v)                               \
+    {                                                                                \
+        if (!h || ch < -1 || ch >= h->n_ch) return HBD_ERR_ARG;                      \
+        std::lock_guard<std::mutex> l(h->mtx);                                       \
+        for (int c = (ch < 0 ? 0 : ch); c < (ch < 0 ? h->n_ch : ch + 1); ++c) {      \
+            h->hc[size_t(c)].FIELD = v;                                              \
+            if (DIRTY) h->hc[size_t(c)].cfg_dirty = true;                            \
+        }                                                                            \
+        return HBD_OK;                                                               \
+    }
+HBD_SETTER(baud, double, baud, true)
+HBD_SETTER(rtty_bits, size_t, rtty_bits, true)
+HBD_SETTER(rtty_stops, float, rtty_stops, true)
+HBD_SETTER(dc_remove, int, dc_remove, true)
+
+// Decoder::lowpass_bw / lowpass_trans re-run the design immediately (Decoder.h:238-257)
+static int set_lp(hbd_decoder* h, int ch, float bw, float trans, bool set_bw)
+{
+    if (!h || ch < -1 || ch >= h->n_ch) return HBD_ERR_ARG;
+    std::lock_guard<std::mutex> l(h->mtx);
+    cudaSetDevice(h->device);
+    std::vector<float> taps;
+    for (int c = (ch < 0 ? 0 : ch); c < (ch < 0 ? h->n_ch : ch + 1); ++c) {
+        HostChan& x = h->hc[size_t(c)];
+        if (set_bw) x.lp_bw = bw; else x.lp_trans = trans;
+        if (!h->fs_in) continue;
+        const double fs_dec = h->fs_in / h->factor;
+        const size_t T = design_lowpass(float(x.lp_bw / fs_dec), x.lp_trans, x.lp_input_size, x.lp_ntaps, taps);
+        if (T != x.lp_ntaps && T <= size_t(kLpMaxTaps)) {
+            x.lp_ntaps = T; x.cfg_dirty = true;
+            if (cudaMemcpy(h->d_lptaps + size_t(c) * kLpMaxTaps, taps.data(), 4 * T, cudaMemcpyHostToDevice) != cudaSuccess) return HBD_ERR_CUDA;
+        }
+    }
+    return HBD_OK;
+}
+int hbd_set_lowpass_bw(hbd_decoder* h, int ch, float bw) { return set_lp(h, ch, bw, 0, true); }
+int hbd_set_lowpass_trans(hbd_decoder* h, int ch, float tr) { return set_lp(h, ch, 0, tr, false); }
+
+double hbd_get_baud(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].baud; }
+size_t hbd_get_rtty_bits(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].rtty_bits; }
+float hbd_get_rtty_stops(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].rtty_stops; }
+float hbd_get_lowpass_bw(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].lp_bw; }
+float hbd_get_lowpass_trans(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].lp_trans; }
+int hbd_get_dc_remove(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].dc_remove; }
+
+static size_t apply_factor(hbd_decoder* h, size_t factor)
+{
+    // a new plan starts from fresh decimators (Decoder.h:283-284: decimation_stages_.clear())
+    std::vector<TapTable> st;
+    if (!plan_for_factor(factor, st)) { h->factor = 1; factor = 0; }
+    else h->factor = int(factor);
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->upload_taps();
+    cudaMemset(h->d_carry, 0, size_t(h->n_ch) * kCarryCap * sizeof(float2));
+    if (h->d_s1) cudaMemset(h->d_s1, 0, size_t(h->n_ch) * h->s1_pitch * sizeof(float2));
+    for (auto& x : h->hc) {
+        x.grown1 = x.grown2 = 0;
+        // unconsumed input stays queued in the reference (iq_in_buffer_ is untouched); it sits at the end of the carry
+    }
+    h->cap_n_in = 0;
+    h->h_plan_uploaded.clear();
+    return factor;
+}
+
+size_t hbd_setup_decimation_factor(hbd_decoder* h, size_t factor)
+{
+    if (!h) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    if (factor < 1 || factor > 256) return size_t(h->factor);
+    return apply_factor(h, factor);
+}
+
+size_t hbd_setup_decimation_bw(hbd_decoder* h, double max_rate)
+{
+    if (!h) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    if (!h->fs_in) return 0;
+    // Decoder.h:350-402 loops "divide by the smallest power of two that gets under the limit" -- with div < 256
+    // in the inner loop the first iteration can take 256 only through the fall-through; the product of the
+    // chosen divisors is what matters for this implementation, which only supports single-plan factors.
+    double rate = h->fs_in;
+    size_t total = 1;
+    while (rate > max_rate) {
+        int div;
+        for (div = 2; div < 256; div *= 2) if (rate / div <= max_rate) break;
+        rate /= div; total *= size_t(div);
+        if (total > 256) break;
+    }
+    if (total > 256) { h->set_error("setup_decimation_bw: cascades beyond one 256x plan are not supported"); return 0; }
+    return apply_factor(h, total);
+}
+
+static int latch_rate(hbd_decoder* h, double fs)
+{
+    if (!h->fs_in) h->fs_in = double(float(fs)); // Decoder::init(const float)
+    return HBD_OK;
+}
+
+static int ensure_stage(hbd_decoder* h, size_t need)
+{
+    if (need <= h->stage_pitch && h->d_stage) return HBD_OK;
+    const size_t np = (std::max(need, h->stage_pitch) + 15) & ~size_t(15);
+    cudaError_t e = grow_rows(&h->d_stage, &h->stage_pitch, np, size_t(h->n_ch), h->stage_pitch, h->stream);
+    if (e != cudaSuccess) { h->set_error(std::string("staging alloc: ") + cudaGetErrorString(e)); return HBD_ERR_CUDA; }
+    return HBD_OK;
+}
+
+int hbd_push_samples(hbd_decoder* h, int ch, const float* iq, size_t n, double fs)
+{
+    HBD_CHECK_CH(h, ch);
+    if (!iq && n) return HBD_ERR_ARG;
+    std::lock_guard<std::mutex> l(h->mtx);
+    if (h->ext) { h->set_error("device push pending"); return HBD_ERR_STATE; }
+    if (cudaSetDevice(h->device) != cudaSuccess) return HBD_ERR_CUDA;
+    HostChan& x = h->hc[size_t(ch)];
+    const int rc = ensure_stage(h, size_t(x.pushed) + n);
+    if (rc) return rc;
+    if (n) {
+        cudaError_t e = cudaMemcpyAsync(h->d_stage + size_t(ch) * h->stage_pitch + x.pushed, iq, n * sizeof(float2), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream); // the caller owns `iq` again on return (Decoder.h:209-213 copies)
+        if (e != cudaSuccess) { h->set_error(cudaGetErrorString(e)); return HBD_ERR_CUDA; }
+    }
+    x.pushed += unsigned(n);
+    return latch_rate(h, fs);
+}
+
+int hbd_push_samples_batch(hbd_decoder* h, const float* iq, size_t n, size_t pitch, double fs)
+{
+    HBD_CHECK_H(h);
+    if ((!iq && n) || pitch < n) return HBD_ERR_ARG;
+    std::lock_guard<std::mutex> l(h->mtx);
+    if (h->ext) { h->set_error("device push pending"); return HBD_ERR_STATE; }
+    if (cudaSetDevice(h->device) != cudaSuccess) return HBD_ERR_CUDA;
+    unsigned base = h->hc[0].pushed;
+    for (auto& x : h->hc) if (x.pushed != base) { h->set_error("batch push needs equal queue depth in all channels"); return HBD_ERR_STATE; }
+    const int rc = ensure_stage(h, size_t(base) + n);
+    if (rc) return rc;
+    if (n) {
+        cudaError_t e = cudaMemcpy2DAsync(h->d_stage + base, h->stage_pitch * sizeof(float2), iq, pitch * sizeof(float2), n * sizeof(float2),
+                                          size_t(h->n_ch), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { h->set_error(cudaGetErrorString(e)); return HBD_ERR_CUDA; }
+    }
+    for (auto& x : h->hc) x.pushed += unsigned(n);
+    return latch_rate(h, fs);
+}
+
+int hbd_push_samples_device(hbd_decoder* h, const float* d_iq, size_t n, size_t pitch, double fs)
+{
+    HBD_CHECK_H(h);
+    if (!d_iq || pitch < n || (pitch & 1) || (reinterpret_cast<uintptr_t>(d_iq) & 15)) return HBD_ERR_ARG;
+    std::lock_guard<std::mutex> l(h->mtx);
+    if (h->ext) { h->set_error("device push pending"); return HBD_ERR_STATE; }
+    for (auto& x : h->hc) if (x.pushed) { h->set_error("host push pending"); return HBD_ERR_STATE; }
+    h->ext = reinterpret_cast<const float2*>(d_iq); h->ext_pitch = pitch; h->ext_n = n;
+    return latch_rate(h, fs);
+}
+
+int hbd_process_async(hbd_decoder* h) { HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); return h->process_async_locked(); }
+int hbd_collect(hbd_decoder* h) { HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); return h->collect_locked(); }
+int hbd_process(hbd_decoder* h)
+{
+    HBD_CHECK_H(h);
+    std::lock_guard<std::mutex> l(h->mtx);
+    const int rc = h->process_async_locked();
+    if (rc) return rc;
+    return h->collect_locked();
+}
+int hbd_synchronize(hbd_decoder* h)
+{
+    HBD_CHECK_H(h);
+    std::lock_guard<std::mutex> l(h->mtx);
+    cudaSetDevice(h->device);
+    return cudaStreamSynchronize(h->stream) == cudaSuccess ? HBD_OK : HBD_ERR_CUDA;
+}
+unsigned long long hbd_kernel_launches(hbd_decoder* h) { return h ? h->launches : 0; }
+
+static size_t copy_out(const std::string& s, char* out, size_t cap)
+{
+    if (out && cap) memcpy(out, s.data(), std::min(cap, s.size()));
+    return s.size();
+}
+
+size_t hbd_get_rtty(hbd_decoder* h, int ch, char* out, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    return copy_out(h->hc[size_t(ch)].text.text_stream, out, cap);
+}
+size_t hbd_get_last_sentence(hbd_decoder* h, int ch, char* out, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    return copy_out(h->hc[size_t(ch)].text.last_sentence, out, cap);
+}
+size_t hbd_poll_chars(hbd_decoder* h, int ch, char* out, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    std::string& s = h->hc[size_t(ch)].text.chars_pending;
+    const size_t n = copy_out(s, out, cap);
+    if (out && cap >= n) s.clear();
+    return n;
+}
+size_t hbd_poll_sentences(hbd_decoder* h, int ch, char* out, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    std::string& s = h->hc[size_t(ch)].text.sentences_pending;
+    const size_t n = copy_out(s, out, cap);
+    if (out && cap >= n) s.clear();
+    return n;
+}
+size_t hbd_poll_raw_chars(hbd_decoder* h, int ch, unsigned char* out, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    auto& v = h->hc[size_t(ch)].text.raw_pending;
+    const size_t n = v.size();
+    if (out && cap) memcpy(out, v.data(), std::min(cap, n));
+    if (out && cap >= n) v.clear();
+    return n;
+}
+int hbd_set_sentence_callback(hbd_decoder* h, hbd_sentence_cb cb, void* user)
+{
+    HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); h->sentence_cb = cb; h->sentence_user = user; return HBD_OK;
+}
+int hbd_set_chars_callback(hbd_decoder* h, hbd_chars_cb cb, void* user)
+{
+    HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); h->chars_cb = cb; h->chars_user = user; return HBD_OK;
+}
+
+int hbd_get_decimation_factor(hbd_decoder* h) { return h ? h->factor : 0; }
+double hbd_get_input_sampling_rate(hbd_decoder* h) { return h ? h->fs_in : 0; }
+double hbd_get_decimated_sampling_rate(hbd_decoder* h) { return h ? h->fs_in / h->factor : 0; }
+double hbd_get_symbol_rate(hbd_decoder* h, int ch) { return hbd_get_baud(h, ch); }
+int hbd_n_channels(hbd_decoder* h) { return h ? h->n_ch : 0; }
+size_t hbd_get_bins_count(hbd_decoder*) { return size_t(kFftN); }
+
+static int fetch_state(hbd_decoder* h, int ch, ChanState* st)
+{
+    cudaSetDevice(h->device);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
+    return cudaMemcpy(st, h->d_state + ch, sizeof(ChanState), cudaMemcpyDeviceToHost) == cudaSuccess ? HBD_OK : HBD_ERR_CUDA;
+}
+static size_t fetch_floats(hbd_decoder* h, const void* dsrc, size_t n, float* out, size_t cap)
+{
+    if (out && cap && n) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        if (cudaMemcpy(out, dsrc, std::min(n, cap) * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    }
+    return n;
+}
+
+size_t hbd_get_fft(hbd_decoder* h, int ch, float* out, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    ChanState st; if (fetch_state(h, ch, &st)) return 0;
+    if (!st.have_spectrum) return 0; // freq_out_ is empty before the first FFT
+    return fetch_floats(h, h->d_spectrum + size_t(ch) * kFftN, 2 * size_t(kFftN), out, cap);
+}
+size_t hbd_get_power_spectrum(hbd_decoder* h, int ch, float* out, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    ChanState st; if (fetch_state(h, ch, &st)) return 0;
+    if (!st.have_spectrum) return 0;
+    return fetch_floats(h, h->d_power + size_t(ch) * kFftN, size_t(kFftN), out, cap);
+}
+size_t hbd_get_demodulated(hbd_decoder* h, int ch, float* out, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    const size_t n = h->hc[size_t(ch)].last_nf;
+    if (!h->d_demod) return 0;
+    return fetch_floats(h, h->d_demod + size_t(ch) * h->demod_pitch, n, out, cap);
+}
+int hbd_get_peaks(hbd_decoder* h, int ch, int* pl, int* pr)
+{
+    HBD_CHECK_CH(h, ch); std::lock_guard<std::mutex> l(h->mtx);
+    ChanState st; const int rc = fetch_state(h, ch, &st); if (rc) return rc;
+    if (pl) *pl = st.gui_left; if (pr) *pr = st.gui_right; return HBD_OK;
+}
+int hbd_get_noise_floor(hbd_decoder* h, int ch, double* nf, double* nv)
+{
+    HBD_CHECK_CH(h, ch); std::lock_guard<std::mutex> l(h->mtx);
+    ChanState st; const int rc = fetch_state(h, ch, &st); if (rc) return rc;
+    if (nf) *nf = st.afc_noise_floor; if (nv) *nv = st.afc_noise_var; return HBD_OK;
+}
+double hbd_get_shift(hbd_decoder* h, int ch)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0; std::lock_guard<std::mutex> l(h->mtx);
+    ChanState st; if (fetch_state(h, ch, &st)) return 0; return st.afc_shift_hz;
+}
+double hbd_get_frequency_correction(hbd_decoder* h, int ch)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0; std::lock_guard<std::mutex> l(h->mtx);
+    ChanState st; if (fetch_state(h, ch, &st)) return 0; return st.afc_correction;
+}
+int hbd_reset_frequency_correction(hbd_decoder* h, int ch, double corr)
+{
+    HBD_CHECK_CH(h, ch); std::lock_guard<std::mutex> l(h->mtx);
+    cudaSetDevice(h->device);
+    if (launch_afc_reset(h->d_state, ch, corr, h->fs_in / h->factor, h->stream) != cudaSuccess) return HBD_ERR_CUDA;
+    ++h->launches;
+    return HBD_OK;
+}
+size_t hbd_get_spectrum_info(hbd_decoder* h, int ch, hbd_spectrum_info* info, float* power, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch || !info) return 0;
+    std::vector<float> p(kFftN);
+    const size_t n = hbd_get_power_spectrum(h, ch, p.data(), p.size());
+    memset(info, 0, sizeof(*info));
+    if (!n) return 0; // Decoder.h:818-819
+    info->min_ = *std::min_element(p.begin(), p.end());
+    info->max_ = *std::max_element(p.begin(), p.end());
+    int pl = 0, pr = 0;
+    hbd_get_peaks(h, ch, &pl, &pr);
+    info->peak_left_ = std::abs(pl); info->peak_left_valid_ = pl > 0;
+    info->peak_right_ = std::abs(pr); info->peak_right_valid_ = pr > 0;
+    hbd_get_noise_floor(h, ch, &info->noise_floor_, &info->noise_variance_);
+    info->sampling_rate_ = hbd_get_decimated_sampling_rate(h);
+    info->shift_ = hbd_get_shift(h, ch);
+    if (power && cap) memcpy(power, p.data(), std::min(cap, n) * sizeof(float));
+    return n;
+}
+
+size_t hbd_debug_stage(hbd_decoder* h, int ch, int stage, float* out, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    const HostChan& x = h->hc[size_t(ch)];
+    switch (stage) {
+    case HBD_STAGE_DECIMATED:
+        if (!h->d_rec_dec) return 0;
+        return fetch_floats(h, h->d_rec_dec + size_t(ch) * h->rec_pitch, 2 * size_t(x.last_n2), out, cap);
+    case HBD_STAGE_FILTERED:
+        if (!h->d_rec_filt) return 0;
+        return fetch_floats(h, h->d_rec_filt + size_t(ch) * h->rec_pitch, 2 * size_t(x.last_nf), out, cap);
+    case HBD_STAGE_DEMOD:
+        if (!h->d_demod) return 0;
+        return fetch_floats(h, h->d_demod + size_t(ch) * h->demod_pitch, size_t(x.last_nf), out, cap);
+    case HBD_STAGE_LPTAPS:
+        return fetch_floats(h, h->d_lptaps + size_t(ch) * kLpMaxTaps, x.lp_ntaps, out, cap);
+    case HBD_STAGE_PENDING: {
+        ChanState st; if (fetch_state(h, ch, &st)) return 0;
+        if (!h->d_slicer) return 0;
+        return fetch_floats(h, h->d_slicer + size_t(ch) * h->slicer_pitch, st.slicer_n, out, cap);
+    }
+    case HBD_STAGE_BITS: {
+        if (!h->d_rec_bits) return 0;
+        cudaSetDevice(h->device); cudaStreamSynchronize(h->stream);
+        unsigned nb = 0;
+        cudaMemcpy(&nb, h->d_rec_bits_n + ch, 4, cudaMemcpyDeviceToHost);
+        nb = std::min(nb, h->rec_bits_pitch);
+        if (out && cap && nb) {
+            std::vector<unsigned char> b(nb);
+            cudaMemcpy(b.data(), h->d_rec_bits + size_t(ch) * h->rec_bits_pitch, nb, cudaMemcpyDeviceToHost);
+            for (size_t i = 0; i < std::min<size_t>(nb, cap); ++i) out[i] = float(b[i]);
+        }
+        return nb;
+    }
+    default: return 0;
+    }
+}
+
+size_t hbd_design_lowpass(float rel_width, float trans, size_t input_size, size_t current_taps, float* out, size_t cap)
+{
+    std::vector<float> taps;
+    const size_t T = design_lowpass(rel_width, trans, input_size, current_taps, taps);
+    if (out && T != current_taps) memcpy(out, taps.data(), std::min(cap, taps.size()) * sizeof(float));
+    return T;
+}
+
+int hbd_extract_sentence(const char* stream, size_t n, char* callsign, char* data, char* crc, size_t cap, size_t* rest)
+{
+    SentenceMatch m;
+    if (!extract_sentence(std::string(stream, n), m)) return 0;
+    auto put = [cap](char* dst, const std::string& s) { if (dst && cap) { const size_t k = std::min(cap - 1, s.size()); memcpy(dst, s.data(), k); dst[k] = 0; } };
+    put(callsign, m.callsign); put(data, m.data); put(crc, m.crc);
+    if (rest) *rest = m.rest_offset;
+    return 1;
+}
+
+void hbd_crc16(const char* s, size_t n, char out[5])
+{
+    const std::string r = crc16_hex(std::string(s, n));
+    memcpy(out, r.data(), 4); out[4] = 0;
+}
+
+} // extern "C"

@@ -1,0 +1,344 @@
+// K1 -- stage-1 FIR decimator, the HBM-bound kernel of the path.
+//
+// Replaces habdec::Decimator<complex<float>,float>::operator() for the first
+// decimation stage (reference: code/Decoder/Decimator.h:99-146, driven from
+// code/Decoder/Decoder.h:440-447 with the tap tables chosen at :286-320):
+//
+//     y[k] = sum_{t=0}^{T-1} x[k*M - (T-1) + t] * h[t]        (x = [history | input])
+//
+// B200 design (not a translation of the CPU loop):
+//  * a WARP is the unit of work.  It owns a "stretch" of consecutive output samples of one
+//    channel and streams the matching input window exactly once, HBM -> shared memory, with
+//    1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) into a private ring of
+//    pieces; no thread ever issues a global load for samples, so memory-level parallelism
+//    is set by the ring depth, not by occupancy or registers.
+//  * polyphase mapping: the input is cut into 64-sample superblocks that END on an output
+//    sample; lane l always sees phase l and l+32 of every superblock (two conflict-free
+//    LDS.64), so its 2*NLIVE taps live in registers for the whole kernel.  Every lane keeps
+//    NLIVE sliding complex accumulators (one per output whose window overlaps the current
+//    superblock); each loaded sample is used for T/M (5.4 .. 6.8) FMAs straight from
+//    registers.  Completed outputs are lane-partials: 16 of them are transposed through a
+//    padded shared tile and summed, so the cross-lane reduction costs ~2 LDS + 2 FADD per
+//    superblock instead of a shuffle tree per output.
+//  * no tensor cores: complex-by-real FIR taps on a per-channel stream are not a dense
+//    contraction (north star), the kernel is bound by the 8 B/sample HBM read.
+//
+// Summation order differs from the reference's sequential t-loop (lane-partials + tree),
+// so results match to ~1e-7 relative, inside the 1e-5 relative-L2 budget of the north star.
+#include "hbd_common.cuh"
+#include "decim1.cuh"
+#include <algorithm>
+
+namespace hbd {
+
+// ---- small PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (TMA, 1-D), completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- compile-time geometry of one (M, T) decimator ---------------------------------------------------------
+template <int M, int T>
+struct Geo {
+    static constexpr int SB    = 64;                   // samples per superblock
+    static constexpr int NOUT  = SB / M;               // outputs ending inside one superblock
+    static constexpr int NLIVE = (T + SB - 1) / M;     // outputs whose window overlaps a superblock
+    static constexpr int RAMP  = 1 + (T - 1 - M) / SB; // superblocks walked before the first owned one
+    static constexpr int gcd_(int a, int b) { return b ? gcd_(b, a % b) : a; }
+    static constexpr int U     = NLIVE / gcd_(NLIVE, NOUT); // accumulator rotation period (superblocks)
+    static constexpr int PSB   = U * ((12 + U - 1) / U);    // superblocks per ring piece (multiple of U, >= 12)
+    static constexpr int PIECE_SAMPLES = PSB * SB;
+    static constexpr int PIECE_BYTES   = (PIECE_SAMPLES + 2) * 8; // +2: 16-byte alignment slack on both sides
+    static_assert(SB % M == 0, "M must divide 64");
+    static_assert(T - 1 >= M, "taps shorter than the decimation factor are not handled by this kernel");
+};
+
+constexpr int kStages      = 3;    // ring depth per warp
+constexpr int kRedOutputs  = 16;   // outputs per cross-lane reduction group
+constexpr int kRedPitch    = 33;   // float2 per row (+1 pad: conflict-free transposed reads)
+
+template <int M, int T>
+struct WarpSmem {
+    alignas(16) unsigned char ring[kStages][Geo<M, T>::PIECE_BYTES];
+    alignas(16) float2 red[kRedOutputs][kRedPitch];
+    alignas(8) uint64_t full[kStages];
+};
+
+// taps for lane position P (0..63) and live output j (1..NLIVE): t = T - M*j + P
+template <int M, int T>
+__device__ __forceinline__ float tap_for(const float* __restrict__ taps, int j, int P)
+{
+    const int t = T - M * j + P;
+    return (t >= 0 && t < T) ? __ldg(taps + t) : 0.0f;
+}
+
+template <int M, int T>
+__global__ void __launch_bounds__(kDecimWarps * 32, 1)
+decim1_kernel(DecimArgs a)
+{
+    using G = Geo<M, T>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSmem<M, T>& sm = reinterpret_cast<WarpSmem<M, T>*>(smem_raw)[warp];
+
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    // taps stay in registers: lane sees positions P0 = lane and P1 = lane + 32 of every superblock
+    float h0[G::NLIVE], h1[G::NLIVE];
+#pragma unroll
+    for (int j = 0; j < G::NLIVE; ++j) {
+        h0[j] = tap_for<M, T>(a.taps, j + 1, lane);
+        h1[j] = tap_for<M, T>(a.taps, j + 1, lane + 32);
+    }
+
+    uint32_t phase_bits = 0; // parity per ring slot
+    const int warps_total = gridDim.x * kDecimWarps;
+    const long long n_items = (long long)a.n_channels * a.stretches_per_channel;
+
+    for (long long item = (long long)blockIdx.x * kDecimWarps + warp; item < n_items; item += warps_total) {
+        const int ch = int(item / a.stretches_per_channel);
+        const int st = int(item % a.stretches_per_channel);
+        const ChanPlan pl = a.plan[ch];
+        if (pl.flags & 1u) continue;
+        // superblock b covers step-local sample positions x in (64(b-1), 64b]; outputs k with
+        // k*M in that range end there.  Owned superblocks of this stretch:
+        const int n_sb_total = int((pl.n1 + G::NOUT - 1) / G::NOUT) + (G::NOUT > 1 ? 1 : 0); // covers k = 0 .. n1-1
+        const int b_lo = st * a.sb_per_stretch;
+        if (b_lo >= n_sb_total) continue;
+        const int b_hi = min(b_lo + a.sb_per_stretch, n_sb_total);
+        const int b_first = b_lo - G::RAMP;                 // walk start (ramp-in superblocks are discarded)
+        const int n_walk = b_hi - b_first;                  // superblocks to walk
+        const int n_pieces = (n_walk + G::PSB - 1) / G::PSB;
+
+        // sample addressing: j = x - r is the index into the pushed chunk (j >= 0) or the carry (j < 0)
+        const long long j0 = 64LL * (b_first - 1) + 1 - (long long)pl.r; // first sample of the walk
+        const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
+        const float2* carry = a.carry + (size_t)ch * kCarryCap + kCarryCap; // carry[j] valid for -kCarryCap <= j < 0
+        const long long j_end_valid = (long long)pl.n;                       // chunk holds j in [0, n)
+
+        // ---- producer: copy piece p into its ring slot (lane 0 issues, everyone helps with ragged edges)
+        auto issue_piece = [&](int p) {
+            const int slot = p % kStages;
+            unsigned char* dst = sm.ring[slot];
+            const long long pj0 = j0 + (long long)p * G::PIECE_SAMPLES;   // first sample wanted
+            const long long pj1 = pj0 + G::PIECE_SAMPLES;                 // one past the last
+            // smem sample s (0 .. PIECE_SAMPLES+1) holds j = A + s, A = pj0 rounded down to even
+            const long long A = pj0 & ~1LL;
+            long long lo = max(A, (long long)-kCarryCap);
+            long long hi = min((pj1 + 1) & ~1LL, j_end_valid);
+            if (hi < lo) hi = lo;
+            // 16-byte aligned interior [lo2, hi2) goes through TMA, ragged edges through plain stores
+            const long long lo2 = (lo + 1) & ~1LL, hi2 = hi & ~1LL;
+            if (lane == 0) {
+                uint32_t bytes = 0;
+                if (hi2 > lo2) {
+                    const long long c_lo = lo2, c_hi = min(hi2, 0LL);  // part served by the carry
+                    const long long d_lo = max(lo2, 0LL), d_hi = hi2;  // part served by the chunk
+                    if (c_hi > c_lo) bytes += uint32_t(c_hi - c_lo) * 8u;
+                    if (d_hi > d_lo) bytes += uint32_t(d_hi - d_lo) * 8u;
+                    mbar_expect_tx(&sm.full[slot], bytes);
+                    if (c_hi > c_lo) tma_load_1d(dst + (c_lo - A) * 8, carry + c_lo, uint32_t(c_hi - c_lo) * 8u, &sm.full[slot]);
+                    if (d_hi > d_lo) tma_load_1d(dst + (d_lo - A) * 8, chunk + d_lo, uint32_t(d_hi - d_lo) * 8u, &sm.full[slot]);
+                } else {
+                    mbar_arrive(&sm.full[slot]);
+                }
+            }
+            // ragged edge (chunk with an odd sample count) goes through a plain store
+            float2* d2 = reinterpret_cast<float2*>(dst);
+            if (hi > hi2 && hi2 >= lo2 && lane == 2) d2[hi2 - A] = (hi2 < 0) ? carry[hi2] : chunk[hi2];
+            // whatever part of the wanted range is not backed by data (past the end of the chunk in the
+            // last piece of a channel) is zero filled: stale shared memory could hold NaN patterns and
+            // 0 * NaN would poison a valid output
+            if (lo > pj0 || hi < pj1) {
+                for (long long j = pj0 + lane; j < pj1; j += 32)
+                    if (j < lo || j >= hi) d2[j - A] = make_float2(0.f, 0.f);
+            }
+        };
+
+        // WAR note: ring slots are only re-filled by the warp that has finished reading them
+        // (program order + __syncwarp), so no "empty" barrier is needed.
+        __syncwarp();
+        for (int p = 0; p < min(kStages - 1, n_pieces); ++p) issue_piece(p);
+
+        float2 acc[G::NLIVE];
+#pragma unroll
+        for (int j = 0; j < G::NLIVE; ++j) acc[j] = make_float2(0.f, 0.f);
+
+        float2* out = a.s1 + (size_t)ch * a.s1_pitch + a.s1_hist;
+        int b = b_first;             // current superblock
+        int emitted = 0;             // outputs staged in sm.red since the last flush
+        long long k_group = 0;       // output index of sm.red[0]
+
+        auto flush = [&](int count) {
+            __syncwarp();
+            const int j = lane >> 1, comp = lane & 1;
+            float s = 0.f;
+            const float* row = reinterpret_cast<const float*>(&sm.red[j][0]) + comp;
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) s += row[2 * l];
+            if (j < count) reinterpret_cast<float*>(out + k_group)[lane] = s;
+            __syncwarp();
+        };
+
+        for (int p = 0; p < n_pieces; ++p) {
+            const int slot = p % kStages;
+            __syncwarp(); // every lane is done reading the slot that is about to be refilled
+            if (p + kStages - 1 < n_pieces) issue_piece(p + kStages - 1);
+            mbar_wait(&sm.full[slot], (phase_bits >> slot) & 1u);
+            phase_bits ^= 1u << slot;
+            __syncwarp();
+            const long long pj0 = j0 + (long long)p * G::PIECE_SAMPLES;
+            const float2* src = reinterpret_cast<const float2*>(sm.ring[slot]) + (pj0 & 1LL);
+
+            for (int g = 0; g < G::PSB / G::U; ++g) {
+#pragma unroll
+                for (int u = 0; u < G::U; ++u) {
+                    const float2 x0 = src[(g * G::U + u) * 64 + lane];
+                    const float2 x1 = src[(g * G::U + u) * 64 + 32 + lane];
+#pragma unroll
+                    for (int j = 0; j < G::NLIVE; ++j) {
+                        const int r = (j + u * G::NOUT) % G::NLIVE; // register holding live output j
+                        // tap index of position P for live output j: t = T - M*(j+1) + P; skip the
+                        // half-superblocks where no lane has a tap (compile-time)
+                        constexpr int tb = T - M * 1;
+                        const int t0 = tb - M * j; // t at P = 0
+                        if (t0 + 31 >= 0 && t0 < T) {
+                            acc[r].x = fmaf(x0.x, h0[j], acc[r].x);
+                            acc[r].y = fmaf(x0.y, h0[j], acc[r].y);
+                        }
+                        if (t0 + 63 >= 0 && t0 + 32 < T) {
+                            acc[r].x = fmaf(x1.x, h1[j], acc[r].x);
+                            acc[r].y = fmaf(x1.y, h1[j], acc[r].y);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < G::NOUT; ++j) {
+                        const int r = (j + u * G::NOUT) % G::NLIVE;
+                        // output index of live slot j in superblock b: k = (b-1)*NOUT + j + 1
+                        const long long k = (long long)(b - 1) * G::NOUT + j + 1;
+                        if (b >= b_lo && b < b_hi && k >= 0 && k < (long long)pl.n1) {
+                            if (emitted == 0) k_group = k;
+                            sm.red[emitted][lane] = acc[r];
+                            if (++emitted == kRedOutputs) { flush(kRedOutputs); emitted = 0; }
+                        }
+                        acc[r] = make_float2(0.f, 0.f);
+                    }
+                    ++b;
+                }
+            }
+        }
+        if (emitted) flush(emitted);
+        __syncwarp();
+    }
+}
+
+// ---- generic fallback: one thread per output.  Used for tap tables whose T/M is large
+// (d_8_r_8, d_4_r_4, d_2_r_2 as FIRST stage, i.e. total factor <= 8: input rates <= 1.3 MS/s).
+__global__ void decim1_generic_kernel(DecimArgs a, int M, int T)
+{
+    const int ch = blockIdx.y;
+    const ChanPlan pl = a.plan[ch];
+    if (pl.flags & 1u) return;
+    const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
+    const float2* carry = a.carry + (size_t)ch * kCarryCap + kCarryCap;
+    float2* out = a.s1 + (size_t)ch * a.s1_pitch + a.s1_hist;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < pl.n1; k += gridDim.x * blockDim.x) {
+        const long long j_first = (long long)k * M - (T - 1) - (long long)pl.r;
+        float re = 0.f, im = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const long long j = j_first + t;
+            const float2 x = (j < 0) ? carry[j] : chunk[j];
+            const float h = __ldg(a.taps + t);
+            re = fmaf(x.x, h, re);
+            im = fmaf(x.y, h, im);
+        }
+        out[k] = make_float2(re, im);
+    }
+}
+
+// factor 1: no decimator at all (Decoder.h:157 default) -- the "stage-1 output" is the input
+__global__ void decim1_copy_kernel(DecimArgs a)
+{
+    const int ch = blockIdx.y;
+    const ChanPlan pl = a.plan[ch];
+    if (pl.flags & 1u) return;
+    const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
+    float2* out = a.s1 + (size_t)ch * a.s1_pitch + a.s1_hist;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < pl.n1; k += gridDim.x * blockDim.x) out[k] = chunk[k];
+}
+
+template <int M, int T>
+static cudaError_t launch_fast(const DecimArgs& a, int n_sms, cudaStream_t stream, int* launches)
+{
+    const size_t smem = sizeof(WarpSmem<M, T>) * kDecimWarps;
+    cudaError_t e = cudaFuncSetAttribute(decim1_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long n_items = (long long)a.n_channels * a.stretches_per_channel;
+    int grid = (int)std::min<long long>(n_sms, (n_items + kDecimWarps - 1) / kDecimWarps);
+    if (grid < 1) grid = 1;
+    decim1_kernel<M, T><<<grid, kDecimWarps * 32, smem, stream>>>(a);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decim1(const DecimArgs& a, int M, int T, unsigned max_n1, int n_sms, cudaStream_t stream, int* launches)
+{
+    if (M == 64 && T == 348) return launch_fast<64, 348>(a, n_sms, stream, launches);
+    if (M == 32 && T == 174) return launch_fast<32, 174>(a, n_sms, stream, launches);
+    if (M == 32 && T == 212) return launch_fast<32, 212>(a, n_sms, stream, launches);
+    if (M == 16 && T == 107) return launch_fast<16, 107>(a, n_sms, stream, launches);
+    if (M == 8 && T == 54) return launch_fast<8, 54>(a, n_sms, stream, launches);
+    dim3 grid((max_n1 + 255) / 256, a.n_channels);
+    if (grid.x < 1) grid.x = 1;
+    if (grid.x > 1024) grid.x = 1024;
+    if (M == 1) decim1_copy_kernel<<<grid, 256, 0, stream>>>(a);
+    else decim1_generic_kernel<<<grid, 256, 0, stream>>>(a, M, T);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+int decim1_sb_per_stretch(int M) { (void)M; return 128; }
+
+} // namespace hbd

@@ -1,0 +1,154 @@
+// Host-side pieces of the path that are not data parallel: low-pass tap design and the
+// character -> sentence layer.  Plain C++17, no CUDA.
+//
+//   lp design        code/Decoder/FirFilter.h:173-209, code/Decoder/habdec_windows.h:27-53
+//   printable filter code/Decoder/Decoder.h:572-580
+//   sentence scan    code/Decoder/Decoder.h:591-613,635-636, code/Decoder/sentence_extract.cpp:58-98
+//   CRC16            code/Decoder/CRC.cpp:21-47
+#include "host_tail.h"
+
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstring>
+
+namespace hbd {
+
+// ---- low-pass design ----------------------------------------------------------------------------------
+// The reference evaluates sin/cos in double on float arguments, multiplies in float, sums in double
+// and normalises float/double; any other mix changes tap bits.
+static float bh4_window(size_t x, size_t N)
+{
+    const float a0 = 0.35874, a1 = 0.48829, a2 = 0.14128, a3 = 0.01168;
+    const float pi2 = 2.0 * M_PI, pi4 = 4.0 * M_PI, pi6 = 6.0 * M_PI;
+    const float n1 = N - 1;
+    const double c1 = ::cos(double(pi2 * x / n1)), c2 = ::cos(double(pi4 * x / n1)), c3 = ::cos(double(pi6 * x / n1));
+    const float w = a0 - a1 * c1 + a2 * c2 - a3 * c3;
+    return w;
+}
+
+static float sinc_without_pi(float x)
+{
+    return x ? float(::sin(double(x)) / x) : 1.0f;
+}
+
+size_t design_lowpass(float rel_width, float trans, size_t input_size, size_t current_taps, std::vector<float>& taps)
+{
+    if (!input_size) return current_taps;                       // "No Input set"
+    const float tbw = trans ? trans : rel_width * rel_width;
+    size_t T = size_t(4.0f / tbw);
+    if (T > input_size) T = input_size;
+    T |= 1;
+    if (T <= 4) return current_taps;
+    if (T == current_taps) return current_taps;                 // same count: the old design stays
+    taps.assign(T, 0.f);
+    double sum = 0;
+    const int mid = int(T / 2);
+    for (int i = 0; i < int(T); ++i) {
+        taps[i] = sinc_without_pi(2.0f * rel_width * (i - mid)) * bh4_window(size_t(i), T);
+        sum += taps[i];
+    }
+    for (size_t i = 0; i < T; ++i) taps[i] /= sum;
+    return T;
+}
+
+// ---- CRC16-CCITT-FALSE, 4 upper-case hex digits --------------------------------------------------------
+std::string crc16_hex(const std::string& s)
+{
+    unsigned crc = 0xffff;
+    for (char ch : s) {
+        crc ^= (unsigned(int(ch)) << 8);
+        for (int j = 0; j < 8; ++j) crc = (crc & 0x8000) ? ((crc << 1) ^ 0x1021) : (crc << 1);
+    }
+    static const char hex[] = "0123456789ABCDEF";
+    std::string r(4, '0');
+    r[0] = hex[(crc >> 12) & 15]; r[1] = hex[(crc >> 8) & 15]; r[2] = hex[(crc >> 4) & 15]; r[3] = hex[crc & 15];
+    return r;
+}
+
+// ---- sentence extraction -------------------------------------------------------------------------------
+// The reference runs std::regex_match (ECMAScript, backtracking, whole string) with
+//     .*?(\$+)([\w,\-,\s]+?),(.+?)(\*|\$)(\w\w\w\w).*
+// on the stream with '\n' replaced by ' '.  std::regex costs tens of microseconds per call, which
+// would make the host the bottleneck at GPU decode rates, so the same match is found directly.
+// Equivalence (also fuzz-tested against std::regex in tests/test_host_tail.py):
+//  * `.*?` lazy  => the earliest start position with a '$' from which the rest can match; a start
+//    inside a run of '$' behaves like the start of that run (`\$+` must swallow the rest of the
+//    run, because '$' is not in the callsign class), so runs are tried left to right.
+//  * callsign `[\w,\-,\s]+?` lazy => the first ',' preceded by >= 1 class characters (',' itself is
+//    in the class); a later ',' can only shrink the set of possible data ends, so if the first one
+//    fails the run fails.
+//  * data `(.+?)` lazy, >= 1 char => the first '*' or '$' at >= comma+2 followed by four \w.
+static inline bool is_word(unsigned char c) { return std::isalnum(c) || c == '_'; }
+static inline bool is_callsign_char(unsigned char c) { return is_word(c) || c == ',' || c == '-' || std::isspace(c); }
+
+bool extract_sentence(const std::string& stream_in, SentenceMatch& m)
+{
+    m.ok = false;
+    const size_t n = stream_in.size();
+    if (stream_in.find('*') == std::string::npos) return false;  // sentence_extract.cpp:74
+    std::string s(stream_in);
+    std::replace(s.begin(), s.end(), '\n', ' ');
+    size_t p = 0;
+    while (p < n) {
+        if (s[p] != '$') { ++p; continue; }
+        size_t q = p;
+        while (q < n && s[q] == '$') ++q;                       // q: first char after the run
+        // callsign: s[q..c), all class chars, c > q, s[c] == ','  -- first such c
+        size_t c = q;
+        bool found_c = false;
+        while (c < n && is_callsign_char((unsigned char)s[c])) {
+            if (s[c] == ',' && c > q) { found_c = true; break; }
+            ++c;
+        }
+        if (found_c) {
+            for (size_t e = c + 2; e + 4 < n; ++e) { // s[e+1..e+4] must exist
+                if ((s[e] == '*' || s[e] == '$') && is_word((unsigned char)s[e + 1]) && is_word((unsigned char)s[e + 2]) &&
+                    is_word((unsigned char)s[e + 3]) && is_word((unsigned char)s[e + 4])) {
+                    m.ok = true;
+                    m.callsign = s.substr(q, c - q);
+                    m.data = s.substr(c + 1, e - (c + 1));
+                    m.crc = s.substr(e + 1, 4);
+                    m.rest_offset = std::min(n, e + 4);           // sentence_extract.cpp:86-87 (keeps the last CRC char)
+                    return true;
+                }
+            }
+        }
+        p = q; // next run
+    }
+    return false;
+}
+
+// ---- per-channel text state: Decoder.h:572-613,635-636 ------------------------------------------------------
+void TextChannel::feed(const unsigned char* raw, size_t n, int ch, const SentenceSink& sink)
+{
+    if (!n) return; // the reference returns before touching the streams when no char was decoded (:568-569)
+    raw_pending.insert(raw_pending.end(), raw, raw + n);
+    size_t added = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const char c = char(raw[i]);
+        if ((std::isprint((unsigned char)c) && (unsigned char)c < 0x80) || c == '\n') { // isprint(char) in the "C" locale
+            text_stream.push_back(c);
+            chars_pending.push_back(c);
+            ++added;
+        }
+    }
+    (void)added;
+    if (text_stream.size() > 20) {
+        SentenceMatch m;
+        while (extract_sentence(text_stream, m)) {
+            std::string rest = text_stream.substr(m.rest_offset);
+            std::replace(rest.begin(), rest.end(), '\n', ' ');    // the reference keeps the space-substituted copy (:599)
+            text_stream.swap(rest);
+            last_sentence = m.callsign + "," + m.data + "*" + m.crc;
+            if (m.crc == crc16_hex(m.callsign + "," + m.data)) {
+                sentences_pending += last_sentence;
+                sentences_pending.push_back('\n');
+                if (sink) sink(ch, m.callsign, m.data, m.crc);
+            }
+        }
+    }
+    if (text_stream.size() > 1000) text_stream.erase(0, text_stream.rfind('$')); // npos => erase everything
+}
+
+} // namespace hbd

@@ -1,0 +1,21 @@
+// K3 launch interface (see slicer.cu)
+#pragma once
+#include "hbd_common.cuh"
+
+namespace hbd {
+
+struct SlicerArgs {
+    ChanState* state;
+    float* slicer; size_t slicer_pitch;  // pending discriminator samples [channel][slicer_pitch]
+    unsigned char* raw;                  // raw UART chars [channel][kRawCap]
+    unsigned* raw_n;                     // [channel]
+    unsigned char* rec_bits;             // optional: every emitted bit [channel][rec_bits_pitch]
+    unsigned* rec_bits_n;
+    unsigned rec_bits_pitch;
+    double fs_dec;
+    int n_channels;
+};
+
+cudaError_t launch_slicer(const SlicerArgs& a, cudaStream_t stream, int* launches);
+
+} // namespace hbd

@@ -1,0 +1,141 @@
+/* habdec_b200 -- C ABI of the B200-native batched RTTY decoder.
+ *
+ * One hbd_decoder = N independent channels, each behaving like one reference
+ * habdec::Decoder<float> (code/Decoder/Decoder.h:51-203 under /root/reference).
+ * Every entry point names the reference member it replaces.  Plain C types only;
+ * the library is libhabdec_b200.so (CUDA, sm_100a).  There is no CPU fallback:
+ * every call fails with HBD_ERR_CUDA when no usable device is present.
+ *
+ * Threading model follows the reference (Decoder.h:146-196): one thread feeds
+ * and processes, other threads may call getters/setters; all entry points take
+ * the handle's mutex.
+ *
+ * Batch-wide by design: the input sampling rate and the decimation plan are
+ * shared by all channels of a handle (they are channels of one capture / one
+ * receiver type); everything else is per channel.  `ch == -1` in a setter
+ * means "all channels".
+ */
+#ifndef HABDEC_B200_H
+#define HABDEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hbd_decoder hbd_decoder;
+
+enum {
+    HBD_OK          = 0,
+    HBD_ERR_ARG     = -1,  /* bad channel index / pointer / size */
+    HBD_ERR_CUDA    = -2,  /* CUDA runtime error, see hbd_last_error() */
+    HBD_ERR_STATE   = -3,  /* call not valid in the current state */
+    HBD_ERR_NOMEM   = -4
+};
+
+/* SpectrumInfo<float> scalars, code/Decoder/SpectrumInfo.h:35-85 + Decoder.h:814-836 */
+typedef struct hbd_spectrum_info {
+    float  min_, max_;
+    double noise_floor_, noise_variance_, sampling_rate_, shift_;
+    int    peak_left_, peak_right_;
+    int    peak_left_valid_, peak_right_valid_;
+} hbd_spectrum_info;
+
+/* callbacks fire on the thread that calls hbd_process(), like the reference's
+ * sentence_callback_ / character_callback_ (Decoder.h:135,138,604-606,625-626) */
+typedef void (*hbd_sentence_cb)(void* user, int ch, const char* callsign, const char* data, const char* crc);
+typedef void (*hbd_chars_cb)(void* user, int ch, const char* chars, size_t n);
+
+/* ---- life cycle ------------------------------------------------------------------------------------- */
+int  hbd_create(int n_channels, int cuda_device, hbd_decoder** out);
+void hbd_destroy(hbd_decoder* h);
+const char* hbd_last_error(hbd_decoder* h);
+/* run all work on this cudaStream_t (default: a private non-blocking stream) */
+int  hbd_set_stream(hbd_decoder* h, void* cuda_stream);
+/* keep per-call stage arrays (decimated IQ, filtered IQ, slicer bits) for hbd_debug_stage(); test use */
+int  hbd_set_record(hbd_decoder* h, int on);
+
+/* ---- configuration (Decoder.h:77-91) ---------------------------------------------------------------- */
+int    hbd_set_baud(hbd_decoder* h, int ch, double baud);              /* Decoder::baud(double)          :656 */
+double hbd_get_baud(hbd_decoder* h, int ch);                           /* Decoder::baud()                :664 */
+int    hbd_set_rtty_bits(hbd_decoder* h, int ch, size_t bits);         /* Decoder::rtty_bits(size_t)     :671 */
+size_t hbd_get_rtty_bits(hbd_decoder* h, int ch);
+int    hbd_set_rtty_stops(hbd_decoder* h, int ch, float stops);        /* Decoder::rtty_stops(float)     :686 */
+float  hbd_get_rtty_stops(hbd_decoder* h, int ch);
+int    hbd_set_lowpass_bw(hbd_decoder* h, int ch, float bw_hz);        /* Decoder::lowpass_bw(float)     :238 */
+float  hbd_get_lowpass_bw(hbd_decoder* h, int ch);
+int    hbd_set_lowpass_trans(hbd_decoder* h, int ch, float trans);     /* Decoder::lowpass_trans(float)  :252 */
+float  hbd_get_lowpass_trans(hbd_decoder* h, int ch);
+int    hbd_set_dc_remove(hbd_decoder* h, int ch, int on);              /* Decoder::dc_remove(bool)       :701 */
+int    hbd_get_dc_remove(hbd_decoder* h, int ch);
+/* returns the new factor; the current one if out of [1,256]; 0 if not a supported power of two (:268-332) */
+size_t hbd_setup_decimation_factor(hbd_decoder* h, size_t factor);
+/* Decoder::setupDecimationStagesBW (:336-412); returns 0 before the first push latched a sampling rate */
+size_t hbd_setup_decimation_bw(hbd_decoder* h, double max_sampling_rate);
+
+/* ---- feed (Decoder::pushSamples, Decoder.h:206-219).  iq = interleaved cf32, n in complex samples.
+ * The first push latches the sampling rate (as float, like Decoder::init :223-225). ------------------------ */
+int hbd_push_samples(hbd_decoder* h, int ch, const float* iq, size_t n_complex, double sampling_rate);
+/* all channels at once: host matrix [n_channels][pitch_complex] */
+int hbd_push_samples_batch(hbd_decoder* h, const float* iq, size_t n_complex, size_t pitch_complex, double sampling_rate);
+/* zero copy: DEVICE matrix [n_channels][pitch_complex], 16-byte aligned rows; it must stay valid and
+ * unchanged until the next hbd_process()/hbd_process_async() has completed (hbd_synchronize) */
+int hbd_push_samples_device(hbd_decoder* h, const float* d_iq, size_t n_complex, size_t pitch_complex, double sampling_rate);
+
+/* ---- run (Decoder::process / operator(), Decoder.h:118-126,416-638) ------------------------------------- */
+int hbd_process(hbd_decoder* h);        /* kernels + result drain + sentence layer + callbacks */
+int hbd_process_async(hbd_decoder* h);  /* kernels only, returns immediately */
+int hbd_collect(hbd_decoder* h);        /* drain results of all async calls so far (sentence layer + callbacks) */
+int hbd_synchronize(hbd_decoder* h);
+/* number of CUDA kernels this handle has launched so far */
+unsigned long long hbd_kernel_launches(hbd_decoder* h);
+
+/* ---- results ------------------------------------------------------------------------------------------ */
+size_t hbd_get_rtty(hbd_decoder* h, int ch, char* out, size_t cap);           /* Decoder::getRTTY()         :642 */
+size_t hbd_get_last_sentence(hbd_decoder* h, int ch, char* out, size_t cap);  /* Decoder::getLastSentence() :649 */
+/* printable characters decoded since the previous poll == concat of character_callback_ payloads */
+size_t hbd_poll_chars(hbd_decoder* h, int ch, char* out, size_t cap);
+/* CRC-valid sentences since the previous poll, "callsign,data*crc\n" each == sentence_callback_ payloads */
+size_t hbd_poll_sentences(hbd_decoder* h, int ch, char* out, size_t cap);
+/* raw UART characters (what the reference hands to SSDV_wraper_t::push, Decoder.h:572-573) since the previous poll */
+size_t hbd_poll_raw_chars(hbd_decoder* h, int ch, unsigned char* out, size_t cap);
+int    hbd_set_sentence_callback(hbd_decoder* h, hbd_sentence_cb cb, void* user);
+int    hbd_set_chars_callback(hbd_decoder* h, hbd_chars_cb cb, void* user);
+
+/* ---- info (Decoder.h:98-101) ------------------------------------------------------------------------ */
+int    hbd_get_decimation_factor(hbd_decoder* h);
+double hbd_get_input_sampling_rate(hbd_decoder* h);
+double hbd_get_decimated_sampling_rate(hbd_decoder* h);
+double hbd_get_symbol_rate(hbd_decoder* h, int ch);
+int    hbd_n_channels(hbd_decoder* h);
+
+/* ---- GUI data (Decoder.h:104-115); sizes in floats, return = floats available -------------------------- */
+size_t hbd_get_bins_count(hbd_decoder* h);
+size_t hbd_get_fft(hbd_decoder* h, int ch, float* out_cf32, size_t cap_floats);
+size_t hbd_get_demodulated(hbd_decoder* h, int ch, float* out, size_t cap_floats);
+size_t hbd_get_power_spectrum(hbd_decoder* h, int ch, float* out, size_t cap_floats);
+int    hbd_get_peaks(hbd_decoder* h, int ch, int* pl, int* pr);
+int    hbd_get_noise_floor(hbd_decoder* h, int ch, double* nf, double* nv);
+double hbd_get_shift(hbd_decoder* h, int ch);
+double hbd_get_frequency_correction(hbd_decoder* h, int ch);
+int    hbd_reset_frequency_correction(hbd_decoder* h, int ch, double frequency_correction);
+size_t hbd_get_spectrum_info(hbd_decoder* h, int ch, hbd_spectrum_info* info, float* power, size_t cap_floats);
+
+/* ---- test hooks ------------------------------------------------------------------------------------------ */
+enum { HBD_STAGE_DECIMATED = 0, HBD_STAGE_FILTERED = 1, HBD_STAGE_DEMOD = 2, HBD_STAGE_LPTAPS = 5,
+       HBD_STAGE_PENDING = 6, HBD_STAGE_BITS = 7 };
+/* arrays of the most recent call (DECIMATED/FILTERED/DEMOD/BITS need hbd_set_record(h,1)); BITS accumulate */
+size_t hbd_debug_stage(hbd_decoder* h, int ch, int stage, float* out, size_t cap_floats);
+/* low-pass tap design alone (FirFilter::LP_BlackmanHarris, FirFilter.h:173-209); returns the tap count */
+size_t hbd_design_lowpass(float rel_width, float trans, size_t input_size, size_t current_taps, float* out, size_t cap);
+/* sentence layer alone (extractSentence + CRC, sentence_extract.cpp:58-98, CRC.cpp:21-47):
+ * returns 1 and fills the fields if a sentence was found; *rest_offset = start of the remaining stream */
+int    hbd_extract_sentence(const char* stream, size_t n, char* callsign, char* data, char* crc, size_t cap, size_t* rest_offset);
+void   hbd_crc16(const char* s, size_t n, char out[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

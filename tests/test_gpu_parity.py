@@ -1,0 +1,173 @@
+"""GPU parity: the CUDA path behind the C ABI vs the CPU oracle on identical synthetic IQ.
+
+Bars (BASELINE.json north_star): characters / sentences / CRC verdicts bit-exact; per-stage float
+arrays within relative L2 <= 1e-5 of the reference's own float path.
+"""
+import numpy as np
+import pytest
+
+from habdec_b200 import api, synth
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+REL_L2 = 1e-5
+
+
+def rel_l2(a, b):
+    a = np.asarray(a).astype(np.complex128 if np.iscomplexobj(a) else np.float64)
+    b = np.asarray(b).astype(a.dtype)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def make_oracle(kind, **cfg):
+    return (po.RefDecoder if kind == "ref" else po.PortDecoder)(po.make_config(**cfg))
+
+
+def run_gpu_single(iq, fs, chunk, **cfg):
+    """One channel through the batch decoder with stage recording; returns dict of concatenated stages."""
+    dec = api.BatchDecoder(1, record=True, **cfg)
+    stages = {"dec": [], "filt": [], "demod": []}
+    for o in range(0, len(iq), chunk):
+        dec.pushSamples(0, iq[o:o + chunk], fs)
+        dec.process()
+        stages["dec"].append(dec.debug_stage(0, api.STAGE_DECIMATED).copy())
+        stages["filt"].append(dec.debug_stage(0, api.STAGE_FILTERED).copy())
+        stages["demod"].append(dec.debug_stage(0, api.STAGE_DEMOD).copy())
+    out = {k: np.concatenate(v) for k, v in stages.items()}
+    out["bits"] = dec.debug_stage(0, api.STAGE_BITS)
+    out["pending"] = dec.debug_stage(0, api.STAGE_PENDING)
+    out["taps"] = dec.debug_stage(0, api.STAGE_LPTAPS)
+    return dec, out
+
+
+CASES = [
+    # fs, baud, bits, stops, factor, snr_db(full band), n_sentences, chunk
+    (2.048e6, 300.0, 8, 2.0, 256, None, 2, 65536),
+    (2.048e6, 300.0, 8, 2.0, 256, -15.0, 2, 65536),
+    (2.048e6, 300.0, 8, 2.0, 256, -24.0, 2, 65536),
+    (2.048e6, 300.0, 8, 2.0, 256, -15.0, 2, 262144),
+    (2.048e6, 300.0, 8, 2.0, 256, -15.0, 1, 40000),      # chunk not a multiple of the factor
+    (2.5e6, 50.0, 7, 2.0, 256, -18.0, 1, 65536),
+    (2.048e6, 100.0, 8, 1.0, 256, -15.0, 1, 65536),
+    (1.024e6, 300.0, 8, 2.0, 128, -14.0, 1, 65536),
+    (0.512e6, 300.0, 8, 2.0, 64, -12.0, 1, 65536),
+    (0.256e6, 300.0, 8, 2.0, 32, -10.0, 1, 65536),
+    (0.128e6, 300.0, 8, 2.0, 16, -8.0, 1, 65536),
+    (64e3, 300.0, 8, 2.0, 8, -6.0, 1, 65536),
+    (32e3, 300.0, 8, 2.0, 4, -4.0, 1, 65536),
+    (16e3, 300.0, 8, 2.0, 2, -3.0, 1, 65536),
+]
+
+
+@pytest.mark.parametrize("fs,baud,bits,stops,factor,snr,nsent,chunk", CASES)
+def test_single_channel_stages_and_chars(oracle_kind, fs, baud, bits, stops, factor, snr, nsent, chunk):
+    iq, text = synth.channel_iq(3, nsent, fs, baud, bits, int(stops), snr_db=snr)
+    cfg = dict(baud=baud, rtty_bits=bits, rtty_stops=stops, dec_factor=factor)
+    ref = make_oracle(oracle_kind, **cfg).run(iq, fs, chunk)
+    dec, got = run_gpu_single(iq, fs, chunk, **cfg)
+
+    # low-pass taps are designed on the host with the reference's exact arithmetic: bit-exact
+    assert np.array_equal(got["taps"].view(np.uint32), ref.stage(po.STAGE_LPTAPS).view(np.uint32))
+    for name, st in (("dec", po.STAGE_DECIMATED), ("filt", po.STAGE_FILTERED), ("demod", po.STAGE_DEMOD)):
+        want = ref.stage(st)
+        assert got[name].shape == want.shape, name
+        err = rel_l2(got[name], want)
+        assert err <= REL_L2, "%s rel L2 %.3g" % (name, err)
+    assert dec.poll_chars(0) == ref.chars()
+    assert dec.poll_sentences(0) == ref.sentences()
+    assert dec.getLastSentence(0) == ref.last_sentence()
+    assert dec.getRTTY(0) == ref.rtty()
+    if snr is None or snr > -20:
+        assert len(ref.sentences()) == nsent          # the workload really decodes
+    # slicer residue: same number of pending samples, same values to float tolerance
+    want_p = ref.stage(po.STAGE_PENDING)
+    assert got["pending"].shape == want_p.shape
+    if len(want_p):
+        assert rel_l2(got["pending"], want_p) <= 1e-4
+
+
+def test_bits_match_port_oracle():
+    """Every bit the slicer emits equals the restatement's (the reference does not expose its bits)."""
+    fs, baud = 2.048e6, 300.0
+    iq, _ = synth.channel_iq(5, 2, fs, baud, snr_db=-22.0)
+    cfg = dict(baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
+    port = po.PortDecoder(po.make_config(**cfg)).run(iq, fs)
+    dec, got = run_gpu_single(iq, fs, 65536, **cfg)
+    assert np.array_equal(got["bits"], port.stage(po.STAGE_BITS))
+    assert dec.poll_raw_chars(0) == bytes(port.stage(po.STAGE_RAWCHARS).astype(np.uint8))
+
+
+def test_batch_mixed_baud_snr_sweep(oracle_kind):
+    """cfg 3 in miniature: channels with 50/100/300 baud and an SNR sweep, decoded as one batch."""
+    fs = 2.048e6
+    n_ch = 12
+    bauds = [50.0, 100.0, 300.0]
+    n = 65536 * 40
+    iqs, cfgs = [], []
+    for c in range(n_ch):
+        baud = bauds[c % 3]
+        snr = -28.0 + 20.0 * c / (n_ch - 1)       # in-band 0 .. 20 dB
+        iq, _ = synth.channel_iq(c, 1, fs, baud, snr_db=snr, n_samples=n)
+        iqs.append(iq)
+        cfgs.append(dict(baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256))
+    iq = np.stack(iqs)
+    dec = api.BatchDecoder(n_ch, dec_factor=256)
+    for c in range(n_ch):
+        dec.baud(cfgs[c]["baud"], c)
+    for o in range(0, n, 65536):
+        dec.pushSamplesBatch(np.ascontiguousarray(iq[:, o:o + 65536]), fs)
+        dec.process()
+    for c in range(n_ch):
+        ref = make_oracle(oracle_kind, **cfgs[c]).run(iq[c], fs)
+        assert dec.poll_chars(c) == ref.chars(), "channel %d" % c
+        assert dec.poll_sentences(c) == ref.sentences(), "channel %d" % c
+
+
+def test_async_steps_equal_sync_steps():
+    """process_async x N + collect gives the same characters as N synchronous process() calls."""
+    fs, baud = 2.048e6, 300.0
+    iq, _ = synth.channel_iq(1, 1, fs, baud, snr_db=-15.0)
+    n = len(iq) // 65536 * 65536
+    a = api.BatchDecoder(1, baud=baud)
+    b = api.BatchDecoder(1, baud=baud)
+    for o in range(0, n, 65536):
+        a.pushSamples(0, iq[o:o + 65536], fs); a.process()
+        b.pushSamples(0, iq[o:o + 65536], fs); b.process_async()
+    b.collect()
+    assert a.poll_chars(0) == b.poll_chars(0)
+    assert a.poll_sentences(0) == b.poll_sentences(0)
+    assert len(a.getLastSentence(0)) > 10
+
+
+def test_fft_and_afc(oracle_kind):
+    """Spectrum vs a float64 DFT of the same decimated frame; AFC scalars vs the oracle."""
+    fs, baud = 2.048e6, 300.0
+    iq, _ = synth.channel_iq(2, 3, fs, baud, snr_db=-15.0, f_off=60.0)
+    cfg = dict(baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
+    ref = make_oracle(oracle_kind, **cfg).run(iq, fs)
+    dec = api.BatchDecoder(1, record=True, **cfg)
+    frames, cur = [], []
+    for o in range(0, len(iq), 65536):
+        dec.pushSamples(0, iq[o:o + 65536], fs)
+        dec.process()
+        d = dec.debug_stage(0, api.STAGE_DECIMATED)
+        cur.extend(d.tolist())
+        if len(cur) >= 4096:
+            frames.append(np.asarray(cur[:4096], dtype=np.complex64)); cur = []
+    spec = dec.getFFT(0)
+    assert spec.shape == (4096,)
+    want = np.fft.fftshift(np.fft.fft(frames[-1].astype(np.complex128)))
+    assert rel_l2(spec, want) <= REL_L2
+    assert rel_l2(spec, ref.stage(po.STAGE_FFT)) <= REL_L2
+    pw, pw_ref = dec.getPowerSpectrum(0), ref.stage(po.STAGE_POWER)
+    assert np.max(np.abs(pw - pw_ref)) < 2e-2      # dB; bins near a spectral null amplify float noise
+    a = ref.afc()
+    assert dec.getPeaks(0) == (a.peak_left, a.peak_right)
+    nf, nv = dec.getNoiseFloor(0)
+    assert abs(nf - a.noise_floor) < 1e-3 and abs(nv - a.noise_variance) < 1e-3
+    assert dec.getShift(0) == pytest.approx(a.shift_hz, abs=1e-9)
+    assert dec.getFrequencyCorrection(0) == pytest.approx(a.frequency_correction, abs=1e-9)
+    info, power = dec.getSpectrumInfo(0)
+    assert info.peak_left_ == abs(a.peak_left) and info.peak_right_ == abs(a.peak_right)
+    assert info.sampling_rate_ == 8000.0
