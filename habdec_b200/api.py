@@ -57,6 +57,8 @@ SIGNATURES = {
     "hbd_collect": (C.c_int, [_H]),
     "hbd_synchronize": (C.c_int, [_H]),
     "hbd_kernel_launches": (C.c_ulonglong, [_H]),
+    "hbd_set_kernel_timing": (C.c_int, [_H, C.c_int]),
+    "hbd_get_kernel_timing": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint)]),
     "hbd_get_rtty": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_get_last_sentence": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_poll_chars": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
@@ -79,6 +81,7 @@ SIGNATURES = {
     "hbd_get_frequency_correction": (C.c_double, [_H, C.c_int]),
     "hbd_reset_frequency_correction": (C.c_int, [_H, C.c_int, C.c_double]),
     "hbd_get_spectrum_info": (C.c_size_t, [_H, C.c_int, C.POINTER(SpectrumInfo), C.c_void_p, C.c_size_t]),
+    "hbd_get_stats_batch": (C.c_size_t, [_H, C.c_void_p, C.c_size_t]),
     "hbd_debug_stage": (C.c_size_t, [_H, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_design_lowpass": (C.c_size_t, [C.c_float, C.c_float, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]),
     "hbd_extract_sentence": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -204,6 +207,12 @@ class BatchDecoder:
     def collect(self): self._chk(self._lib.hbd_collect(self._h))
     def synchronize(self): self._chk(self._lib.hbd_synchronize(self._h))
     def kernel_launches(self) -> int: return int(self._lib.hbd_kernel_launches(self._h))
+    def set_kernel_timing(self, on: bool): self._chk(self._lib.hbd_set_kernel_timing(self._h, int(on)))
+    def kernel_timing(self, which: int):
+        """(total_ms, launches) of K1 (which=0) or of the rest of the step (which=1) since set_kernel_timing."""
+        ms, cnt = C.c_double(0), C.c_uint(0)
+        self._chk(self._lib.hbd_get_kernel_timing(self._h, which, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
 
     # ---- results
     def _bytes(self, fn, ch) -> bytes:
@@ -259,6 +268,12 @@ class BatchDecoder:
         power = np.empty(4096, dtype=np.float32)
         n = self._lib.hbd_get_spectrum_info(self._h, ch, C.byref(info), power.ctypes.data, power.size)
         return info, power[:n]
+
+    def stats_all(self) -> np.ndarray:
+        """[n_channels, 6] float64: frequency correction, shift, noise floor, noise variance, peak left, peak right."""
+        out = np.zeros((self.n_channels, 6), dtype=np.float64)
+        self._lib.hbd_get_stats_batch(self._h, out.ctypes.data, out.size)
+        return out
 
     def debug_stage(self, ch, stage) -> np.ndarray:
         return self._floats(self._lib.hbd_debug_stage, ch, stage, complex_=stage in (STAGE_DECIMATED, STAGE_FILTERED))

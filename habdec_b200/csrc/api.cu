@@ -141,6 +141,15 @@ struct hbd_decoder {
     float* h_pinned = nullptr; size_t pinned_bytes = 0;  // staging for pageable host memory
 
     int pending_marks = 0;   // async calls since the last collect
+    // optional per-kernel CUDA-event timing (bench roofline): one event pair per K1 launch / per rest-of-step
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_k1, ev_rest; // pairs: [2i] start, [2i+1] stop
+    size_t ev_used_k1 = 0, ev_used_rest = 0;
+    cudaEvent_t next_event(std::vector<cudaEvent_t>& pool, size_t& used)
+    {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
     size_t cap_n_in = 0;     // largest (r + n) the per-call buffers are sized for
 
     hbd_sentence_cb sentence_cb = nullptr; void* sentence_user = nullptr;
@@ -256,6 +265,8 @@ void hbd_decoder::free_all()
                     d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_pinned) cudaFreeHost(h_pinned);
+    for (cudaEvent_t e : ev_k1) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_rest) cudaEventDestroy(e);
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -398,8 +409,11 @@ int hbd_decoder::process_async_locked()
         da.sb_per_stretch = decim1_sb_per_stretch(M1);
         const unsigned n_sb = (M1 > 1) ? (max_n1 * unsigned(M1) + 63) / 64 + 2 : 1;
         da.stretches_per_channel = int((n_sb + da.sb_per_stretch - 1) / da.sb_per_stretch);
+        if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), stream));
         HBD_CUDA_CHECK(launch_decim1(da, M1, T1, max_n1, n_sms, stream, &nl));
+        if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), stream));
     }
+    if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), stream));
     {
         TailArgs ta{};
         ta.plan = d_plan; ta.state = d_state; ta.chunk = chunk; ta.chunk_pitch = chunk_pitch; ta.carry = d_carry; ta.T1 = T1;
@@ -423,6 +437,7 @@ int hbd_decoder::process_async_locked()
     mark_kernel<<<(n_ch + 255) / 256, 256, 0, stream>>>(d_raw_n, d_mark + size_t(pending_marks) * n, n_ch);
     ++nl;
     HBD_CUDA_CHECK(cudaGetLastError());
+    if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), stream));
     launches += unsigned(nl);
     ++pending_marks;
     ext = nullptr; ext_n = 0;
@@ -710,6 +725,34 @@ int hbd_synchronize(hbd_decoder* h)
 }
 unsigned long long hbd_kernel_launches(hbd_decoder* h) { return h ? h->launches : 0; }
 
+int hbd_set_kernel_timing(hbd_decoder* h, int on)
+{
+    HBD_CHECK_H(h);
+    std::lock_guard<std::mutex> l(h->mtx);
+    h->timing = on != 0;
+    h->ev_used_k1 = h->ev_used_rest = 0;
+    return HBD_OK;
+}
+
+int hbd_get_kernel_timing(hbd_decoder* h, int which, double* total_ms, unsigned* count)
+{
+    HBD_CHECK_H(h);
+    std::lock_guard<std::mutex> l(h->mtx);
+    cudaSetDevice(h->device);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
+    const std::vector<cudaEvent_t>& pool = which == 0 ? h->ev_k1 : h->ev_rest;
+    const size_t used = which == 0 ? h->ev_used_k1 : h->ev_used_rest;
+    double tot = 0; unsigned cnt = 0;
+    for (size_t i = 0; i + 1 < used; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, pool[i], pool[i + 1]) != cudaSuccess) return HBD_ERR_CUDA;
+        tot += ms; ++cnt;
+    }
+    if (total_ms) *total_ms = tot;
+    if (count) *count = cnt;
+    return HBD_OK;
+}
+
 static size_t copy_out(const std::string& s, char* out, size_t cap)
 {
     if (out && cap) memcpy(out, s.data(), std::min(cap, s.size()));
@@ -842,6 +885,25 @@ int hbd_reset_frequency_correction(hbd_decoder* h, int ch, double corr)
     ++h->launches;
     return HBD_OK;
 }
+// all channels in one device->host copy: out[ch*6 + {0..5}] = correction, shift, noise floor, noise variance, peak l, peak r
+size_t hbd_get_stats_batch(hbd_decoder* h, double* out, size_t cap_doubles)
+{
+    if (!h) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    const size_t n = size_t(h->n_ch);
+    if (!out || cap_doubles < 6 * n) return 6 * n;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    std::vector<ChanState> st(n);
+    if (cudaMemcpy(st.data(), h->d_state, n * sizeof(ChanState), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    for (size_t c = 0; c < n; ++c) {
+        out[6 * c + 0] = st[c].afc_correction; out[6 * c + 1] = st[c].afc_shift_hz;
+        out[6 * c + 2] = st[c].afc_noise_floor; out[6 * c + 3] = st[c].afc_noise_var;
+        out[6 * c + 4] = st[c].gui_left; out[6 * c + 5] = st[c].gui_right;
+    }
+    return 6 * n;
+}
+
 size_t hbd_get_spectrum_info(hbd_decoder* h, int ch, hbd_spectrum_info* info, float* power, size_t cap)
 {
     if (!h || ch < 0 || ch >= h->n_ch || !info) return 0;

@@ -66,3 +66,79 @@ def channel_iq(channel: int, n_sentences: int, fs: float, baud: float, nbits: in
     bits = uart_bits(text.encode(), nbits, nstops, lead_in, lead_out)
     iq = fsk_iq(bits, fs, baud, shift, f_off, snr_db, seed=1234 + channel, n_samples=n_samples)
     return iq, text
+
+
+# ---------------------------------------------------------------------------------------------------
+# Periodic "ring" workload for bench.py (BASELINE.json configs[3]: 300 baud 8N2, many channels).
+# One ring = 192 bit periods = 17 UART characters + 5 idle bits; at fs = 2.048 MS/s and 300 baud that is
+# exactly 1 310 720 samples (3 bits == 20 480 samples), i.e. 5 chunks of 262 144 or 20 of 65 536.
+# A sub-Hz frequency trim makes the phase wrap exactly, so replaying the ring is an endless,
+# continuous-phase RTTY stream that repeats one CRC-valid sentence per pass.
+# ---------------------------------------------------------------------------------------------------
+RING_BITS = 192
+
+
+def ring_sentence(channel: int) -> str:
+    body = "C%04d,%03d" % (channel % 10000, (channel * 7 + 123) % 1000)
+    return "$$" + body + "*" + crc16_ccitt(body.encode()) + "\n"      # 17 characters
+
+
+def ring_bits(channel: int, nbits: int = 8, nstops: int = 2) -> np.ndarray:
+    bits = uart_bits(ring_sentence(channel).encode(), nbits, nstops, lead_in=0, lead_out=0)
+    assert len(bits) <= RING_BITS
+    return np.concatenate([bits, np.ones(RING_BITS - len(bits), dtype=np.int8)])
+
+
+def ring_length(fs: float, baud: float) -> int:
+    n = RING_BITS * fs / baud
+    assert abs(n - round(n)) < 1e-9, "ring must be a whole number of samples"
+    return int(round(n))
+
+
+def ring_iq_numpy(channel: int, fs: float = 2.048e6, baud: float = 300.0, shift: float = 425.0,
+                  snr_db: float | None = -15.0) -> np.ndarray:
+    """One channel of the ring workload, complex64[ring_length]."""
+    L = ring_length(fs, baud)
+    bits = ring_bits(channel)
+    n = np.arange(L, dtype=np.float64)
+    bi = np.minimum((n * (baud / fs)).astype(np.int64), RING_BITS - 1)
+    f = np.where(bits[bi] > 0, 0.5 * shift, -0.5 * shift)
+    total = 2.0 * np.pi * f.sum() / fs
+    trim = (np.round(total / (2 * np.pi)) * 2 * np.pi - total) / L          # radians per sample, |trim| tiny
+    ph = np.cumsum(2.0 * np.pi * f / fs + trim)
+    iq = np.empty(L, dtype=np.complex64)
+    iq.real = np.cos(ph)
+    iq.imag = np.sin(ph)
+    if snr_db is not None:
+        rng = np.random.default_rng(99991 + channel)
+        sigma = 10.0 ** (-snr_db / 20.0) / np.sqrt(2.0)
+        iq.real += (sigma * rng.standard_normal(L)).astype(np.float32)
+        iq.imag += (sigma * rng.standard_normal(L)).astype(np.float32)
+    return iq
+
+
+def ring_iq_torch(ch0: int, n_ch: int, device, fs: float = 2.048e6, baud: float = 300.0, shift: float = 425.0,
+                  snr_db: float | None = -15.0, slice_channels: int = 32):
+    """Channels ch0..ch0+n_ch-1 of the ring workload generated on `device`: float32 tensor [n_ch, L, 2]
+    (interleaved cf32, row pitch L samples).  Same construction as ring_iq_numpy (different noise stream)."""
+    import torch
+    L = ring_length(fs, baud)
+    out = torch.empty((n_ch, L, 2), dtype=torch.float32, device=device)
+    n = torch.arange(L, dtype=torch.float64, device=device)
+    bi = torch.clamp((n * (baud / fs)).to(torch.int64), max=RING_BITS - 1)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(424242 + ch0)
+    sigma = None if snr_db is None else 10.0 ** (-snr_db / 20.0) / np.sqrt(2.0)
+    for s in range(0, n_ch, slice_channels):
+        e = min(n_ch, s + slice_channels)
+        bits = torch.from_numpy(np.stack([ring_bits(ch0 + c) for c in range(s, e)])).to(device)
+        f = torch.where(bits[:, bi] > 0, 0.5 * shift, -0.5 * shift).to(torch.float64)
+        total = 2.0 * np.pi * f.sum(dim=1, keepdim=True) / fs
+        trim = (torch.round(total / (2 * np.pi)) * 2 * np.pi - total) / L
+        ph = torch.cumsum(2.0 * np.pi * f / fs + trim, dim=1)
+        out[s:e, :, 0] = torch.cos(ph).to(torch.float32)
+        out[s:e, :, 1] = torch.sin(ph).to(torch.float32)
+        del f, ph
+        if sigma is not None:
+            out[s:e] += sigma * torch.randn((e - s, L, 2), dtype=torch.float32, device=device, generator=gen)
+    return out

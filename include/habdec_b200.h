@@ -91,6 +91,10 @@ int hbd_collect(hbd_decoder* h);        /* drain results of all async calls so f
 int hbd_synchronize(hbd_decoder* h);
 /* number of CUDA kernels this handle has launched so far */
 unsigned long long hbd_kernel_launches(hbd_decoder* h);
+/* measurement hook: record CUDA events around every K1 (stage-1 decimator) launch and around the rest of the
+ * step; `which` 0 = K1, 1 = rest.  Calling set (on or off) clears the accumulated samples. */
+int hbd_set_kernel_timing(hbd_decoder* h, int on);
+int hbd_get_kernel_timing(hbd_decoder* h, int which, double* total_ms, unsigned* count);
 
 /* ---- results ------------------------------------------------------------------------------------------ */
 size_t hbd_get_rtty(hbd_decoder* h, int ch, char* out, size_t cap);           /* Decoder::getRTTY()         :642 */
@@ -122,6 +126,9 @@ double hbd_get_shift(hbd_decoder* h, int ch);
 double hbd_get_frequency_correction(hbd_decoder* h, int ch);
 int    hbd_reset_frequency_correction(hbd_decoder* h, int ch, double frequency_correction);
 size_t hbd_get_spectrum_info(hbd_decoder* h, int ch, hbd_spectrum_info* info, float* power, size_t cap_floats);
+/* the per-channel record that is gathered to rank 0: out[6*ch + 0..5] = frequency correction, shift, noise floor,
+ * noise variance, peak left, peak right (one device->host copy for all channels); returns 6*n_channels */
+size_t hbd_get_stats_batch(hbd_decoder* h, double* out, size_t cap_doubles);
 
 /* ---- test hooks ------------------------------------------------------------------------------------------ */
 enum { HBD_STAGE_DECIMATED = 0, HBD_STAGE_FILTERED = 1, HBD_STAGE_DEMOD = 2, HBD_STAGE_LPTAPS = 5,
