@@ -76,29 +76,39 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 }
 
 // ---- compile-time geometry of one (M, T) decimator ---------------------------------------------------------
+#ifndef HBD_K1_STAGES
+#define HBD_K1_STAGES 3
+#endif
+#ifndef HBD_K1_PSB_MIN
+#define HBD_K1_PSB_MIN 12
+#endif
 template <int M, int T>
 struct Geo {
     static constexpr int SB    = 64;                   // samples per superblock
     static constexpr int NOUT  = SB / M;               // outputs ending inside one superblock
     static constexpr int NLIVE = (T + SB - 1) / M;     // outputs whose window overlaps a superblock
-    static constexpr int RAMP  = 1 + (T - 1 - M) / SB; // superblocks walked before the first owned one
+    static constexpr int RAMP  = 1 + (T - 1 - M) / SB; // superblocks needed before the first owned one
     static constexpr int gcd_(int a, int b) { return b ? gcd_(b, a % b) : a; }
-    static constexpr int U     = NLIVE / gcd_(NLIVE, NOUT); // accumulator rotation period (superblocks)
-    static constexpr int PSB   = U * ((12 + U - 1) / U);    // superblocks per ring piece (multiple of U, >= 12)
+    static constexpr int U     = NLIVE / gcd_(NLIVE, NOUT);       // accumulator rotation period (superblocks)
+    static constexpr int RAMP_GROUPS = (RAMP + U - 1) / U;        // ramp-in walked as whole groups of U
+    static constexpr int PSB   = U * ((HBD_K1_PSB_MIN + U - 1) / U); // superblocks per ring piece (multiple of U)
+    static constexpr int GROUPS_PER_PIECE = PSB / U;
     static constexpr int PIECE_SAMPLES = PSB * SB;
     static constexpr int PIECE_BYTES   = (PIECE_SAMPLES + 2) * 8; // +2: 16-byte alignment slack on both sides
+    // cross-lane reduction tile: one row per completed output, 32 lane-partials (+1 pad) per row
+    static constexpr int RED_ROWS = (NOUT == 1) ? PSB : 16;
     static_assert(SB % M == 0, "M must divide 64");
     static_assert(T - 1 >= M, "taps shorter than the decimation factor are not handled by this kernel");
+    static_assert(RED_ROWS <= 16, "reduction tile maps (row, re/im) onto the 32 lanes");
 };
 
-constexpr int kStages      = 3;    // ring depth per warp
-constexpr int kRedOutputs  = 16;   // outputs per cross-lane reduction group
-constexpr int kRedPitch    = 33;   // float2 per row (+1 pad: conflict-free transposed reads)
+constexpr int kStages   = HBD_K1_STAGES; // ring depth per warp
+constexpr int kRedPitch = 33;            // float2 per row (+1 pad: conflict-free transposed reads)
 
 template <int M, int T>
 struct WarpSmem {
     alignas(16) unsigned char ring[kStages][Geo<M, T>::PIECE_BYTES];
-    alignas(16) float2 red[kRedOutputs][kRedPitch];
+    alignas(16) float2 red[Geo<M, T>::RED_ROWS][kRedPitch];
     alignas(8) uint64_t full[kStages];
 };
 
@@ -108,6 +118,25 @@ __device__ __forceinline__ float tap_for(const float* __restrict__ taps, int j, 
 {
     const int t = T - M * j + P;
     return (t >= 0 && t < T) ? __ldg(taps + t) : 0.0f;
+}
+
+// Sum the 32 lane-partials of up to 16 staged outputs (lane = 2*row + re/im) and store the ones whose
+// output index lies in [k_lo, k_hi).  Row r of the tile is output k_first + r.
+__device__ __forceinline__ void reduce_rows(const float2 (*red)[kRedPitch], int rows, int k_first, int k_lo, int k_hi,
+                                            float2* __restrict__ out, int lane)
+{
+    __syncwarp();
+    const int row = lane >> 1, comp = lane & 1;
+    const float* src = reinterpret_cast<const float*>(&red[row][0]) + comp;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int l = 0; l < 32; l += 4) {
+        s0 += src[2 * l]; s1 += src[2 * l + 2]; s2 += src[2 * l + 4]; s3 += src[2 * l + 6];
+    }
+    const float s = (s0 + s1) + (s2 + s3);
+    const int k = k_first + row;
+    if (row < rows && k >= k_lo && k < k_hi) reinterpret_cast<float*>(out + k)[comp] = s;
+    __syncwarp();
 }
 
 template <int M, int T>
@@ -135,69 +164,65 @@ decim1_kernel(DecimArgs a)
 
     uint32_t phase_bits = 0; // parity per ring slot
     const int warps_total = gridDim.x * kDecimWarps;
-    const long long n_items = (long long)a.n_channels * a.stretches_per_channel;
+    const int n_items = a.n_channels * a.stretches_per_channel;
 
-    for (long long item = (long long)blockIdx.x * kDecimWarps + warp; item < n_items; item += warps_total) {
-        const int ch = int(item / a.stretches_per_channel);
-        const int st = int(item % a.stretches_per_channel);
+    for (int item = blockIdx.x * kDecimWarps + warp; item < n_items; item += warps_total) {
+        const int ch = item / a.stretches_per_channel;
+        const int st = item - ch * a.stretches_per_channel;
         const ChanPlan pl = a.plan[ch];
         if (pl.flags & 1u) continue;
-        // superblock b covers step-local sample positions x in (64(b-1), 64b]; outputs k with
-        // k*M in that range end there.  Owned superblocks of this stretch:
-        const int n_sb_total = int((pl.n1 + G::NOUT - 1) / G::NOUT) + (G::NOUT > 1 ? 1 : 0); // covers k = 0 .. n1-1
+        // superblock b covers step-local sample positions x in (64(b-1), 64b]; the outputs k with
+        // (b-1)*NOUT < k <= b*NOUT end inside it.  This stretch owns superblocks [b_lo, b_hi).
+        const int n1 = int(pl.n1);
+        const int n_sb_total = (n1 - 1 + G::NOUT - 1) / G::NOUT + 1;       // superblocks 0 .. ceil((n1-1)/NOUT)
         const int b_lo = st * a.sb_per_stretch;
         if (b_lo >= n_sb_total) continue;
         const int b_hi = min(b_lo + a.sb_per_stretch, n_sb_total);
-        const int b_first = b_lo - G::RAMP;                 // walk start (ramp-in superblocks are discarded)
-        const int n_walk = b_hi - b_first;                  // superblocks to walk
-        const int n_pieces = (n_walk + G::PSB - 1) / G::PSB;
+        const int b_first = b_lo - G::RAMP_GROUPS * G::U;                   // ramp-in: whole groups, outputs discarded
+        const int n_groups = (b_hi - b_first + G::U - 1) / G::U;
+        const int n_pieces = (n_groups + G::GROUPS_PER_PIECE - 1) / G::GROUPS_PER_PIECE;
+        // outputs this stretch may store
+        const int k_lo = max(0, (b_lo - 1) * G::NOUT + 1), k_hi = min(n1, (b_hi - 1) * G::NOUT + 1);
 
-        // sample addressing: j = x - r is the index into the pushed chunk (j >= 0) or the carry (j < 0)
-        const long long j0 = 64LL * (b_first - 1) + 1 - (long long)pl.r; // first sample of the walk
+        // sample addressing: j = x - r indexes the pushed chunk (j >= 0) or the carry (j < 0);
+        // everything below is relative to the first sample of the walk, jw = j - j0 >= 0
+        const int j0 = 64 * (b_first - 1) + 1 - int(pl.r);
         const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
         const float2* carry = a.carry + (size_t)ch * kCarryCap + kCarryCap; // carry[j] valid for -kCarryCap <= j < 0
-        const long long j_end_valid = (long long)pl.n;                       // chunk holds j in [0, n)
+        const int odd = j0 & 1;                // ring sample s holds j = (j0 - odd) + p*PIECE_SAMPLES + s
+        const int j_cap_lo = -kCarryCap, j_end = int(pl.n);
 
-        // ---- producer: copy piece p into its ring slot (lane 0 issues, everyone helps with ragged edges)
+        // ---- producer: copy piece p into its ring slot ----------------------------------------------------
         auto issue_piece = [&](int p) {
             const int slot = p % kStages;
             unsigned char* dst = sm.ring[slot];
-            const long long pj0 = j0 + (long long)p * G::PIECE_SAMPLES;   // first sample wanted
-            const long long pj1 = pj0 + G::PIECE_SAMPLES;                 // one past the last
-            // smem sample s (0 .. PIECE_SAMPLES+1) holds j = A + s, A = pj0 rounded down to even
-            const long long A = pj0 & ~1LL;
-            long long lo = max(A, (long long)-kCarryCap);
-            long long hi = min((pj1 + 1) & ~1LL, j_end_valid);
-            if (hi < lo) hi = lo;
-            // 16-byte aligned interior [lo2, hi2) goes through TMA, ragged edges through plain stores
-            const long long lo2 = (lo + 1) & ~1LL, hi2 = hi & ~1LL;
+            const int A = j0 - odd + p * G::PIECE_SAMPLES;          // j of ring sample 0 (even)
+            const int want_lo = A + odd, want_hi = want_lo + G::PIECE_SAMPLES;
+            const int lo = max(A, j_cap_lo);                          // even
+            const int hi = min(A + G::PIECE_SAMPLES + 2 * odd, j_end);
+            const int hi2 = max(hi & ~1, lo);                         // 16-byte granular end of the TMA part
             if (lane == 0) {
-                uint32_t bytes = 0;
-                if (hi2 > lo2) {
-                    const long long c_lo = lo2, c_hi = min(hi2, 0LL);  // part served by the carry
-                    const long long d_lo = max(lo2, 0LL), d_hi = hi2;  // part served by the chunk
-                    if (c_hi > c_lo) bytes += uint32_t(c_hi - c_lo) * 8u;
-                    if (d_hi > d_lo) bytes += uint32_t(d_hi - d_lo) * 8u;
-                    mbar_expect_tx(&sm.full[slot], bytes);
-                    if (c_hi > c_lo) tma_load_1d(dst + (c_lo - A) * 8, carry + c_lo, uint32_t(c_hi - c_lo) * 8u, &sm.full[slot]);
-                    if (d_hi > d_lo) tma_load_1d(dst + (d_lo - A) * 8, chunk + d_lo, uint32_t(d_hi - d_lo) * 8u, &sm.full[slot]);
+                if (hi2 > lo) {
+                    const int c_hi = min(hi2, 0), d_lo = max(lo, 0);
+                    mbar_expect_tx(&sm.full[slot], uint32_t(hi2 - lo) * 8u);
+                    if (c_hi > lo) tma_load_1d(dst + (lo - A) * 8, carry + lo, uint32_t(c_hi - lo) * 8u, &sm.full[slot]);
+                    if (hi2 > d_lo) tma_load_1d(dst + (d_lo - A) * 8, chunk + d_lo, uint32_t(hi2 - d_lo) * 8u, &sm.full[slot]);
                 } else {
                     mbar_arrive(&sm.full[slot]);
                 }
             }
-            // ragged edge (chunk with an odd sample count) goes through a plain store
-            float2* d2 = reinterpret_cast<float2*>(dst);
-            if (hi > hi2 && hi2 >= lo2 && lane == 2) d2[hi2 - A] = (hi2 < 0) ? carry[hi2] : chunk[hi2];
-            // whatever part of the wanted range is not backed by data (past the end of the chunk in the
-            // last piece of a channel) is zero filled: stale shared memory could hold NaN patterns and
-            // 0 * NaN would poison a valid output
-            if (lo > pj0 || hi < pj1) {
-                for (long long j = pj0 + lane; j < pj1; j += 32)
-                    if (j < lo || j >= hi) d2[j - A] = make_float2(0.f, 0.f);
+            if (lo > want_lo || hi2 < want_hi) { // rare: TMA part does not cover the wanted range (ends of a channel)
+                float2* d2 = reinterpret_cast<float2*>(dst);
+                for (int j = want_lo + lane; j < want_hi; j += 32) {
+                    if (j >= lo && j < hi2) continue;                 // delivered by the bulk copy
+                    // odd trailing sample of an odd-length chunk: plain copy; everything not backed by data: zero
+                    // (stale shared memory could hold NaN patterns and 0 * NaN would poison a valid output)
+                    d2[j - A] = (j >= lo && j < hi) ? ((j < 0) ? carry[j] : chunk[j]) : make_float2(0.f, 0.f);
+                }
             }
         };
 
-        // WAR note: ring slots are only re-filled by the warp that has finished reading them
+        // WAR note: a ring slot is only re-filled by the warp that has finished reading it
         // (program order + __syncwarp), so no "empty" barrier is needed.
         __syncwarp();
         for (int p = 0; p < min(kStages - 1, n_pieces); ++p) issue_piece(p);
@@ -207,20 +232,8 @@ decim1_kernel(DecimArgs a)
         for (int j = 0; j < G::NLIVE; ++j) acc[j] = make_float2(0.f, 0.f);
 
         float2* out = a.s1 + (size_t)ch * a.s1_pitch + a.s1_hist;
-        int b = b_first;             // current superblock
-        int emitted = 0;             // outputs staged in sm.red since the last flush
-        long long k_group = 0;       // output index of sm.red[0]
-
-        auto flush = [&](int count) {
-            __syncwarp();
-            const int j = lane >> 1, comp = lane & 1;
-            float s = 0.f;
-            const float* row = reinterpret_cast<const float*>(&sm.red[j][0]) + comp;
-#pragma unroll 8
-            for (int l = 0; l < 32; ++l) s += row[2 * l];
-            if (j < count) reinterpret_cast<float*>(out + k_group)[lane] = s;
-            __syncwarp();
-        };
+        int k_next = (b_first - 1) * G::NOUT + 1;   // output index that completes next
+        int staged = 0;                              // NOUT > 1 only: rows waiting in sm.red
 
         for (int p = 0; p < n_pieces; ++p) {
             const int slot = p % kStages;
@@ -229,21 +242,20 @@ decim1_kernel(DecimArgs a)
             mbar_wait(&sm.full[slot], (phase_bits >> slot) & 1u);
             phase_bits ^= 1u << slot;
             __syncwarp();
-            const long long pj0 = j0 + (long long)p * G::PIECE_SAMPLES;
-            const float2* src = reinterpret_cast<const float2*>(sm.ring[slot]) + (pj0 & 1LL);
+            const float2* src = reinterpret_cast<const float2*>(sm.ring[slot]) + odd + lane;
 
-            for (int g = 0; g < G::PSB / G::U; ++g) {
+#pragma unroll 1
+            for (int g = 0; g < G::GROUPS_PER_PIECE; ++g) {
 #pragma unroll
                 for (int u = 0; u < G::U; ++u) {
-                    const float2 x0 = src[(g * G::U + u) * 64 + lane];
-                    const float2 x1 = src[(g * G::U + u) * 64 + 32 + lane];
+                    const float2 x0 = src[(g * G::U + u) * 64];
+                    const float2 x1 = src[(g * G::U + u) * 64 + 32];
 #pragma unroll
                     for (int j = 0; j < G::NLIVE; ++j) {
                         const int r = (j + u * G::NOUT) % G::NLIVE; // register holding live output j
-                        // tap index of position P for live output j: t = T - M*(j+1) + P; skip the
+                        // tap index of position P for live output j (0-based): t = T - M*(j+1) + P; skip the
                         // half-superblocks where no lane has a tap (compile-time)
-                        constexpr int tb = T - M * 1;
-                        const int t0 = tb - M * j; // t at P = 0
+                        const int t0 = T - M * (j + 1);
                         if (t0 + 31 >= 0 && t0 < T) {
                             acc[r].x = fmaf(x0.x, h0[j], acc[r].x);
                             acc[r].y = fmaf(x0.y, h0[j], acc[r].y);
@@ -256,20 +268,23 @@ decim1_kernel(DecimArgs a)
 #pragma unroll
                     for (int j = 0; j < G::NOUT; ++j) {
                         const int r = (j + u * G::NOUT) % G::NLIVE;
-                        // output index of live slot j in superblock b: k = (b-1)*NOUT + j + 1
-                        const long long k = (long long)(b - 1) * G::NOUT + j + 1;
-                        if (b >= b_lo && b < b_hi && k >= 0 && k < (long long)pl.n1) {
-                            if (emitted == 0) k_group = k;
-                            sm.red[emitted][lane] = acc[r];
-                            if (++emitted == kRedOutputs) { flush(kRedOutputs); emitted = 0; }
+                        if (G::NOUT == 1) {
+                            sm.red[g * G::U + u][lane] = acc[r];            // row = superblock within the piece
+                        } else {
+                            sm.red[staged][lane] = acc[r];
+                            if (++staged == 16) { reduce_rows(sm.red, 16, k_next + j - 15, k_lo, k_hi, out, lane); staged = 0; }
                         }
                         acc[r] = make_float2(0.f, 0.f);
                     }
-                    ++b;
+                    if (G::NOUT > 1) k_next += G::NOUT;
                 }
             }
+            if (G::NOUT == 1) {
+                reduce_rows(sm.red, G::PSB, k_next, k_lo, k_hi, out, lane);
+                k_next += G::PSB;
+            }
         }
-        if (emitted) flush(emitted);
+        if (G::NOUT > 1 && staged) reduce_rows(sm.red, staged, k_next - staged, k_lo, k_hi, out, lane);
         __syncwarp();
     }
 }
