@@ -654,6 +654,23 @@ void orc_afc(void* h, hbo_afc_info* o)
 
 void orc_reset_frequency_correction(void* h, double corr) { static_cast<Port*>(h)->afc.reset_correction(corr); }
 
+// std::regex sentence extraction alone (the reference's extractSentence), for fuzzing the product's matcher
+int orc_extract_sentence(const char* stream, size_t n, char* callsign, char* data, char* crc, size_t cap, size_t* rest)
+{
+    Sentence s = extract_sentence(std::string(stream, n));
+    if (!s.ok) return 0;
+    auto put = [cap](char* dst, const std::string& v) { if (dst && cap) { const size_t k = std::min(cap - 1, v.size()); memcpy(dst, v.data(), k); dst[k] = 0; } };
+    put(callsign, s.callsign); put(data, s.data); put(crc, s.crc);
+    if (rest) *rest = n - s.rest.size();
+    return 1;
+}
+
+void orc_crc16(const char* s, size_t n, char out[5])
+{
+    const std::string r = crc16_hex(std::string(s, n));
+    memcpy(out, r.data(), 4); out[4] = 0;
+}
+
 double orc_bench(const hbo_config* cfg, int n_threads, const float* iq, size_t n, size_t stride,
                  size_t chunk, double fs, int reps, uint64_t* o_chars)
 {

@@ -80,6 +80,10 @@ typedef struct hbo_afc_info {
 HBO_DECL(ref)
 HBO_DECL(orc)
 
+/* port only: the sentence layer alone (std::regex, like sentence_extract.cpp:58-98) and the CRC */
+int  orc_extract_sentence(const char* stream, size_t n, char* callsign, char* data, char* crc, size_t cap, size_t* rest_offset);
+void orc_crc16(const char* s, size_t n, char out[5]);
+
 #ifdef __cplusplus
 }
 #endif

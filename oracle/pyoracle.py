@@ -158,3 +158,23 @@ def bench(kind: str, cfg: Config, iq: np.ndarray, n_threads: int, fs: float, chu
     secs = getattr(lib, kind + "_bench")(C.byref(cfg), n_threads, iq.ctypes.data, n, stride, chunk, float(fs), reps,
                                          C.byref(chars))
     return secs, chars.value
+
+
+def port_extract_sentence(stream: bytes):
+    """std::regex extraction of the restatement (== the reference's extractSentence); None if no match."""
+    lib = _load("orc")
+    lib.orc_extract_sentence.restype = C.c_int
+    lib.orc_extract_sentence.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    cs, data, crc = (C.create_string_buffer(len(stream) + 8) for _ in range(3))
+    rest = C.c_size_t(0)
+    if not lib.orc_extract_sentence(stream, len(stream), cs, data, crc, len(stream) + 8, C.byref(rest)):
+        return None
+    return cs.value, data.value, crc.value, rest.value
+
+
+def port_crc16(s: bytes) -> bytes:
+    lib = _load("orc")
+    lib.orc_crc16.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p]
+    out = C.create_string_buffer(5)
+    lib.orc_crc16(s, len(s), out)
+    return out.value

@@ -171,3 +171,35 @@ def test_fft_and_afc(oracle_kind):
     info, power = dec.getSpectrumInfo(0)
     assert info.peak_left_ == abs(a.peak_left) and info.peak_right_ == abs(a.peak_right)
     assert info.sampling_rate_ == 8000.0
+
+
+# ---- golden fixtures produced by the unmodified reference (tests/golden/make_golden.py) ---------------------
+import glob
+import os
+
+_GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", _GOLD, ids=[os.path.basename(p)[:-4] for p in _GOLD])
+def test_gpu_matches_golden_reference_vectors(path):
+    g = np.load(path)
+    q = g["iq_q"]
+    iq = (q[:, 0].astype(np.float32) / np.float32(32.0) + 1j * (q[:, 1].astype(np.float32) / np.float32(32.0))).astype(np.complex64)
+    cfg = dict(baud=float(g["baud"]), rtty_bits=int(g["bits"]), rtty_stops=float(g["stops"]), dec_factor=int(g["factor"]),
+               dc_remove=bool(g["dc_remove"]))
+    dec, got = run_gpu_single(iq, float(g["fs"]), int(g["chunk"]), **cfg)
+    assert np.array_equal(got["taps"].view(np.uint32), g["lptaps"].view(np.uint32))
+    for name in ("decimated", "filtered", "demod"):
+        a = got[{"decimated": "dec", "filtered": "filt", "demod": "demod"}[name]]
+        assert a.shape == g[name].shape, name
+        assert rel_l2(a, g[name]) <= REL_L2, name
+    assert dec.poll_chars(0) == g["chars"].tobytes()
+    assert dec.getRTTY(0) == g["rtty"].tobytes()
+    assert dec.getLastSentence(0) == g["last_sentence"].tobytes()
+    assert b"\n".join(dec.poll_sentences(0)) == g["sentences"].tobytes()
+    assert got["pending"].shape == g["pending"].shape
+    if len(g["power"]):
+        afc = g["afc"]
+        assert dec.getPeaks(0) == (int(afc[4]), int(afc[5]))
+        assert dec.getFrequencyCorrection(0) == pytest.approx(afc[0], abs=1e-9)
+        assert dec.getShift(0) == pytest.approx(afc[1], abs=1e-9)

@@ -1,0 +1,93 @@
+"""CPU tier: host logic of the product that needs no GPU -- ABI surface, low-pass design, sentence layer, sharding."""
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from habdec_b200 import api, dist as hdist, synth
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = api.load()
+    header = open(os.path.join(ROOT, "include", "habdec_b200.h")).read()
+    declared = set(re.findall(r"\b(hbd_[a-z0-9_]+)\s*\(", header))
+    declared -= {"hbd_sentence_cb", "hbd_chars_cb"}
+    assert len(declared) >= 50
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libhabdec_b200.so does not export %s" % name
+        assert name in api.SIGNATURES, "python binding misses %s" % name
+    assert set(api.SIGNATURES) <= declared
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.HbdError):
+        api.BatchDecoder(1)
+
+
+def test_crc_known_answers():
+    assert api.crc16(b"CALL,1,12:00:00,52.1234,21.5678,1000") == b"2BEE"
+    for s in (b"", b"A", b"CH0011,0,12:00:00,52.1234,21.5678,1000", bytes(range(32, 127))):
+        assert api.crc16(s) == po.port_crc16(s) == synth.crc16_ccitt(s).encode()
+
+
+@pytest.mark.parametrize("bw,fs_dec,trans,n", [(1500.0, 8000.0, 0.025, 256), (1500.0, 9765.625, 0.025, 1024), (1500.0, 78125.0, 0.025, 256),
+                                               (800.0, 8000.0, 0.05, 256), (1500.0, 8000.0, 0.01, 256), (1500.0, 8000.0, 0.0, 256)])
+def test_lowpass_design_bit_exact(bw, fs_dec, trans, n):
+    taps = api.design_lowpass(np.float32(bw / fs_dec), trans, n)
+    # drive the port's filter through one call so it designs with the same inputs, then read its taps back
+    d = po.PortDecoder(po.make_config(baud=300.0, lowpass_bw=bw, lowpass_trans=trans, dec_factor=2))
+    d.push_process(np.zeros(2 * n, dtype=np.complex64), 2 * fs_dec)
+    want = d.stage(po.STAGE_LPTAPS)
+    assert taps.shape == want.shape and np.array_equal(taps.view(np.uint32), want.view(np.uint32))
+    if (bw, fs_dec, trans) == (1500.0, 8000.0, 0.025):
+        assert len(taps) == 161 and abs(taps[80] - 0.119366) < 1e-6 and abs(taps.sum() - 1.0) < 1e-6
+
+
+def test_sentence_matcher_equals_std_regex_on_fuzz():
+    rng = random.Random(7)
+    alphabet = "$$$**,,,  --__AB12ab#\n"
+    checked = matched = 0
+    for it in range(6000):
+        n = rng.randint(0, 60)
+        s = "".join(rng.choice(alphabet) for _ in range(n))
+        if it % 3 == 0:   # plant something sentence-like
+            body = "".join(rng.choice("AB12,-_ ") for _ in range(rng.randint(1, 8)))
+            s = s[:n // 2] + "$" * rng.randint(1, 3) + body + "," + "".join(rng.choice("12,.ab$") for _ in range(rng.randint(0, 6))) + \
+                rng.choice("*$") + "".join(rng.choice("0123ABCD_#") for _ in range(rng.randint(0, 6))) + s[n // 2:]
+        b = s.encode()
+        got, want = api.extract_sentence(b), po.port_extract_sentence(b)
+        assert got == want, repr(s)
+        checked += 1
+        matched += want is not None
+    assert matched > 300 and checked == 6000
+
+
+def test_sentence_matcher_real_sentences():
+    s = synth.make_sentence(12, 3)
+    stream = ("noise" + s + s[:20]).encode()
+    cs, data, crc, rest = api.extract_sentence(stream)
+    assert cs == b"CH0012" and crc == api.crc16(cs + b"," + data)
+    assert stream[rest:rest + 1] == crc[-1:]          # the reference keeps the last CRC character in the stream
+
+
+def test_block_partition():
+    for n, w in ((4096, 8), (4096, 1), (10, 4), (3, 8)):
+        got = [c for r in range(w) for c in hdist.shard(n, w, r)]
+        assert got == list(range(n))
+    assert len(hdist.shard(4096, 8, 3)) == 512
+
+
+def test_ring_workload_properties():
+    L = synth.ring_length(2.048e6, 300.0)
+    assert L == 1310720 and L % 65536 == 0 and L % 262144 == 0
+    s = synth.ring_sentence(77)
+    assert len(s) == 17 and s.startswith("$$C0077,")
+    assert len(synth.ring_bits(77)) == synth.RING_BITS

@@ -1,0 +1,105 @@
+"""CPU tier: the oracle itself.
+
+ * the CPU restatement (oracle/habdec_oracle.cpp) against the golden fixtures that were produced by the
+   UNMODIFIED reference (tests/golden/make_golden.py) -- bit-exact floats, identical characters;
+ * where the compiled reference is present (oracle/_ref, dev container and shipped .so): restatement vs
+   reference on fresh seeded inputs, every stage.
+"""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from habdec_b200 import synth
+from oracle import pyoracle as po
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+SCALE = 32.0
+
+
+def load_gold(path):
+    g = np.load(path)
+    q = g["iq_q"]
+    iq = (q[:, 0].astype(np.float32) / np.float32(SCALE) + 1j * (q[:, 1].astype(np.float32) / np.float32(SCALE))).astype(np.complex64)
+    cfg = dict(baud=float(g["baud"]), rtty_bits=int(g["bits"]), rtty_stops=float(g["stops"]), dec_factor=int(g["factor"]),
+               dc_remove=bool(g["dc_remove"]))
+    return g, iq, cfg
+
+
+def bits_equal(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_port_matches_golden_reference_vectors(path):
+    g, iq, cfg = load_gold(path)
+    d = po.PortDecoder(po.make_config(**cfg)).run(iq, float(g["fs"]), int(g["chunk"]))
+    assert bits_equal(d.stage(po.STAGE_LPTAPS), g["lptaps"])
+    assert bits_equal(d.stage(po.STAGE_DECIMATED), g["decimated"])
+    assert bits_equal(d.stage(po.STAGE_FILTERED), g["filtered"])
+    assert bits_equal(d.stage(po.STAGE_DEMOD), g["demod"])
+    assert bits_equal(d.stage(po.STAGE_PENDING), g["pending"])
+    assert hashlib.sha256(d.stage(po.STAGE_FFT).tobytes()).hexdigest() == str(g["fft_sha"])
+    assert bits_equal(d.stage(po.STAGE_POWER), g["power"])
+    assert d.chars() == g["chars"].tobytes()
+    assert d.rtty() == g["rtty"].tobytes()
+    assert d.last_sentence() == g["last_sentence"].tobytes()
+    assert b"\n".join(d.sentences()) == g["sentences"].tobytes()
+    a = d.afc()
+    assert [a.frequency_correction, a.shift_hz, a.noise_floor, a.noise_variance, a.peak_left, a.peak_right] == list(g["afc"])
+
+
+def test_golden_set_is_meaningful():
+    assert len(GOLD) >= 3
+    g, _, _ = load_gold([p for p in GOLD if "g2_" in p][0])
+    assert g["sentences"].tobytes().startswith(b"CH0011,0,12:00:00") and len(g["chars"]) > 40
+
+
+needs_ref = pytest.mark.skipif(not po.available("ref"), reason="oracle/_ref/libhabdec_ref.so not built (needs /root/reference)")
+
+FRESH = [
+    # fs, baud, bits, stops, factor, snr, nsent, chunk, f_off, dc
+    (2.048e6, 300.0, 8, 2.0, 256, -15.0, 1, 65536, 0.0, False),
+    (2.048e6, 300.0, 8, 2.0, 256, -27.0, 1, 65536, 0.0, False),
+    (2.048e6, 300.0, 8, 2.0, 256, -15.0, 1, 262144, 90.0, True),
+    (1.024e6, 100.0, 7, 1.0, 128, -14.0, 1, 65536, 0.0, False),
+    (0.512e6, 300.0, 8, 1.5, 64, -12.0, 1, 50000, 0.0, False),
+    (0.128e6, 300.0, 8, 2.0, 16, -8.0, 2, 65536, 0.0, False),
+    (64e3, 300.0, 8, 2.0, 8, -6.0, 2, 65536, -40.0, False),
+    (32e3, 600.0, 8, 2.0, 4, -3.0, 2, 16384, 0.0, False),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("fs,baud,bits,stops,factor,snr,nsent,chunk,foff,dc", FRESH)
+def test_port_matches_compiled_reference(fs, baud, bits, stops, factor, snr, nsent, chunk, foff, dc):
+    iq, _ = synth.channel_iq(21, nsent, fs, baud, bits, int(np.ceil(stops)), snr_db=snr, f_off=foff)
+    cfg = dict(baud=baud, rtty_bits=bits, rtty_stops=stops, dec_factor=factor, dc_remove=dc)
+    r = po.RefDecoder(po.make_config(**cfg)).run(iq, fs, chunk)
+    p = po.PortDecoder(po.make_config(**cfg)).run(iq, fs, chunk)
+    for st in (po.STAGE_LPTAPS, po.STAGE_DECIMATED, po.STAGE_FILTERED, po.STAGE_DEMOD, po.STAGE_PENDING, po.STAGE_FFT, po.STAGE_POWER):
+        assert bits_equal(r.stage(st), p.stage(st)), "stage %d" % st
+    assert r.chars() == p.chars() and len(r.chars()) > 10
+    assert r.sentences() == p.sentences()
+    assert r.rtty() == p.rtty() and r.last_sentence() == p.last_sentence()
+    ra, pa = r.afc(), p.afc()
+    for f, _ in po.AfcInfo._fields_:
+        assert getattr(ra, f) == getattr(pa, f), f
+
+
+@needs_ref
+def test_reference_afc_reset_matches_port():
+    fs, baud = 2.048e6, 300.0
+    iq, _ = synth.channel_iq(4, 2, fs, baud, snr_db=-12.0, f_off=150.0)
+    r = po.RefDecoder(po.make_config(baud=baud)); p = po.PortDecoder(po.make_config(baud=baud))
+    half = len(iq) // 2 // 65536 * 65536
+    for d in (r, p):
+        d.run(iq[:half], fs)
+        d.reset_frequency_correction(d.afc().frequency_correction)
+        d.run(iq[half:], fs)
+    ra, pa = r.afc(), p.afc()
+    for f, _ in po.AfcInfo._fields_:
+        assert getattr(ra, f) == getattr(pa, f), f
