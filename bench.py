@@ -38,8 +38,8 @@ METRIC = "aggregate IQ MSamples/s decoded (chars bit-exact)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--channels", type=int, default=TOTAL_CHANNELS, help="total channels over all ranks")
     ap.add_argument("--chunk", type=int, default=65536, help="complex samples per channel per step")
@@ -62,34 +62,47 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled while the timed region runs."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled (NVML, every 5 ms) while the timed region runs."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self._stop, self.th = index, [], False, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
-            self.proc = None
+            self.nv = None
+            return
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((clk, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        self._stop = True
+        if self.th:
+            self.th.join(timeout=1.0)
+        if not getattr(self, "nv", None) or not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons = sorted({name for _, rs in self.rows for name, b in bits.items() if rs & b})
+        return {"sm_mhz": float(np.median([c for c, _ in self.rows])), "sm_max_mhz": float(self.mx), "reasons": reasons, "samples": len(self.rows)}
 
 
 def workload_config(args, world, impl):
@@ -248,7 +261,8 @@ def run_ours(args):
         return
 
     peak, peak_src = load_peaks()
-    k1_bytes = ALGO_BYTES_PER_SAMPLE_K1 * C * args.chunk
+    # K1 is launched once per channel group per step: algorithmic bytes of one launch = step bytes / launches per step
+    k1_bytes = ALGO_BYTES_PER_SAMPLE_K1 * C * args.chunk * args.steps / max(k1_cnt, 1)
     k1_avg_ms = k1_ms / max(k1_cnt, 1)
     achieved = k1_bytes / (k1_avg_ms * 1e-3) / 1e9 if k1_cnt else None
     exp_sent = args.steps * args.chunk // L

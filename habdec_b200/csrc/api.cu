@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -98,8 +99,24 @@ struct hbd_decoder {
     std::mutex mtx;
     std::string err;
     int n_ch = 0, device = 0, n_sms = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // the caller's stream: inputs are ordered on it, it waits until inputs are consumed
     bool own_stream = false;
+    // channel groups: each group runs K1 -> carry -> K2 -> K4 -> K3 in order on its own stream, so the HBM-bound K1
+    // of one group overlaps the FP32/latency-bound tail kernels of the other (no data is shared between groups)
+    //   hi (high priority): K1 + carry of every group, in group order
+    //   lo (low priority):  K2 / K4 / K3 of every group; they fill the SM resources K1 leaves free
+    int n_groups = 1;
+    cudaStream_t hi = nullptr, lo = nullptr;
+    std::vector<cudaEvent_t> ev_consumed;   // per group: K1 + carry done (input consumed, stage-1 output ready)
+    std::vector<cudaEvent_t> ev_tail;       // per group: K2..K3 done (stage-1 buffer of the group may be overwritten)
+    std::vector<char> tail_pending;
+    cudaEvent_t ev_in = nullptr;
+    int sync_groups()
+    {
+        if (hi && cudaStreamSynchronize(hi) != cudaSuccess) return HBD_ERR_CUDA;
+        if (lo && cudaStreamSynchronize(lo) != cudaSuccess) return HBD_ERR_CUDA;
+        return HBD_OK;
+    }
     bool record = false;
     unsigned long long launches = 0;
 
@@ -259,7 +276,13 @@ int hbd_decoder::upload_taps()
 void hbd_decoder::free_all()
 {
     cudaSetDevice(device);
+    sync_groups();
     if (stream) cudaStreamSynchronize(stream);
+    if (hi) cudaStreamDestroy(hi);
+    if (lo) cudaStreamDestroy(lo);
+    for (cudaEvent_t e : ev_consumed) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_tail) cudaEventDestroy(e);
+    if (ev_in) cudaEventDestroy(ev_in);
     void* ptrs[] = {d_state, d_plan, d_carry, d_s1, d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_raw, d_raw_n,
                     d_mark, d_offsets, d_packed, d_taps1, d_taps2, d_twiddle, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps,
                     d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage};
@@ -327,7 +350,12 @@ int hbd_decoder::process_async_locked()
         }
         max_n1 = std::max(max_n1, p.n1);
     }
+    if (max_total > cap_n_in || !d_s1) { // buffers are about to be reallocated: nothing may be in flight
+        if (sync_groups()) return HBD_ERR_CUDA;
+    }
     { const int rc = ensure_call_capacity(max_total); if (rc) return rc; }
+    bool groups_idle = false; // set once we had to wait for the group streams (rare host-side state changes)
+    auto quiesce = [&]() -> int { if (!groups_idle) { if (sync_groups()) return HBD_ERR_CUDA; groups_idle = true; } return HBD_OK; };
 
     bool cfg_dirty_any = false;
     std::vector<float> new_taps;
@@ -343,6 +371,7 @@ int hbd_decoder::process_async_locked()
             const size_t need = size_t(p.consumed) + size_t(T1) + size_t(M1);
             if (x.grown1 < need) {
                 x.grown1 = need;
+                if (quiesce()) return HBD_ERR_CUDA;
                 HBD_CUDA_CHECK(cudaMemsetAsync(d_carry + c * kCarryCap + (kCarryCap - (T1 - 1) - p.r), 0, sizeof(float2) * size_t(T1 - 1), stream));
             }
         }
@@ -350,6 +379,7 @@ int hbd_decoder::process_async_locked()
             const size_t need = size_t(p.n1) + size_t(T2) + size_t(M2);
             if (x.grown2 < need) {
                 x.grown2 = need;
+                if (quiesce()) return HBD_ERR_CUDA;
                 HBD_CUDA_CHECK(cudaMemsetAsync(d_s1 + c * s1_pitch, 0, sizeof(float2) * kS1Hist, stream));
             }
         }
@@ -366,17 +396,20 @@ int hbd_decoder::process_async_locked()
             if (T > size_t(kLpMaxTaps)) { set_error("low-pass needs more than kLpMaxTaps taps"); return HBD_ERR_ARG; }
             x.lp_ntaps = T;
             x.cfg_dirty = true;
+            if (quiesce()) return HBD_ERR_CUDA;
             HBD_CUDA_CHECK(cudaMemcpyAsync(d_lptaps + c * kLpMaxTaps, new_taps.data(), 4 * T, cudaMemcpyHostToDevice, stream));
             HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // new_taps is reused
         }
         const size_t need = size_t(nf) + x.lp_ntaps;
         if (x.grown_lp < need) { // FirFilter.h:141-147
             x.grown_lp = need;
+            if (quiesce()) return HBD_ERR_CUDA;
             HBD_CUDA_CHECK(cudaMemsetAsync(d_decq + c * dq_pitch, 0, sizeof(float2) * kLpHist, stream));
         }
         cfg_dirty_any |= x.cfg_dirty;
     }
     if (cfg_dirty_any) {
+        if (quiesce()) return HBD_ERR_CUDA;
         std::vector<double> b(n); std::vector<float> s(n); std::vector<int> bi(n), dc(n), nt(n); std::vector<unsigned char> d(n);
         for (size_t c = 0; c < n; ++c) {
             b[c] = hc[c].baud; s[c] = hc[c].rtty_stops; bi[c] = int(hc[c].rtty_bits); dc[c] = hc[c].dc_remove; nt[c] = int(hc[c].lp_ntaps);
@@ -393,6 +426,7 @@ int hbd_decoder::process_async_locked()
         HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // host vectors go out of scope
     }
     if (h_plan_uploaded.size() != n || memcmp(h_plan.data(), h_plan_uploaded.data(), n * sizeof(ChanPlan)) != 0) {
+        if (quiesce()) return HBD_ERR_CUDA;
         HBD_CUDA_CHECK(cudaMemcpyAsync(d_plan, h_plan.data(), n * sizeof(ChanPlan), cudaMemcpyHostToDevice, stream));
         HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
         h_plan_uploaded = h_plan;
@@ -401,43 +435,59 @@ int hbd_decoder::process_async_locked()
     const float2* chunk = ext ? ext : d_stage;
     const size_t chunk_pitch = ext ? ext_pitch : stage_pitch;
     int nl = 0;
-    if (any_work) {
-        DecimArgs da{};
-        da.chunk = chunk; da.chunk_pitch = chunk_pitch; da.carry = d_carry;
-        da.s1 = d_s1; da.s1_pitch = s1_pitch; da.s1_hist = kS1Hist;
-        da.plan = d_plan; da.taps = d_taps1; da.n_channels = n_ch;
-        da.sb_per_stretch = decim1_sb_per_stretch(M1);
-        const unsigned n_sb = (M1 > 1) ? (max_n1 * unsigned(M1) + 63) / 64 + 2 : 1;
-        da.stretches_per_channel = int((n_sb + da.sb_per_stretch - 1) / da.sb_per_stretch);
-        if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), stream));
-        HBD_CUDA_CHECK(launch_decim1(da, M1, T1, max_n1, n_sms, stream, &nl));
-        if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), stream));
+    // everything the caller (and the host-side updates above) put on `stream` happens before the groups start
+    HBD_CUDA_CHECK(cudaEventRecord(ev_in, stream));
+    HBD_CUDA_CHECK(cudaStreamWaitEvent(hi, ev_in, 0));
+    for (int g = 0; g < n_groups; ++g) {
+        const int c0 = int((long long)n_ch * g / n_groups), c1 = int((long long)n_ch * (g + 1) / n_groups);
+        const int nc = c1 - c0;
+        // K1 of this group overwrites the group's stage-1 buffer: the previous call's tail must be done with it
+        if (tail_pending[size_t(g)]) HBD_CUDA_CHECK(cudaStreamWaitEvent(hi, ev_tail[size_t(g)], 0));
+        if (any_work) {
+            DecimArgs da{};
+            da.chunk = chunk; da.chunk_pitch = chunk_pitch; da.carry = d_carry;
+            da.s1 = d_s1; da.s1_pitch = s1_pitch; da.s1_hist = kS1Hist;
+            da.plan = d_plan; da.taps = d_taps1; da.ch0 = c0; da.n_channels = nc;
+            da.sb_per_stretch = decim1_sb_per_stretch(M1);
+            const unsigned n_sb = (M1 > 1) ? (max_n1 * unsigned(M1) + 63) / 64 + 2 : 1;
+            da.stretches_per_channel = int((n_sb + da.sb_per_stretch - 1) / da.sb_per_stretch);
+            if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), hi));
+            HBD_CUDA_CHECK(launch_decim1(da, M1, T1, max_n1, n_sms, hi, &nl));
+            if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), hi));
+        }
+        HBD_CUDA_CHECK(launch_carry(d_plan, chunk, chunk_pitch, d_carry, T1, c0, nc, hi, &nl));
+        HBD_CUDA_CHECK(cudaEventRecord(ev_consumed[size_t(g)], hi)); // input no longer needed by this group; stage-1 output ready
+        HBD_CUDA_CHECK(cudaStreamWaitEvent(lo, ev_consumed[size_t(g)], 0));
+        if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
+        if (any_work) {
+            TailArgs ta{};
+            ta.plan = d_plan; ta.state = d_state; ta.ch0 = c0;
+            ta.s1 = d_s1; ta.s1_pitch = s1_pitch; ta.taps2 = d_taps2; ta.M2 = M2; ta.T2 = T2;
+            ta.decq = d_decq; ta.dq_pitch = dq_pitch; ta.fs_dec = fs_dec; ta.fftbuf = d_fftbuf; ta.lptaps = d_lptaps;
+            ta.slicer = d_slicer; ta.slicer_pitch = slicer_pitch; ta.demod_last = d_demod; ta.demod_pitch = demod_pitch;
+            ta.rec_decimated = record ? d_rec_dec : nullptr; ta.rec_filtered = record ? d_rec_filt : nullptr; ta.rec_pitch = rec_pitch;
+            ta.smem_window = tail_smem_window(M2, T2);
+            HBD_CUDA_CHECK(launch_tail(ta, nc, lo, &nl));
+            FftArgs fa{};
+            fa.state = d_state; fa.fftbuf = d_fftbuf; fa.spectrum = d_spectrum; fa.power = d_power; fa.twiddle = d_twiddle; fa.fs_dec = fs_dec;
+            fa.ch0 = c0;
+            HBD_CUDA_CHECK(launch_fft_afc(fa, nc, lo, &nl));
+            SlicerArgs sa{};
+            sa.state = d_state; sa.slicer = d_slicer; sa.slicer_pitch = slicer_pitch; sa.raw = d_raw; sa.raw_n = d_raw_n;
+            sa.rec_bits = record ? d_rec_bits : nullptr; sa.rec_bits_n = d_rec_bits_n; sa.rec_bits_pitch = rec_bits_pitch;
+            sa.fs_dec = fs_dec; sa.ch0 = c0; sa.n_channels = nc;
+            HBD_CUDA_CHECK(launch_slicer(sa, lo, &nl));
+        }
+        cudaFuncSetAttribute(mark_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        mark_kernel<<<(nc + 255) / 256, 256, 0, lo>>>(d_raw_n + c0, d_mark + size_t(pending_marks) * n + c0, nc);
+        ++nl;
+        HBD_CUDA_CHECK(cudaGetLastError());
+        if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
+        HBD_CUDA_CHECK(cudaEventRecord(ev_tail[size_t(g)], lo));
+        tail_pending[size_t(g)] = 1;
     }
-    if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), stream));
-    {
-        TailArgs ta{};
-        ta.plan = d_plan; ta.state = d_state; ta.chunk = chunk; ta.chunk_pitch = chunk_pitch; ta.carry = d_carry; ta.T1 = T1;
-        ta.s1 = d_s1; ta.s1_pitch = s1_pitch; ta.taps2 = d_taps2; ta.M2 = M2; ta.T2 = T2;
-        ta.decq = d_decq; ta.dq_pitch = dq_pitch; ta.fs_dec = fs_dec; ta.fftbuf = d_fftbuf; ta.lptaps = d_lptaps;
-        ta.slicer = d_slicer; ta.slicer_pitch = slicer_pitch; ta.demod_last = d_demod; ta.demod_pitch = demod_pitch;
-        ta.rec_decimated = record ? d_rec_dec : nullptr; ta.rec_filtered = record ? d_rec_filt : nullptr; ta.rec_pitch = rec_pitch;
-        ta.smem_window = tail_smem_window(M2, T2);
-        HBD_CUDA_CHECK(launch_tail(ta, n_ch, stream, &nl));
-    }
-    if (any_work) {
-        FftArgs fa{};
-        fa.state = d_state; fa.fftbuf = d_fftbuf; fa.spectrum = d_spectrum; fa.power = d_power; fa.twiddle = d_twiddle; fa.fs_dec = fs_dec;
-        HBD_CUDA_CHECK(launch_fft_afc(fa, n_ch, stream, &nl));
-        SlicerArgs sa{};
-        sa.state = d_state; sa.slicer = d_slicer; sa.slicer_pitch = slicer_pitch; sa.raw = d_raw; sa.raw_n = d_raw_n;
-        sa.rec_bits = record ? d_rec_bits : nullptr; sa.rec_bits_n = d_rec_bits_n; sa.rec_bits_pitch = rec_bits_pitch;
-        sa.fs_dec = fs_dec; sa.n_channels = n_ch;
-        HBD_CUDA_CHECK(launch_slicer(sa, stream, &nl));
-    }
-    mark_kernel<<<(n_ch + 255) / 256, 256, 0, stream>>>(d_raw_n, d_mark + size_t(pending_marks) * n, n_ch);
-    ++nl;
-    HBD_CUDA_CHECK(cudaGetLastError());
-    if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), stream));
+    // the caller's stream resumes once every group has consumed the input (it does not wait for the tail kernels)
+    for (int g = 0; g < n_groups; ++g) HBD_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_consumed[size_t(g)], 0));
     launches += unsigned(nl);
     ++pending_marks;
     ext = nullptr; ext_n = 0;
@@ -447,6 +497,7 @@ int hbd_decoder::process_async_locked()
 int hbd_decoder::collect_locked()
 {
     HBD_CUDA_CHECK(cudaSetDevice(device));
+    if (sync_groups()) { set_error("group stream sync failed"); return HBD_ERR_CUDA; }
     HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
     if (!pending_marks) return HBD_OK;
     const size_t n = size_t(n_ch);
@@ -511,6 +562,22 @@ int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
     h->hc.resize(size_t(n_channels));
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return HBD_ERR_CUDA; }
     h->own_stream = true;
+    {
+        const char* env = getenv("HBD_GROUPS");
+        int g = env ? atoi(env) : (n_channels >= 256 ? 2 : 1);
+        g = std::max(1, std::min(g, std::min(n_channels, 8)));
+        h->n_groups = g;
+        h->ev_consumed.resize(size_t(g)); h->ev_tail.resize(size_t(g)); h->tail_pending.assign(size_t(g), 0);
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); // numerically lower = higher priority
+        if (cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&h->lo, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { h->free_all(); delete h; return HBD_ERR_CUDA; }
+        for (int i = 0; i < g; ++i) {
+            if (cudaEventCreateWithFlags(&h->ev_consumed[size_t(i)], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->ev_tail[size_t(i)], cudaEventDisableTiming) != cudaSuccess) { h->free_all(); delete h; return HBD_ERR_CUDA; }
+        }
+        if (cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess) { h->free_all(); delete h; return HBD_ERR_CUDA; }
+    }
     const int rc = h->alloc_fixed();
     if (rc) { h->free_all(); delete h; return rc; }
     *out = h;
@@ -531,6 +598,7 @@ int hbd_set_stream(hbd_decoder* h, void* s)
     HBD_CHECK_H(h);
     std::lock_guard<std::mutex> l(h->mtx);
     cudaSetDevice(h->device);
+    h->sync_groups();
     cudaStreamSynchronize(h->stream);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     h->stream = (cudaStream_t)s; h->own_stream = false;
@@ -568,6 +636,7 @@ static int set_lp(hbd_decoder* h, int ch, float bw, float trans, bool set_bw)
     if (!h || ch < -1 || ch >= h->n_ch) return HBD_ERR_ARG;
     std::lock_guard<std::mutex> l(h->mtx);
     cudaSetDevice(h->device);
+    h->sync_groups();
     std::vector<float> taps;
     for (int c = (ch < 0 ? 0 : ch); c < (ch < 0 ? h->n_ch : ch + 1); ++c) {
         HostChan& x = h->hc[size_t(c)];
@@ -599,6 +668,7 @@ static size_t apply_factor(hbd_decoder* h, size_t factor)
     if (!plan_for_factor(factor, st)) { h->factor = 1; factor = 0; }
     else h->factor = int(factor);
     cudaSetDevice(h->device);
+    h->sync_groups();
     cudaStreamSynchronize(h->stream);
     h->upload_taps();
     cudaMemset(h->d_carry, 0, size_t(h->n_ch) * kCarryCap * sizeof(float2));
@@ -721,6 +791,7 @@ int hbd_synchronize(hbd_decoder* h)
     HBD_CHECK_H(h);
     std::lock_guard<std::mutex> l(h->mtx);
     cudaSetDevice(h->device);
+    if (h->sync_groups()) return HBD_ERR_CUDA;
     return cudaStreamSynchronize(h->stream) == cudaSuccess ? HBD_OK : HBD_ERR_CUDA;
 }
 unsigned long long hbd_kernel_launches(hbd_decoder* h) { return h ? h->launches : 0; }
@@ -739,7 +810,7 @@ int hbd_get_kernel_timing(hbd_decoder* h, int which, double* total_ms, unsigned*
     HBD_CHECK_H(h);
     std::lock_guard<std::mutex> l(h->mtx);
     cudaSetDevice(h->device);
-    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
+    if (h->sync_groups() || cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
     const std::vector<cudaEvent_t>& pool = which == 0 ? h->ev_k1 : h->ev_rest;
     const size_t used = which == 0 ? h->ev_used_k1 : h->ev_used_rest;
     double tot = 0; unsigned cnt = 0;
@@ -818,13 +889,14 @@ size_t hbd_get_bins_count(hbd_decoder*) { return size_t(kFftN); }
 static int fetch_state(hbd_decoder* h, int ch, ChanState* st)
 {
     cudaSetDevice(h->device);
-    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
+    if (h->sync_groups() || cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
     return cudaMemcpy(st, h->d_state + ch, sizeof(ChanState), cudaMemcpyDeviceToHost) == cudaSuccess ? HBD_OK : HBD_ERR_CUDA;
 }
 static size_t fetch_floats(hbd_decoder* h, const void* dsrc, size_t n, float* out, size_t cap)
 {
     if (out && cap && n) {
         cudaSetDevice(h->device);
+        h->sync_groups();
         cudaStreamSynchronize(h->stream);
         if (cudaMemcpy(out, dsrc, std::min(n, cap) * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     }
@@ -881,7 +953,9 @@ int hbd_reset_frequency_correction(hbd_decoder* h, int ch, double corr)
 {
     HBD_CHECK_CH(h, ch); std::lock_guard<std::mutex> l(h->mtx);
     cudaSetDevice(h->device);
+    h->sync_groups(); // ordered after everything in flight, like a call between two process() calls
     if (launch_afc_reset(h->d_state, ch, corr, h->fs_in / h->factor, h->stream) != cudaSuccess) return HBD_ERR_CUDA;
+    cudaStreamSynchronize(h->stream);
     ++h->launches;
     return HBD_OK;
 }
@@ -893,6 +967,7 @@ size_t hbd_get_stats_batch(hbd_decoder* h, double* out, size_t cap_doubles)
     const size_t n = size_t(h->n_ch);
     if (!out || cap_doubles < 6 * n) return 6 * n;
     cudaSetDevice(h->device);
+    h->sync_groups();
     cudaStreamSynchronize(h->stream);
     std::vector<ChanState> st(n);
     if (cudaMemcpy(st.data(), h->d_state, n * sizeof(ChanState), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
@@ -948,7 +1023,7 @@ size_t hbd_debug_stage(hbd_decoder* h, int ch, int stage, float* out, size_t cap
     }
     case HBD_STAGE_BITS: {
         if (!h->d_rec_bits) return 0;
-        cudaSetDevice(h->device); cudaStreamSynchronize(h->stream);
+        cudaSetDevice(h->device); h->sync_groups(); cudaStreamSynchronize(h->stream);
         unsigned nb = 0;
         cudaMemcpy(&nb, h->d_rec_bits_n + ch, 4, cudaMemcpyDeviceToHost);
         nb = std::min(nb, h->rec_bits_pitch);

@@ -167,8 +167,9 @@ decim1_kernel(DecimArgs a)
     const int n_items = a.n_channels * a.stretches_per_channel;
 
     for (int item = blockIdx.x * kDecimWarps + warp; item < n_items; item += warps_total) {
-        const int ch = item / a.stretches_per_channel;
-        const int st = item - ch * a.stretches_per_channel;
+        const int chl = item / a.stretches_per_channel;
+        const int st = item - chl * a.stretches_per_channel;
+        const int ch = a.ch0 + chl;
         const ChanPlan pl = a.plan[ch];
         if (pl.flags & 1u) continue;
         // superblock b covers step-local sample positions x in (64(b-1), 64b]; the outputs k with
@@ -293,7 +294,7 @@ decim1_kernel(DecimArgs a)
 // (d_8_r_8, d_4_r_4, d_2_r_2 as FIRST stage, i.e. total factor <= 8: input rates <= 1.3 MS/s).
 __global__ void decim1_generic_kernel(DecimArgs a, int M, int T)
 {
-    const int ch = blockIdx.y;
+    const int ch = a.ch0 + blockIdx.y;
     const ChanPlan pl = a.plan[ch];
     if (pl.flags & 1u) return;
     const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
@@ -316,7 +317,7 @@ __global__ void decim1_generic_kernel(DecimArgs a, int M, int T)
 // factor 1: no decimator at all (Decoder.h:157 default) -- the "stage-1 output" is the input
 __global__ void decim1_copy_kernel(DecimArgs a)
 {
-    const int ch = blockIdx.y;
+    const int ch = a.ch0 + blockIdx.y;
     const ChanPlan pl = a.plan[ch];
     if (pl.flags & 1u) return;
     const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
@@ -330,6 +331,9 @@ static cudaError_t launch_fast(const DecimArgs& a, int n_sms, cudaStream_t strea
     const size_t smem = sizeof(WarpSmem<M, T>) * kDecimWarps;
     cudaError_t e = cudaFuncSetAttribute(decim1_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // all kernels of the path ask for the same (maximum) shared-memory carve-out so that the low-priority tail kernels can
+    // co-reside with K1 on an SM instead of forcing a carve-out reconfiguration
+    cudaFuncSetAttribute(decim1_kernel<M, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     const long long n_items = (long long)a.n_channels * a.stretches_per_channel;
     int grid = (int)std::min<long long>(n_sms, (n_items + kDecimWarps - 1) / kDecimWarps);
     if (grid < 1) grid = 1;

@@ -15,7 +15,8 @@ struct DecimArgs {
     int s1_hist;
     const ChanPlan* plan;      // per channel
     const float* taps;         // T floats (device)
-    int n_channels;
+    int ch0;                   // first channel of this launch
+    int n_channels;            // channels in this launch
     int stretches_per_channel; // ceil(max superblocks / sb_per_stretch)
     int sb_per_stretch;        // owned superblocks per work item
 };

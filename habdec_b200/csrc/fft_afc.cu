@@ -167,7 +167,7 @@ fft_afc_kernel(FftArgs a)
     __shared__ int s_ai[kFftThreads / 32];
     __shared__ int s_bad;
 
-    const int ch = blockIdx.x, t = threadIdx.x;
+    const int ch = a.ch0 + blockIdx.x, t = threadIdx.x;
     ChanState& st = a.state[ch];
     const bool do_fft = st.fft_ready != 0;
     const bool do_tick = st.afc_tick != 0;
@@ -296,6 +296,7 @@ cudaError_t launch_fft_afc(const FftArgs& a, int n_channels, cudaStream_t stream
     const size_t smem = size_t(16 * 16 * 17) * 8 + size_t(kFftN) * 4;
     cudaError_t e = cudaFuncSetAttribute(fft_afc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(fft_afc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     fft_afc_kernel<<<n_channels, kFftThreads, smem, stream>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();

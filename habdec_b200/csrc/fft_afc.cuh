@@ -11,6 +11,7 @@ struct FftArgs {
     float* power;           // [channel][kFftN] last power spectrum in dB (getPowerSpectrum)
     const float2* twiddle;  // [kFftN] exp(-2 pi i e / kFftN), evaluated in float64 on the host
     double fs_dec;
+    int ch0;                // first channel of this launch
 };
 
 cudaError_t launch_fft_afc(const FftArgs& a, int n_channels, cudaStream_t stream, int* launches);

@@ -130,8 +130,9 @@ __global__ void __launch_bounds__(kSlicerWarps * 32)
 slicer_kernel(SlicerArgs a)
 {
     const int lane = threadIdx.x & 31;
-    const int ch = blockIdx.x * kSlicerWarps + (threadIdx.x >> 5);
-    if (ch >= a.n_channels) return;
+    const int chl = blockIdx.x * kSlicerWarps + (threadIdx.x >> 5);
+    if (chl >= a.n_channels) return;
+    const int ch = a.ch0 + chl;
     ChanState& st = a.state[ch];
     if (st.n_filtered == 0) return; // the reference only reaches the slicer after a low-pass/demod pass
     float* v = a.slicer + (size_t)ch * a.slicer_pitch;
@@ -209,6 +210,7 @@ slicer_kernel(SlicerArgs a)
 cudaError_t launch_slicer(const SlicerArgs& a, cudaStream_t stream, int* launches)
 {
     const int grid = (a.n_channels + kSlicerWarps - 1) / kSlicerWarps;
+    cudaFuncSetAttribute(slicer_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     slicer_kernel<<<grid, kSlicerWarps * 32, 0, stream>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();

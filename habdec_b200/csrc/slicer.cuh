@@ -13,7 +13,8 @@ struct SlicerArgs {
     unsigned* rec_bits_n;
     unsigned rec_bits_pitch;
     double fs_dec;
-    int n_channels;
+    int ch0;                             // first channel of this launch
+    int n_channels;                      // channels in this launch
 };
 
 cudaError_t launch_slicer(const SlicerArgs& a, cudaStream_t stream, int* launches);

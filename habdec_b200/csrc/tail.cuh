@@ -7,10 +7,7 @@ namespace hbd {
 struct TailArgs {
     const ChanPlan* plan;
     ChanState* state;
-    // stage-1 carry update
-    const float2* chunk; size_t chunk_pitch;
-    float2* carry;
-    int T1;
+    int ch0;                  // first channel of this launch (channel groups run on their own streams)
     // stage 2
     float2* s1; size_t s1_pitch;
     const float* taps2; int M2, T2;
@@ -31,6 +28,9 @@ struct TailArgs {
 };
 
 cudaError_t launch_tail(const TailArgs& a, int n_channels, cudaStream_t stream, int* launches);
+// stage-1 carry (history + unconsumed remainder) for the next call; must run after K1 of the same call
+cudaError_t launch_carry(const ChanPlan* plan, const float2* chunk, size_t chunk_pitch, float2* carry, int T1, int ch0, int n_channels,
+                         cudaStream_t stream, int* launches);
 int tail_smem_window(int M2, int T2);
 
 } // namespace hbd
