@@ -200,10 +200,14 @@ def run_ours(args):
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    t_issue = 0.0
     for k in range(args.steps):
+        t_h = time.perf_counter()
         step(n_done); n_done += 1
+        t_issue += time.perf_counter() - t_h
         if (k + 1) % 32 == 0:
             dec.collect()
+    host_issue_ms = t_issue * 1e3 / max(args.steps, 1)   # host time to enqueue one step, collects excluded (diagnostic)
     dec.collect()                       # results drained (D2H + sentence layer) inside the timed region
     ev1.record(stream)
     barrier()
@@ -274,7 +278,7 @@ def run_ours(args):
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_ms, "launches_timed": k1_cnt,
                          "k1_share_of_step": (k1_ms / ms) if ms else None, "rest_of_step_ms": rest_ms / max(rest_cnt, 1)},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "host_issue_ms_per_step": host_issue_ms,
             "results": {"channels_gathered": len(gathered) if gathered else 0, "sentences_expected_per_channel_approx": exp_sent,
                         "sentences_min": min(got_sent) if got_sent else None, "sentences_max": max(got_sent) if got_sent else None}}
 

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhabdec_b200.so")
+LIB_PATH = os.environ.get("HBD_LIB") or os.path.join(_HERE, "libhabdec_b200.so")   # HBD_LIB: tuning variants
 
 HBD_OK, HBD_ERR_ARG, HBD_ERR_CUDA, HBD_ERR_STATE, HBD_ERR_NOMEM = 0, -1, -2, -3, -4
 STAGE_DECIMATED, STAGE_FILTERED, STAGE_DEMOD, STAGE_LPTAPS, STAGE_PENDING, STAGE_BITS = 0, 1, 2, 5, 6, 7

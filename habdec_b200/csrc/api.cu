@@ -60,7 +60,7 @@ struct HostChan {
     unsigned pushed = 0;     // samples waiting in the staging row
     unsigned last_nf = 0, last_n2 = 0;
     bool cfg_dirty = true;
-    TextChannel text;
+    bool lp_dirty = true;    // bw / trans / input size changed since the last design attempt
 };
 
 constexpr int kMarkSlots = 64; // async calls that may be outstanding between two collects
@@ -123,7 +123,8 @@ struct hbd_decoder {
     double fs_in = 0;
     int factor = 1;
     int M1 = 1, T1 = 1, M2 = 1, T2 = 1;
-    std::vector<HostChan> hc;
+    std::vector<HostChan> hc;        // compact, scanned on every call
+    std::vector<TextChannel> text;   // sentence layer state, touched only when a channel produced characters
 
     // device state
     ChanState* d_state = nullptr;
@@ -390,8 +391,9 @@ int hbd_decoder::process_async_locked()
         x.dec_pending = total_dec - nf;
         x.last_nf = nf;
         // low-pass design, Decoder.h:536-538
-        x.lp_input_size = nf;
-        const size_t T = design_lowpass(float(x.lp_bw / fs_dec), x.lp_trans, x.lp_input_size, x.lp_ntaps, new_taps);
+        if (x.lp_input_size != nf) { x.lp_input_size = nf; x.lp_dirty = true; }
+        const size_t T = x.lp_dirty ? design_lowpass(float(x.lp_bw / fs_dec), x.lp_trans, x.lp_input_size, x.lp_ntaps, new_taps) : x.lp_ntaps;
+        x.lp_dirty = false;
         if (T != x.lp_ntaps) {
             if (T > size_t(kLpMaxTaps)) { set_error("low-pass needs more than kLpMaxTaps taps"); return HBD_ERR_ARG; }
             x.lp_ntaps = T;
@@ -478,7 +480,6 @@ int hbd_decoder::process_async_locked()
             sa.fs_dec = fs_dec; sa.ch0 = c0; sa.n_channels = nc;
             HBD_CUDA_CHECK(launch_slicer(sa, lo, &nl));
         }
-        cudaFuncSetAttribute(mark_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         mark_kernel<<<(nc + 255) / 256, 256, 0, lo>>>(d_raw_n + c0, d_mark + size_t(pending_marks) * n + c0, nc);
         ++nl;
         HBD_CUDA_CHECK(cudaGetLastError());
@@ -531,14 +532,14 @@ int hbd_decoder::collect_locked()
     for (size_t c = 0; c < n; ++c) {
         if (!final_n[c]) continue;
         unsigned prev = 0;
-        const size_t before = hc[c].text.chars_pending.size();
+        const size_t before = text[c].chars_pending.size();
         for (int s = 0; s < pending_marks; ++s) {
             const unsigned upto = std::min(marks[size_t(s) * n + c], unsigned(kRawCap));
-            if (upto > prev) hc[c].text.feed(packed.data() + offs[c] + prev, upto - prev, int(c), sink);
+            if (upto > prev) text[c].feed(packed.data() + offs[c] + prev, upto - prev, int(c), sink);
             prev = std::max(prev, upto);
         }
-        if (chars_cb && hc[c].text.chars_pending.size() > before)
-            chars_cb(chars_user, int(c), hc[c].text.chars_pending.data() + before, hc[c].text.chars_pending.size() - before);
+        if (chars_cb && text[c].chars_pending.size() > before)
+            chars_cb(chars_user, int(c), text[c].chars_pending.data() + before, text[c].chars_pending.size() - before);
     }
     pending_marks = 0;
     return HBD_OK;
@@ -560,6 +561,7 @@ int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) h->n_sms = prop.multiProcessorCount;
     h->hc.resize(size_t(n_channels));
+    h->text.resize(size_t(n_channels));
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return HBD_ERR_CUDA; }
     h->own_stream = true;
     {
@@ -641,6 +643,7 @@ static int set_lp(hbd_decoder* h, int ch, float bw, float trans, bool set_bw)
     for (int c = (ch < 0 ? 0 : ch); c < (ch < 0 ? h->n_ch : ch + 1); ++c) {
         HostChan& x = h->hc[size_t(c)];
         if (set_bw) x.lp_bw = bw; else x.lp_trans = trans;
+        x.lp_dirty = true;
         if (!h->fs_in) continue;
         const double fs_dec = h->fs_in / h->factor;
         const size_t T = design_lowpass(float(x.lp_bw / fs_dec), x.lp_trans, x.lp_input_size, x.lp_ntaps, taps);
@@ -834,19 +837,19 @@ size_t hbd_get_rtty(hbd_decoder* h, int ch, char* out, size_t cap)
 {
     if (!h || ch < 0 || ch >= h->n_ch) return 0;
     std::lock_guard<std::mutex> l(h->mtx);
-    return copy_out(h->hc[size_t(ch)].text.text_stream, out, cap);
+    return copy_out(h->text[size_t(ch)].text_stream, out, cap);
 }
 size_t hbd_get_last_sentence(hbd_decoder* h, int ch, char* out, size_t cap)
 {
     if (!h || ch < 0 || ch >= h->n_ch) return 0;
     std::lock_guard<std::mutex> l(h->mtx);
-    return copy_out(h->hc[size_t(ch)].text.last_sentence, out, cap);
+    return copy_out(h->text[size_t(ch)].last_sentence, out, cap);
 }
 size_t hbd_poll_chars(hbd_decoder* h, int ch, char* out, size_t cap)
 {
     if (!h || ch < 0 || ch >= h->n_ch) return 0;
     std::lock_guard<std::mutex> l(h->mtx);
-    std::string& s = h->hc[size_t(ch)].text.chars_pending;
+    std::string& s = h->text[size_t(ch)].chars_pending;
     const size_t n = copy_out(s, out, cap);
     if (out && cap >= n) s.clear();
     return n;
@@ -855,7 +858,7 @@ size_t hbd_poll_sentences(hbd_decoder* h, int ch, char* out, size_t cap)
 {
     if (!h || ch < 0 || ch >= h->n_ch) return 0;
     std::lock_guard<std::mutex> l(h->mtx);
-    std::string& s = h->hc[size_t(ch)].text.sentences_pending;
+    std::string& s = h->text[size_t(ch)].sentences_pending;
     const size_t n = copy_out(s, out, cap);
     if (out && cap >= n) s.clear();
     return n;
@@ -864,7 +867,7 @@ size_t hbd_poll_raw_chars(hbd_decoder* h, int ch, unsigned char* out, size_t cap
 {
     if (!h || ch < 0 || ch >= h->n_ch) return 0;
     std::lock_guard<std::mutex> l(h->mtx);
-    auto& v = h->hc[size_t(ch)].text.raw_pending;
+    auto& v = h->text[size_t(ch)].raw_pending;
     const size_t n = v.size();
     if (out && cap) memcpy(out, v.data(), std::min(cap, n));
     if (out && cap >= n) v.clear();

@@ -329,11 +329,15 @@ template <int M, int T>
 static cudaError_t launch_fast(const DecimArgs& a, int n_sms, cudaStream_t stream, int* launches)
 {
     const size_t smem = sizeof(WarpSmem<M, T>) * kDecimWarps;
-    cudaError_t e = cudaFuncSetAttribute(decim1_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    // all kernels of the path ask for the same (maximum) shared-memory carve-out so that the low-priority tail kernels can
-    // co-reside with K1 on an SM instead of forcing a carve-out reconfiguration
-    cudaFuncSetAttribute(decim1_kernel<M, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    static bool configured = false; // one device per process (one process per GPU)
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(decim1_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        // all kernels of the path ask for the same (maximum) shared-memory carve-out so that the low-priority tail kernels
+        // can co-reside with K1 on an SM instead of forcing a carve-out reconfiguration
+        cudaFuncSetAttribute(decim1_kernel<M, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
     const long long n_items = (long long)a.n_channels * a.stretches_per_channel;
     int grid = (int)std::min<long long>(n_sms, (n_items + kDecimWarps - 1) / kDecimWarps);
     if (grid < 1) grid = 1;

@@ -4,7 +4,10 @@
 
 namespace hbd {
 
-constexpr int kDecimWarps = 8; // warps per CTA; each warp runs its own TMA ring
+#ifndef HBD_K1_WARPS
+#define HBD_K1_WARPS 8
+#endif
+constexpr int kDecimWarps = HBD_K1_WARPS; // warps per CTA; each warp runs its own TMA ring
 
 struct DecimArgs {
     const float2* chunk;       // pushed samples, [channel][chunk_pitch] cf32, chunk[j] for j in [0, n)

@@ -294,9 +294,13 @@ fft_afc_kernel(FftArgs a)
 cudaError_t launch_fft_afc(const FftArgs& a, int n_channels, cudaStream_t stream, int* launches)
 {
     const size_t smem = size_t(16 * 16 * 17) * 8 + size_t(kFftN) * 4;
-    cudaError_t e = cudaFuncSetAttribute(fft_afc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(fft_afc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fft_afc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(fft_afc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
     fft_afc_kernel<<<n_channels, kFftThreads, smem, stream>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();

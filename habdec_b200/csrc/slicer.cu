@@ -210,7 +210,8 @@ slicer_kernel(SlicerArgs a)
 cudaError_t launch_slicer(const SlicerArgs& a, cudaStream_t stream, int* launches)
 {
     const int grid = (a.n_channels + kSlicerWarps - 1) / kSlicerWarps;
-    cudaFuncSetAttribute(slicer_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    static bool configured = false;
+    if (!configured) { cudaFuncSetAttribute(slicer_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); configured = true; }
     slicer_kernel<<<grid, kSlicerWarps * 32, 0, stream>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();

@@ -317,7 +317,8 @@ tail_kernel(TailArgs a)
 cudaError_t launch_carry(const ChanPlan* plan, const float2* chunk, size_t chunk_pitch, float2* carry, int T1, int ch0, int n_channels,
                          cudaStream_t stream, int* launches)
 {
-    cudaFuncSetAttribute(carry_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    static bool configured = false;
+    if (!configured) { cudaFuncSetAttribute(carry_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); configured = true; }
     carry_kernel<<<n_channels, 128, 0, stream>>>(plan, chunk, chunk_pitch, carry, T1, ch0);
     if (launches) ++*launches;
     return cudaGetLastError();
@@ -326,9 +327,13 @@ cudaError_t launch_carry(const ChanPlan* plan, const float2* chunk, size_t chunk
 cudaError_t launch_tail(const TailArgs& a, int n_channels, cudaStream_t stream, int* launches)
 {
     const size_t smem = size_t(a.smem_window) * 8 + size_t(kLpMaxTaps + 7) * 4 + size_t(kTile + 1) * 8;
-    cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    static size_t configured_smem = 0;
+    if (configured_smem < smem) {
+        cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured_smem = smem;
+    }
     tail_kernel<<<n_channels, kTailThreads, smem, stream>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();
