@@ -55,6 +55,7 @@ SIGNATURES = {
     "hbd_process": (C.c_int, [_H]),
     "hbd_process_async": (C.c_int, [_H]),
     "hbd_collect": (C.c_int, [_H]),
+    "hbd_collect_ready": (C.c_int, [_H, C.c_uint]),
     "hbd_synchronize": (C.c_int, [_H]),
     "hbd_kernel_launches": (C.c_ulonglong, [_H]),
     "hbd_set_kernel_timing": (C.c_int, [_H, C.c_int]),
@@ -205,6 +206,7 @@ class BatchDecoder:
     __call__ = process
     def process_async(self): self._chk(self._lib.hbd_process_async(self._h))
     def collect(self): self._chk(self._lib.hbd_collect(self._h))
+    def collect_ready(self, lag: int): self._chk(self._lib.hbd_collect_ready(self._h, int(lag)))
     def synchronize(self): self._chk(self._lib.hbd_synchronize(self._h))
     def kernel_launches(self) -> int: return int(self._lib.hbd_kernel_launches(self._h))
     def set_kernel_timing(self, on: bool): self._chk(self._lib.hbd_set_kernel_timing(self._h, int(on)))

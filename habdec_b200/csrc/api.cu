@@ -63,23 +63,7 @@ struct HostChan {
     bool lp_dirty = true;    // bw / trans / input size changed since the last design attempt
 };
 
-constexpr int kMarkSlots = 64; // async calls that may be outstanding between two collects
-
-__global__ void pack_raw_kernel(const unsigned char* raw, const unsigned* raw_n, const unsigned* offsets, unsigned char* packed, int n_ch)
-{
-    const int ch = blockIdx.x;
-    if (ch >= n_ch) return;
-    const unsigned n = min(raw_n[ch], unsigned(kRawCap));
-    const unsigned char* src = raw + (size_t)ch * kRawCap;
-    unsigned char* dst = packed + offsets[ch];
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-}
-
-__global__ void mark_kernel(const unsigned* raw_n, unsigned* mark, int n_ch)
-{
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch < n_ch) mark[ch] = raw_n[ch];
-}
+constexpr unsigned kMaxCallsBetweenCollects = 256; // process_async forces a drain beyond this (log capacity)
 
 __global__ void init_cfg_kernel(ChanState* st, const double* baud, const float* stops, const int* bits, const int* dc, const int* ntaps,
                                 const unsigned char* dirty, int n_ch)
@@ -139,11 +123,16 @@ struct hbd_decoder {
     float* d_lptaps = nullptr;
     float* d_slicer = nullptr;   size_t slicer_pitch = 0;
     float* d_demod = nullptr;    size_t demod_pitch = 0;
-    unsigned char* d_raw = nullptr;
-    unsigned* d_raw_n = nullptr;
-    unsigned* d_mark = nullptr;          // [kMarkSlots][n_ch]
-    unsigned* d_offsets = nullptr;
-    unsigned char* d_packed = nullptr;   size_t packed_cap = 0;
+    uint2* d_log = nullptr;              // decoded-character log (ring, kLogCap entries)
+    unsigned* d_log_head = nullptr;      // monotonic append counter
+    unsigned log_tail = 0;               // host: entries below this index are already processed
+    unsigned call_seq = 0;               // calls enqueued so far (24 bits travel in the log entries)
+    unsigned calls_collected = 0;        // calls whose characters went through the sentence layer
+    std::vector<cudaEvent_t> ev_call;    // ring: completion of call (seq % size)
+    cudaStream_t copy_stream = nullptr;  // result read-back, independent of the compute streams
+    std::vector<uint2> h_log;            // host staging
+    std::vector<std::string> call_chars; // per channel: raw chars of the call being replayed
+    std::vector<int> touched;
     float* d_taps1 = nullptr; float* d_taps2 = nullptr;
     float2* d_twiddle = nullptr;
     // config upload scratch
@@ -178,7 +167,7 @@ struct hbd_decoder {
     int alloc_fixed();
     int upload_taps();
     int process_async_locked();
-    int collect_locked();
+    int collect_locked(unsigned lag);
     void free_all();
 };
 
@@ -235,11 +224,13 @@ int hbd_decoder::alloc_fixed()
     HBD_CUDA_CHECK(cudaMemset(d_power, 0, n * kFftN * sizeof(float)));
     HBD_CUDA_CHECK(dalloc(&d_lptaps, n * kLpMaxTaps));
     HBD_CUDA_CHECK(cudaMemset(d_lptaps, 0, n * kLpMaxTaps * sizeof(float)));
-    HBD_CUDA_CHECK(dalloc(&d_raw, n * kRawCap));
-    HBD_CUDA_CHECK(dalloc(&d_raw_n, n));
-    HBD_CUDA_CHECK(cudaMemset(d_raw_n, 0, n * sizeof(unsigned)));
-    HBD_CUDA_CHECK(dalloc(&d_mark, n * kMarkSlots));
-    HBD_CUDA_CHECK(dalloc(&d_offsets, n));
+    HBD_CUDA_CHECK(dalloc(&d_log, size_t(kLogCap)));
+    HBD_CUDA_CHECK(dalloc(&d_log_head, 1));
+    HBD_CUDA_CHECK(cudaMemset(d_log_head, 0, sizeof(unsigned)));
+    HBD_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    ev_call.resize(kMaxCallsBetweenCollects * 2);
+    for (auto& e : ev_call) HBD_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    call_chars.resize(n);
     HBD_CUDA_CHECK(dalloc(&d_taps1, 512));
     HBD_CUDA_CHECK(dalloc(&d_taps2, 512));
     HBD_CUDA_CHECK(dalloc(&d_twiddle, kFftN));
@@ -284,11 +275,13 @@ void hbd_decoder::free_all()
     for (cudaEvent_t e : ev_consumed) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_tail) cudaEventDestroy(e);
     if (ev_in) cudaEventDestroy(ev_in);
-    void* ptrs[] = {d_state, d_plan, d_carry, d_s1, d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_raw, d_raw_n,
-                    d_mark, d_offsets, d_packed, d_taps1, d_taps2, d_twiddle, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps,
+    void* ptrs[] = {d_state, d_plan, d_carry, d_s1, d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_log, d_log_head,
+                    d_taps1, d_taps2, d_twiddle, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps,
                     d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_pinned) cudaFreeHost(h_pinned);
+    for (cudaEvent_t e : ev_call) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     for (cudaEvent_t e : ev_k1) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_rest) cudaEventDestroy(e);
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -326,7 +319,7 @@ int hbd_decoder::process_async_locked()
 {
     if (!fs_in) return HBD_OK; // Decoder.h:418-419: uninitialised -> silently nothing
     HBD_CUDA_CHECK(cudaSetDevice(device));
-    if (pending_marks >= kMarkSlots) { const int rc = collect_locked(); if (rc) return rc; }
+    if (call_seq - calls_collected >= kMaxCallsBetweenCollects) { const int rc = collect_locked(0); if (rc) return rc; }
     const size_t n = size_t(n_ch);
     const double fs_dec = fs_in / factor;
 
@@ -475,14 +468,11 @@ int hbd_decoder::process_async_locked()
             fa.ch0 = c0;
             HBD_CUDA_CHECK(launch_fft_afc(fa, nc, lo, &nl));
             SlicerArgs sa{};
-            sa.state = d_state; sa.slicer = d_slicer; sa.slicer_pitch = slicer_pitch; sa.raw = d_raw; sa.raw_n = d_raw_n;
+            sa.state = d_state; sa.slicer = d_slicer; sa.slicer_pitch = slicer_pitch; sa.log = d_log; sa.log_head = d_log_head; sa.call_seq = call_seq & 0xffffffu;
             sa.rec_bits = record ? d_rec_bits : nullptr; sa.rec_bits_n = d_rec_bits_n; sa.rec_bits_pitch = rec_bits_pitch;
             sa.fs_dec = fs_dec; sa.ch0 = c0; sa.n_channels = nc;
             HBD_CUDA_CHECK(launch_slicer(sa, lo, &nl));
         }
-        mark_kernel<<<(nc + 255) / 256, 256, 0, lo>>>(d_raw_n + c0, d_mark + size_t(pending_marks) * n + c0, nc);
-        ++nl;
-        HBD_CUDA_CHECK(cudaGetLastError());
         if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
         HBD_CUDA_CHECK(cudaEventRecord(ev_tail[size_t(g)], lo));
         tail_pending[size_t(g)] = 1;
@@ -490,58 +480,82 @@ int hbd_decoder::process_async_locked()
     // the caller's stream resumes once every group has consumed the input (it does not wait for the tail kernels)
     for (int g = 0; g < n_groups; ++g) HBD_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_consumed[size_t(g)], 0));
     launches += unsigned(nl);
+    HBD_CUDA_CHECK(cudaEventRecord(ev_call[call_seq % ev_call.size()], lo)); // everything of this call is done
+    ++call_seq;
     ++pending_marks;
     ext = nullptr; ext_n = 0;
     return HBD_OK;
 }
 
-int hbd_decoder::collect_locked()
+// Drain decoded characters of all calls up to (last enqueued - lag) and run the sentence layer on them, call by
+// call like Decoder::process().  lag == 0 waits for everything; lag > 0 leaves the newest calls in flight so the GPU
+// keeps working while the host is busy here.
+int hbd_decoder::collect_locked(unsigned lag)
 {
     HBD_CUDA_CHECK(cudaSetDevice(device));
-    if (sync_groups()) { set_error("group stream sync failed"); return HBD_ERR_CUDA; }
-    HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
-    if (!pending_marks) return HBD_OK;
-    const size_t n = size_t(n_ch);
-    std::vector<unsigned> marks(size_t(pending_marks) * n);
-    HBD_CUDA_CHECK(cudaMemcpyAsync(marks.data(), d_mark, marks.size() * 4, cudaMemcpyDeviceToHost, stream));
-    HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
-    const unsigned* final_n = marks.data() + size_t(pending_marks - 1) * n;
-    std::vector<unsigned> offs(n);
-    size_t total = 0;
-    for (size_t c = 0; c < n; ++c) { offs[c] = unsigned(total); total += std::min(final_n[c], unsigned(kRawCap)); }
-    std::vector<unsigned char> packed(total);
-    if (total) {
-        if (packed_cap < total) {
-            if (d_packed) cudaFree(d_packed);
-            packed_cap = std::max<size_t>(total * 2, 1 << 16);
-            HBD_CUDA_CHECK(dalloc(&d_packed, packed_cap));
-        }
-        HBD_CUDA_CHECK(cudaMemcpyAsync(d_offsets, offs.data(), 4 * n, cudaMemcpyHostToDevice, stream));
-        pack_raw_kernel<<<n_ch, 64, 0, stream>>>(d_raw, d_raw_n, d_offsets, d_packed, n_ch);
-        ++launches;
-        HBD_CUDA_CHECK(cudaMemcpyAsync(packed.data(), d_packed, total, cudaMemcpyDeviceToHost, stream));
+    if (call_seq == calls_collected) {
+        if (lag == 0) { if (sync_groups()) return HBD_ERR_CUDA; HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); }
+        return HBD_OK;
     }
-    HBD_CUDA_CHECK(cudaMemsetAsync(d_raw_n, 0, 4 * n, stream));
-    HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
-    // sentence layer, call by call like Decoder::process()
+    if (call_seq - calls_collected <= lag) return HBD_OK;
+    const unsigned upto = call_seq - lag;            // calls [calls_collected, upto) get drained
+    if (lag == 0) {
+        if (sync_groups()) { set_error("stream sync failed"); return HBD_ERR_CUDA; }
+        HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
+    } else {
+        HBD_CUDA_CHECK(cudaEventSynchronize(ev_call[(upto - 1) % ev_call.size()]));
+    }
+    unsigned head = 0;
+    HBD_CUDA_CHECK(cudaMemcpyAsync(&head, d_log_head, sizeof(unsigned), cudaMemcpyDeviceToHost, copy_stream));
+    HBD_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+    const unsigned avail = head - log_tail;
+    if (avail > kLogCap) { set_error("decoded-character log overflow: collect more often"); return HBD_ERR_STATE; }
+    h_log.resize(avail);
+    if (avail) {
+        const unsigned i0 = log_tail & (kLogCap - 1u);
+        const unsigned first = std::min(avail, kLogCap - i0);
+        HBD_CUDA_CHECK(cudaMemcpyAsync(h_log.data(), d_log + i0, size_t(first) * sizeof(uint2), cudaMemcpyDeviceToHost, copy_stream));
+        if (avail > first)
+            HBD_CUDA_CHECK(cudaMemcpyAsync(h_log.data() + first, d_log, size_t(avail - first) * sizeof(uint2), cudaMemcpyDeviceToHost, copy_stream));
+        HBD_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+    }
     SentenceSink sink;
     if (sentence_cb) {
         hbd_sentence_cb cb = sentence_cb; void* user = sentence_user;
         sink = [cb, user](int ch, const std::string& cs, const std::string& d, const std::string& crc) { cb(user, ch, cs.c_str(), d.c_str(), crc.c_str()); };
     }
-    for (size_t c = 0; c < n; ++c) {
-        if (!final_n[c]) continue;
-        unsigned prev = 0;
-        const size_t before = text[c].chars_pending.size();
-        for (int s = 0; s < pending_marks; ++s) {
-            const unsigned upto = std::min(marks[size_t(s) * n + c], unsigned(kRawCap));
-            if (upto > prev) text[c].feed(packed.data() + offs[c] + prev, upto - prev, int(c), sink);
-            prev = std::max(prev, upto);
+    std::vector<size_t> chars_before;
+    std::vector<int> cb_channels;
+    // the log is sorted by call; replay call by call, channel by channel
+    size_t i = 0;
+    const unsigned upto24 = upto & 0xffffffu;
+    while (i < h_log.size()) {
+        const unsigned seq = h_log[i].y >> 8;
+        if (((upto24 - seq - 1u) & 0xffffffu) >= 0x800000u) break; // seq >= upto: belongs to a call still in flight
+        touched.clear();
+        size_t j = i;
+        for (; j < h_log.size() && (h_log[j].y >> 8) == seq; ++j) {
+            const int ch = int(h_log[j].x);
+            if (ch < 0 || ch >= n_ch) continue;
+            if (call_chars[size_t(ch)].empty()) touched.push_back(ch);
+            call_chars[size_t(ch)].push_back(char(h_log[j].y & 0xffu));
         }
-        if (chars_cb && text[c].chars_pending.size() > before)
-            chars_cb(chars_user, int(c), text[c].chars_pending.data() + before, text[c].chars_pending.size() - before);
+        for (int ch : touched) {
+            std::string& cc = call_chars[size_t(ch)];
+            TextChannel& tc = text[size_t(ch)];
+            if (chars_cb) { cb_channels.push_back(ch); chars_before.push_back(tc.chars_pending.size()); }
+            tc.feed(reinterpret_cast<const unsigned char*>(cc.data()), cc.size(), ch, sink);
+            if (chars_cb) {
+                const size_t before = chars_before.back();
+                if (tc.chars_pending.size() > before) chars_cb(chars_user, ch, tc.chars_pending.data() + before, tc.chars_pending.size() - before);
+            }
+            cc.clear();
+        }
+        i = j;
     }
-    pending_marks = 0;
+    log_tail += unsigned(i);
+    calls_collected = upto;
+    pending_marks = int(call_seq - calls_collected);
     return HBD_OK;
 }
 
@@ -780,14 +794,15 @@ int hbd_push_samples_device(hbd_decoder* h, const float* d_iq, size_t n, size_t 
 }
 
 int hbd_process_async(hbd_decoder* h) { HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); return h->process_async_locked(); }
-int hbd_collect(hbd_decoder* h) { HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); return h->collect_locked(); }
+int hbd_collect(hbd_decoder* h) { HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); return h->collect_locked(0); }
+int hbd_collect_ready(hbd_decoder* h, unsigned lag) { HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); return h->collect_locked(lag); }
 int hbd_process(hbd_decoder* h)
 {
     HBD_CHECK_H(h);
     std::lock_guard<std::mutex> l(h->mtx);
     const int rc = h->process_async_locked();
     if (rc) return rc;
-    return h->collect_locked();
+    return h->collect_locked(0);
 }
 int hbd_synchronize(hbd_decoder* h)
 {

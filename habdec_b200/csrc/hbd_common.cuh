@@ -26,7 +26,7 @@ constexpr int kLpBatch      = 256;    // Decoder.h:492 batch_size
 constexpr int kFftN         = 4096;   // Decoder.h:163 fft_bins_cnt_
 constexpr int kSlicerVent   = 30000;  // SymbolExtractor.h:116 safety vent (3e4)
 constexpr int kBitsCap      = 16384;  // bits the slicer may emit in one call (+ pending UART bits)
-constexpr int kRawCap       = 2048;   // raw UART chars kept per channel between host drains
+constexpr unsigned kLogCap   = 1u << 20; // decoded-character log entries (ring) between host drains
 
 // ---- per-channel persistent state (device resident, one struct per channel) -----------------------
 struct ChanState {
@@ -49,9 +49,6 @@ struct ChanState {
     unsigned slicer_n;      // pending slicer samples
     unsigned uart_n;        // pending UART bits (< one frame)
     unsigned long long uart_win; // those bits, LSB = oldest
-    unsigned raw_n;         // raw chars waiting for the host
-    unsigned raw_overflow;  // raw chars dropped because the host did not drain (diagnostic)
-    unsigned bits_overflow;
 
     // AFC (AFC.h:72-90): two Average<double>(100), two Average<int>(4)
     double   afc_correction, afc_noise_floor, afc_noise_var, afc_shift_hz;

@@ -153,8 +153,6 @@ slicer_kernel(SlicerArgs a)
     const int adv = 1 + nbits + int(nstops);                // i += nstops_ truncates (size_t += float)
     unsigned long long win = st.uart_win;                   // pending bits, LSB first
     int have = int(st.uart_n);
-    unsigned raw_n = a.raw_n[ch];
-    unsigned char* raw = a.raw + (size_t)ch * kRawCap;
     unsigned char* rec_bits = a.rec_bits ? a.rec_bits + (size_t)ch * a.rec_bits_pitch : nullptr;
     unsigned rec_n = a.rec_bits ? a.rec_bits_n[ch] : 0;
 
@@ -178,8 +176,10 @@ slicer_kernel(SlicerArgs a)
                 const bool ok = ((win & 1ull) == 0ull) && stops == ((1u << stop_chk) - 1u);
                 if (ok) {
                     const unsigned char cc = (unsigned char)((win >> 1) & ((1ull << nbits) - 1ull));
-                    if (raw_n < unsigned(kRawCap)) { if (lane == 0) raw[raw_n] = cc; ++raw_n; }
-                    else if (lane == 0) st.raw_overflow++;
+                    if (lane == 0) {
+                        const unsigned pos = atomicAdd(a.log_head, 1u);
+                        a.log[pos & (kLogCap - 1u)] = make_uint2(unsigned(ch), (a.call_seq << 8) | unsigned(cc));
+                    }
                     win >>= adv; have -= adv;
                 } else {
                     win >>= 1; have -= 1;
@@ -190,7 +190,6 @@ slicer_kernel(SlicerArgs a)
     if (lane == 0) {
         st.uart_win = win;
         st.uart_n = unsigned(have);
-        a.raw_n[ch] = raw_n;
         if (a.rec_bits) a.rec_bits_n[ch] = rec_n;
     }
     if (!any) return;

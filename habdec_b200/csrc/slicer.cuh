@@ -7,8 +7,10 @@ namespace hbd {
 struct SlicerArgs {
     ChanState* state;
     float* slicer; size_t slicer_pitch;  // pending discriminator samples [channel][slicer_pitch]
-    unsigned char* raw;                  // raw UART chars [channel][kRawCap]
-    unsigned* raw_n;                     // [channel]
+    // decoded characters go to one device-wide append log (ring of kLogCap entries, monotonic head):
+    // entry = (channel, call_seq << 8 | char).  Kernels of successive calls run in stream order, so the log is
+    // sorted by call and, per channel, by time.
+    uint2* log; unsigned* log_head; unsigned call_seq;
     unsigned char* rec_bits;             // optional: every emitted bit [channel][rec_bits_pitch]
     unsigned* rec_bits_n;
     unsigned rec_bits_pitch;

@@ -88,6 +88,8 @@ int hbd_push_samples_device(hbd_decoder* h, const float* d_iq, size_t n_complex,
 int hbd_process(hbd_decoder* h);        /* kernels + result drain + sentence layer + callbacks */
 int hbd_process_async(hbd_decoder* h);  /* kernels only, returns immediately */
 int hbd_collect(hbd_decoder* h);        /* drain results of all async calls so far (sentence layer + callbacks) */
+/* like hbd_collect but leaves the newest `lag` calls in flight: the GPU keeps running while the host drains */
+int hbd_collect_ready(hbd_decoder* h, unsigned lag);
 int hbd_synchronize(hbd_decoder* h);
 /* number of CUDA kernels this handle has launched so far */
 unsigned long long hbd_kernel_launches(hbd_decoder* h);
