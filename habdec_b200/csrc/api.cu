@@ -18,7 +18,6 @@
 #include "fft_afc.cuh"
 #include "hbd_common.cuh"
 #include "host_tail.h"
-#include "slicer.cuh"
 #include "tail.cuh"
 
 using namespace hbd;
@@ -114,7 +113,8 @@ struct hbd_decoder {
     ChanState* d_state = nullptr;
     ChanPlan* d_plan = nullptr;
     std::vector<ChanPlan> h_plan, h_plan_uploaded;
-    float2* d_carry = nullptr;
+    float2* d_carry2[2] = {nullptr, nullptr}; // stage-1 carry, ping-pong: K1 reads [carry_cur], writes [carry_cur ^ 1]
+    int carry_cur = 0;
     float2* d_s1 = nullptr;      size_t s1_pitch = 0;
     float2* d_decq = nullptr;    size_t dq_pitch = 0;
     float2* d_fftbuf = nullptr;
@@ -148,6 +148,7 @@ struct hbd_decoder {
     float* h_pinned = nullptr; size_t pinned_bytes = 0;  // staging for pageable host memory
 
     int pending_marks = 0;   // async calls since the last collect
+    int sv_override = -1;
     // optional per-kernel CUDA-event timing (bench roofline): one event pair per K1 launch / per rest-of-step
     bool timing = false;
     std::vector<cudaEvent_t> ev_k1, ev_rest; // pairs: [2i] start, [2i+1] stop
@@ -214,8 +215,10 @@ int hbd_decoder::alloc_fixed()
         HBD_CUDA_CHECK(cudaMemcpy(d_state, all.data(), n * sizeof(ChanState), cudaMemcpyHostToDevice));
     }
     HBD_CUDA_CHECK(dalloc(&d_plan, n));
-    HBD_CUDA_CHECK(dalloc(&d_carry, n * kCarryCap));
-    HBD_CUDA_CHECK(cudaMemset(d_carry, 0, n * kCarryCap * sizeof(float2)));
+    for (int i = 0; i < 2; ++i) {
+        HBD_CUDA_CHECK(dalloc(&d_carry2[i], n * kCarryCap));
+        HBD_CUDA_CHECK(cudaMemset(d_carry2[i], 0, n * kCarryCap * sizeof(float2)));
+    }
     HBD_CUDA_CHECK(dalloc(&d_fftbuf, n * kFftN));
     HBD_CUDA_CHECK(cudaMemset(d_fftbuf, 0, n * kFftN * sizeof(float2)));
     HBD_CUDA_CHECK(dalloc(&d_spectrum, n * kFftN));
@@ -275,7 +278,7 @@ void hbd_decoder::free_all()
     for (cudaEvent_t e : ev_consumed) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_tail) cudaEventDestroy(e);
     if (ev_in) cudaEventDestroy(ev_in);
-    void* ptrs[] = {d_state, d_plan, d_carry, d_s1, d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_log, d_log_head,
+    void* ptrs[] = {d_state, d_plan, d_carry2[0], d_carry2[1], d_s1, d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_log, d_log_head,
                     d_taps1, d_taps2, d_twiddle, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps,
                     d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -352,10 +355,13 @@ int hbd_decoder::process_async_locked()
     auto quiesce = [&]() -> int { if (!groups_idle) { if (sync_groups()) return HBD_ERR_CUDA; groups_idle = true; } return HBD_OK; };
 
     bool cfg_dirty_any = false;
+    unsigned max_nf = 0;
     std::vector<float> new_taps;
     for (size_t c = 0; c < n; ++c) {
         HostChan& x = hc[c];
         const ChanPlan& p = h_plan[c];
+        ChanPlan& pw = h_plan[c];
+        pw.dec_pending = x.dec_pending; pw.lp_ntaps = unsigned(x.lp_ntaps);
         x.in_r = p.r + p.n - p.consumed;
         x.pushed = 0;
         x.last_n2 = p.n2; x.last_nf = 0;
@@ -366,7 +372,7 @@ int hbd_decoder::process_async_locked()
             if (x.grown1 < need) {
                 x.grown1 = need;
                 if (quiesce()) return HBD_ERR_CUDA;
-                HBD_CUDA_CHECK(cudaMemsetAsync(d_carry + c * kCarryCap + (kCarryCap - (T1 - 1) - p.r), 0, sizeof(float2) * size_t(T1 - 1), stream));
+                HBD_CUDA_CHECK(cudaMemsetAsync(d_carry2[carry_cur] + c * kCarryCap + (kCarryCap - (T1 - 1) - p.r), 0, sizeof(float2) * size_t(T1 - 1), stream));
             }
         }
         if (M2 > 1) {
@@ -395,6 +401,8 @@ int hbd_decoder::process_async_locked()
             HBD_CUDA_CHECK(cudaMemcpyAsync(d_lptaps + c * kLpMaxTaps, new_taps.data(), 4 * T, cudaMemcpyHostToDevice, stream));
             HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // new_taps is reused
         }
+        pw.lp_ntaps = unsigned(x.lp_ntaps);
+        max_nf = std::max(max_nf, nf);
         const size_t need = size_t(nf) + x.lp_ntaps;
         if (x.grown_lp < need) { // FirFilter.h:141-147
             x.grown_lp = need;
@@ -427,6 +435,19 @@ int hbd_decoder::process_async_locked()
         h_plan_uploaded = h_plan;
     }
 
+    // what the tail kernel stages in shared memory: sized from host-side knowledge of all channels
+    bool plan_uniform = true;
+    size_t max_lp_taps = 1;
+    double max_spb = 1;
+    for (size_t c = 0; c < n; ++c) {
+        if (plan_uniform && c && memcmp(&h_plan[c], &h_plan[0], sizeof(ChanPlan)) != 0) plan_uniform = false;
+        max_lp_taps = std::max(max_lp_taps, hc[c].lp_ntaps);
+        if (hc[c].baud > 0) max_spb = std::max(max_spb, fs_dec / hc[c].baud);
+    }
+    // a channel normally holds < ~12 symbols of pending samples after a slicer pass (plus this call's batch)
+    int sv_want = int(std::min<double>(6144.0, 16.0 * max_spb + double(max_nf) + 64.0));
+    if (sv_override >= 0) sv_want = sv_override;   // test hook (HBD_SV_WANT): 0 forces the slicer's HBM path
+
     const float2* chunk = ext ? ext : d_stage;
     const size_t chunk_pitch = ext ? ext_pitch : stage_pitch;
     int nl = 0;
@@ -438,40 +459,34 @@ int hbd_decoder::process_async_locked()
         const int nc = c1 - c0;
         // K1 of this group overwrites the group's stage-1 buffer: the previous call's tail must be done with it
         if (tail_pending[size_t(g)]) HBD_CUDA_CHECK(cudaStreamWaitEvent(hi, ev_tail[size_t(g)], 0));
-        if (any_work) {
+        {   // K1 also writes the next call's carry (even when no channel has a full decimation block yet)
             DecimArgs da{};
-            da.chunk = chunk; da.chunk_pitch = chunk_pitch; da.carry = d_carry;
+            da.chunk = chunk; da.chunk_pitch = chunk_pitch; da.carry = d_carry2[carry_cur]; da.carry_next = d_carry2[carry_cur ^ 1];
             da.s1 = d_s1; da.s1_pitch = s1_pitch; da.s1_hist = kS1Hist;
             da.plan = d_plan; da.taps = d_taps1; da.ch0 = c0; da.n_channels = nc;
-            da.sb_per_stretch = decim1_sb_per_stretch(M1);
-            const unsigned n_sb = (M1 > 1) ? (max_n1 * unsigned(M1) + 63) / 64 + 2 : 1;
-            da.stretches_per_channel = int((n_sb + da.sb_per_stretch - 1) / da.sb_per_stretch);
             if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), hi));
             HBD_CUDA_CHECK(launch_decim1(da, M1, T1, max_n1, n_sms, hi, &nl));
             if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), hi));
         }
-        HBD_CUDA_CHECK(launch_carry(d_plan, chunk, chunk_pitch, d_carry, T1, c0, nc, hi, &nl));
         HBD_CUDA_CHECK(cudaEventRecord(ev_consumed[size_t(g)], hi)); // input no longer needed by this group; stage-1 output ready
         HBD_CUDA_CHECK(cudaStreamWaitEvent(lo, ev_consumed[size_t(g)], 0));
         if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
         if (any_work) {
             TailArgs ta{};
-            ta.plan = d_plan; ta.state = d_state; ta.ch0 = c0;
+            ta.plan = d_plan; ta.uplan = h_plan[0]; ta.uniform = plan_uniform ? 1 : 0; ta.state = d_state; ta.ch0 = c0;
             ta.s1 = d_s1; ta.s1_pitch = s1_pitch; ta.taps2 = d_taps2; ta.M2 = M2; ta.T2 = T2;
             ta.decq = d_decq; ta.dq_pitch = dq_pitch; ta.fs_dec = fs_dec; ta.fftbuf = d_fftbuf; ta.lptaps = d_lptaps;
-            ta.slicer = d_slicer; ta.slicer_pitch = slicer_pitch; ta.demod_last = d_demod; ta.demod_pitch = demod_pitch;
+            ta.max_lp_taps = int(max_lp_taps);
+            ta.slicer = d_slicer; ta.slicer_pitch = slicer_pitch; ta.sv_want = sv_want;
+            ta.log = d_log; ta.log_head = d_log_head; ta.call_seq = call_seq & 0xffffffu;
+            ta.demod_last = d_demod; ta.demod_pitch = demod_pitch;
             ta.rec_decimated = record ? d_rec_dec : nullptr; ta.rec_filtered = record ? d_rec_filt : nullptr; ta.rec_pitch = rec_pitch;
-            ta.smem_window = tail_smem_window(M2, T2);
+            ta.rec_bits = record ? d_rec_bits : nullptr; ta.rec_bits_n = d_rec_bits_n; ta.rec_bits_pitch = rec_bits_pitch;
             HBD_CUDA_CHECK(launch_tail(ta, nc, lo, &nl));
             FftArgs fa{};
             fa.state = d_state; fa.fftbuf = d_fftbuf; fa.spectrum = d_spectrum; fa.power = d_power; fa.twiddle = d_twiddle; fa.fs_dec = fs_dec;
             fa.ch0 = c0;
             HBD_CUDA_CHECK(launch_fft_afc(fa, nc, lo, &nl));
-            SlicerArgs sa{};
-            sa.state = d_state; sa.slicer = d_slicer; sa.slicer_pitch = slicer_pitch; sa.log = d_log; sa.log_head = d_log_head; sa.call_seq = call_seq & 0xffffffu;
-            sa.rec_bits = record ? d_rec_bits : nullptr; sa.rec_bits_n = d_rec_bits_n; sa.rec_bits_pitch = rec_bits_pitch;
-            sa.fs_dec = fs_dec; sa.ch0 = c0; sa.n_channels = nc;
-            HBD_CUDA_CHECK(launch_slicer(sa, lo, &nl));
         }
         if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
         HBD_CUDA_CHECK(cudaEventRecord(ev_tail[size_t(g)], lo));
@@ -479,6 +494,7 @@ int hbd_decoder::process_async_locked()
     }
     // the caller's stream resumes once every group has consumed the input (it does not wait for the tail kernels)
     for (int g = 0; g < n_groups; ++g) HBD_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_consumed[size_t(g)], 0));
+    carry_cur ^= 1;
     launches += unsigned(nl);
     HBD_CUDA_CHECK(cudaEventRecord(ev_call[call_seq % ev_call.size()], lo)); // everything of this call is done
     ++call_seq;
@@ -579,6 +595,7 @@ int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return HBD_ERR_CUDA; }
     h->own_stream = true;
     {
+        if (const char* sv = getenv("HBD_SV_WANT")) h->sv_override = atoi(sv);
         const char* env = getenv("HBD_GROUPS");
         int g = env ? atoi(env) : (n_channels >= 256 ? 2 : 1);
         g = std::max(1, std::min(g, std::min(n_channels, 8)));
@@ -688,7 +705,7 @@ static size_t apply_factor(hbd_decoder* h, size_t factor)
     h->sync_groups();
     cudaStreamSynchronize(h->stream);
     h->upload_taps();
-    cudaMemset(h->d_carry, 0, size_t(h->n_ch) * kCarryCap * sizeof(float2));
+    for (int i = 0; i < 2; ++i) cudaMemset(h->d_carry2[i], 0, size_t(h->n_ch) * kCarryCap * sizeof(float2));
     if (h->d_s1) cudaMemset(h->d_s1, 0, size_t(h->n_ch) * h->s1_pitch * sizeof(float2));
     for (auto& x : h->hc) {
         x.grown1 = x.grown2 = 0;

@@ -163,33 +163,37 @@ decim1_kernel(DecimArgs a)
     }
 
     uint32_t phase_bits = 0; // parity per ring slot
-    const int warps_total = gridDim.x * kDecimWarps;
-    const int n_items = a.n_channels * a.stretches_per_channel;
+    // Work = the (channel, superblock) plane flattened; every warp takes ONE contiguous span of it, so the
+    // ramp-in (RAMP superblocks whose outputs are discarded) is paid once per span and once per channel start
+    // instead of once per 128 superblocks, and all warps finish together (no wave quantisation).
+    const long long total_sb = (long long)a.n_channels * a.sb_per_channel;
+    long long g = (long long)(blockIdx.x * kDecimWarps + warp) * a.span;
+    const long long g_end = g + a.span < total_sb ? g + a.span : total_sb;
 
-    for (int item = blockIdx.x * kDecimWarps + warp; item < n_items; item += warps_total) {
-        const int chl = item / a.stretches_per_channel;
-        const int st = item - chl * a.stretches_per_channel;
+    while (g < g_end) {
+        const int chl = int(g / a.sb_per_channel);
+        const int b_lo = int(g - (long long)chl * a.sb_per_channel);
+        const int b_span_hi = int(g_end - g < (long long)(a.sb_per_channel - b_lo) ? b_lo + (g_end - g) : a.sb_per_channel);
+        g += b_span_hi - b_lo;
         const int ch = a.ch0 + chl;
         const ChanPlan pl = a.plan[ch];
-        if (pl.flags & 1u) continue;
+        const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
+        const float2* carry = a.carry + (size_t)ch * kCarryCap + kCarryCap; // carry[j] valid for -kCarryCap <= j < 0
         // superblock b covers step-local sample positions x in (64(b-1), 64b]; the outputs k with
-        // (b-1)*NOUT < k <= b*NOUT end inside it.  This stretch owns superblocks [b_lo, b_hi).
+        // (b-1)*NOUT < k <= b*NOUT end inside it.  This span owns superblocks [b_lo, b_hi) of the channel.
         const int n1 = int(pl.n1);
         const int n_sb_total = (n1 - 1 + G::NOUT - 1) / G::NOUT + 1;       // superblocks 0 .. ceil((n1-1)/NOUT)
-        const int b_lo = st * a.sb_per_stretch;
-        if (b_lo >= n_sb_total) continue;
-        const int b_hi = min(b_lo + a.sb_per_stretch, n_sb_total);
+        if (!(pl.flags & 1u) && b_lo < n_sb_total) {
+        const int b_hi = min(b_span_hi, n_sb_total);
         const int b_first = b_lo - G::RAMP_GROUPS * G::U;                   // ramp-in: whole groups, outputs discarded
         const int n_groups = (b_hi - b_first + G::U - 1) / G::U;
         const int n_pieces = (n_groups + G::GROUPS_PER_PIECE - 1) / G::GROUPS_PER_PIECE;
-        // outputs this stretch may store
+        // outputs this span may store
         const int k_lo = max(0, (b_lo - 1) * G::NOUT + 1), k_hi = min(n1, (b_hi - 1) * G::NOUT + 1);
 
         // sample addressing: j = x - r indexes the pushed chunk (j >= 0) or the carry (j < 0);
         // everything below is relative to the first sample of the walk, jw = j - j0 >= 0
         const int j0 = 64 * (b_first - 1) + 1 - int(pl.r);
-        const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
-        const float2* carry = a.carry + (size_t)ch * kCarryCap + kCarryCap; // carry[j] valid for -kCarryCap <= j < 0
         const int odd = j0 & 1;                // ring sample s holds j = (j0 - odd) + p*PIECE_SAMPLES + s
         const int j_cap_lo = -kCarryCap, j_end = int(pl.n);
 
@@ -257,14 +261,8 @@ decim1_kernel(DecimArgs a)
                         // tap index of position P for live output j (0-based): t = T - M*(j+1) + P; skip the
                         // half-superblocks where no lane has a tap (compile-time)
                         const int t0 = T - M * (j + 1);
-                        if (t0 + 31 >= 0 && t0 < T) {
-                            acc[r].x = fmaf(x0.x, h0[j], acc[r].x);
-                            acc[r].y = fmaf(x0.y, h0[j], acc[r].y);
-                        }
-                        if (t0 + 63 >= 0 && t0 + 32 < T) {
-                            acc[r].x = fmaf(x1.x, h1[j], acc[r].x);
-                            acc[r].y = fmaf(x1.y, h1[j], acc[r].y);
-                        }
+                        if (t0 + 31 >= 0 && t0 < T) acc[r] = cfma(x0, h0[j], acc[r]);
+                        if (t0 + 63 >= 0 && t0 + 32 < T) acc[r] = cfma(x1, h1[j], acc[r]);
                     }
 #pragma unroll
                     for (int j = 0; j < G::NOUT; ++j) {
@@ -287,6 +285,20 @@ decim1_kernel(DecimArgs a)
         }
         if (G::NOUT > 1 && staged) reduce_rows(sm.red, staged, k_next - staged, k_lo, k_hi, out, lane);
         __syncwarp();
+        }
+        // The span that reaches the end of a channel also writes the channel's carry for the NEXT call
+        // (Decimator.h:141-143 history + Decoder.h:432-435 unconsumed remainder): the last T-1 + r' samples of
+        // [carry | chunk], r' = r + n - consumed.  It goes to the other half of a ping-pong pair because spans
+        // of the same channel owned by other warps may still be reading the current carry.
+        if (b_span_hi == a.sb_per_channel) {
+            const int keep = T - 1 + int(pl.r + pl.n - pl.consumed);       // <= kCarryCap (host checked)
+            float2* next = a.carry_next + (size_t)ch * kCarryCap + kCarryCap;
+            const int jn = int(pl.n);
+            for (int i = lane; i < keep; i += 32) {
+                const int j = jn - keep + i;
+                next[i - keep] = (j < 0) ? carry[j] : chunk[j];
+            }
+        }
     }
 }
 
@@ -325,9 +337,37 @@ __global__ void decim1_copy_kernel(DecimArgs a)
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < pl.n1; k += gridDim.x * blockDim.x) out[k] = chunk[k];
 }
 
-template <int M, int T>
-static cudaError_t launch_fast(const DecimArgs& a, int n_sms, cudaStream_t stream, int* launches)
+// ---- stage-1 carry for the NEXT call when K1 is not the TMA kernel: last (T1-1 + r') samples of [carry | chunk] ----
+__global__ void __launch_bounds__(128)
+carry_kernel(const ChanPlan* __restrict__ plan, const float2* __restrict__ chunk_base, size_t chunk_pitch, const float2* __restrict__ carry_base,
+             float2* __restrict__ next_base, int T1, int ch0)
 {
+    const int ch = ch0 + blockIdx.x;
+    const ChanPlan pl = plan[ch];
+    const int keep = T1 - 1 + int(pl.r + pl.n - pl.consumed);             // <= kCarryCap (host checked)
+    const float2* carry = carry_base + (size_t)ch * kCarryCap + kCarryCap;
+    float2* next = next_base + (size_t)ch * kCarryCap + kCarryCap;
+    const float2* chunk = chunk_base + (size_t)ch * chunk_pitch;
+    for (int i = threadIdx.x; i < keep; i += 128) {
+        const long long j = (long long)pl.n - keep + i;
+        next[i - keep] = (j < 0) ? carry[j] : chunk[j];
+    }
+}
+
+cudaError_t launch_carry(const ChanPlan* plan, const float2* chunk, size_t chunk_pitch, const float2* carry, float2* carry_next, int T1, int ch0,
+                         int n_channels, cudaStream_t stream, int* launches)
+{
+    carry_kernel<<<n_channels, 128, 0, stream>>>(plan, chunk, chunk_pitch, carry, carry_next, T1, ch0);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+constexpr int kMinSpan = 48; // superblocks: keeps the ramp-in below ~12 % when there are few channels
+
+template <int M, int T>
+static cudaError_t launch_fast(DecimArgs a, unsigned max_n1, int n_sms, cudaStream_t stream, int* launches)
+{
+    using G = Geo<M, T>;
     const size_t smem = sizeof(WarpSmem<M, T>) * kDecimWarps;
     static bool configured = false; // one device per process (one process per GPU)
     if (!configured) {
@@ -338,30 +378,37 @@ static cudaError_t launch_fast(const DecimArgs& a, int n_sms, cudaStream_t strea
         cudaFuncSetAttribute(decim1_kernel<M, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
-    const long long n_items = (long long)a.n_channels * a.stretches_per_channel;
-    int grid = (int)std::min<long long>(n_sms, (n_items + kDecimWarps - 1) / kDecimWarps);
+    a.sb_per_channel = max_n1 ? int((max_n1 - 1 + G::NOUT - 1) / G::NOUT + 1) : 1;
+    const long long total_sb = (long long)a.n_channels * a.sb_per_channel;
+    const long long warps_max = (long long)n_sms * kDecimWarps;
+    long long span = (total_sb + warps_max - 1) / warps_max;
+    if (span < kMinSpan) span = kMinSpan;
+    a.span = (int)span;
+    const long long n_spans = (total_sb + span - 1) / span;
+    int grid = (int)std::min<long long>(n_sms, (n_spans + kDecimWarps - 1) / kDecimWarps);
     if (grid < 1) grid = 1;
     decim1_kernel<M, T><<<grid, kDecimWarps * 32, smem, stream>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
 
-cudaError_t launch_decim1(const DecimArgs& a, int M, int T, unsigned max_n1, int n_sms, cudaStream_t stream, int* launches)
+cudaError_t launch_decim1(DecimArgs a, int M, int T, unsigned max_n1, int n_sms, cudaStream_t stream, int* launches)
 {
-    if (M == 64 && T == 348) return launch_fast<64, 348>(a, n_sms, stream, launches);
-    if (M == 32 && T == 174) return launch_fast<32, 174>(a, n_sms, stream, launches);
-    if (M == 32 && T == 212) return launch_fast<32, 212>(a, n_sms, stream, launches);
-    if (M == 16 && T == 107) return launch_fast<16, 107>(a, n_sms, stream, launches);
-    if (M == 8 && T == 54) return launch_fast<8, 54>(a, n_sms, stream, launches);
-    dim3 grid((max_n1 + 255) / 256, a.n_channels);
-    if (grid.x < 1) grid.x = 1;
-    if (grid.x > 1024) grid.x = 1024;
-    if (M == 1) decim1_copy_kernel<<<grid, 256, 0, stream>>>(a);
-    else decim1_generic_kernel<<<grid, 256, 0, stream>>>(a, M, T);
-    if (launches) ++*launches;
-    return cudaGetLastError();
+    if (M == 64 && T == 348) return launch_fast<64, 348>(a, max_n1, n_sms, stream, launches);
+    if (M == 32 && T == 174) return launch_fast<32, 174>(a, max_n1, n_sms, stream, launches);
+    if (M == 32 && T == 212) return launch_fast<32, 212>(a, max_n1, n_sms, stream, launches);
+    if (M == 16 && T == 107) return launch_fast<16, 107>(a, max_n1, n_sms, stream, launches);
+    if (M == 8 && T == 54) return launch_fast<8, 54>(a, max_n1, n_sms, stream, launches);
+    if (max_n1) {
+        dim3 grid((max_n1 + 255) / 256, a.n_channels);
+        if (grid.x > 1024) grid.x = 1024;
+        if (M == 1) decim1_copy_kernel<<<grid, 256, 0, stream>>>(a);
+        else decim1_generic_kernel<<<grid, 256, 0, stream>>>(a, M, T);
+        if (launches) ++*launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return launch_carry(a.plan, a.chunk, a.chunk_pitch, a.carry, a.carry_next, T, a.ch0, a.n_channels, stream, launches);
 }
-
-int decim1_sb_per_stretch(int M) { (void)M; return 128; }
 
 } // namespace hbd

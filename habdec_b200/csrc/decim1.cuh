@@ -20,12 +20,16 @@ struct DecimArgs {
     const float* taps;         // T floats (device)
     int ch0;                   // first channel of this launch
     int n_channels;            // channels in this launch
-    int stretches_per_channel; // ceil(max superblocks / sb_per_stretch)
-    int sb_per_stretch;        // owned superblocks per work item
+    float2* carry_next;        // other half of the carry ping-pong pair: K1 writes the next call's carry here
+    int sb_per_channel;        // superblock slots per channel (uniform upper bound; set by launch_decim1)
+    int span;                  // superblocks per warp (contiguous in the flattened (channel, superblock) plane)
 };
 
-// M == 1 means "no decimator" (copy).  `launches` is incremented per kernel launched.
-cudaError_t launch_decim1(const DecimArgs& a, int M, int T, unsigned max_n1, int n_sms, cudaStream_t stream, int* launches);
-int decim1_sb_per_stretch(int M);
+// M == 1 means "no decimator" (copy).  `launches` is incremented per kernel launched.  Writes the carry of the
+// next call into a.carry_next (inside K1 on the fast path, by carry_kernel otherwise).
+cudaError_t launch_decim1(DecimArgs a, int M, int T, unsigned max_n1, int n_sms, cudaStream_t stream, int* launches);
+// stage-1 carry (history + unconsumed remainder) for the next call: carry -> carry_next
+cudaError_t launch_carry(const ChanPlan* plan, const float2* chunk, size_t chunk_pitch, const float2* carry, float2* carry_next, int T1, int ch0,
+                         int n_channels, cudaStream_t stream, int* launches);
 
 } // namespace hbd

@@ -6,11 +6,9 @@
 // kernels with no host round trip:
 //
 //   K1 decim1   stage-1 FIR decimator          (Decimator.h:99-146, first stage)
-//   K2 tail     stage-2 FIR -> DC-remove -> FFT frame -> low-pass -> discriminator
-//               (Decoder.h:440-555, FirFilter.h:117-169, FSK2_Demod.h:30-42)
+//   K2 tail     stage-2 FIR -> DC-remove -> FFT frame -> low-pass -> discriminator -> bit slicer + UART
+//               (Decoder.h:440-555, FirFilter.h:117-169, FSK2_Demod.h:30-42, SymbolExtractor.h:108-255, RTTY.h:77-137)
 //   K4 fft_afc  4096-pt FFT + power + peaks + AFC state machine (FFT.cpp:77-99, AFC.h:92-329)
-//   K3 slicer   bit slicer + UART deframer, one warp per channel
-//               (SymbolExtractor.h:108-255, RTTY.h:77-137)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -72,6 +70,8 @@ struct ChanPlan {
     unsigned n1;        // stage-1 outputs  = consumed / M1
     unsigned n2;        // decimated outputs = consumed / factor
     unsigned flags;     // bit0: nothing to do this call
+    unsigned dec_pending; // decimated samples queued in front of the low-pass BEFORE this call (host mirror of ChanState)
+    unsigned lp_ntaps;  // low-pass tap count in force for this call
 };
 
 struct DecimGeometry {
@@ -81,6 +81,20 @@ struct DecimGeometry {
 };
 
 __host__ __device__ inline unsigned hbd_min_u(unsigned a, unsigned b) { return a < b ? a : b; }
+
+#ifdef __CUDACC__
+// complex sample x real tap, accumulated: ONE packed FFMA2 (fma.rn.f32x2, sm_100+) instead of two FFMA.  Each half is an
+// IEEE fused multiply-add, so the value equals fmaf() per component; the FMA pipe does the same work, the issue
+// slot count halves (tools/micro/ffma2_bench.cu: same 127 FMA/clk/SM at half the instructions).
+__device__ __forceinline__ float2 cfma(float2 x, float h, float2 acc)
+{
+    float2 hh = make_float2(h, h);
+    unsigned long long rx = *reinterpret_cast<unsigned long long*>(&x), rh = *reinterpret_cast<unsigned long long*>(&hh),
+                       ra = *reinterpret_cast<unsigned long long*>(&acc), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(rx), "l"(rh), "l"(ra));
+    return *reinterpret_cast<float2*>(&rd);
+}
+#endif
 
 } // namespace hbd
 

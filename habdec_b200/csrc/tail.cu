@@ -1,4 +1,4 @@
-// K2 -- everything between the first decimator and the bit slicer, one CTA per channel.
+// K2 -- everything after the first decimator, one CTA (128 threads) per channel, ONE kernel:
 //
 //   stage-2 FIR decimator     code/Decoder/Decimator.h:99-146 (second entry of Decoder.h:286-320)
 //   DC removal (optional)     code/Decoder/Decoder.h:450-459
@@ -7,22 +7,32 @@
 //   low-pass FIR              code/Decoder/FirFilter.h:117-169 (taps designed on the host, host_tail.cpp)
 //   FM/FSK discriminator      code/Decoder/FSK2_Demod.h:30-42  (carry kept PER CHANNEL, not per thread)
 //   slicer input append       code/Decoder/SymbolExtractor.h:108-125 (3e4 safety vent included)
-// and, as a separate tiny kernel, the stage-1 carry update (Decimator.h:141-143 + Decoder.h:432-435).
+//   bit slicer + UART         SymbolExtractor.h:129-241, RTTY.h:77-137 (warp 0, slicer_dev.cuh)
 //
-// The data here is 1/64 .. 1/256 of the input rate, so this kernel is FP32/LDS bound and runs in the shadow
-// of K1 (other channel group, other stream).  Both FIRs are register tiled: a thread owns TWO consecutive
-// outputs and slides a small sample window through registers, so shared memory is read once per sample pair
-// (LDS.128) instead of once per multiply:
-//   stage 2 (M2 = 4):  per tap group of 4:  2 LDS.128 samples + 1 LDS.128 taps -> 16 FFMA
-//   low-pass:          per tap pair:        1 LDS.128 samples + 1 LDS.64 taps  ->  8 FFMA
+// This kernel runs in the shadow of the HBM-bound K1 (other channel group / other stream) with only a couple of
+// CTAs per SM, while K1 keeps the memory system saturated: what costs time here is the number of DEPENDENT global
+// round trips, not flops.  So the whole chain stays in shared memory:
+//   round trip 1   plan (kernel argument when uniform) -> state, stage-1 window, low-pass history + pending,
+//                  taps: all issued at once (cp.async, no registers held)
+//   round trip 2   the channel's pending slicer samples (their count is in the state); overlaps the FIR work
+//   then           stage 2 -> [DC] -> FFT frame -> low-pass -> discriminator -> slicer -> UART, all on shared memory
+//   finally        write-only stores of the new histories / queues / state
+// Both FIRs are register tiled: a thread owns TWO consecutive outputs and slides a small sample window through
+// registers, so shared memory is read once per sample pair (LDS.128) instead of once per multiply, and every
+// complex-by-real multiply-add is one packed FFMA2:
+//   stage 2 (M2 = 4):  per tap group of 4:  2 LDS.128 samples + 1 LDS.128 taps -> 8 FFMA2
+//   low-pass:          per tap pair:        1 LDS.128 samples + 1 LDS.64 taps  ->  4 FFMA2
 // The stage-2 window tile is padded by 2 samples every 16 so that the 64-byte thread stride is bank-conflict free.
 #include "hbd_common.cuh"
+#include "slicer_dev.cuh"
 #include "tail.cuh"
+#include <algorithm>
 
 namespace hbd {
 
 constexpr int kTailThreads = 128;
-constexpr int kTile = 2 * kTailThreads; // outputs per tile (two per thread)
+constexpr int kTile = 2 * kTailThreads; // outputs per tile (two per thread) == kLpBatch
+static_assert(kTile == kLpBatch, "one low-pass batch per stage-2 tile");
 
 __device__ __forceinline__ float2 cmul_conj_ieee(float2 a, float2 b) // a * conj(b), separately rounded products (no FMA)
 {
@@ -34,79 +44,125 @@ __device__ __forceinline__ float2 cmul_conj_ieee(float2 a, float2 b) // a * conj
 
 __host__ __device__ __forceinline__ int pad16(int s) { return s + 2 * (s >> 4); } // 2 float2 of padding per 16 samples
 
-__device__ __forceinline__ void fma2(float2& acc, float2 x, float h)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src)
 {
-    acc.x = fmaf(x.x, h, acc.x);
-    acc.y = fmaf(x.y, h, acc.y);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
 }
-
-// ---- stage-1 carry for the NEXT call: last (T1-1 + r') samples of [carry | chunk] ---------------------------
-__global__ void __launch_bounds__(128)
-carry_kernel(const ChanPlan* __restrict__ plan, const float2* __restrict__ chunk_base, size_t chunk_pitch, float2* carry_base, int T1, int ch0)
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src)
 {
-    const int ch = ch0 + blockIdx.x, tid = threadIdx.x;
-    const ChanPlan pl = plan[ch];
-    const unsigned r_next = (pl.r + pl.n) - pl.consumed;
-    const int keep = T1 - 1 + int(r_next);                 // <= kCarryCap (host checked)
-    float2* carry = carry_base + (size_t)ch * kCarryCap + kCarryCap;
-    const float2* chunk = chunk_base + (size_t)ch * chunk_pitch;
-    // two passes through registers: source and destination may overlap inside the carry
-    float2 tmp[kCarryCap / 128];
-#pragma unroll
-    for (int u = 0; u < kCarryCap / 128; ++u) {
-        const int i = tid + u * 128;
-        const long long j = (long long)pl.n - keep + i;
-        tmp[u] = (i < keep) ? ((j < 0) ? carry[j] : chunk[j]) : make_float2(0.f, 0.f);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < kCarryCap / 128; ++u) {
-        const int i = tid + u * 128;
-        if (i < keep) carry[-keep + i] = tmp[u];
-    }
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kTailThreads)
 tail_kernel(TailArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* s_x = reinterpret_cast<float2*>(smem_raw);                // tile input window (padded layout for stage 2)
-    float*  s_h = reinterpret_cast<float*>(s_x + a.smem_window);      // taps (zero padded to a multiple of 4)
-    float2* s_f = reinterpret_cast<float2*>(s_h + kLpMaxTaps + 7);    // filtered tile (+1 previous sample)
-    __shared__ unsigned sh_total, sh_nf, sh_slicer_base;
+    float2* s_x = reinterpret_cast<float2*>(smem_raw);            // stage-2 window tile (padded layout)
+    float2* s_q = s_x + a.xw;                                     // low-pass input: [skew | history | pending | new]
+    float2* s_f = s_q + a.qcap;                                   // filtered tile (+1 previous sample)
+    float*  s_h2 = reinterpret_cast<float*>(s_f + kTile + 2);     // stage-2 taps (shifted, zero padded)
+    float*  s_hl = s_h2 + a.h2cap;                                // low-pass taps (shifted, zero padded)
+    float*  s_v  = s_hl + a.hlcap;                                // slicer samples: [old pending | this call's]
+    unsigned char* s_chars = reinterpret_cast<unsigned char*>(s_v + a.sv_cap);
+    __shared__ ChanState s_st;
+    __shared__ float2 sh_dc_wp;
 
-    const int ch = a.ch0 + blockIdx.x, tid = threadIdx.x;
-    const ChanPlan pl = a.plan[ch];
-    ChanState& st = a.state[ch];
+    const int ch = a.ch0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const ChanPlan pl = a.uniform ? a.uplan : a.plan[ch];
     if (pl.flags & 1u) return; // fewer than `factor` samples queued: Decoder.h:429-430
 
-    const unsigned n1 = pl.n1, n2 = pl.n2;
+    ChanState& gst = a.state[ch];
+    const unsigned n2 = pl.n2;
     float2* s1 = a.s1 + (size_t)ch * a.s1_pitch;
     float2* dq = a.decq + (size_t)ch * a.dq_pitch;
-    const unsigned dec_pending = st.dec_pending;
-    float2* ynew = dq + kLpHist + dec_pending; // where this call's decimated samples go
+    const int T = int(pl.lp_ntaps);                      // 0 until the first design (host, Decoder.h:536-538)
+    const int hist = T > 0 ? T - 1 : 0;
+    const unsigned dec_pending = pl.dec_pending;
+    const int T2 = a.T2, M2 = a.M2;
+    // stage-2 geometry (M2 == 4): window starts `lead` samples before the tile, lead = T2-1 rounded up to 4
+    const int lead = (M2 == 4) ? ((T2 - 1 + 3) & ~3) : (T2 - 1);
+    const int skew2 = lead - (T2 - 1);
+    const int n_blocks = (skew2 + T2 + 3) / 4;
+    // low-pass geometry: s_q[i] = q[qbase - qskew + i]; history starts at s_q[qskew]
+    const long long qbase = (long long)kLpHist - hist;
+    const int qskew = int(qbase & 1);
+    const int n_pairs = (qskew + T + 2) / 2;
 
-    // ---- stage 2 ------------------------------------------------------------------------------------------
-    if (a.M2 == 4) {
-        const int T2 = a.T2;
-        const int lead = (T2 - 1 + 3) & ~3;                          // 140 for T2 = 139
-        const int skew = lead - (T2 - 1);                            // leading samples that get a zero tap
-        const int n_blocks = (skew + T2 + 3) / 4;
-        // taps stored shifted by `skew` and zero padded: s_h[u] = h[u - skew]
-        for (int u = tid; u < 4 * n_blocks; u += kTailThreads) s_h[u] = (u >= skew && u - skew < T2) ? a.taps2[u - skew] : 0.f;
-        for (unsigned k0 = 0; k0 < n2; k0 += kTile) {
-            const unsigned nk = hbd_min_u(kTile, n2 - k0);
-            // y[k] = sum_t x[4k - (T2-1) + t] h[t]; x index 0 is s1[kS1Hist].  The tile holds x from
-            // 4*k0 - (T2-1) rounded DOWN to a multiple of 4 samples (keeps LDS.128 aligned).
-            const long long x0 = 4LL * k0 - lead;
-            const int win = int(nk) * 4 + lead;                      // samples 0 .. 4*nk + lead - 1
+    // ---- round trip 1 -------------------------------------------------------------------------------------
+    for (int i = tid; i < a.qcap; i += kTailThreads) s_q[i] = make_float2(0.f, 0.f); // zero taps must meet finite samples
+    __syncthreads();
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(&gst);
+        unsigned* dst = reinterpret_cast<unsigned*>(&s_st);
+        for (int i = tid; i < int(sizeof(ChanState) / 4); i += kTailThreads) cp_async4(dst + i, src + i);
+    }
+    auto load_window = [&](unsigned k0, unsigned nk) {
+        if (M2 > 1) {
+            const long long x0 = (long long)k0 * M2 - lead;
+            const int win = int(nk) * M2 + lead;
+            if (M2 == 4) { for (int i = tid; i < win; i += kTailThreads) cp_async8(&s_x[pad16(i)], &s1[kS1Hist + x0 + i]); }
+            else         { for (int i = tid; i < win; i += kTailThreads) cp_async8(&s_x[i], &s1[kS1Hist + x0 + i]); }
+        }
+    };
+    load_window(0, hbd_min_u(kTile, n2));
+    for (int i = tid; i < hist + int(dec_pending); i += kTailThreads) cp_async8(&s_q[qskew + i], &dq[qbase + i]);
+    cp_async_commit();
+    if (M2 == 4) { for (int u = tid; u < 4 * n_blocks; u += kTailThreads) s_h2[u] = (u >= skew2 && u - skew2 < T2) ? a.taps2[u - skew2] : 0.f; }
+    else if (M2 > 1) { for (int i = tid; i < T2; i += kTailThreads) s_h2[i] = a.taps2[i]; }
+    {
+        const float* taps = a.lptaps + (size_t)ch * kLpMaxTaps;
+        for (int u = tid; u < 2 * n_pairs; u += kTailThreads) s_hl[u] = (u >= qskew && u - qskew < T) ? taps[u - qskew] : 0.f;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- batch gate (Decoder.h:492-527) and slicer vent (SymbolExtractor.h:116-120) ------------------------
+    const unsigned total = dec_pending + n2;
+    unsigned nf = 0, new_pending = total;
+    bool tick = false;
+    if (total >= unsigned(kLpBatch)) {
+        tick = true;
+        if (a.fs_dec > 4 * 40e3) new_pending = 0;     // everything queued is dropped, nothing decoded
+        else { nf = total - total % unsigned(kLpBatch); new_pending = total - nf; }
+    }
+    unsigned n_old = s_st.slicer_n;
+    if (nf && n_old > unsigned(kSlicerVent)) n_old = 0; // checked before the append, only when there is something to append
+    const bool smem_mode = nf && (n_old + nf <= unsigned(a.sv_cap));
+    float* v_g = a.slicer + (size_t)ch * a.slicer_pitch;
+    // ---- round trip 2: pending slicer samples (consumed after the FIRs) ------------------------------------
+    if (smem_mode) for (unsigned i = tid; i < n_old; i += kTailThreads) cp_async4(&s_v[i], &v_g[i]);
+    cp_async_commit();
+
+    const unsigned fft_have0 = s_st.fft_have;
+    const unsigned fft_take = (fft_have0 < unsigned(kFftN)) ? hbd_min_u(kFftN - fft_have0, n2) : 0u;
+    const bool dc = s_st.dc_remove != 0;
+    float2 carry_prev = make_float2(s_st.demod_last_re, s_st.demod_last_im);
+    const bool primed = s_st.demod_primed != 0;
+    float* dlast = a.demod_last ? a.demod_last + (size_t)ch * a.demod_pitch : nullptr;
+
+    int qpos = qskew;              // s_q index where the current low-pass history starts
+    unsigned have_q = dec_pending; // samples queued behind the history
+    unsigned produced = 0;         // low-pass outputs so far in this call
+
+    for (unsigned k0 = 0; k0 < n2; k0 += kTile) {
+        const unsigned nk = hbd_min_u(kTile, n2 - k0);
+        float2* ynew = s_q + qpos + hist + have_q;  // where this tile's decimated samples go
+        if (k0) { // later tiles of a long call: the window was not prefetched
             __syncthreads();
-            for (int i = tid; i < win; i += kTailThreads) s_x[pad16(i)] = s1[kS1Hist + x0 + i];
+            load_window(k0, nk);
+            cp_async_commit();
+            cp_async_wait_all();
             __syncthreads();
+        }
+        // ---- stage 2 ------------------------------------------------------------------------------------------
+        if (M2 == 4) {
+            // y[k] = sum_t x[4k - (T2-1) + t] h[t]; the tile holds x from 4*k0 - lead (a multiple of 4 samples, keeps
+            // LDS.128 aligned); taps are applied as h'[u] = h[u - skew2] (zero for u < skew2)
             const int k = 2 * tid; // first of this thread's two outputs
             if (k < int(nk)) {
-                // with the window shifted by `skew`, output k uses tile samples 4k + skew + t; taps are applied
-                // as h'[u] = h[u - skew] (zero for u < skew) over u = 0 .. lead+? so blocks stay 4-aligned
                 float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
                 float2 b0[4], b1[4];
                 {
@@ -114,236 +170,220 @@ tail_kernel(TailArgs a)
                     const float4 p1 = *reinterpret_cast<const float4*>(&s_x[pad16(4 * k + 2)]);
                     b0[0] = make_float2(p0.x, p0.y); b0[1] = make_float2(p0.z, p0.w); b0[2] = make_float2(p1.x, p1.y); b0[3] = make_float2(p1.z, p1.w);
                 }
+#pragma unroll 2
                 for (int blk = 0; blk < n_blocks; ++blk) {
                     const float4 q0 = *reinterpret_cast<const float4*>(&s_x[pad16(4 * (k + blk + 1))]);
                     const float4 q1 = *reinterpret_cast<const float4*>(&s_x[pad16(4 * (k + blk + 1) + 2)]);
                     b1[0] = make_float2(q0.x, q0.y); b1[1] = make_float2(q0.z, q0.w); b1[2] = make_float2(q1.x, q1.y); b1[3] = make_float2(q1.z, q1.w);
-                    // taps for tile offsets 4*blk .. 4*blk+3 (one broadcast LDS.128)
-                    const float4 h4 = *reinterpret_cast<const float4*>(&s_h[4 * blk]);
+                    const float4 h4 = *reinterpret_cast<const float4*>(&s_h2[4 * blk]); // taps for tile offsets 4*blk .. 4*blk+3
                     const float hh[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) { fma2(acc0, b0[c], hh[c]); fma2(acc1, b1[c], hh[c]); }
+                    for (int c = 0; c < 4; ++c) { acc0 = cfma(b0[c], hh[c], acc0); acc1 = cfma(b1[c], hh[c], acc1); }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) b0[c] = b1[c];
                 }
-                ynew[k0 + k] = acc0;
-                if (k + 1 < int(nk)) ynew[k0 + k + 1] = acc1;
+                ynew[k] = acc0;
+                if (k + 1 < int(nk)) ynew[k + 1] = acc1;
             }
-        }
-        __syncthreads();
-    } else if (a.M2 > 1) { // M2 == 2 (69 taps): half-rate inputs (<= 512 kS/s), simple form
-        const int T2 = a.T2, M2 = a.M2;
-        for (int i = tid; i < T2; i += kTailThreads) s_h[i] = a.taps2[i];
-        for (unsigned k0 = 0; k0 < n2; k0 += kTile) {
-            const unsigned nk = hbd_min_u(kTile, n2 - k0);
-            const int win = int(nk) * M2 + T2 - M2;
-            const long long x0 = (long long)k0 * M2 - (T2 - 1);
-            __syncthreads();
-            for (int i = tid; i < win; i += kTailThreads) s_x[i] = s1[kS1Hist + x0 + i];
-            __syncthreads();
+        } else if (M2 > 1) { // M2 == 2 (69 taps): half-rate inputs (<= 512 kS/s), simple form
             for (int k = tid; k < int(nk); k += kTailThreads) {
                 const float2* w = s_x + k * M2;
                 float2 acc = make_float2(0.f, 0.f);
-                for (int t = 0; t < T2; ++t) fma2(acc, w[t], s_h[t]);
-                ynew[k0 + k] = acc;
-            }
-        }
-        __syncthreads();
-    } else {
-        for (unsigned k = tid; k < n2; k += kTailThreads) ynew[k] = s1[kS1Hist + k];
-    }
-    if (a.M2 > 1) {
-        // history for the next call: last T2-1 stage-1 samples (source may overlap when n1 < T2-1)
-        const int T2 = a.T2;
-        float2 keep2[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int i = tid + u * kTailThreads;
-            keep2[u] = (i < T2 - 1) ? s1[kS1Hist + (long long)n1 - (T2 - 1) + i] : make_float2(0.f, 0.f);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int i = tid + u * kTailThreads;
-            if (i < T2 - 1) s1[kS1Hist - (T2 - 1) + i] = keep2[u];
-        }
-    }
-    __syncthreads();
-
-    // ---- DC removal, sequential recurrence re-seeded from the first sample of the call ---------------------
-    if (st.dc_remove && tid == 0 && n2) {
-        float2 wp = make_float2(__fmul_rn(.97f, ynew[0].x), __fmul_rn(.97f, ynew[0].y));
-        for (unsigned i = 0; i < n2; ++i) {
-            const float2 x = ynew[i];
-            const float2 w = make_float2(__fadd_rn(x.x, __fmul_rn(.97f, wp.x)), __fadd_rn(x.y, __fmul_rn(.97f, wp.y)));
-            ynew[i] = make_float2(__fadd_rn(w.x, -wp.x), __fadd_rn(w.y, -wp.y));
-            wp = w;
-        }
-    }
-    __syncthreads();
-
-    // ---- per-call copy of the decimated block for parity tests / GUI (optional) -----------------------------
-    if (a.rec_decimated) {
-        float2* rec = a.rec_decimated + (size_t)ch * a.rec_pitch;
-        for (unsigned k = tid; k < n2; k += kTailThreads) rec[k] = ynew[k];
-    }
-
-    // ---- FFT frame: the first min(4096 - have, n2) samples of this call ------------------------------------
-    {
-        const unsigned have = st.fft_have;
-        if (have < kFftN && n2) {
-            const unsigned take = hbd_min_u(kFftN - have, n2);
-            float2* fb = a.fftbuf + (size_t)ch * kFftN;
-            for (unsigned i = tid; i < take; i += kTailThreads) fb[have + i] = ynew[i];
-            if (tid == 0) {
-                st.fft_have = have + take;
-                if (have + take >= kFftN) st.fft_ready = 1;
-            }
-        }
-    }
-
-    // ---- batch gate ---------------------------------------------------------------------------------------
-    if (tid == 0) {
-        const unsigned total = dec_pending + n2;
-        unsigned nf = 0;
-        st.afc_tick = 0;
-        if (total >= kLpBatch) {
-            st.afc_tick = 1;
-            if (a.fs_dec > 4 * 40e3) {
-                st.dec_pending = 0; // Decoder.h:522-527: everything queued is dropped, nothing decoded
-            } else {
-                nf = total - total % kLpBatch;
-                st.dec_pending = total - nf;
+                for (int t = 0; t < T2; ++t) acc = cfma(w[t], s_h2[t], acc);
+                ynew[k] = acc;
             }
         } else {
-            st.dec_pending = total;
+            for (unsigned k = tid; k < nk; k += kTailThreads) ynew[k] = s1[kS1Hist + k0 + k];
         }
-        st.n_filtered = nf;
-        sh_total = total;
-        sh_nf = nf;
-        // slicer vent, SymbolExtractor.h:116-120: checked before the append, only when there is something to append
-        unsigned base = st.slicer_n;
-        if (nf) {
-            if (base > unsigned(kSlicerVent)) base = 0;
-            st.slicer_n = base + nf;
+        // stage-2 history for the next call: the last T2-1 stage-1 samples, taken from the last tile's window
+        if (M2 > 1 && k0 + nk == n2) {
+            const int win = int(nk) * M2 + lead;
+            for (int i = tid; i < T2 - 1; i += kTailThreads) {
+                const int w = win - (T2 - 1) + i;
+                s1[kS1Hist - (T2 - 1) + i] = s_x[M2 == 4 ? pad16(w) : w];
+            }
         }
-        sh_slicer_base = base;
-    }
-    __syncthreads();
-    const unsigned total = sh_total, nf = sh_nf;
-    if (!nf) return;
-
-    // ---- low-pass FIR + discriminator ---------------------------------------------------------------------
-    const int T = st.lp_ntaps;
-    const float* taps = a.lptaps + (size_t)ch * kLpMaxTaps;
-    float* pend = a.slicer + (size_t)ch * a.slicer_pitch + sh_slicer_base;
-    float* dlast = a.demod_last ? a.demod_last + (size_t)ch * a.demod_pitch : nullptr;
-    float2 carry_prev = make_float2(st.demod_last_re, st.demod_last_im);
-    const bool primed = st.demod_primed != 0;
-    // y[i] = sum_t q[i + t] h[t]; the tile is loaded from an even sample index so LDS.128 stays aligned
-    const long long qbase = (long long)kLpHist - (T - 1);
-    const int qskew = int(qbase & 1);          // tile sample 0 is q[-qskew]
-    const float2* q = dq + qbase - qskew;
-    const int n_pairs = (qskew + T + 2) / 2;
-    // taps stored shifted by qskew and zero padded: s_h[u] = h[u - qskew]
-    __syncthreads();
-    for (int u = tid; u < 2 * n_pairs; u += kTailThreads) s_h[u] = (u >= qskew && u - qskew < T) ? taps[u - qskew] : 0.f;
-
-    for (unsigned i0 = 0; i0 < nf; i0 += kTile) { // nf is a multiple of 256 == kTile
         __syncthreads();
-        for (int i = tid; i < kTile + T + 2; i += kTailThreads) s_x[i] = q[i0 + i];
-        __syncthreads();
-        const int o = 2 * tid; // outputs o, o+1; output o uses tile samples o + qskew + t
-        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-        float2 w0, w1;
-        {
-            const float4 p = *reinterpret_cast<const float4*>(&s_x[o]);
-            w0 = make_float2(p.x, p.y); w1 = make_float2(p.z, p.w);
+
+        // ---- DC removal: sequential recurrence re-seeded from the first sample of the call ----------------------
+        if (dc) {
+            if (tid == 0) {
+                float2 wp = k0 ? sh_dc_wp : make_float2(__fmul_rn(.97f, ynew[0].x), __fmul_rn(.97f, ynew[0].y));
+                for (unsigned i = 0; i < nk; ++i) {
+                    const float2 x = ynew[i];
+                    const float2 w = make_float2(__fadd_rn(x.x, __fmul_rn(.97f, wp.x)), __fadd_rn(x.y, __fmul_rn(.97f, wp.y)));
+                    ynew[i] = make_float2(__fadd_rn(w.x, -wp.x), __fadd_rn(w.y, -wp.y));
+                    wp = w;
+                }
+                sh_dc_wp = wp;
+            }
+            __syncthreads();
         }
+        // ---- per-call copy of the decimated block (parity tests) and FFT frame (first fft_take samples) ---------
+        if (a.rec_decimated) {
+            float2* rec = a.rec_decimated + (size_t)ch * a.rec_pitch;
+            for (unsigned k = tid; k < nk; k += kTailThreads) rec[k0 + k] = ynew[k];
+        }
+        if (k0 < fft_take) {
+            float2* fb = a.fftbuf + (size_t)ch * kFftN + fft_have0;
+            for (unsigned k = tid; k < nk && k0 + k < fft_take; k += kTailThreads) fb[k0 + k] = ynew[k];
+        }
+        have_q += nk;
+
+        // ---- low-pass FIR + discriminator on one batch of 256 --------------------------------------------------
+        if (produced < nf && have_q >= unsigned(kLpBatch)) {
+            const float2* q = s_q + (qpos - qskew);  // even index: LDS.128 stays aligned
+            const int o = 2 * tid; // outputs o, o+1; output o uses samples q[o + qskew + t]
+            float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+            float2 w0, w1;
+            {
+                const float4 p = *reinterpret_cast<const float4*>(&q[o]);
+                w0 = make_float2(p.x, p.y); w1 = make_float2(p.z, p.w);
+            }
 #pragma unroll 4
-        for (int pr = 0; pr < n_pairs; ++pr) {
-            const float4 p = *reinterpret_cast<const float4*>(&s_x[o + 2 * pr + 2]);
-            const float2 w2 = make_float2(p.x, p.y), w3 = make_float2(p.z, p.w);
-            const float2 hp = *reinterpret_cast<const float2*>(&s_h[2 * pr]); // taps for tile offsets 2pr, 2pr+1
-            const float ha = hp.x, hb = hp.y;
-            fma2(acc0, w0, ha); fma2(acc0, w1, hb);
-            fma2(acc1, w1, ha); fma2(acc1, w2, hb);
-            w0 = w2; w1 = w3;
+            for (int pr = 0; pr < n_pairs; ++pr) {
+                const float4 p = *reinterpret_cast<const float4*>(&q[o + 2 * pr + 2]);
+                const float2 w2 = make_float2(p.x, p.y), w3 = make_float2(p.z, p.w);
+                const float2 hp = *reinterpret_cast<const float2*>(&s_hl[2 * pr]); // taps for offsets 2pr, 2pr+1
+                acc0 = cfma(w0, hp.x, acc0); acc0 = cfma(w1, hp.y, acc0);
+                acc1 = cfma(w1, hp.x, acc1); acc1 = cfma(w2, hp.y, acc1);
+                w0 = w2; w1 = w3;
+            }
+            s_f[o + 1] = acc0;
+            s_f[o + 2] = acc1;
+            if (tid == 0) s_f[0] = (produced == 0) ? (primed ? carry_prev : acc0) : carry_prev;
+            cp_async_wait_all();       // the pending slicer samples have landed (smem mode)
+            __syncthreads();
+            const float2 prev = s_f[o];
+            const float2 p0 = cmul_conj_ieee(acc0, prev), p1 = cmul_conj_ieee(acc1, acc0);
+            const float d0 = atan2f(p0.y, p0.x), d1 = atan2f(p1.y, p1.x);
+            float* pend = (smem_mode ? s_v : v_g) + n_old;
+            pend[produced + o] = d0; pend[produced + o + 1] = d1;
+            if (dlast) { dlast[produced + o] = d0; dlast[produced + o + 1] = d1; }
+            if (a.rec_filtered) {
+                a.rec_filtered[(size_t)ch * a.rec_pitch + produced + o] = acc0;
+                a.rec_filtered[(size_t)ch * a.rec_pitch + produced + o + 1] = acc1;
+            }
+            carry_prev = s_f[kTile]; // last filtered sample of this batch (same value in every thread)
+            produced += kLpBatch;
+            have_q -= kLpBatch;
+            qpos += kLpBatch;
         }
-        s_f[o + 1] = acc0;
-        s_f[o + 2] = acc1;
-        if (tid == 0) s_f[0] = (i0 == 0) ? (primed ? carry_prev : acc0) : carry_prev;
-        __syncthreads();
-        const float2 prev = s_f[o];
-        const float2 p0 = cmul_conj_ieee(acc0, prev), p1 = cmul_conj_ieee(acc1, acc0);
-        const float d0 = atan2f(p0.y, p0.x), d1 = atan2f(p1.y, p1.x);
-        pend[i0 + o] = d0; pend[i0 + o + 1] = d1;   // (the queue base can be odd: no vector store)
-        if (dlast) { dlast[i0 + o] = d0; dlast[i0 + o + 1] = d1; }
-        if (a.rec_filtered) {
-            a.rec_filtered[(size_t)ch * a.rec_pitch + i0 + o] = acc0;
-            a.rec_filtered[(size_t)ch * a.rec_pitch + i0 + o + 1] = acc1;
+        // ---- more tiles follow: slide the queue back to the front of s_q ---------------------------------------
+        if (k0 + nk < n2 && qpos != qskew) {
+            const int n_move = hist + int(have_q);
+            for (int m0 = 0; m0 < n_move; m0 += kTailThreads) {
+                const int m = m0 + tid;
+                __syncthreads();
+                float2 t = make_float2(0.f, 0.f);
+                if (m < n_move) t = s_q[qpos + m];
+                __syncthreads();
+                if (m < n_move) s_q[qskew + m] = t;
+            }
+            qpos = qskew;
         }
-        carry_prev = s_f[kTile]; // last filtered sample of this tile (same value in every thread)
     }
     __syncthreads();
-    if (tid == 0) {
-        st.demod_last_re = carry_prev.x;
-        st.demod_last_im = carry_prev.y;
-        st.demod_primed = 1;
+
+    // ---- persist: low-pass history + unfiltered remainder (write only) ---------------------------------------
+    if (!(tick && nf == 0)) { // the >160 kS/s cut-off drops the queue and leaves the history alone
+        const int n_keep = hist + int(have_q);
+        for (int m = tid; m < n_keep; m += kTailThreads) dq[kLpHist - hist + m] = s_q[qpos + m];
     }
 
-    // ---- queue shuffle: new low-pass history + unfiltered remainder ----------------------------------------
-    {
-        const int hist = T - 1;
-        const unsigned rem = total - nf;
-        const int n_move = hist + int(rem);
-        // element m of the new front region [kLpHist-hist, kLpHist+rem) comes from old index m + nf
-        constexpr int kPer = (kLpHist + kLpBatch + kTailThreads - 1) / kTailThreads;
-        float2 tmp[kPer];
-#pragma unroll
-        for (int u = 0; u < kPer; ++u) {
-            const int m = tid + u * kTailThreads;
-            tmp[u] = (m < n_move) ? dq[kLpHist - hist + m + nf] : make_float2(0.f, 0.f);
-        }
+    // ---- slicer: position masks by all threads, then the sequential search + UART on warp 0 ----------------------
+    int spb = 0, R = 0;
+    const int n_sl = int(n_old + nf);
+    const bool slicing = nf && slicer_geometry(n_sl, a.fs_dec, s_st.baud, spb, R);
+    unsigned* s_maskA = reinterpret_cast<unsigned*>(s_x);           // the stage-2 window is dead by now
+    unsigned* s_maskN = s_maskA + ((a.sv_cap + 31) >> 5);
+    if (slicing && smem_mode) {
+        slicer_build_masks(s_v, n_sl, R, s_maskA, s_maskN, tid >> 5, kTailThreads / 32, lane);
         __syncthreads();
-#pragma unroll
-        for (int u = 0; u < kPer; ++u) {
-            const int m = tid + u * kTailThreads;
-            if (m < n_move) dq[kLpHist - hist + m] = tmp[u];
+    }
+    if (tid < 32) {
+        unsigned slicer_n = s_st.slicer_n;
+        unsigned long long win = s_st.uart_win;
+        int have = int(s_st.uart_n);
+        if (nf) {
+            const int n = n_sl;
+            const float* v = smem_mode ? s_v : v_g;
+            CharSink sink{s_chars, 0, a.log, a.log_head, a.call_seq, unsigned(ch)};
+            unsigned char* rec_bits = a.rec_bits ? a.rec_bits + (size_t)ch * a.rec_bits_pitch : nullptr;
+            unsigned rec_n = a.rec_bits ? a.rec_bits_n[ch] : 0;
+            int erase = 0;
+            if (slicing)
+                erase = slice_channel(v, n, spb, R, smem_mode ? s_maskA : nullptr, smem_mode ? s_maskN : nullptr, s_st.rtty_bits,
+                                      s_st.rtty_stops, win, have, sink, rec_bits, rec_n, a.rec_bits_pitch, lane);
+            sink_flush(sink, lane);
+            if (a.rec_bits && lane == 0) a.rec_bits_n[ch] = rec_n;
+            // erase consumed samples (SymbolExtractor.h:156-157) / write the queue back
+            const int keep = n - erase;
+            if (smem_mode) {
+                const int from = erase ? 0 : int(n_old);    // nothing erased: only the new samples are missing in HBM
+                for (int k = from + lane; k < keep; k += 32) v_g[k] = s_v[erase + k];
+            } else if (erase) {
+                for (int base = 0; base < keep; base += 32) {
+                    const int k = base + lane;
+                    float x = 0.f;
+                    if (k < keep) x = v_g[k + erase];
+                    __syncwarp();
+                    if (k < keep) v_g[k] = x;
+                    __syncwarp();
+                }
+            }
+            slicer_n = unsigned(keep);
+        }
+        if (lane == 0) {
+            gst.dec_pending = new_pending;
+            gst.afc_tick = tick ? 1u : 0u;
+            gst.n_filtered = nf;
+            if (fft_take) {
+                gst.fft_have = fft_have0 + fft_take;
+                if (fft_have0 + fft_take >= unsigned(kFftN)) gst.fft_ready = 1;
+            }
+            if (nf) {
+                gst.demod_last_re = carry_prev.x;
+                gst.demod_last_im = carry_prev.y;
+                gst.demod_primed = 1;
+                gst.slicer_n = slicer_n;
+                gst.uart_win = win;
+                gst.uart_n = unsigned(have);
+            }
         }
     }
 }
 
-cudaError_t launch_carry(const ChanPlan* plan, const float2* chunk, size_t chunk_pitch, float2* carry, int T1, int ch0, int n_channels,
-                         cudaStream_t stream, int* launches)
+// shared-memory layout of one launch (all sizes in elements of the respective arrays)
+static void tail_layout(TailArgs& a, size_t* bytes)
 {
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(carry_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); configured = true; }
-    carry_kernel<<<n_channels, 128, 0, stream>>>(plan, chunk, chunk_pitch, carry, T1, ch0);
-    if (launches) ++*launches;
-    return cudaGetLastError();
+    const int w2 = (a.M2 == 4) ? pad16(kTile * 4 + ((a.T2 - 1 + 3) & ~3) + 8) : (a.M2 > 1 ? kTile * a.M2 + a.T2 + 8 : 4);
+    a.xw = (w2 + 3) & ~3;
+    const int Tm = a.max_lp_taps > 0 ? a.max_lp_taps : 1;
+    a.qcap = (1 + (Tm - 1) + 2 * kLpBatch + 8 + 3) & ~3;
+    a.h2cap = (a.T2 + 8 + 3) & ~3;
+    a.hlcap = (Tm + 8 + 3) & ~3;
+    a.sv_cap = (a.sv_want + 3) & ~3;
+    const int mask_f2 = ((a.sv_cap + 31) >> 5) + 1;  // two bit masks over the staged slicer samples alias the window
+    if (a.xw < mask_f2) a.xw = (mask_f2 + 3) & ~3;
+    *bytes = size_t(a.xw + a.qcap + kTile + 2) * 8 + size_t(a.h2cap + a.hlcap + a.sv_cap) * 4 + kCharBuf;
 }
 
-cudaError_t launch_tail(const TailArgs& a, int n_channels, cudaStream_t stream, int* launches)
+cudaError_t launch_tail(TailArgs a, int n_channels, cudaStream_t stream, int* launches)
 {
-    const size_t smem = size_t(a.smem_window) * 8 + size_t(kLpMaxTaps + 7) * 4 + size_t(kTile + 1) * 8;
+    size_t smem = 0;
+    tail_layout(a, &smem);
     static size_t configured_smem = 0;
     if (configured_smem < smem) {
-        cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const size_t want = std::max<size_t>(smem, 64 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
         if (e != cudaSuccess) return e;
         cudaFuncSetAttribute(tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured_smem = smem;
+        configured_smem = want;
     }
     tail_kernel<<<n_channels, kTailThreads, smem, stream>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();
-}
-
-int tail_smem_window(int M2, int T2)
-{
-    const int w2 = (M2 > 1) ? pad16(kTile * M2 + T2 + 8) : 0;
-    const int wl = kTile + kLpMaxTaps + 8;
-    return ((w2 > wl ? w2 : wl) + 8 + 3) & ~3; // multiple of 4 float2: keeps the tap array 16-byte aligned
 }
 
 } // namespace hbd

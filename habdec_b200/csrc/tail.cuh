@@ -5,7 +5,9 @@
 namespace hbd {
 
 struct TailArgs {
-    const ChanPlan* plan;
+    const ChanPlan* plan;     // per-channel plans (read only when !uniform)
+    ChanPlan uplan;           // the plan of every channel when uniform (saves a dependent global load)
+    int uniform;
     ChanState* state;
     int ch0;                  // first channel of this launch (channel groups run on their own streams)
     // stage 2
@@ -18,19 +20,23 @@ struct TailArgs {
     float2* fftbuf;
     // low-pass taps [channel][kLpMaxTaps]
     const float* lptaps;
+    int max_lp_taps;          // largest lp_ntaps of any channel (sizes the shared-memory queue)
     // slicer pending samples [channel][slicer_pitch]
     float* slicer; size_t slicer_pitch;
+    int sv_want;              // slicer samples to stage in shared memory (channels with more run from HBM)
+    // decoded characters go to one device-wide append log (ring of kLogCap entries, monotonic head):
+    // entry = (channel, call_seq << 8 | char).  Kernels of successive calls run in stream order, so the log is
+    // sorted by call and, per channel, by time.
+    uint2* log; unsigned* log_head; unsigned call_seq;
     // last call's discriminator output for getDemodulated() [channel][demod_pitch] (may be null)
     float* demod_last; size_t demod_pitch;
     // optional per-call stage recordings for parity tests [channel][rec_pitch]
     float2* rec_decimated; float2* rec_filtered; size_t rec_pitch;
-    int smem_window; // float2 slots of the tile window (tail_smem_window)
+    unsigned char* rec_bits; unsigned* rec_bits_n; unsigned rec_bits_pitch;  // every emitted bit [channel][rec_bits_pitch]
+    // shared-memory layout, filled by launch_tail
+    int xw, qcap, h2cap, hlcap, sv_cap;
 };
 
-cudaError_t launch_tail(const TailArgs& a, int n_channels, cudaStream_t stream, int* launches);
-// stage-1 carry (history + unconsumed remainder) for the next call; must run after K1 of the same call
-cudaError_t launch_carry(const ChanPlan* plan, const float2* chunk, size_t chunk_pitch, float2* carry, int T1, int ch0, int n_channels,
-                         cudaStream_t stream, int* launches);
-int tail_smem_window(int M2, int T2);
+cudaError_t launch_tail(TailArgs a, int n_channels, cudaStream_t stream, int* launches);
 
 } // namespace hbd
