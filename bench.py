@@ -41,14 +41,20 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--channels", type=int, default=TOTAL_CHANNELS, help="total channels over all ranks")
+    ap.add_argument("--channels", type=int, default=None, help="total channels over all ranks (default: 4096 per GPU, weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 4096 channels per GPU (BASELINE configs[3] as the per-GPU shard); strong: 4096 channels in total")
     ap.add_argument("--chunk", type=int, default=65536, help="complex samples per channel per step")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-passes", type=int, default=8, help="reference arm: ring passes per host thread per step")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.channels is None:
+        world = int(os.environ.get("WORLD_SIZE", "1"))   # ranks actually launched (torchrun); --gpus is informational
+        a.channels = TOTAL_CHANNELS * (max(world, 1) if a.scaling == "weak" else 1)
+    return a
 
 
 def load_peaks():
@@ -106,8 +112,8 @@ class ClockSampler:
 
 
 def workload_config(args, world, impl):
-    return {"workload": "BASELINE configs[3]: %d RTTY channels total (%d per GPU), 2.048 MS/s cf32, 300 baud 8N2, 425 Hz shift, "
-                        "dec=8 (factor 256), lowpass 1500 Hz, chunk %d samples/channel/step" % (args.channels, args.channels // world, args.chunk),
+    return {"workload": "BASELINE configs[3]: %d RTTY channels per GPU (%d in total, %s scaling), 2.048 MS/s cf32, 300 baud 8N2, 425 Hz shift, "
+                        "dec=8 (factor 256), lowpass 1500 Hz, chunk %d samples/channel/step" % (args.channels // world, args.channels, args.scaling, args.chunk),
             "channels_total": args.channels, "channels_per_gpu": args.channels // world, "chunk": args.chunk,
             "snr_db_fullband": SNR_DB, "l2_policy": "inputs larger than L2: every step reads a different %.2f GiB slice of a ring resident in HBM"
             % (args.channels // world * args.chunk * 8 / 2**30), "parallelism": "channels block-partitioned, %d rank(s)" % world}
@@ -137,9 +143,9 @@ def run_reference(args):
     samples = float(cores) * L * P * args.steps
     value = samples / secs / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "MSamples/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, max(args.gpus, 1), "reference"),
+            "config": workload_config(args, max(int(os.environ.get("WORLD_SIZE", "1")), 1), "reference"),
             "cpu_baseline": {"value": value, "unit": "MSamples/s", "cores": cores, "kind": "reference" if kind == "ref" else "port",
                              "sample": "%d host threads x %d steps x %d ring passes of %d samples each (one Decoder per thread), wall %.1f s, %d chars decoded"
                              % (cores, args.steps, P, L, wall, chars)},
@@ -272,7 +278,7 @@ def run_ours(args):
     exp_sent = args.steps * args.chunk // L
     got_sent = [len(v["sentences"]) for v in gathered.values()] if gathered else []
     line = {"metric": METRIC, "value": value, "unit": "MSamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, world, "ours"),
             "roofline": {"bound": "hbm", "kernel": "decim1_kernel<64,348> (K1, stage-1 FIR decimator)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,

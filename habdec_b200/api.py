@@ -52,6 +52,11 @@ SIGNATURES = {
     "hbd_push_samples": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_size_t, C.c_double]),
     "hbd_push_samples_batch": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t, C.c_double]),
     "hbd_push_samples_device": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t, C.c_double]),
+    "hbd_set_nco": (C.c_int, [_H, C.c_int, C.c_double]),
+    "hbd_get_nco": (C.c_double, [_H, C.c_int]),
+    "hbd_afc_retune": (C.c_int, [_H, C.c_double, C.c_void_p]),
+    "hbd_push_wideband": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_double]),
+    "hbd_push_wideband_device": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_double]),
     "hbd_process": (C.c_int, [_H]),
     "hbd_process_async": (C.c_int, [_H]),
     "hbd_collect": (C.c_int, [_H]),
@@ -200,6 +205,26 @@ class BatchDecoder:
 
     def pushSamplesDevice(self, ptr: int, n: int, pitch: int, fs: float):
         self._chk(self._lib.hbd_push_samples_device(self._h, ptr, n, pitch, float(fs)))
+
+    # ---- NCO pre-mixer / wideband channeliser (include/habdec_b200.h)
+    def set_nco(self, freq_hz: float, ch=-1): self._chk(self._lib.hbd_set_nco(self._h, ch, float(freq_hz)))
+    def get_nco(self, ch=0) -> float: return self._lib.hbd_get_nco(self._h, ch)
+
+    def afc_retune(self, min_abs_hz: float = 100.0) -> np.ndarray:
+        """Close the AFC loop for all channels on the GPU; returns the applied corrections [n_channels] (0 = none)."""
+        out = np.zeros(self.n_channels, dtype=np.float64)
+        rc = self._lib.hbd_afc_retune(self._h, float(min_abs_hz), out.ctypes.data)
+        if rc < 0:
+            self._chk(rc)
+        return out
+
+    def pushWideband(self, iq: np.ndarray, fs: float):
+        """iq: complex64 [n], pushed to every channel through its NCO"""
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        self._chk(self._lib.hbd_push_wideband(self._h, iq.ctypes.data, iq.size, float(fs)))
+
+    def pushWidebandDevice(self, ptr: int, n: int, fs: float):
+        self._chk(self._lib.hbd_push_wideband_device(self._h, ptr, n, float(fs)))
 
     # ---- run
     def process(self): self._chk(self._lib.hbd_process(self._h))

@@ -18,6 +18,7 @@
 #include "fft_afc.cuh"
 #include "hbd_common.cuh"
 #include "host_tail.h"
+#include "nco.cuh"
 #include "tail.cuh"
 
 using namespace hbd;
@@ -58,6 +59,7 @@ struct HostChan {
     size_t lp_input_size = 0, lp_ntaps = 0;
     unsigned pushed = 0;     // samples waiting in the staging row
     unsigned last_nf = 0, last_n2 = 0;
+    double nco_freq = 0, nco_phase = 0; // pre-mixer: frequency in Hz, phase (cycles) of the next pushed sample
     bool cfg_dirty = true;
     bool lp_dirty = true;    // bw / trans / input size changed since the last design attempt
 };
@@ -147,6 +149,11 @@ struct hbd_decoder {
     const float2* ext = nullptr; size_t ext_pitch = 0; size_t ext_n = 0; // zero-copy device push
     float* h_pinned = nullptr; size_t pinned_bytes = 0;  // staging for pageable host memory
 
+    // NCO pre-mixer (nco.cu)
+    NcoChan* d_nco = nullptr; std::vector<NcoChan> h_nco;
+    float2* d_wide = nullptr; size_t wide_cap = 0;       // wideband capture row shared by all channels
+    bool nco_active() const { for (const auto& x : hc) if (x.nco_freq != 0 || x.nco_phase != 0) return true; return false; }
+    int mix_into_stage(const float2* src, size_t src_pitch, int c0, int nc, size_t dst_off, size_t n);
     int pending_marks = 0;   // async calls since the last collect
     int sv_override = -1;
     // optional per-kernel CUDA-event timing (bench roofline): one event pair per K1 launch / per rest-of-step
@@ -243,6 +250,8 @@ int hbd_decoder::alloc_fixed()
     HBD_CUDA_CHECK(dalloc(&d_cfg_dc, n));
     HBD_CUDA_CHECK(dalloc(&d_cfg_ntaps, n));
     HBD_CUDA_CHECK(dalloc(&d_cfg_dirty, n));
+    HBD_CUDA_CHECK(dalloc(&d_nco, n));
+    h_nco.resize(n);
     std::vector<float2> tw(kFftN);
     for (int e = 0; e < kFftN; ++e) {
         const double ang = -2.0 * M_PI * double(e) / double(kFftN);
@@ -280,7 +289,7 @@ void hbd_decoder::free_all()
     if (ev_in) cudaEventDestroy(ev_in);
     void* ptrs[] = {d_state, d_plan, d_carry2[0], d_carry2[1], d_s1, d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_log, d_log_head,
                     d_taps1, d_taps2, d_twiddle, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps,
-                    d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage};
+                    d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage, d_nco, d_wide};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_pinned) cudaFreeHost(h_pinned);
     for (cudaEvent_t e : ev_call) cudaEventDestroy(e);
@@ -759,6 +768,29 @@ static int ensure_stage(hbd_decoder* h, size_t need)
     return HBD_OK;
 }
 
+// Mix `n` samples per channel of channels [c0, c0+nc) from src into the staging rows at dst_off and advance the
+// channels' NCO phases.  src_pitch 0: one shared (wideband) row.  Runs on the handle's stream.
+int hbd_decoder::mix_into_stage(const float2* src, size_t src_pitch, int c0, int nc, size_t dst_off, size_t n)
+{
+    if (!n) return HBD_OK;
+    for (int c = c0; c < c0 + nc; ++c) {
+        HostChan& x = hc[size_t(c)];
+        NcoChan& k = h_nco[size_t(c)];
+        k.inc = x.nco_freq / fs_in;
+        k.ph0 = x.nco_phase;
+        const double a = -2.0 * M_PI * k.inc * double(kNcoThreads);
+        k.step_re = std::cos(a); k.step_im = std::sin(a);
+        double ph = x.nco_phase + double(n) * k.inc;
+        x.nco_phase = ph - std::floor(ph);
+    }
+    HBD_CUDA_CHECK(cudaMemcpyAsync(d_nco + c0, h_nco.data() + c0, sizeof(NcoChan) * size_t(nc), cudaMemcpyHostToDevice, stream));
+    int nl = 0;
+    HBD_CUDA_CHECK(launch_nco_mix(src, src_pitch, d_stage, stage_pitch, dst_off, n, d_nco, c0, nc, stream, &nl));
+    launches += unsigned(nl);
+    HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // h_nco is rewritten by the next push
+    return HBD_OK;
+}
+
 int hbd_push_samples(hbd_decoder* h, int ch, const float* iq, size_t n, double fs)
 {
     HBD_CHECK_CH(h, ch);
@@ -774,8 +806,14 @@ int hbd_push_samples(hbd_decoder* h, int ch, const float* iq, size_t n, double f
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream); // the caller owns `iq` again on return (Decoder.h:209-213 copies)
         if (e != cudaSuccess) { h->set_error(cudaGetErrorString(e)); return HBD_ERR_CUDA; }
     }
+    latch_rate(h, fs);
+    if (x.nco_freq != 0 || x.nco_phase != 0) {
+        const float2* row = h->d_stage + size_t(ch) * h->stage_pitch + x.pushed;
+        const int rc2 = h->mix_into_stage(row - size_t(ch) * h->stage_pitch, h->stage_pitch, ch, 1, x.pushed, n); // in place
+        if (rc2) return rc2;
+    }
     x.pushed += unsigned(n);
-    return latch_rate(h, fs);
+    return HBD_OK;
 }
 
 int hbd_push_samples_batch(hbd_decoder* h, const float* iq, size_t n, size_t pitch, double fs)
@@ -795,9 +833,56 @@ int hbd_push_samples_batch(hbd_decoder* h, const float* iq, size_t n, size_t pit
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) { h->set_error(cudaGetErrorString(e)); return HBD_ERR_CUDA; }
     }
+    latch_rate(h, fs);
+    if (h->nco_active()) {
+        const int rc2 = h->mix_into_stage(h->d_stage + base, h->stage_pitch, 0, h->n_ch, base, n); // in place
+        if (rc2) return rc2;
+    }
     for (auto& x : h->hc) x.pushed += unsigned(n);
-    return latch_rate(h, fs);
+    return HBD_OK;
 }
+
+// One capture shared by every channel (frequency-offset channels of a wideband capture): each channel receives
+// iq * exp(-2 pi i f_nco t).  `device` != 0: iq is a device pointer.
+static int push_wideband(hbd_decoder* h, const float* iq, size_t n, double fs, bool device)
+{
+    HBD_CHECK_H(h);
+    if (!iq && n) return HBD_ERR_ARG;
+    std::lock_guard<std::mutex> l(h->mtx);
+    if (h->ext) { h->set_error("device push pending"); return HBD_ERR_STATE; }
+    if (cudaSetDevice(h->device) != cudaSuccess) return HBD_ERR_CUDA;
+    const unsigned base = h->hc[0].pushed;
+    for (auto& x : h->hc) if (x.pushed != base) { h->set_error("wideband push needs equal queue depth in all channels"); return HBD_ERR_STATE; }
+    const int rc = ensure_stage(h, size_t(base) + n);
+    if (rc) return rc;
+    latch_rate(h, fs);
+    const float2* src = reinterpret_cast<const float2*>(iq);
+    if (!device) {
+        if (n > h->wide_cap) {
+            if (h->d_wide) { cudaStreamSynchronize(h->stream); cudaFree(h->d_wide); h->d_wide = nullptr; }
+            if (cudaMalloc((void**)&h->d_wide, n * sizeof(float2)) != cudaSuccess) { h->set_error("wideband buffer alloc"); return HBD_ERR_NOMEM; }
+            h->wide_cap = n;
+        }
+        cudaError_t e = cudaMemcpyAsync(h->d_wide, iq, n * sizeof(float2), cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) { h->set_error(cudaGetErrorString(e)); return HBD_ERR_CUDA; }
+        src = h->d_wide;
+    }
+    const int rc2 = h->mix_into_stage(src, 0, 0, h->n_ch, base, n);
+    if (rc2) return rc2;
+    for (auto& x : h->hc) x.pushed += unsigned(n);
+    return HBD_OK;
+}
+int hbd_push_wideband(hbd_decoder* h, const float* iq, size_t n, double fs) { return push_wideband(h, iq, n, fs, false); }
+int hbd_push_wideband_device(hbd_decoder* h, const float* d_iq, size_t n, double fs) { return push_wideband(h, d_iq, n, fs, true); }
+
+int hbd_set_nco(hbd_decoder* h, int ch, double freq_hz)
+{
+    if (!h || ch < -1 || ch >= h->n_ch) return HBD_ERR_ARG;
+    std::lock_guard<std::mutex> l(h->mtx);
+    for (int c = (ch < 0 ? 0 : ch); c < (ch < 0 ? h->n_ch : ch + 1); ++c) h->hc[size_t(c)].nco_freq = freq_hz;
+    return HBD_OK;
+}
+double hbd_get_nco(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].nco_freq; }
 
 int hbd_push_samples_device(hbd_decoder* h, const float* d_iq, size_t n, size_t pitch, double fs)
 {
@@ -805,9 +890,21 @@ int hbd_push_samples_device(hbd_decoder* h, const float* d_iq, size_t n, size_t 
     if (!d_iq || pitch < n || (pitch & 1) || (reinterpret_cast<uintptr_t>(d_iq) & 15)) return HBD_ERR_ARG;
     std::lock_guard<std::mutex> l(h->mtx);
     if (h->ext) { h->set_error("device push pending"); return HBD_ERR_STATE; }
+    latch_rate(h, fs);
+    if (h->nco_active()) { // zero copy is not possible: the mixed samples go through the staging matrix
+        if (cudaSetDevice(h->device) != cudaSuccess) return HBD_ERR_CUDA;
+        const unsigned base = h->hc[0].pushed;
+        for (auto& x : h->hc) if (x.pushed != base) { h->set_error("batch push needs equal queue depth in all channels"); return HBD_ERR_STATE; }
+        const int rc = ensure_stage(h, size_t(base) + n);
+        if (rc) return rc;
+        const int rc2 = h->mix_into_stage(reinterpret_cast<const float2*>(d_iq), pitch, 0, h->n_ch, base, n);
+        if (rc2) return rc2;
+        for (auto& x : h->hc) x.pushed += unsigned(n);
+        return HBD_OK;
+    }
     for (auto& x : h->hc) if (x.pushed) { h->set_error("host push pending"); return HBD_ERR_STATE; }
     h->ext = reinterpret_cast<const float2*>(d_iq); h->ext_pitch = pitch; h->ext_n = n;
-    return latch_rate(h, fs);
+    return HBD_OK;
 }
 
 int hbd_process_async(hbd_decoder* h) { HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); return h->process_async_locked(); }
@@ -993,6 +1090,30 @@ int hbd_reset_frequency_correction(hbd_decoder* h, int ch, double corr)
     cudaStreamSynchronize(h->stream);
     ++h->launches;
     return HBD_OK;
+}
+// AFC loop closed on the GPU for all channels (see afc_retune_kernel); returns the number of channels retuned
+int hbd_afc_retune(hbd_decoder* h, double min_abs_hz, double* applied_out)
+{
+    HBD_CHECK_H(h);
+    std::lock_guard<std::mutex> l(h->mtx);
+    cudaSetDevice(h->device);
+    if (h->sync_groups()) return HBD_ERR_CUDA;
+    const size_t n = size_t(h->n_ch);
+    double* d_applied = nullptr;
+    if (cudaMalloc((void**)&d_applied, n * sizeof(double)) != cudaSuccess) return HBD_ERR_NOMEM;
+    std::vector<double> applied(n, 0.0);
+    cudaError_t e = launch_afc_retune(h->d_state, h->n_ch, min_abs_hz, h->fs_in / h->factor, d_applied, h->stream);
+    ++h->launches;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(applied.data(), d_applied, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_applied);
+    if (e != cudaSuccess) { h->set_error(cudaGetErrorString(e)); return HBD_ERR_CUDA; }
+    int count = 0;
+    for (size_t c = 0; c < n; ++c) {
+        if (applied[c] != 0.0) { h->hc[c].nco_freq += applied[c]; ++count; }
+        if (applied_out) applied_out[c] = applied[c];
+    }
+    return count;
 }
 // all channels in one device->host copy: out[ch*6 + {0..5}] = correction, shift, noise floor, noise variance, peak l, peak r
 size_t hbd_get_stats_batch(hbd_decoder* h, double* out, size_t cap_doubles)

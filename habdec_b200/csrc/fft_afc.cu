@@ -325,4 +325,29 @@ cudaError_t launch_afc_reset(ChanState* state, int ch, double corr, double fs_de
     return cudaGetLastError();
 }
 
+// The retune decision of DECODER_THREAD (code/websocketServer/main.cpp:248-265) for every channel at once: where
+// |frequency_correction| exceeds min_abs_hz the correction is handed to the caller (who adds it to the channel's
+// NCO) and the AFC is reset exactly like resetFrequencyCorrection(); applied[ch] = 0 elsewhere.
+__global__ void afc_retune_kernel(ChanState* state, int n_ch, double min_abs_hz, double fs_dec, double* applied)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_ch) return;
+    ChanState& st = state[ch];
+    const double corr = st.afc_correction;
+    if (!(min_abs_hz < fabs(corr))) { applied[ch] = 0.0; return; }
+    applied[ch] = corr;
+    const double bins_per_hz = st.have_spectrum ? __ddiv_rn(double(kFftN), fs_dec) : __ddiv_rn(0.0, 0.0);
+    const double l = __dsub_rn(avg_get_i(st.pl_sum, st.pl_cnt), __dmul_rn(corr, bins_per_hz));
+    const double r = __dsub_rn(avg_get_i(st.pr_sum, st.pr_cnt), __dmul_rn(corr, bins_per_hz));
+    st.pl_sum = int(fmax(0.0, l)); st.pl_cnt = 1;
+    st.pr_sum = int(fmax(0.0, r)); st.pr_cnt = 1;
+    st.afc_correction = 0;
+}
+
+cudaError_t launch_afc_retune(ChanState* state, int n_ch, double min_abs_hz, double fs_dec, double* applied, cudaStream_t stream)
+{
+    afc_retune_kernel<<<(n_ch + 127) / 128, 128, 0, stream>>>(state, n_ch, min_abs_hz, fs_dec, applied);
+    return cudaGetLastError();
+}
+
 } // namespace hbd

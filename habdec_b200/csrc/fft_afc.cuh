@@ -16,5 +16,6 @@ struct FftArgs {
 
 cudaError_t launch_fft_afc(const FftArgs& a, int n_channels, cudaStream_t stream, int* launches);
 cudaError_t launch_afc_reset(ChanState* state, int ch, double corr, double fs_dec, cudaStream_t stream);
+cudaError_t launch_afc_retune(ChanState* state, int n_ch, double min_abs_hz, double fs_dec, double* applied, cudaStream_t stream);
 
 } // namespace hbd

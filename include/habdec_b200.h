@@ -84,6 +84,22 @@ int hbd_push_samples_batch(hbd_decoder* h, const float* iq, size_t n_complex, si
  * unchanged until the next hbd_process()/hbd_process_async() has completed (hbd_synchronize) */
 int hbd_push_samples_device(hbd_decoder* h, const float* d_iq, size_t n_complex, size_t pitch_complex, double sampling_rate);
 
+/* ---- NCO pre-mixer (new; the reference retunes the SDR instead: websocketServer/main.cpp:247-265) -----------
+ * Channel `ch` (-1: all) is mixed down by freq_hz before the decimator: x[i] * exp(-2 pi i f t), phase kept in
+ * float64 and continuous across pushes and frequency changes.  With it, one wideband capture can feed many
+ * frequency-offset channels (hbd_push_wideband*), and the AFC loop closes without touching the radio:
+ *   corr = hbd_get_frequency_correction(h, ch); hbd_set_nco(h, ch, hbd_get_nco(h, ch) + corr);
+ *   hbd_reset_frequency_correction(h, ch, corr);      -- same sequence as main.cpp:248-265 */
+int    hbd_set_nco(hbd_decoder* h, int ch, double freq_hz);
+double hbd_get_nco(hbd_decoder* h, int ch);
+/* the whole loop for every channel in one call: where |frequency correction| > min_abs_hz (the reference uses
+ * 100 Hz) the NCO is moved by the correction and the AFC is reset; applied[n_channels] (may be NULL) receives the
+ * corrections, the return value is the number of channels retuned (< 0: error) */
+int    hbd_afc_retune(hbd_decoder* h, double min_abs_hz, double* applied);
+/* one capture (host / device cf32 row of n_complex samples) pushed to EVERY channel through its NCO */
+int hbd_push_wideband(hbd_decoder* h, const float* iq, size_t n_complex, double sampling_rate);
+int hbd_push_wideband_device(hbd_decoder* h, const float* d_iq, size_t n_complex, double sampling_rate);
+
 /* ---- run (Decoder::process / operator(), Decoder.h:118-126,416-638) ------------------------------------- */
 int hbd_process(hbd_decoder* h);        /* kernels + result drain + sentence layer + callbacks */
 int hbd_process_async(hbd_decoder* h);  /* kernels only, returns immediately */

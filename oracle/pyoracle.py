@@ -146,6 +146,27 @@ class PortDecoder(_Decoder):
     kind = "orc"
 
 
+def premix(iq: np.ndarray, fs: float, f_hz: float, phase0: float = 0.0):
+    """The oracle of the NCO pre-mixer ("CPU pre-mix, then the reference Decoder").
+
+    y[i] = x[i] * exp(-2 pi i * frac(phase0 + i * f_hz / fs)): phase in float64, phasor rounded to cf32, product
+    formed like std::complex<float>::operator* (four float products, one float add/sub each, no FMA).
+    Returns (y complex64, phase of the sample after the last one)."""
+    iq = np.ascontiguousarray(iq, dtype=np.complex64)
+    inc = float(f_hz) / float(fs)
+    i = np.arange(iq.size, dtype=np.float64)
+    ph = phase0 + i * inc
+    ph -= np.floor(ph)
+    pr = np.cos(2.0 * np.pi * ph).astype(np.float32)
+    pi = (-np.sin(2.0 * np.pi * ph)).astype(np.float32)
+    xr, xi = iq.real.copy(), iq.imag.copy()
+    y = np.empty(iq.size, dtype=np.complex64)
+    y.real = (xr * pr).astype(np.float32) - (xi * pi).astype(np.float32)
+    y.imag = (xr * pi).astype(np.float32) + (xi * pr).astype(np.float32)
+    end = phase0 + iq.size * inc
+    return y, end - np.floor(end)
+
+
 def bench(kind: str, cfg: Config, iq: np.ndarray, n_threads: int, fs: float, chunk: int = 65536,
           reps: int = 1, stride: int = 0):
     """Returns (seconds, total_chars). iq: complex64[n] (stride 0: shared) or [n_threads, n]."""

@@ -1,0 +1,218 @@
+"""GPU parity of the NCO pre-mixer, the wideband channeliser front-end (BASELINE configs[4]) and the closed AFC
+loop (BASELINE configs[1]).  Oracle = CPU pre-mix (oracle/pyoracle.premix: float64 phase, cf32 product) followed by
+the reference Decoder, with the retune decisions of code/websocketServer/main.cpp:247-265 applied on both sides.
+"""
+import numpy as np
+import pytest
+
+from habdec_b200 import api, synth
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+REL_L2 = 1e-5
+CHUNK = 65536
+
+
+def rel_l2(a, b):
+    a = np.asarray(a).astype(np.complex128 if np.iscomplexobj(a) else np.float64)
+    b = np.asarray(b).astype(a.dtype)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def make_oracle(kind, **cfg):
+    return (po.RefDecoder if kind == "ref" else po.PortDecoder)(po.make_config(**cfg))
+
+
+def short_sentence(c, k=0):
+    # > 20 characters: the reference only scans for sentences beyond that (Decoder.h:591)
+    body = "WIDE%02d,%d,12:00:%02d,%d" % (c, k, c, 700 * c + k)
+    return "$$" + body + "*" + synth.crc16_ccitt(body.encode()) + "\n"
+
+
+def test_offset_channel_per_channel_push(oracle_kind):
+    """One channel 37 kHz off centre: NCO on the GPU vs premix + reference; stage floats and characters."""
+    fs, baud, f_c = 2.048e6, 300.0, 37000.0
+    iq, _ = synth.channel_iq(4, 1, fs, baud, f_off=f_c, snr_db=-14.0)
+    cfg = dict(baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
+    ref = make_oracle(oracle_kind, **cfg)
+    dec = api.BatchDecoder(1, record=True, **cfg)
+    dec.set_nco(f_c, 0)
+    assert dec.get_nco(0) == f_c
+    ph = 0.0
+    got = {"dec": [], "demod": []}
+    for o in range(0, len(iq), CHUNK):
+        mixed, ph = po.premix(iq[o:o + CHUNK], fs, f_c, ph)
+        ref.push_process(mixed, fs)
+        dec.pushSamples(0, iq[o:o + CHUNK], fs)
+        dec.process()
+        got["dec"].append(dec.debug_stage(0, api.STAGE_DECIMATED).copy())
+        got["demod"].append(dec.debug_stage(0, api.STAGE_DEMOD).copy())
+    assert rel_l2(np.concatenate(got["dec"]), ref.stage(po.STAGE_DECIMATED)) <= REL_L2
+    assert rel_l2(np.concatenate(got["demod"]), ref.stage(po.STAGE_DEMOD)) <= REL_L2
+    assert dec.poll_chars(0) == ref.chars()
+    assert dec.poll_sentences(0) == ref.sentences() and len(ref.sentences()) == 1
+
+
+def _wideband(fs, offsets, bauds, n_sent, snr_db, seed=7):
+    texts = ["".join(short_sentence(c, k) for k in range(n_sent)) for c in range(len(offsets))]
+    bit_streams = [synth.uart_bits(t.encode(), 8, 2, 30, 40) for t in texts]
+    n = max(int(len(b) * fs / bd) for b, bd in zip(bit_streams, bauds))
+    wide = np.zeros(n, dtype=np.complex64)
+    for c, (b, bd, f) in enumerate(zip(bit_streams, bauds, offsets)):
+        wide += synth.fsk_iq(b, fs, bd, 425.0, f, None, n_samples=n, phase0=0.3 * c)
+    rng = np.random.default_rng(seed)
+    sigma = 10.0 ** (-snr_db / 20.0) / np.sqrt(2.0)
+    wide.real += (sigma * rng.standard_normal(n)).astype(np.float32)
+    wide.imag += (sigma * rng.standard_normal(n)).astype(np.float32)
+    return wide, texts
+
+
+@pytest.mark.parametrize("fs,offsets,bauds", [
+    (2.5e6, [-900e3, -310e3, -40e3, 55e3, 420e3, 1.1e6], [600.0, 300.0, 600.0, 300.0, 600.0, 600.0]),
+    (20e6, [-7.3e6, -1.25e6, 0.6e6, 8.8e6], [600.0, 600.0, 600.0, 600.0]),   # cfg 5: 20 MS/s capture, 600 baud bursts, dec=8
+])
+def test_wideband_channeliser(oracle_kind, fs, offsets, bauds):
+    """One capture, many frequency-offset channels: hbd_push_wideband + per-channel NCO vs premix + reference."""
+    wide, texts = _wideband(fs, offsets, bauds, 1, snr_db=-8.0)
+    n = len(wide) // CHUNK * CHUNK
+    n_ch = len(offsets)
+    dec = api.BatchDecoder(n_ch, dec_factor=256)
+    for c in range(n_ch):
+        dec.baud(bauds[c], c)
+        dec.set_nco(offsets[c], c)
+    for o in range(0, n, CHUNK):
+        dec.pushWideband(wide[o:o + CHUNK], fs)
+        dec.process()
+    decoded = 0
+    for c in range(n_ch):
+        ref = make_oracle(oracle_kind, baud=bauds[c], rtty_bits=8, rtty_stops=2.0, dec_factor=256)
+        ph = 0.0
+        for o in range(0, n, CHUNK):
+            mixed, ph = po.premix(wide[o:o + CHUNK], fs, offsets[c], ph)
+            ref.push_process(mixed, fs)
+        assert dec.poll_chars(c) == ref.chars(), "channel %d" % c
+        assert dec.poll_sentences(c) == ref.sentences(), "channel %d" % c
+        decoded += len(ref.sentences())
+    assert decoded == n_ch      # every channel's sentence came through the channeliser
+
+
+def test_device_push_with_nco_matches_host_push():
+    """hbd_push_samples_device with an active NCO goes through the staging matrix and equals the host path."""
+    import torch
+    fs, baud = 2.048e6, 300.0
+    n_ch = 3
+    offs = [0.0, 12500.0, -48000.0]
+    iqs = [synth.channel_iq(c, 1, fs, baud, f_off=offs[c], snr_db=-12.0)[0] for c in range(n_ch)]
+    n = min(len(x) for x in iqs) // CHUNK * CHUNK
+    iq = np.stack([x[:n] for x in iqs])
+    a = api.BatchDecoder(n_ch, baud=baud)
+    b = api.BatchDecoder(n_ch, baud=baud)
+    for c in range(n_ch):
+        a.set_nco(offs[c], c); b.set_nco(offs[c], c)
+    dev = torch.from_numpy(iq.view(np.float32).reshape(n_ch, n, 2)).cuda()
+    torch.cuda.synchronize()
+    for o in range(0, n, CHUNK):
+        a.pushSamplesBatch(np.ascontiguousarray(iq[:, o:o + CHUNK]), fs); a.process()
+        b.pushSamplesDevice(dev.data_ptr() + o * 8, CHUNK, n, fs); b.process()
+    for c in range(n_ch):
+        ca = a.poll_chars(c)
+        assert ca == b.poll_chars(c) and len(ca) > 30
+        assert len(a.poll_sentences(c)) == 1
+
+
+def _retune_loop(push_process, get_corr, retune, fs, n_total, period_s):
+    """DECODER_THREAD's AFC policy (main.cpp:247-265) on stream time: once `period_s` has passed since the last
+    retune, every call checks the correction and retunes when it exceeds 100 Hz."""
+    last = 0.0
+    log = []
+    for o in range(0, n_total, CHUNK):
+        push_process(o)
+        t = (o + CHUNK) / fs
+        if t - last > period_s:
+            corr = get_corr()
+            if 100 < abs(corr):
+                retune(corr)
+                log.append((o, corr))
+                last = t
+    return log
+
+
+def test_afc_closed_loop_drifting_carrier(oracle_kind):
+    """cfg 2: 2.5 MS/s, 50 baud 7N2, carrier 1.5 kHz off and drifting; the AFC measures, the NCO follows.
+    Without the loop nothing decodes (tones must straddle DC)."""
+    fs, baud = 2.5e6, 50.0
+    sentence = short_sentence(2, 5)
+    text = "U" * 15 + "\n" + sentence          # a preamble with both tones on air lets the two-peak AFC lock
+    bits = synth.uart_bits(text.encode(), 7, 2, lead_in=40, lead_out=40)
+    n = int(len(bits) * fs / baud) // CHUNK * CHUNK
+    t = np.arange(n, dtype=np.float64) / fs
+    f_off = 1500.0 + 15.0 * t                      # Hz, drifting upwards
+    iq = synth.fsk_iq(bits, fs, baud, 425.0, f_off, snr_db=-16.0, seed=5, n_samples=n)
+    cfg = dict(baud=baud, rtty_bits=7, rtty_stops=2.0, dec_factor=256)
+    period = 1.5                                   # seconds of stream time (the reference waits 5 s of wall clock)
+
+    ref = make_oracle(oracle_kind, **cfg)
+    st = {"f": 0.0, "ph": 0.0}
+
+    def ref_push(o):
+        mixed, st["ph"] = po.premix(iq[o:o + CHUNK], fs, st["f"], st["ph"])
+        ref.push_process(mixed, fs)
+
+    def ref_retune(corr):
+        st["f"] += corr
+        ref.reset_frequency_correction(corr)
+
+    log_ref = _retune_loop(ref_push, lambda: ref.afc().frequency_correction, ref_retune, fs, n, period)
+
+    dec = api.BatchDecoder(1, **cfg)
+
+    def gpu_push(o):
+        dec.pushSamples(0, iq[o:o + CHUNK], fs)
+        dec.process()
+
+    def gpu_retune(corr):
+        dec.set_nco(dec.get_nco(0) + corr, 0)
+        dec.resetFrequencyCorrection(corr, 0)
+
+    log_gpu = _retune_loop(gpu_push, lambda: dec.getFrequencyCorrection(0), gpu_retune, fs, n, period)
+
+    assert len(log_ref) >= 2 and abs(log_ref[0][1] - 1520.0) < 100.0        # the AFC found the offset, then followed the drift
+    assert [o for o, _ in log_gpu] == [o for o, _ in log_ref]               # same retune instants
+    assert np.allclose([c for _, c in log_gpu], [c for _, c in log_ref], atol=1e-6)
+    assert dec.poll_chars(0) == ref.chars()
+    assert dec.poll_sentences(0) == ref.sentences()
+    assert ref.sentences() == [sentence.strip()[2:].encode()]               # the loop made the channel decodable
+
+
+def test_afc_retune_all_channels_on_gpu():
+    """hbd_afc_retune == per-channel get / set_nco / reset sequence."""
+    fs, baud = 2.048e6, 300.0
+    offs = [0.0, 700.0, -900.0, 30.0]
+    n_ch = len(offs)
+    iqs = [synth.channel_iq(c, 3, fs, baud, f_off=offs[c], snr_db=-12.0)[0] for c in range(n_ch)]
+    n = min(len(x) for x in iqs) // CHUNK * CHUNK
+    iq = np.stack([x[:n] for x in iqs])
+    a = api.BatchDecoder(n_ch, baud=baud)
+    b = api.BatchDecoder(n_ch, baud=baud)
+    half = (n // CHUNK // 2) * CHUNK
+    for o in range(0, half, CHUNK):
+        blk = np.ascontiguousarray(iq[:, o:o + CHUNK])
+        a.pushSamplesBatch(blk, fs); a.process()
+        b.pushSamplesBatch(blk, fs); b.process()
+    corr = [a.getFrequencyCorrection(c) for c in range(n_ch)]
+    for c in range(n_ch):
+        if 100 < abs(corr[c]):
+            a.set_nco(a.get_nco(c) + corr[c], c)
+            a.resetFrequencyCorrection(corr[c], c)
+    applied = b.afc_retune(100.0)
+    assert np.allclose(applied, [x if 100 < abs(x) else 0.0 for x in corr], atol=1e-9)
+    assert abs(applied[1] - 700.0) < 100.0 and abs(applied[2] + 900.0) < 100.0 and applied[0] == 0.0 and applied[3] == 0.0
+    for o in range(half, n, CHUNK):
+        blk = np.ascontiguousarray(iq[:, o:o + CHUNK])
+        a.pushSamplesBatch(blk, fs); a.process()
+        b.pushSamplesBatch(blk, fs); b.process()
+    for c in range(n_ch):
+        assert a.poll_chars(c) == b.poll_chars(c)
+        assert a.getPeaks(c) == b.getPeaks(c)
+        assert a.get_nco(c) == b.get_nco(c)
