@@ -45,6 +45,14 @@ public:
     bool pushSamples(const std::complex<float>* host_matrix, size_t n, size_t pitch, double fs) { return hbd_push_samples_batch(h_, reinterpret_cast<const float*>(host_matrix), n, pitch, fs) == HBD_OK; }
     bool pushSamplesDevice(const void* device_matrix, size_t n, size_t pitch, double fs) { return hbd_push_samples_device(h_, static_cast<const float*>(device_matrix), n, pitch, fs) == HBD_OK; }
 
+    // one wideband capture for all channels, each through its own NCO (frequency-offset channels)
+    bool pushWideband(const IQVector& v) { return hbd_push_wideband(h_, reinterpret_cast<const float*>(v.data()), v.size(), v.samplingRate()) == HBD_OK; }
+    bool pushWidebandDevice(const void* device_row, size_t n, double fs) { return hbd_push_wideband_device(h_, static_cast<const float*>(device_row), n, fs) == HBD_OK; }
+    // NCO pre-mixer: replaces the SDR retune of code/websocketServer/main.cpp:247-265
+    void nco(double freq_hz, int ch = -1) { hbd_set_nco(h_, ch, freq_hz); }
+    double nco(int ch) const { return hbd_get_nco(h_, ch); }
+    int afcRetune(double min_abs_hz = 100.0, double* applied = nullptr) { return hbd_afc_retune(h_, min_abs_hz, applied); }
+
     // configure (ch = -1: every channel)
     void baud(double v, int ch = -1) { hbd_set_baud(h_, ch, v); }
     double baud(int ch) const { return hbd_get_baud(h_, ch); }

@@ -2,6 +2,7 @@
 import os
 import random
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -91,3 +92,29 @@ def test_ring_workload_properties():
     s = synth.ring_sentence(77)
     assert len(s) == 17 and s.startswith("$$C0077,")
     assert len(synth.ring_bits(77)) == synth.RING_BITS
+
+
+# ---- the step in front of the decoder: cf32 file IQ source (include/habdec_b200/IQSource.hpp) ---------------
+def _build_cpp(tmp_path, src, name, extra=()):
+    import subprocess
+    exe = str(tmp_path / name)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle"), src, "-o", exe,
+                    "-lpthread", *extra], check=True)
+    return exe
+
+
+def test_iqsource_file_matches_reference_transcript(tmp_path):
+    """Same scripted session (options, EOF, loop, short reads, stop quirk) as the reference's IQSource_File<float>:
+    golden transcript generated from the reference itself (tests/golden/make_iqsource_golden.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_iqsource_golden as g
+    exe = _build_cpp(tmp_path, os.path.join(ROOT, "tests", "cpp", "iqsource_ours.cpp"), "iqsource_ours")
+    path = str(tmp_path / "cap.cf32")
+    g.make_file(path)
+    ours = g.transcript(exe, path)
+    golden = open(os.path.join(ROOT, "tests", "golden", "iqsource_transcript.txt")).read()
+    assert ours == golden
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "iqsource_ref")
+    if os.path.exists(ref_bin):
+        assert g.transcript(ref_bin, path) == golden
