@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true", help="diagnostic: no CUDA events around K1 (no roofline numbers)")
     ap.add_argument("--ref-passes", type=int, default=8, help="reference arm: ring passes per host thread per step")
     a = ap.parse_args()
     if a.channels is None:
@@ -199,7 +200,7 @@ def run_ours(args):
         step(n_done); n_done += 1
     dec.collect()
     launches0 = dec.kernel_launches()
-    dec.set_kernel_timing(True)
+    dec.set_kernel_timing(not args.no_kernel_timing)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

@@ -86,14 +86,16 @@ struct hbd_decoder {
     int n_ch = 0, device = 0, n_sms = 148;
     cudaStream_t stream = nullptr;   // the caller's stream: inputs are ordered on it, it waits until inputs are consumed
     bool own_stream = false;
-    // channel groups: each group runs K1 -> carry -> K2 -> K4 -> K3 in order on its own stream, so the HBM-bound K1
-    // of one group overlaps the FP32/latency-bound tail kernels of the other (no data is shared between groups)
-    //   hi (high priority): K1 + carry of every group, in group order
-    //   lo (low priority):  K2 / K4 / K3 of every group; they fill the SM resources K1 leaves free
+    // Two streams: the HBM-bound K1 of call s+1 overlaps the FP32/latency-bound tail kernels of call s (the stage-1
+    // stream and the carry are double buffered over calls, so K1 only ever waits for the tail of call s-1).
+    //   hi (high priority): K1 (+ carry) of every call
+    //   lo (low priority):  K2 tail / K4 fft_afc; they fill the SM resources K1 leaves free
+    // Optionally the channels are cut into groups (HBD_GROUPS) so that K1 of one group overlaps the tail of the other
+    // inside ONE call; that only helps callers that cannot pipeline calls.
     int n_groups = 1;
     cudaStream_t hi = nullptr, lo = nullptr;
     std::vector<cudaEvent_t> ev_consumed;   // per group: K1 + carry done (input consumed, stage-1 output ready)
-    std::vector<cudaEvent_t> ev_tail;       // per group: K2..K3 done (stage-1 buffer of the group may be overwritten)
+    std::vector<cudaEvent_t> ev_tail;       // per (group, stage-1 buffer): tail done, that buffer may be overwritten by K1
     std::vector<char> tail_pending;
     cudaEvent_t ev_in = nullptr;
     int sync_groups()
@@ -117,7 +119,8 @@ struct hbd_decoder {
     std::vector<ChanPlan> h_plan, h_plan_uploaded;
     float2* d_carry2[2] = {nullptr, nullptr}; // stage-1 carry, ping-pong: K1 reads [carry_cur], writes [carry_cur ^ 1]
     int carry_cur = 0;
-    float2* d_s1 = nullptr;      size_t s1_pitch = 0;
+    float2* d_s1x[2] = {nullptr, nullptr}; size_t s1_pitch = 0, s1_pitch_b = 0; // stage-1 stream, ping-pong over calls:
+    int s1_cur = 0;              // K1 + tail of a call use [s1_cur]; the tail leaves the stage-2 history in [s1_cur ^ 1]
     float2* d_decq = nullptr;    size_t dq_pitch = 0;
     float2* d_fftbuf = nullptr;
     float2* d_spectrum = nullptr;
@@ -287,7 +290,7 @@ void hbd_decoder::free_all()
     for (cudaEvent_t e : ev_consumed) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_tail) cudaEventDestroy(e);
     if (ev_in) cudaEventDestroy(ev_in);
-    void* ptrs[] = {d_state, d_plan, d_carry2[0], d_carry2[1], d_s1, d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_log, d_log_head,
+    void* ptrs[] = {d_state, d_plan, d_carry2[0], d_carry2[1], d_s1x[0], d_s1x[1], d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_log, d_log_head,
                     d_taps1, d_taps2, d_twiddle, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps,
                     d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage, d_nco, d_wide};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -302,11 +305,12 @@ void hbd_decoder::free_all()
 // size the per-call buffers for pushes of up to n_in_max (carried + new) samples per channel
 int hbd_decoder::ensure_call_capacity(size_t n_in_max)
 {
-    if (n_in_max <= cap_n_in && d_s1) return HBD_OK;
+    if (n_in_max <= cap_n_in && d_s1x[0]) return HBD_OK;
     const size_t n = size_t(n_ch);
     const size_t grow_to = std::max(n_in_max, cap_n_in);
     const size_t n1_max = grow_to / size_t(M1) + 2, n2_max = grow_to / size_t(factor) + 2;
-    HBD_CUDA_CHECK(grow_rows(&d_s1, &s1_pitch, (kS1Hist + n1_max + 15) & ~size_t(15), n, kS1Hist, stream));
+    HBD_CUDA_CHECK(grow_rows(&d_s1x[0], &s1_pitch, (kS1Hist + n1_max + 15) & ~size_t(15), n, kS1Hist, stream));
+    HBD_CUDA_CHECK(grow_rows(&d_s1x[1], &s1_pitch_b, (kS1Hist + n1_max + 15) & ~size_t(15), n, kS1Hist, stream));
     HBD_CUDA_CHECK(grow_rows(&d_decq, &dq_pitch, (kLpHist + kLpBatch + n2_max + 15) & ~size_t(15), n, kLpHist + kLpBatch, stream));
     HBD_CUDA_CHECK(grow_rows(&d_slicer, &slicer_pitch, (size_t(kSlicerVent) + 1 + kLpBatch + n2_max + 15) & ~size_t(15), n,
                              slicer_pitch, stream));
@@ -356,7 +360,7 @@ int hbd_decoder::process_async_locked()
         }
         max_n1 = std::max(max_n1, p.n1);
     }
-    if (max_total > cap_n_in || !d_s1) { // buffers are about to be reallocated: nothing may be in flight
+    if (max_total > cap_n_in || !d_s1x[0]) { // buffers are about to be reallocated: nothing may be in flight
         if (sync_groups()) return HBD_ERR_CUDA;
     }
     { const int rc = ensure_call_capacity(max_total); if (rc) return rc; }
@@ -389,7 +393,7 @@ int hbd_decoder::process_async_locked()
             if (x.grown2 < need) {
                 x.grown2 = need;
                 if (quiesce()) return HBD_ERR_CUDA;
-                HBD_CUDA_CHECK(cudaMemsetAsync(d_s1 + c * s1_pitch, 0, sizeof(float2) * kS1Hist, stream));
+                HBD_CUDA_CHECK(cudaMemsetAsync(d_s1x[s1_cur] + c * s1_pitch, 0, sizeof(float2) * kS1Hist, stream));
             }
         }
         const unsigned total_dec = x.dec_pending + p.n2;
@@ -467,11 +471,11 @@ int hbd_decoder::process_async_locked()
         const int c0 = int((long long)n_ch * g / n_groups), c1 = int((long long)n_ch * (g + 1) / n_groups);
         const int nc = c1 - c0;
         // K1 of this group overwrites the group's stage-1 buffer: the previous call's tail must be done with it
-        if (tail_pending[size_t(g)]) HBD_CUDA_CHECK(cudaStreamWaitEvent(hi, ev_tail[size_t(g)], 0));
+        if (tail_pending[size_t(2 * g + s1_cur)]) HBD_CUDA_CHECK(cudaStreamWaitEvent(hi, ev_tail[size_t(2 * g + s1_cur)], 0));
         {   // K1 also writes the next call's carry (even when no channel has a full decimation block yet)
             DecimArgs da{};
             da.chunk = chunk; da.chunk_pitch = chunk_pitch; da.carry = d_carry2[carry_cur]; da.carry_next = d_carry2[carry_cur ^ 1];
-            da.s1 = d_s1; da.s1_pitch = s1_pitch; da.s1_hist = kS1Hist;
+            da.s1 = d_s1x[s1_cur]; da.s1_pitch = s1_pitch; da.s1_hist = kS1Hist;
             da.plan = d_plan; da.taps = d_taps1; da.ch0 = c0; da.n_channels = nc;
             if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), hi));
             HBD_CUDA_CHECK(launch_decim1(da, M1, T1, max_n1, n_sms, hi, &nl));
@@ -483,7 +487,7 @@ int hbd_decoder::process_async_locked()
         if (any_work) {
             TailArgs ta{};
             ta.plan = d_plan; ta.uplan = h_plan[0]; ta.uniform = plan_uniform ? 1 : 0; ta.state = d_state; ta.ch0 = c0;
-            ta.s1 = d_s1; ta.s1_pitch = s1_pitch; ta.taps2 = d_taps2; ta.M2 = M2; ta.T2 = T2;
+            ta.s1 = d_s1x[s1_cur]; ta.s1_next = d_s1x[s1_cur ^ 1]; ta.s1_pitch = s1_pitch; ta.taps2 = d_taps2; ta.M2 = M2; ta.T2 = T2;
             ta.decq = d_decq; ta.dq_pitch = dq_pitch; ta.fs_dec = fs_dec; ta.fftbuf = d_fftbuf; ta.lptaps = d_lptaps;
             ta.max_lp_taps = int(max_lp_taps);
             ta.slicer = d_slicer; ta.slicer_pitch = slicer_pitch; ta.sv_want = sv_want;
@@ -498,12 +502,13 @@ int hbd_decoder::process_async_locked()
             HBD_CUDA_CHECK(launch_fft_afc(fa, nc, lo, &nl));
         }
         if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
-        HBD_CUDA_CHECK(cudaEventRecord(ev_tail[size_t(g)], lo));
-        tail_pending[size_t(g)] = 1;
+        HBD_CUDA_CHECK(cudaEventRecord(ev_tail[size_t(2 * g + s1_cur)], lo));
+        tail_pending[size_t(2 * g + s1_cur)] = 1;
     }
     // the caller's stream resumes once every group has consumed the input (it does not wait for the tail kernels)
     for (int g = 0; g < n_groups; ++g) HBD_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_consumed[size_t(g)], 0));
     carry_cur ^= 1;
+    if (any_work) s1_cur ^= 1; // the tail (which moves the stage-2 history to the other buffer) ran
     launches += unsigned(nl);
     HBD_CUDA_CHECK(cudaEventRecord(ev_call[call_seq % ev_call.size()], lo)); // everything of this call is done
     ++call_seq;
@@ -606,17 +611,20 @@ int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
     {
         if (const char* sv = getenv("HBD_SV_WANT")) h->sv_override = atoi(sv);
         const char* env = getenv("HBD_GROUPS");
-        int g = env ? atoi(env) : (n_channels >= 256 ? 2 : 1);
+        // one group: with the stage-1 stream double buffered over calls, K1 of call s+1 already overlaps the tail of call s;
+        // more groups only help synchronous callers (hbd_process) that cannot pipeline calls
+        int g = env ? atoi(env) : 1;
         g = std::max(1, std::min(g, std::min(n_channels, 8)));
         h->n_groups = g;
-        h->ev_consumed.resize(size_t(g)); h->ev_tail.resize(size_t(g)); h->tail_pending.assign(size_t(g), 0);
+        h->ev_consumed.resize(size_t(g)); h->ev_tail.resize(size_t(2 * g)); h->tail_pending.assign(size_t(2 * g), 0);
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); // numerically lower = higher priority
         if (cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
             cudaStreamCreateWithPriority(&h->lo, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { h->free_all(); delete h; return HBD_ERR_CUDA; }
         for (int i = 0; i < g; ++i) {
             if (cudaEventCreateWithFlags(&h->ev_consumed[size_t(i)], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&h->ev_tail[size_t(i)], cudaEventDisableTiming) != cudaSuccess) { h->free_all(); delete h; return HBD_ERR_CUDA; }
+                cudaEventCreateWithFlags(&h->ev_tail[size_t(2 * i)], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->ev_tail[size_t(2 * i + 1)], cudaEventDisableTiming) != cudaSuccess) { h->free_all(); delete h; return HBD_ERR_CUDA; }
         }
         if (cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess) { h->free_all(); delete h; return HBD_ERR_CUDA; }
     }
@@ -715,7 +723,7 @@ static size_t apply_factor(hbd_decoder* h, size_t factor)
     cudaStreamSynchronize(h->stream);
     h->upload_taps();
     for (int i = 0; i < 2; ++i) cudaMemset(h->d_carry2[i], 0, size_t(h->n_ch) * kCarryCap * sizeof(float2));
-    if (h->d_s1) cudaMemset(h->d_s1, 0, size_t(h->n_ch) * h->s1_pitch * sizeof(float2));
+    for (int i = 0; i < 2; ++i) if (h->d_s1x[i]) cudaMemset(h->d_s1x[i], 0, size_t(h->n_ch) * h->s1_pitch * sizeof(float2));
     for (auto& x : h->hc) {
         x.grown1 = x.grown2 = 0;
         // unconsumed input stays queued in the reference (iq_in_buffer_ is untouched); it sits at the end of the carry

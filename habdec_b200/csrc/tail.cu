@@ -72,11 +72,15 @@ tail_kernel(TailArgs a)
 
     const int ch = a.ch0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const ChanPlan pl = a.uniform ? a.uplan : a.plan[ch];
-    if (pl.flags & 1u) return; // fewer than `factor` samples queued: Decoder.h:429-430
+    const float2* s1 = a.s1 + (size_t)ch * a.s1_pitch;
+    float2* s1n = a.s1_next + (size_t)ch * a.s1_pitch;
+    if (pl.flags & 1u) { // fewer than `factor` samples queued (Decoder.h:429-430): only carry the stage-2 history over
+        if (a.M2 > 1) for (int i = tid; i < a.T2 - 1; i += kTailThreads) s1n[kS1Hist - (a.T2 - 1) + i] = s1[kS1Hist - (a.T2 - 1) + i];
+        return;
+    }
 
     ChanState& gst = a.state[ch];
     const unsigned n2 = pl.n2;
-    float2* s1 = a.s1 + (size_t)ch * a.s1_pitch;
     float2* dq = a.decq + (size_t)ch * a.dq_pitch;
     const int T = int(pl.lp_ntaps);                      // 0 until the first design (host, Decoder.h:536-538)
     const int hist = T > 0 ? T - 1 : 0;
@@ -200,7 +204,7 @@ tail_kernel(TailArgs a)
             const int win = int(nk) * M2 + lead;
             for (int i = tid; i < T2 - 1; i += kTailThreads) {
                 const int w = win - (T2 - 1) + i;
-                s1[kS1Hist - (T2 - 1) + i] = s_x[M2 == 4 ? pad16(w) : w];
+                s1n[kS1Hist - (T2 - 1) + i] = s_x[M2 == 4 ? pad16(w) : w];
             }
         }
         __syncthreads();

@@ -11,7 +11,7 @@ struct TailArgs {
     ChanState* state;
     int ch0;                  // first channel of this launch (channel groups run on their own streams)
     // stage 2
-    float2* s1; size_t s1_pitch;
+    float2* s1; float2* s1_next; size_t s1_pitch;  // this call's stage-1 stream; the next call's buffer (receives the stage-2 history)
     const float* taps2; int M2, T2;
     // decimated queue: [kLpHist history slots | pending]
     float2* decq; size_t dq_pitch;
