@@ -18,8 +18,8 @@
 //    NLIVE sliding complex accumulators (one per output whose window overlaps the current
 //    superblock); each loaded sample is used for T/M (5.4 .. 6.8) FMAs straight from
 //    registers.  Completed outputs are lane-partials: 16 of them are transposed through a
-//    padded shared tile and summed, so the cross-lane reduction costs ~2 LDS + 2 FADD per
-//    superblock instead of a shuffle tree per output.
+//    padded shared tile and summed (LDS.128 + packed FADD2), so the cross-lane reduction costs
+//    ~1 LDS + 1.5 FADD2 per superblock instead of a shuffle tree per output.
 //  * no tensor cores: complex-by-real FIR taps on a per-channel stream are not a dense
 //    contraction (north star), the kernel is bound by the 8 B/sample HBM read.
 //
@@ -103,7 +103,7 @@ struct Geo {
 };
 
 constexpr int kStages   = HBD_K1_STAGES; // ring depth per warp
-constexpr int kRedPitch = 33;            // float2 per row (+1 pad: conflict-free transposed reads)
+constexpr int kRedPitch = 36;            // float2 per row: 16-byte aligned rows, 32 B mod 128 B (see reduce_rows)
 
 template <int M, int T>
 struct WarpSmem {
@@ -120,22 +120,28 @@ __device__ __forceinline__ float tap_for(const float* __restrict__ taps, int j, 
     return (t >= 0 && t < T) ? __ldg(taps + t) : 0.0f;
 }
 
-// Sum the 32 lane-partials of up to 16 staged outputs (lane = 2*row + re/im) and store the ones whose
-// output index lies in [k_lo, k_hi).  Row r of the tile is output k_first + r.
+// Sum the 32 lane-partials of up to 16 staged outputs and store the ones whose output index lies in [k_lo, k_hi).
+// Row r of the tile is output k_first + r.  Lane = 2*row + h: it adds the 16 partials held in the row's float4 slots
+// 2i + h (8 LDS.128, packed FADD2 tree), the two halves meet through one shuffle.  The row pitch of 36 float2
+// (288 B = 32 B mod 128 B) makes the eight lanes of every LDS.128 phase hit eight different 16-byte bank groups.
 __device__ __forceinline__ void reduce_rows(const float2 (*red)[kRedPitch], int rows, int k_first, int k_lo, int k_hi,
                                             float2* __restrict__ out, int lane)
 {
     __syncwarp();
-    const int row = lane >> 1, comp = lane & 1;
-    const float* src = reinterpret_cast<const float*>(&red[row][0]) + comp;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const int row = lane >> 1, h = lane & 1;
+    const float4* src = reinterpret_cast<const float4*>(&red[min(row, rows - 1)][0]) + h;  // lanes beyond `rows` re-read the last row
+    float2 s[8];
 #pragma unroll
-    for (int l = 0; l < 32; l += 4) {
-        s0 += src[2 * l]; s1 += src[2 * l + 2]; s2 += src[2 * l + 4]; s3 += src[2 * l + 6];
+    for (int i = 0; i < 8; ++i) {
+        const float4 v = src[2 * i];
+        s[i] = cadd2(make_float2(v.x, v.y), make_float2(v.z, v.w));
     }
-    const float s = (s0 + s1) + (s2 + s3);
+    const float2 a = cadd2(cadd2(s[0], s[1]), cadd2(s[2], s[3])), b = cadd2(cadd2(s[4], s[5]), cadd2(s[6], s[7]));
+    float2 t = cadd2(a, b);
+    t.x += __shfl_xor_sync(0xffffffffu, t.x, 1);
+    t.y += __shfl_xor_sync(0xffffffffu, t.y, 1);
     const int k = k_first + row;
-    if (row < rows && k >= k_lo && k < k_hi) reinterpret_cast<float*>(out + k)[comp] = s;
+    if (h == 0 && row < rows && k >= k_lo && k < k_hi) out[k] = t;
     __syncwarp();
 }
 

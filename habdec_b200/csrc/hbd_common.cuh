@@ -94,6 +94,12 @@ __device__ __forceinline__ float2 cfma(float2 x, float h, float2 acc)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(rx), "l"(rh), "l"(ra));
     return *reinterpret_cast<float2*>(&rd);
 }
+__device__ __forceinline__ float2 cadd2(float2 a, float2 b) // packed FADD2
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
 #endif
 
 } // namespace hbd
