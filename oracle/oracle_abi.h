@@ -80,6 +80,24 @@ typedef struct hbo_afc_info {
 HBO_DECL(ref)
 HBO_DECL(orc)
 
+/* ---- websocket wire formats (the step right after the path) -------------------------
+ * PWR_ payload of "cmd::power:res=R,zoom=Z" and DEM_ payload of "cmd::demod:res=R":
+ *   code/websocketServer/habdec_ws_protocol.cpp:338-429, NetTransport.h:29-102, CompressedVector.cpp:72-116
+ * ref_*: header + quantisation by the reference's own SerializeSpectrum / SerializeDemodulation /
+ *        CompressedVector (compiled from /root/reference), zoom / peak shift / ShrinkVector restated from
+ *        habdec_ws_protocol.cpp (that file needs boost and cannot be compiled here);
+ * orc_*: everything restated. */
+typedef struct hbo_spectrum_meta {
+    double noise_floor, noise_variance, sampling_rate, shift;
+    int    peak_left, peak_right;   /* signed GUI peaks as returned by Decoder::getPeaks (negative = not stable) */
+} hbo_spectrum_meta;
+#define HBO_WIRE_DECL(P) \
+    size_t P##_spectrum_frame(const float* power, size_t n, const hbo_spectrum_meta* meta, float zoom, int resolution, \
+                              int type_size, unsigned char* out, size_t cap); \
+    size_t P##_demod_frame(const float* demod, size_t n, int resolution, int type_size, unsigned char* out, size_t cap);
+HBO_WIRE_DECL(ref)
+HBO_WIRE_DECL(orc)
+
 /* port only: the sentence layer alone (std::regex, like sentence_extract.cpp:58-98) and the CRC */
 int  orc_extract_sentence(const char* stream, size_t n, char* callsign, char* data, char* crc, size_t cap, size_t* rest_offset);
 void orc_crc16(const char* s, size_t n, char out[5]);

@@ -146,6 +146,37 @@ class PortDecoder(_Decoder):
     kind = "orc"
 
 
+class SpectrumMeta(C.Structure):
+    _fields_ = [("noise_floor", C.c_double), ("noise_variance", C.c_double), ("sampling_rate", C.c_double), ("shift", C.c_double),
+                ("peak_left", C.c_int), ("peak_right", C.c_int)]
+
+
+def spectrum_frame(kind: str, power: np.ndarray, meta: SpectrumMeta, zoom: float, resolution: int, type_size: int) -> bytes:
+    """PWR_ payload (header + quantised bins) of cmd::power:res=R,zoom=Z -- habdec_ws_protocol.cpp:353-404."""
+    lib = _load(kind)
+    fn = getattr(lib, kind + "_spectrum_frame")
+    fn.restype = C.c_size_t
+    fn.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(SpectrumMeta), C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    power = np.ascontiguousarray(power, dtype=np.float32)
+    n = fn(power.ctypes.data, power.size, C.byref(meta), zoom, resolution, type_size, None, 0)
+    buf = C.create_string_buffer(max(n, 1))
+    fn(power.ctypes.data, power.size, C.byref(meta), zoom, resolution, type_size, buf, n)
+    return buf.raw[:n]
+
+
+def demod_frame(kind: str, demod: np.ndarray, resolution: int, type_size: int) -> bytes:
+    """DEM_ payload of cmd::demod:res=R -- habdec_ws_protocol.cpp:408-429."""
+    lib = _load(kind)
+    fn = getattr(lib, kind + "_demod_frame")
+    fn.restype = C.c_size_t
+    fn.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    demod = np.ascontiguousarray(demod, dtype=np.float32)
+    n = fn(demod.ctypes.data, demod.size, resolution, type_size, None, 0)
+    buf = C.create_string_buffer(max(n, 1))
+    fn(demod.ctypes.data, demod.size, resolution, type_size, buf, n)
+    return buf.raw[:n]
+
+
 def premix(iq: np.ndarray, fs: float, f_hz: float, phase0: float = 0.0):
     """The oracle of the NCO pre-mixer ("CPU pre-mix, then the reference Decoder").
 

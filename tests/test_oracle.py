@@ -15,7 +15,7 @@ import pytest
 from habdec_b200 import synth
 from oracle import pyoracle as po
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "g[0-9]*.npz")))
 SCALE = 32.0
 
 
@@ -124,3 +124,21 @@ def test_premix_oracle_is_phase_continuous_and_invertible():
     tone = np.exp(2j * np.pi * f / fs * np.arange(4096)).astype(np.complex64)
     dc, _ = po.premix(tone, fs, f)
     assert np.max(np.abs(dc - 1.0)) < 1e-5
+
+
+def test_wire_format_restatement_matches_reference_serialisation():
+    """PWR_/DEM_ payloads: restatement == golden bytes produced by the reference's own SerializeSpectrum /
+    CompressedVector code (tests/golden/make_wire_golden.py), and == the live reference build when present."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_wire_golden as g
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "wire_frames.npz"))
+    port = g.frames("orc")
+    assert set(port) == set(gold.files)
+    for k in gold.files:
+        assert port[k].tobytes() == gold[k].tobytes(), k
+        assert len(gold[k]) > 20
+    if po.available("ref"):
+        live = g.frames("ref")
+        for k in gold.files:
+            assert live[k].tobytes() == gold[k].tobytes(), k
