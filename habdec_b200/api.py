@@ -88,6 +88,11 @@ SIGNATURES = {
     "hbd_reset_frequency_correction": (C.c_int, [_H, C.c_int, C.c_double]),
     "hbd_get_spectrum_info": (C.c_size_t, [_H, C.c_int, C.POINTER(SpectrumInfo), C.c_void_p, C.c_size_t]),
     "hbd_get_stats_batch": (C.c_size_t, [_H, C.c_void_p, C.c_size_t]),
+    "hbd_get_spectrum_frame": (C.c_size_t, [_H, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_get_spectrum_frames": (C.c_size_t, [_H, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "hbd_set_demod_accumulate": (C.c_int, [_H, C.c_int]),
+    "hbd_get_demod_frame": (C.c_size_t, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_get_demod_frames": (C.c_size_t, [_H, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "hbd_debug_stage": (C.c_size_t, [_H, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_design_lowpass": (C.c_size_t, [C.c_float, C.c_float, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]),
     "hbd_extract_sentence": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -295,6 +300,36 @@ class BatchDecoder:
         power = np.empty(4096, dtype=np.float32)
         n = self._lib.hbd_get_spectrum_info(self._h, ch, C.byref(info), power.ctypes.data, power.size)
         return info, power[:n]
+
+    # ---- websocket wire formats (PWR_ / DEM_ payloads, habdec_ws_protocol.cpp:353-429)
+    def spectrum_frame(self, ch: int, zoom: float, resolution: int, type_size: int) -> bytes:
+        n = self._lib.hbd_get_spectrum_frame(self._h, ch, zoom, resolution, type_size, None, 0)
+        buf = C.create_string_buffer(max(n, 1))
+        self._lib.hbd_get_spectrum_frame(self._h, ch, zoom, resolution, type_size, buf, n)
+        return buf.raw[:n]
+
+    def _frames(self, fn, *args) -> list[bytes]:
+        sizes = np.zeros(self.n_channels, dtype=np.uint32)
+        longest = fn(self._h, *args, None, 0, sizes.ctypes.data)
+        if not longest:
+            return [b""] * self.n_channels
+        out = np.zeros((self.n_channels, longest), dtype=np.uint8)
+        fn(self._h, *args, out.ctypes.data, longest, sizes.ctypes.data)
+        return [out[c, :sizes[c]].tobytes() for c in range(self.n_channels)]
+
+    def spectrum_frames(self, zoom: float, resolution: int, type_size: int) -> list[bytes]:
+        return self._frames(self._lib.hbd_get_spectrum_frames, zoom, resolution, type_size)
+
+    def set_demod_accumulate(self, on: bool): self._chk(self._lib.hbd_set_demod_accumulate(self._h, int(on)))
+
+    def demod_frame(self, ch: int, resolution: int, type_size: int) -> bytes:
+        n = self._lib.hbd_get_demod_frame(self._h, ch, resolution, type_size, None, 0)
+        buf = C.create_string_buffer(max(n, 1))
+        self._lib.hbd_get_demod_frame(self._h, ch, resolution, type_size, buf, n)
+        return buf.raw[:n]
+
+    def demod_frames(self, resolution: int, type_size: int) -> list[bytes]:
+        return self._frames(self._lib.hbd_get_demod_frames, resolution, type_size)
 
     def stats_all(self) -> np.ndarray:
         """[n_channels, 6] float64: frequency correction, shift, noise floor, noise variance, peak left, peak right."""

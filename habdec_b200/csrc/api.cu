@@ -20,6 +20,7 @@
 #include "host_tail.h"
 #include "nco.cuh"
 #include "tail.cuh"
+#include "wire.cuh"
 
 using namespace hbd;
 
@@ -59,6 +60,7 @@ struct HostChan {
     size_t lp_input_size = 0, lp_ntaps = 0;
     unsigned pushed = 0;     // samples waiting in the staging row
     unsigned last_nf = 0, last_n2 = 0;
+    unsigned demod_n = 0;    // size of the reference's demodulated_ (last call that produced any; Decoder.h:546-555)
     double nco_freq = 0, nco_phase = 0; // pre-mixer: frequency in Hz, phase (cycles) of the next pushed sample
     bool cfg_dirty = true;
     bool lp_dirty = true;    // bw / trans / input size changed since the last design attempt
@@ -152,6 +154,13 @@ struct hbd_decoder {
     const float2* ext = nullptr; size_t ext_pitch = 0; size_t ext_n = 0; // zero-copy device push
     float* h_pinned = nullptr; size_t pinned_bytes = 0;  // staging for pageable host memory
 
+    // websocket wire formats (wire.cu)
+    bool demod_acc_on = false;
+    float* d_dacc = nullptr; size_t dacc_pitch = 0; unsigned* d_dacc_n = nullptr;
+    unsigned char* d_frames = nullptr; size_t frames_pitch = 0; unsigned* d_frame_sizes = nullptr;
+    std::vector<unsigned> h_frame_sizes;
+    int ensure_frames(size_t pitch);
+    int ensure_dacc();
     // NCO pre-mixer (nco.cu)
     NcoChan* d_nco = nullptr; std::vector<NcoChan> h_nco;
     float2* d_wide = nullptr; size_t wide_cap = 0;       // wideband capture row shared by all channels
@@ -292,7 +301,7 @@ void hbd_decoder::free_all()
     if (ev_in) cudaEventDestroy(ev_in);
     void* ptrs[] = {d_state, d_plan, d_carry2[0], d_carry2[1], d_s1x[0], d_s1x[1], d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_log, d_log_head,
                     d_taps1, d_taps2, d_twiddle, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps,
-                    d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage, d_nco, d_wide};
+                    d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage, d_nco, d_wide, d_dacc, d_dacc_n, d_frames, d_frame_sizes};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_pinned) cudaFreeHost(h_pinned);
     for (cudaEvent_t e : ev_call) cudaEventDestroy(e);
@@ -364,6 +373,7 @@ int hbd_decoder::process_async_locked()
         if (sync_groups()) return HBD_ERR_CUDA;
     }
     { const int rc = ensure_call_capacity(max_total); if (rc) return rc; }
+    if (demod_acc_on) { const int rc = ensure_dacc(); if (rc) return rc; }
     bool groups_idle = false; // set once we had to wait for the group streams (rare host-side state changes)
     auto quiesce = [&]() -> int { if (!groups_idle) { if (sync_groups()) return HBD_ERR_CUDA; groups_idle = true; } return HBD_OK; };
 
@@ -402,6 +412,7 @@ int hbd_decoder::process_async_locked()
         const unsigned nf = total_dec - total_dec % unsigned(kLpBatch);
         x.dec_pending = total_dec - nf;
         x.last_nf = nf;
+        x.demod_n = nf;
         // low-pass design, Decoder.h:536-538
         if (x.lp_input_size != nf) { x.lp_input_size = nf; x.lp_dirty = true; }
         const size_t T = x.lp_dirty ? design_lowpass(float(x.lp_bw / fs_dec), x.lp_trans, x.lp_input_size, x.lp_ntaps, new_taps) : x.lp_ntaps;
@@ -500,6 +511,12 @@ int hbd_decoder::process_async_locked()
             fa.state = d_state; fa.fftbuf = d_fftbuf; fa.spectrum = d_spectrum; fa.power = d_power; fa.twiddle = d_twiddle; fa.fs_dec = fs_dec;
             fa.ch0 = c0;
             HBD_CUDA_CHECK(launch_fft_afc(fa, nc, lo, &nl));
+        }
+        if (demod_acc_on && d_demod) { // main.cpp:267-282 runs after EVERY process(), also when nothing new was demodulated
+            DemodAccArgs aa{};
+            aa.state = d_state; aa.demod = d_demod; aa.demod_pitch = demod_pitch; aa.acc = d_dacc; aa.acc_pitch = dacc_pitch; aa.acc_n = d_dacc_n;
+            aa.fs_dec = fs_dec; aa.ch0 = c0;
+            HBD_CUDA_CHECK(launch_demod_accumulate(aa, nc, lo, &nl));
         }
         if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
         HBD_CUDA_CHECK(cudaEventRecord(ev_tail[size_t(2 * g + s1_cur)], lo));
@@ -1063,7 +1080,7 @@ size_t hbd_get_demodulated(hbd_decoder* h, int ch, float* out, size_t cap)
 {
     if (!h || ch < 0 || ch >= h->n_ch) return 0;
     std::lock_guard<std::mutex> l(h->mtx);
-    const size_t n = h->hc[size_t(ch)].last_nf;
+    const size_t n = h->hc[size_t(ch)].demod_n;   // a call that demodulates nothing leaves the previous block in place
     if (!h->d_demod) return 0;
     return fetch_floats(h, h->d_demod + size_t(ch) * h->demod_pitch, n, out, cap);
 }
@@ -1099,6 +1116,110 @@ int hbd_reset_frequency_correction(hbd_decoder* h, int ch, double corr)
     ++h->launches;
     return HBD_OK;
 }
+// ---- websocket wire formats ---------------------------------------------------------------------------------
+int hbd_decoder::ensure_frames(size_t pitch)
+{
+    if (pitch <= frames_pitch && d_frames) return HBD_OK;
+    if (d_frames) cudaFree(d_frames);
+    d_frames = nullptr;
+    pitch = (pitch + 255) & ~size_t(255);
+    HBD_CUDA_CHECK(cudaMalloc((void**)&d_frames, size_t(n_ch) * pitch));
+    frames_pitch = pitch;
+    if (!d_frame_sizes) HBD_CUDA_CHECK(dalloc(&d_frame_sizes, size_t(n_ch)));
+    h_frame_sizes.resize(size_t(n_ch));
+    return HBD_OK;
+}
+
+// accumulation buffers: 50 symbols of the slowest channel plus one call's worth of new samples
+int hbd_decoder::ensure_dacc()
+{
+    const double fs_dec = fs_in / factor;
+    size_t need = 0;
+    for (const auto& x : hc) if (x.baud > 0) need = std::max(need, size_t(fs_dec / x.baud * 50));
+    need += demod_pitch + 64;
+    if (!d_dacc_n) { HBD_CUDA_CHECK(dalloc(&d_dacc_n, size_t(n_ch))); HBD_CUDA_CHECK(cudaMemset(d_dacc_n, 0, sizeof(unsigned) * size_t(n_ch))); }
+    if (need > dacc_pitch) {
+        if (sync_groups()) return HBD_ERR_CUDA;
+        HBD_CUDA_CHECK(grow_rows(&d_dacc, &dacc_pitch, (need + 15) & ~size_t(15), size_t(n_ch), dacc_pitch, stream));
+    }
+    return HBD_OK;
+}
+
+extern "C" int hbd_set_demod_accumulate(hbd_decoder* h, int on)
+{
+    HBD_CHECK_H(h);
+    std::lock_guard<std::mutex> l(h->mtx);
+    h->demod_acc_on = on != 0;
+    return HBD_OK;
+}
+
+// frames of channels [ch0, ch0 + nc) into the device scratch, then one copy of sizes + one of payloads
+static size_t fetch_frames(hbd_decoder* h, int ch0, int nc, bool spectrum, float zoom, int resolution, int type_size,
+                           unsigned char* out, size_t pitch, unsigned* sizes)
+{
+    if (type_size != 1 && type_size != 2 && type_size != 4) return 0;
+    if (resolution < 0) resolution = 0;
+    cudaSetDevice(h->device);
+    if (h->sync_groups() || cudaStreamSynchronize(h->stream) != cudaSuccess) return 0;
+    const size_t hdr = spectrum ? size_t(kSpectrumHeaderBytes) : size_t(kDemodHeaderBytes);
+    const size_t max_n = spectrum ? size_t(kFftN) : std::max<size_t>(h->dacc_pitch, 1);
+    const size_t need = hdr + std::min<size_t>(max_n, size_t(resolution)) * size_t(type_size);
+    if (h->ensure_frames(need)) return 0;
+    int nl = 0;
+    cudaError_t e;
+    if (spectrum) {
+        SpectrumFrameArgs a{};
+        a.state = h->d_state; a.power = h->d_power; a.fs_dec = h->fs_in / h->factor; a.zoom = zoom; a.resolution = resolution; a.type_size = type_size;
+        a.out = h->d_frames; a.out_pitch = h->frames_pitch; a.sizes = h->d_frame_sizes; a.ch0 = ch0;
+        e = launch_spectrum_frames(a, nc, h->stream, &nl);
+    } else {
+        if (!h->d_dacc || !h->d_dacc_n) return 0;
+        DemodFrameArgs a{};
+        a.acc = h->d_dacc; a.acc_pitch = h->dacc_pitch; a.acc_n = h->d_dacc_n; a.resolution = resolution; a.type_size = type_size;
+        a.out = h->d_frames; a.out_pitch = h->frames_pitch; a.sizes = h->d_frame_sizes; a.ch0 = ch0;
+        e = launch_demod_frames(a, nc, h->stream, &nl);
+    }
+    h->launches += unsigned(nl);
+    if (e != cudaSuccess) { h->set_error(cudaGetErrorString(e)); return 0; }
+    if (cudaMemcpyAsync(h->h_frame_sizes.data(), h->d_frame_sizes, sizeof(unsigned) * size_t(nc), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return 0;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return 0;
+    size_t longest = 0;
+    for (int i = 0; i < nc; ++i) longest = std::max<size_t>(longest, h->h_frame_sizes[size_t(i)]);
+    if (sizes) for (int i = 0; i < nc; ++i) sizes[i] = h->h_frame_sizes[size_t(i)];
+    if (out && pitch && longest) {
+        const size_t w = std::min(pitch, longest);
+        if (cudaMemcpy2D(out, pitch, h->d_frames, h->frames_pitch, w, size_t(nc), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    }
+    return longest;
+}
+
+extern "C" {
+size_t hbd_get_spectrum_frame(hbd_decoder* h, int ch, float zoom, int resolution, int type_size, unsigned char* out, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    return fetch_frames(h, ch, 1, true, zoom, resolution, type_size, out, cap, nullptr);
+}
+size_t hbd_get_spectrum_frames(hbd_decoder* h, float zoom, int resolution, int type_size, unsigned char* out, size_t pitch, unsigned* sizes)
+{
+    if (!h) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    return fetch_frames(h, 0, h->n_ch, true, zoom, resolution, type_size, out, pitch, sizes);
+}
+size_t hbd_get_demod_frame(hbd_decoder* h, int ch, int resolution, int type_size, unsigned char* out, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    return fetch_frames(h, ch, 1, false, 0.f, resolution, type_size, out, cap, nullptr);
+}
+size_t hbd_get_demod_frames(hbd_decoder* h, int resolution, int type_size, unsigned char* out, size_t pitch, unsigned* sizes)
+{
+    if (!h) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    return fetch_frames(h, 0, h->n_ch, false, 0.f, resolution, type_size, out, pitch, sizes);
+}
+} // extern "C"
+
 // AFC loop closed on the GPU for all channels (see afc_retune_kernel); returns the number of channels retuned
 int hbd_afc_retune(hbd_decoder* h, double min_abs_hz, double* applied_out)
 {

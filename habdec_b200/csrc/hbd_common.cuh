@@ -44,6 +44,7 @@ struct ChanState {
     unsigned demod_primed;  // discriminator carry valid
     float    demod_last_re, demod_last_im;
     unsigned n_filtered;    // low-pass outputs produced by this call (multiple of 256)
+    unsigned demod_n;       // size of the reference's demodulated_ vector: n_filtered of the last call that produced any
     unsigned slicer_n;      // pending slicer samples
     unsigned uart_n;        // pending UART bits (< one frame)
     unsigned long long uart_win; // those bits, LSB = oldest

@@ -350,6 +350,7 @@ tail_kernel(TailArgs a)
                 gst.demod_last_re = carry_prev.x;
                 gst.demod_last_im = carry_prev.y;
                 gst.demod_primed = 1;
+                gst.demod_n = nf;
                 gst.slicer_n = slicer_n;
                 gst.uart_win = win;
                 gst.uart_n = unsigned(have);

@@ -148,6 +148,19 @@ size_t hbd_get_spectrum_info(hbd_decoder* h, int ch, hbd_spectrum_info* info, fl
  * noise variance, peak left, peak right (one device->host copy for all channels); returns 6*n_channels */
 size_t hbd_get_stats_batch(hbd_decoder* h, double* out, size_t cap_doubles);
 
+/* ---- websocket wire formats, produced on the GPU (the step after the path) -----------------------------------
+ * PWR_ payload of "cmd::power:res=R,zoom=Z" (habdec_ws_protocol.cpp:353-404): SpectrumInfoHeader (NetTransport.h:29-47)
+ * + the zoomed / shrunk dB spectrum as type_size-byte values (1: u8, 2: u16 min/max quantised like CompressedVector,
+ * 4: f32).  Returns the payload size in bytes (0 before the first spectrum); copies min(cap, size). */
+size_t hbd_get_spectrum_frame(hbd_decoder* h, int ch, float zoom, int resolution, int type_size, unsigned char* out, size_t cap);
+/* all channels in one go: out[ch * pitch ...], sizes[ch]; returns the longest payload */
+size_t hbd_get_spectrum_frames(hbd_decoder* h, float zoom, int resolution, int type_size, unsigned char* out, size_t pitch, unsigned* sizes);
+/* DEM_ payload of "cmd::demod:res=R" (:408-429): DemodHeader + the accumulated discriminator output (last 50 symbols,
+ * appended after every process() like websocketServer/main.cpp:267-282).  Accumulation is off until switched on. */
+int    hbd_set_demod_accumulate(hbd_decoder* h, int on);
+size_t hbd_get_demod_frame(hbd_decoder* h, int ch, int resolution, int type_size, unsigned char* out, size_t cap);
+size_t hbd_get_demod_frames(hbd_decoder* h, int resolution, int type_size, unsigned char* out, size_t pitch, unsigned* sizes);
+
 /* ---- test hooks ------------------------------------------------------------------------------------------ */
 enum { HBD_STAGE_DECIMATED = 0, HBD_STAGE_FILTERED = 1, HBD_STAGE_DEMOD = 2, HBD_STAGE_LPTAPS = 5,
        HBD_STAGE_PENDING = 6, HBD_STAGE_BITS = 7 };
