@@ -203,3 +203,32 @@ def test_gpu_matches_golden_reference_vectors(path):
         assert dec.getPeaks(0) == (int(afc[4]), int(afc[5]))
         assert dec.getFrequencyCorrection(0) == pytest.approx(afc[0], abs=1e-9)
         assert dec.getShift(0) == pytest.approx(afc[1], abs=1e-9)
+
+
+def test_cfg3_256_channels_mixed_baud_snr_sweep(oracle_kind):
+    """BASELINE configs[2] at full width: 256 channels on one GPU, 50/100/300 baud round robin, in-band SNR swept
+    0..20 dB (full band -28..-8 dB); every channel's characters -- including the wrong ones at low SNR -- equal the
+    reference's.  The oracle side runs one reference Decoder per channel."""
+    fs = 2.048e6
+    n_ch = 256
+    bauds = [50.0, 100.0, 300.0]
+    n = 65536 * 24
+    iq = np.empty((n_ch, n), dtype=np.complex64)
+    for c in range(n_ch):
+        snr = -28.0 + 20.0 * c / (n_ch - 1)
+        iq[c] = synth.channel_iq(c, 1, fs, bauds[c % 3], snr_db=snr, n_samples=n, lead_in=12)[0]
+    dec = api.BatchDecoder(n_ch, dec_factor=256)
+    for c in range(n_ch):
+        dec.baud(bauds[c % 3], c)
+    for o in range(0, n, 65536):
+        dec.pushSamplesBatch(np.ascontiguousarray(iq[:, o:o + 65536]), fs)
+        dec.process_async()
+    dec.collect()
+    n_chars = 0
+    for c in range(n_ch):
+        ref = make_oracle(oracle_kind, baud=bauds[c % 3], rtty_bits=8, rtty_stops=2.0, dec_factor=256).run(iq[c], fs)
+        got = dec.poll_chars(c)
+        assert got == ref.chars(), "channel %d" % c
+        assert dec.poll_sentences(c) == ref.sentences(), "channel %d" % c
+        n_chars += len(got)
+    assert n_chars > 2000
