@@ -35,6 +35,7 @@ SIGNATURES = {
     "hbd_last_error": (C.c_char_p, [_H]),
     "hbd_set_stream": (C.c_int, [_H, C.c_void_p]),
     "hbd_set_record": (C.c_int, [_H, C.c_int]),
+    "hbd_set_fft_size": (C.c_int, [_H, C.c_size_t]),
     "hbd_set_baud": (C.c_int, [_H, C.c_int, C.c_double]),
     "hbd_get_baud": (C.c_double, [_H, C.c_int]),
     "hbd_set_rtty_bits": (C.c_int, [_H, C.c_int, C.c_size_t]),
@@ -151,7 +152,7 @@ class BatchDecoder:
 
     def __init__(self, n_channels: int, device: int = 0, baud: float = 300.0, rtty_bits: int = 8, rtty_stops: float = 2.0,
                  lowpass_bw: float = 1500.0, lowpass_trans: float = 0.025, dec_factor: int = 256, dc_remove: bool = False,
-                 record: bool = False):
+                 record: bool = False, fft_bins: int = 4096):
         self._lib = load()
         h = _H()
         rc = self._lib.hbd_create(n_channels, device, C.byref(h))
@@ -165,6 +166,8 @@ class BatchDecoder:
         self.lowpass_bw(lowpass_bw); self.lowpass_trans(lowpass_trans)
         if record:
             self._chk(self._lib.hbd_set_record(self._h, 1))
+        if fft_bins != 4096:
+            self.set_fft_size(fft_bins)
         if self.setupDecimationStagesFactor(dec_factor) != dec_factor:
             raise HbdError("unsupported decimation factor %r" % dec_factor)
 
@@ -179,6 +182,8 @@ class BatchDecoder:
             self._h = None
 
     __del__ = close
+
+    def set_fft_size(self, n_bins: int): self._chk(self._lib.hbd_set_fft_size(self._h, int(n_bins)))
 
     def set_stream(self, cuda_stream_ptr: int):
         self._chk(self._lib.hbd_set_stream(self._h, cuda_stream_ptr))
@@ -297,7 +302,7 @@ class BatchDecoder:
     def resetFrequencyCorrection(self, corr, ch=0): self._chk(self._lib.hbd_reset_frequency_correction(self._h, ch, float(corr)))
     def getSpectrumInfo(self, ch=0):
         info = SpectrumInfo()
-        power = np.empty(4096, dtype=np.float32)
+        power = np.empty(self.getBinsCount(), dtype=np.float32)
         n = self._lib.hbd_get_spectrum_info(self._h, ch, C.byref(info), power.ctypes.data, power.size)
         return info, power[:n]
 

@@ -112,6 +112,8 @@ struct hbd_decoder {
     double fs_in = 0;
     int factor = 1;
     int M1 = 1, T1 = 1, M2 = 1, T2 = 1;
+    int fft_n = kFftN;       // spectrum size: 4096 like the reference, or 16384 (hbd_set_fft_size)
+    int alloc_fft();
     std::vector<HostChan> hc;        // compact, scanned on every call
     std::vector<TextChannel> text;   // sentence layer state, touched only when a channel produced characters
 
@@ -238,12 +240,7 @@ int hbd_decoder::alloc_fixed()
         HBD_CUDA_CHECK(dalloc(&d_carry2[i], n * kCarryCap));
         HBD_CUDA_CHECK(cudaMemset(d_carry2[i], 0, n * kCarryCap * sizeof(float2)));
     }
-    HBD_CUDA_CHECK(dalloc(&d_fftbuf, n * kFftN));
-    HBD_CUDA_CHECK(cudaMemset(d_fftbuf, 0, n * kFftN * sizeof(float2)));
-    HBD_CUDA_CHECK(dalloc(&d_spectrum, n * kFftN));
-    HBD_CUDA_CHECK(cudaMemset(d_spectrum, 0, n * kFftN * sizeof(float2)));
-    HBD_CUDA_CHECK(dalloc(&d_power, n * kFftN));
-    HBD_CUDA_CHECK(cudaMemset(d_power, 0, n * kFftN * sizeof(float)));
+    { const int rc = alloc_fft(); if (rc) return rc; }
     HBD_CUDA_CHECK(dalloc(&d_lptaps, n * kLpMaxTaps));
     HBD_CUDA_CHECK(cudaMemset(d_lptaps, 0, n * kLpMaxTaps * sizeof(float)));
     HBD_CUDA_CHECK(dalloc(&d_log, size_t(kLogCap)));
@@ -255,7 +252,6 @@ int hbd_decoder::alloc_fixed()
     call_chars.resize(n);
     HBD_CUDA_CHECK(dalloc(&d_taps1, 512));
     HBD_CUDA_CHECK(dalloc(&d_taps2, 512));
-    HBD_CUDA_CHECK(dalloc(&d_twiddle, kFftN));
     HBD_CUDA_CHECK(dalloc(&d_cfg_baud, n));
     HBD_CUDA_CHECK(dalloc(&d_cfg_stops, n));
     HBD_CUDA_CHECK(dalloc(&d_cfg_bits, n));
@@ -264,12 +260,28 @@ int hbd_decoder::alloc_fixed()
     HBD_CUDA_CHECK(dalloc(&d_cfg_dirty, n));
     HBD_CUDA_CHECK(dalloc(&d_nco, n));
     h_nco.resize(n);
-    std::vector<float2> tw(kFftN);
-    for (int e = 0; e < kFftN; ++e) {
-        const double ang = -2.0 * M_PI * double(e) / double(kFftN);
+    return HBD_OK;
+}
+
+// spectrum buffers + twiddle table for the current fft_n (also called by hbd_set_fft_size)
+int hbd_decoder::alloc_fft()
+{
+    const size_t n = size_t(n_ch), N = size_t(fft_n);
+    for (void* p : {(void*)d_fftbuf, (void*)d_spectrum, (void*)d_power, (void*)d_twiddle}) if (p) cudaFree(p);
+    d_fftbuf = d_spectrum = nullptr; d_power = nullptr; d_twiddle = nullptr;
+    HBD_CUDA_CHECK(dalloc(&d_fftbuf, n * N));
+    HBD_CUDA_CHECK(cudaMemset(d_fftbuf, 0, n * N * sizeof(float2)));
+    HBD_CUDA_CHECK(dalloc(&d_spectrum, n * N));
+    HBD_CUDA_CHECK(cudaMemset(d_spectrum, 0, n * N * sizeof(float2)));
+    HBD_CUDA_CHECK(dalloc(&d_power, n * N));
+    HBD_CUDA_CHECK(cudaMemset(d_power, 0, n * N * sizeof(float)));
+    HBD_CUDA_CHECK(dalloc(&d_twiddle, N));
+    std::vector<float2> tw(N);
+    for (size_t e = 0; e < N; ++e) {
+        const double ang = -2.0 * M_PI * double(e) / double(N);
         tw[e] = make_float2(float(std::cos(ang)), float(std::sin(ang)));
     }
-    HBD_CUDA_CHECK(cudaMemcpy(d_twiddle, tw.data(), sizeof(float2) * kFftN, cudaMemcpyHostToDevice));
+    HBD_CUDA_CHECK(cudaMemcpy(d_twiddle, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
     return HBD_OK;
 }
 
@@ -499,7 +511,7 @@ int hbd_decoder::process_async_locked()
             TailArgs ta{};
             ta.plan = d_plan; ta.uplan = h_plan[0]; ta.uniform = plan_uniform ? 1 : 0; ta.state = d_state; ta.ch0 = c0;
             ta.s1 = d_s1x[s1_cur]; ta.s1_next = d_s1x[s1_cur ^ 1]; ta.s1_pitch = s1_pitch; ta.taps2 = d_taps2; ta.M2 = M2; ta.T2 = T2;
-            ta.decq = d_decq; ta.dq_pitch = dq_pitch; ta.fs_dec = fs_dec; ta.fftbuf = d_fftbuf; ta.lptaps = d_lptaps;
+            ta.decq = d_decq; ta.dq_pitch = dq_pitch; ta.fs_dec = fs_dec; ta.fftbuf = d_fftbuf; ta.fft_n = fft_n; ta.lptaps = d_lptaps;
             ta.max_lp_taps = int(max_lp_taps);
             ta.slicer = d_slicer; ta.slicer_pitch = slicer_pitch; ta.sv_want = sv_want;
             ta.log = d_log; ta.log_head = d_log_head; ta.call_seq = call_seq & 0xffffffu;
@@ -509,7 +521,7 @@ int hbd_decoder::process_async_locked()
             HBD_CUDA_CHECK(launch_tail(ta, nc, lo, &nl));
             FftArgs fa{};
             fa.state = d_state; fa.fftbuf = d_fftbuf; fa.spectrum = d_spectrum; fa.power = d_power; fa.twiddle = d_twiddle; fa.fs_dec = fs_dec;
-            fa.ch0 = c0;
+            fa.ch0 = c0; fa.fft_n = fft_n;
             HBD_CUDA_CHECK(launch_fft_afc(fa, nc, lo, &nl));
         }
         if (demod_acc_on && d_demod) { // main.cpp:267-282 runs after EVERY process(), also when nothing new was demodulated
@@ -669,6 +681,31 @@ int hbd_set_stream(hbd_decoder* h, void* s)
     cudaStreamSynchronize(h->stream);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     h->stream = (cudaStream_t)s; h->own_stream = false;
+    return HBD_OK;
+}
+
+// 4096 (the reference's fft_bins_cnt_) or 16384; restarts spectrum collection and the AFC of every channel
+int hbd_set_fft_size(hbd_decoder* h, size_t n_bins)
+{
+    HBD_CHECK_H(h);
+    if (n_bins != size_t(kFftN) && n_bins != size_t(kFftNMax)) return HBD_ERR_ARG;
+    std::lock_guard<std::mutex> l(h->mtx);
+    cudaSetDevice(h->device);
+    if (h->sync_groups() || cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
+    if (int(n_bins) == h->fft_n) return HBD_OK;
+    h->fft_n = int(n_bins);
+    const int rc = h->alloc_fft();
+    if (rc) return rc;
+    // spectrum / AFC state back to a freshly constructed decoder's (Average<T> starts with one 0 sample)
+    std::vector<ChanState> st(size_t(h->n_ch));
+    if (cudaMemcpy(st.data(), h->d_state, st.size() * sizeof(ChanState), cudaMemcpyDeviceToHost) != cudaSuccess) return HBD_ERR_CUDA;
+    for (auto& s : st) {
+        s.fft_have = s.fft_ready = s.have_spectrum = 0;
+        s.afc_correction = s.afc_noise_floor = s.afc_noise_var = s.afc_shift_hz = 0;
+        s.nf_sum = s.nv_sum = 0; s.pl_sum = s.pr_sum = 0; s.nf_cnt = s.nv_cnt = s.pl_cnt = s.pr_cnt = 1;
+        s.gui_left = s.gui_right = 0; s.spec_ok = 0;
+    }
+    if (cudaMemcpy(h->d_state, st.data(), st.size() * sizeof(ChanState), cudaMemcpyHostToDevice) != cudaSuccess) return HBD_ERR_CUDA;
     return HBD_OK;
 }
 
@@ -1041,7 +1078,7 @@ double hbd_get_input_sampling_rate(hbd_decoder* h) { return h ? h->fs_in : 0; }
 double hbd_get_decimated_sampling_rate(hbd_decoder* h) { return h ? h->fs_in / h->factor : 0; }
 double hbd_get_symbol_rate(hbd_decoder* h, int ch) { return hbd_get_baud(h, ch); }
 int hbd_n_channels(hbd_decoder* h) { return h ? h->n_ch : 0; }
-size_t hbd_get_bins_count(hbd_decoder*) { return size_t(kFftN); }
+size_t hbd_get_bins_count(hbd_decoder* h) { return h ? size_t(h->fft_n) : size_t(kFftN); }
 
 static int fetch_state(hbd_decoder* h, int ch, ChanState* st)
 {
@@ -1066,7 +1103,7 @@ size_t hbd_get_fft(hbd_decoder* h, int ch, float* out, size_t cap)
     std::lock_guard<std::mutex> l(h->mtx);
     ChanState st; if (fetch_state(h, ch, &st)) return 0;
     if (!st.have_spectrum) return 0; // freq_out_ is empty before the first FFT
-    return fetch_floats(h, h->d_spectrum + size_t(ch) * kFftN, 2 * size_t(kFftN), out, cap);
+    return fetch_floats(h, h->d_spectrum + size_t(ch) * size_t(h->fft_n), 2 * size_t(h->fft_n), out, cap);
 }
 size_t hbd_get_power_spectrum(hbd_decoder* h, int ch, float* out, size_t cap)
 {
@@ -1074,7 +1111,7 @@ size_t hbd_get_power_spectrum(hbd_decoder* h, int ch, float* out, size_t cap)
     std::lock_guard<std::mutex> l(h->mtx);
     ChanState st; if (fetch_state(h, ch, &st)) return 0;
     if (!st.have_spectrum) return 0;
-    return fetch_floats(h, h->d_power + size_t(ch) * kFftN, size_t(kFftN), out, cap);
+    return fetch_floats(h, h->d_power + size_t(ch) * size_t(h->fft_n), size_t(h->fft_n), out, cap);
 }
 size_t hbd_get_demodulated(hbd_decoder* h, int ch, float* out, size_t cap)
 {
@@ -1111,7 +1148,7 @@ int hbd_reset_frequency_correction(hbd_decoder* h, int ch, double corr)
     HBD_CHECK_CH(h, ch); std::lock_guard<std::mutex> l(h->mtx);
     cudaSetDevice(h->device);
     h->sync_groups(); // ordered after everything in flight, like a call between two process() calls
-    if (launch_afc_reset(h->d_state, ch, corr, h->fs_in / h->factor, h->stream) != cudaSuccess) return HBD_ERR_CUDA;
+    if (launch_afc_reset(h->d_state, ch, corr, h->fs_in / h->factor, h->fft_n, h->stream) != cudaSuccess) return HBD_ERR_CUDA;
     cudaStreamSynchronize(h->stream);
     ++h->launches;
     return HBD_OK;
@@ -1162,14 +1199,14 @@ static size_t fetch_frames(hbd_decoder* h, int ch0, int nc, bool spectrum, float
     cudaSetDevice(h->device);
     if (h->sync_groups() || cudaStreamSynchronize(h->stream) != cudaSuccess) return 0;
     const size_t hdr = spectrum ? size_t(kSpectrumHeaderBytes) : size_t(kDemodHeaderBytes);
-    const size_t max_n = spectrum ? size_t(kFftN) : std::max<size_t>(h->dacc_pitch, 1);
+    const size_t max_n = spectrum ? size_t(h->fft_n) : std::max<size_t>(h->dacc_pitch, 1);
     const size_t need = hdr + std::min<size_t>(max_n, size_t(resolution)) * size_t(type_size);
     if (h->ensure_frames(need)) return 0;
     int nl = 0;
     cudaError_t e;
     if (spectrum) {
         SpectrumFrameArgs a{};
-        a.state = h->d_state; a.power = h->d_power; a.fs_dec = h->fs_in / h->factor; a.zoom = zoom; a.resolution = resolution; a.type_size = type_size;
+        a.state = h->d_state; a.power = h->d_power; a.fft_n = h->fft_n; a.fs_dec = h->fs_in / h->factor; a.zoom = zoom; a.resolution = resolution; a.type_size = type_size;
         a.out = h->d_frames; a.out_pitch = h->frames_pitch; a.sizes = h->d_frame_sizes; a.ch0 = ch0;
         e = launch_spectrum_frames(a, nc, h->stream, &nl);
     } else {
@@ -1231,7 +1268,7 @@ int hbd_afc_retune(hbd_decoder* h, double min_abs_hz, double* applied_out)
     double* d_applied = nullptr;
     if (cudaMalloc((void**)&d_applied, n * sizeof(double)) != cudaSuccess) return HBD_ERR_NOMEM;
     std::vector<double> applied(n, 0.0);
-    cudaError_t e = launch_afc_retune(h->d_state, h->n_ch, min_abs_hz, h->fs_in / h->factor, d_applied, h->stream);
+    cudaError_t e = launch_afc_retune(h->d_state, h->n_ch, min_abs_hz, h->fs_in / h->factor, d_applied, h->fft_n, h->stream);
     ++h->launches;
     if (e == cudaSuccess) e = cudaMemcpyAsync(applied.data(), d_applied, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -1267,7 +1304,7 @@ size_t hbd_get_stats_batch(hbd_decoder* h, double* out, size_t cap_doubles)
 size_t hbd_get_spectrum_info(hbd_decoder* h, int ch, hbd_spectrum_info* info, float* power, size_t cap)
 {
     if (!h || ch < 0 || ch >= h->n_ch || !info) return 0;
-    std::vector<float> p(kFftN);
+    std::vector<float> p(size_t(h->fft_n));
     const size_t n = hbd_get_power_spectrum(h, ch, p.data(), p.size());
     memset(info, 0, sizeof(*info));
     if (!n) return 0; // Decoder.h:818-819

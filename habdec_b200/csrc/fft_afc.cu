@@ -124,7 +124,7 @@ __device__ __forceinline__ double avg_add_i(int& sum, unsigned& cnt, unsigned ca
     return diff;
 }
 
-__device__ void afc_step(ChanState& st, double fs_dec)
+__device__ void afc_step(ChanState& st, double fs_dec, int n_fft)
 {
     if (!st.have_spectrum || !st.spec_ok) { st.afc_correction = 0; return; } // AFC.h:96-100
     st.afc_noise_floor = st.spec_nf;
@@ -148,20 +148,71 @@ __device__ void afc_step(ChanState& st, double fs_dec)
     if (stable_l && stable_r) {
         const int pl = int(round(la)), pr = int(round(ra));
         const int dist = pr - pl;
-        const double hz_per_bin = __ddiv_rn(fs_dec, double(kFftN));
+        const double hz_per_bin = __ddiv_rn(fs_dec, double(n_fft));
         st.afc_shift_hz = __dmul_rn(hz_per_bin, double(dist));
         const double mid = double(pl + dist / 2);
-        const double err = __dsub_rn(mid, double(kFftN) / 2);
+        const double err = __dsub_rn(mid, double(n_fft) / 2);
         if (4 < fabs(err)) st.afc_correction = __dmul_rn(hz_per_bin, err);
     }
 }
 
+// 4096-point forward DFT of x[stride * n + offset] (n = 0 .. 4095) by 256 threads: three register-resident radix-16
+// passes, two exchanges through s_a (16*16*17 float2).  tw[e * tw_step] = exp(-2 pi i e / 4096).  Bin k is handed
+// to store(k, value).
+template <typename Store>
+__device__ __forceinline__ void fft4096(const float2* __restrict__ x, int stride, int offset, const float2* __restrict__ tw, int tw_step,
+                                        float2* s_a, Store store)
+{
+    const int t = threadIdx.x;
+    float2 v[16];
+    // pass 1: n = 256*n1 + t, DFT over n1 -> k1; twiddle W_4096^(t*k1); A[k1][t]
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = x[(size_t)stride * (256 * i + t) + offset];
+    dft16(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+        float2 y = v[bin16(k1)];
+        if (k1) y = cmul(y, tw[(t * k1) * tw_step]);
+        s_a[k1 * 256 + t] = y;
+    }
+    __syncthreads();
+    // pass 2: thread (k1, m2): n2 = 16*m1 + m2, DFT over m1 -> j1; twiddle W_256^(m2*j1); B[k1][j1][m2] (row pitch 17)
+    {
+        const int k1 = t >> 4, m2 = t & 15;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = s_a[k1 * 256 + 16 * i + m2];
+        dft16(v);
+        __syncthreads();
+#pragma unroll
+        for (int j1 = 0; j1 < 16; ++j1) {
+            float2 y = v[bin16(j1)];
+            if (j1) y = cmul(y, tw[(16 * m2 * j1) * tw_step]);
+            s_a[k1 * (16 * 17) + j1 * 17 + m2] = y;
+        }
+    }
+    __syncthreads();
+    // pass 3: thread (k1, j1): DFT over m2 -> j2; X[k1 + 16*j1 + 256*j2]
+    {
+        const int k1 = t >> 4, j1 = t & 15;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = s_a[k1 * (16 * 17) + j1 * 17 + i];
+        dft16(v);
+        __syncthreads();
+#pragma unroll
+        for (int j2 = 0; j2 < 16; ++j2) store(k1 + 16 * j1 + 256 * j2, v[bin16(j2)]);
+    }
+}
+
+// N = 4096 (the reference's fft_bins_cnt_, Decoder.h:163) or 16384 (the 16k-bin spectrum of BASELINE configs[1]:
+// four 4096-point sub-transforms of the decimated-by-4 phases + one radix-4 combining pass, all in shared memory).
+template <int N>
 __global__ void __launch_bounds__(kFftThreads)
 fft_afc_kernel(FftArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* s_a = reinterpret_cast<float2*>(smem_raw);          // 4096 float2 (+ padding for the 2nd exchange)
-    float* s_p = reinterpret_cast<float*>(s_a + 16 * 16 * 17);  // 4096 floats: power spectrum
+    float2* s_a = reinterpret_cast<float2*>(smem_raw);          // exchange area of the 4096-point transform
+    float2* s_f = s_a + 16 * 16 * 17;                           // N == 16384: the four sub-spectra [4][4096]
+    float* s_p = reinterpret_cast<float*>(s_a + 16 * 16 * 17);  // N == 4096: power spectrum (4096 floats)
     __shared__ double s_red[kFftThreads / 32];
     __shared__ float s_av[kFftThreads / 32];
     __shared__ int s_ai[kFftThreads / 32];
@@ -174,72 +225,45 @@ fft_afc_kernel(FftArgs a)
     if (!do_fft && !do_tick) return;
 
     if (do_fft) {
-        const float2* x = a.fftbuf + (size_t)ch * kFftN;
-        const float2* __restrict__ tw = a.twiddle; // tw[e] = exp(-2 pi i e / 4096)
-        float2 v[16];
-        // pass 1: n = 256*n1 + t, DFT over n1 -> k1; twiddle W_4096^(t*k1); A[k1][t]
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = x[256 * i + t];
-        dft16(v);
-#pragma unroll
-        for (int k1 = 0; k1 < 16; ++k1) {
-            float2 y = v[bin16(k1)];
-            if (k1) y = cmul(y, tw[t * k1]);
-            s_a[k1 * 256 + t] = y;
-        }
-        __syncthreads();
-        // pass 2: thread (k1, m2): n2 = 16*m1 + m2, DFT over m1 -> j1; twiddle W_256^(m2*j1); B[k1][j1][m2] (row pitch 17)
-        {
-            const int k1 = t >> 4, m2 = t & 15;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = s_a[k1 * 256 + 16 * i + m2];
-            dft16(v);
-            __syncthreads();
-#pragma unroll
-            for (int j1 = 0; j1 < 16; ++j1) {
-                float2 y = v[bin16(j1)];
-                if (j1) y = cmul(y, tw[16 * m2 * j1]);
-                s_a[k1 * (16 * 17) + j1 * 17 + m2] = y;
-            }
-        }
-        __syncthreads();
-        // pass 3: thread (k1, j1): DFT over m2 -> j2; X[k1 + 16*j1 + 256*j2]
-        {
-            const int k1 = t >> 4, j1 = t & 15;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = s_a[k1 * (16 * 17) + j1 * 17 + i];
-            dft16(v);
-            __syncthreads();
-#pragma unroll
-            for (int j2 = 0; j2 < 16; ++j2) {
-                const int k = k1 + 16 * j1 + 256 * j2;
-                s_a[(k + kFftN / 2) & (kFftN - 1)] = v[bin16(j2)]; // swap halves (FFT.cpp:77-87)
-            }
-        }
+        const float2* x = a.fftbuf + (size_t)ch * N;
+        const float2* __restrict__ tw = a.twiddle; // tw[e] = exp(-2 pi i e / N)
+        float2* spec = a.spectrum + (size_t)ch * N;
+        float* pw = a.power + (size_t)ch * N;
         if (t == 0) s_bad = 0;
-        __syncthreads();
-
-        // spectrum out + FftPower (AFC.h:236-286)
-        float2* spec = a.spectrum + (size_t)ch * kFftN;
-        float* pw = a.power + (size_t)ch * kFftN;
         int bad = 0;
-        for (int i = t; i < kFftN; i += kFftThreads) {
-            const float2 z = s_a[i];
+        // FftPower of one bin (AFC.h:236-286), spectrum out with the halves swapped (FFT.cpp:77-87)
+        auto emit = [&](int k, float2 z) {
+            const int i = (k + N / 2) & (N - 1);
             spec[i] = z;
             if (z.x != z.x || z.y != z.y || isinf(z.x) || isinf(z.y)) bad = 1;
-            float p = __fadd_rn(__fmul_rn(z.x, z.x), __fmul_rn(z.y, z.y)) / float(kFftN);
+            float p = __fadd_rn(__fmul_rn(z.x, z.x), __fmul_rn(z.y, z.y)) / float(N);
             p = __fmul_rn(p, p);
             p = float(__ddiv_rn(double(p), a.fs_dec));
             p = __fmul_rn(10.0f, log10f(p));
-            s_p[i] = p;
+            if (N == 4096) s_p[i] = p; else pw[i] = p;
+        };
+        if (N == 4096) {
+            fft4096(x, 1, 0, tw, 1, s_a, emit);
+        } else {
+            for (int r = 0; r < 4; ++r) {
+                fft4096(x, 4, r, tw, 4, s_a, [&](int k, float2 z) { s_f[r * 4096 + k] = z; });
+                __syncthreads();
+            }
+            // X[k + 4096 q] = sum_r W_N^(r k) F_r[k] W_4^(r q)
+            for (int k = t; k < 4096; k += kFftThreads) {
+                float2 y0 = s_f[k], y1 = cmul(s_f[4096 + k], tw[k]), y2 = cmul(s_f[8192 + k], tw[2 * k]), y3 = cmul(s_f[12288 + k], tw[3 * k]);
+                dft4(y0, y1, y2, y3);
+                emit(k, y0); emit(k + 4096, y1); emit(k + 8192, y2); emit(k + 12288, y3);
+            }
         }
         if (bad) s_bad = 1;
         __syncthreads();
+        const float* P = (N == 4096) ? s_p : pw;   // N == 16384: the dB values are re-read from HBM/L2 (written by this CTA)
         int bad2 = 0;
         if (!s_bad) {
-            for (int i = t; i < kFftN; i += kFftThreads) {
-                const float p = s_p[i];
-                pw[i] = p;
+            for (int i = t; i < N; i += kFftThreads) {
+                const float p = P[i];
+                if (N == 4096) pw[i] = p;
                 if (p != p || isinf(p)) bad2 = 1;
             }
         }
@@ -249,29 +273,29 @@ fft_afc_kernel(FftArgs a)
         if (ok) {
             // noise floor = mean, "variance" = standard deviation, both float64 (AFC.h:103-104,225-232)
             double s = 0;
-            for (int i = t; i < kFftN; i += kFftThreads) s += double(s_p[i]);
-            const double nf = block_sum(s, s_red) / double(kFftN);
+            for (int i = t; i < N; i += kFftThreads) s += double(P[i]);
+            const double nf = block_sum(s, s_red) / double(N);
             double q = 0;
-            for (int i = t; i < kFftN; i += kFftThreads) { const double d = double(s_p[i]) - nf; q += d * d; }
-            const double nv = sqrt(block_sum(q, s_red) / double(kFftN));
+            for (int i = t; i < N; i += kFftThreads) { const double d = double(P[i]) - nf; q += d * d; }
+            const double nv = sqrt(block_sum(q, s_red) / double(N));
             // FindPeaks (AFC.h:290-329)
             float bv = -INFINITY; int bi = 0x7fffffff;
-            for (int i = t; i < kFftN; i += kFftThreads) { const float p = s_p[i]; if (p > bv) { bv = p; bi = i; } }
+            for (int i = t; i < N; i += kFftThreads) { const float p = P[i]; if (p > bv) { bv = p; bi = i; } }
             float p1v; int p1;
             block_argmax(bv, bi, s_av, s_ai, p1v, p1);
             const float rel_sep = float(500.0f / a.fs_dec);
-            int sep = int(round(double(rel_sep) * double(kFftN)));
+            int sep = int(round(double(rel_sep) * double(N)));
             sep = max(8, sep);
-            const int lo = max(p1 - 2 * sep, 0), hi = min(p1 + 2 * sep, kFftN);
+            const int lo = max(p1 - 2 * sep, 0), hi = min(p1 + 2 * sep, N);
             bv = -INFINITY; bi = 0x7fffffff;
             for (int i = lo + t; i < hi; i += kFftThreads) {
-                const float p = s_p[i];
+                const float p = P[i];
                 if (abs(i - p1) > sep / 2 && p > bv) { bv = p; bi = i; }
             }
             float p2v; int p2;
             block_argmax(bv, bi, s_av, s_ai, p2v, p2);
             if (t == 0) {
-                if (!(p2v > s_p[0])) { p2 = 0; p2v = s_p[0]; } // running best starts at v[0], index 0
+                if (!(p2v > P[0])) { p2 = 0; p2v = P[0]; } // running best starts at v[0], index 0
                 if (p2 < p1) { const int ti = p1; p1 = p2; p2 = ti; const float tv = p1v; p1v = p2v; p2v = tv; }
                 st.spec_nf = nf; st.spec_nv = nv;
                 st.spec_p1 = p1; st.spec_p2 = p2; st.spec_p1_val = p1v; st.spec_p2_val = p2v;
@@ -286,32 +310,39 @@ fft_afc_kernel(FftArgs a)
         __syncthreads();
     }
     if (do_tick && t == 0) {
-        afc_step(st, a.fs_dec);
+        afc_step(st, a.fs_dec, N);
         st.afc_tick = 0;
     }
 }
 
-cudaError_t launch_fft_afc(const FftArgs& a, int n_channels, cudaStream_t stream, int* launches)
+template <int N>
+static cudaError_t launch_fft_n(const FftArgs& a, int n_channels, cudaStream_t stream, int* launches)
 {
-    const size_t smem = size_t(16 * 16 * 17) * 8 + size_t(kFftN) * 4;
+    const size_t smem = size_t(16 * 16 * 17) * 8 + (N == 4096 ? size_t(4096) * 4 : size_t(16384) * 8);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fft_afc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fft_afc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        cudaFuncSetAttribute(fft_afc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(fft_afc_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
-    fft_afc_kernel<<<n_channels, kFftThreads, smem, stream>>>(a);
+    fft_afc_kernel<N><<<n_channels, kFftThreads, smem, stream>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
 
+cudaError_t launch_fft_afc(const FftArgs& a, int n_channels, cudaStream_t stream, int* launches)
+{
+    if (a.fft_n == 16384) return launch_fft_n<16384>(a, n_channels, stream, launches);
+    return launch_fft_n<4096>(a, n_channels, stream, launches);
+}
+
 // AFC::resetFrequencyCorrection (AFC.h:188-194), one thread per call
-__global__ void afc_reset_kernel(ChanState* state, int ch, double corr, double fs_dec)
+__global__ void afc_reset_kernel(ChanState* state, int ch, double corr, double fs_dec, int n_fft)
 {
     ChanState& st = state[ch];
     // the reference divides fft_samples_.size() by its sampling rate: both are 0 before the first spectrum
-    const double bins_per_hz = st.have_spectrum ? __ddiv_rn(double(kFftN), fs_dec) : __ddiv_rn(0.0, 0.0);
+    const double bins_per_hz = st.have_spectrum ? __ddiv_rn(double(n_fft), fs_dec) : __ddiv_rn(0.0, 0.0);
     const double l = __dsub_rn(avg_get_i(st.pl_sum, st.pl_cnt), __dmul_rn(corr, bins_per_hz));
     const double r = __dsub_rn(avg_get_i(st.pr_sum, st.pr_cnt), __dmul_rn(corr, bins_per_hz));
     st.pl_sum = int(fmax(0.0, l)); st.pl_cnt = 1;
@@ -319,16 +350,16 @@ __global__ void afc_reset_kernel(ChanState* state, int ch, double corr, double f
     st.afc_correction = 0;
 }
 
-cudaError_t launch_afc_reset(ChanState* state, int ch, double corr, double fs_dec, cudaStream_t stream)
+cudaError_t launch_afc_reset(ChanState* state, int ch, double corr, double fs_dec, int n_fft, cudaStream_t stream)
 {
-    afc_reset_kernel<<<1, 1, 0, stream>>>(state, ch, corr, fs_dec);
+    afc_reset_kernel<<<1, 1, 0, stream>>>(state, ch, corr, fs_dec, n_fft);
     return cudaGetLastError();
 }
 
 // The retune decision of DECODER_THREAD (code/websocketServer/main.cpp:248-265) for every channel at once: where
 // |frequency_correction| exceeds min_abs_hz the correction is handed to the caller (who adds it to the channel's
 // NCO) and the AFC is reset exactly like resetFrequencyCorrection(); applied[ch] = 0 elsewhere.
-__global__ void afc_retune_kernel(ChanState* state, int n_ch, double min_abs_hz, double fs_dec, double* applied)
+__global__ void afc_retune_kernel(ChanState* state, int n_ch, double min_abs_hz, double fs_dec, double* applied, int n_fft)
 {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= n_ch) return;
@@ -336,7 +367,7 @@ __global__ void afc_retune_kernel(ChanState* state, int n_ch, double min_abs_hz,
     const double corr = st.afc_correction;
     if (!(min_abs_hz < fabs(corr))) { applied[ch] = 0.0; return; }
     applied[ch] = corr;
-    const double bins_per_hz = st.have_spectrum ? __ddiv_rn(double(kFftN), fs_dec) : __ddiv_rn(0.0, 0.0);
+    const double bins_per_hz = st.have_spectrum ? __ddiv_rn(double(n_fft), fs_dec) : __ddiv_rn(0.0, 0.0);
     const double l = __dsub_rn(avg_get_i(st.pl_sum, st.pl_cnt), __dmul_rn(corr, bins_per_hz));
     const double r = __dsub_rn(avg_get_i(st.pr_sum, st.pr_cnt), __dmul_rn(corr, bins_per_hz));
     st.pl_sum = int(fmax(0.0, l)); st.pl_cnt = 1;
@@ -344,9 +375,9 @@ __global__ void afc_retune_kernel(ChanState* state, int n_ch, double min_abs_hz,
     st.afc_correction = 0;
 }
 
-cudaError_t launch_afc_retune(ChanState* state, int n_ch, double min_abs_hz, double fs_dec, double* applied, cudaStream_t stream)
+cudaError_t launch_afc_retune(ChanState* state, int n_ch, double min_abs_hz, double fs_dec, double* applied, int n_fft, cudaStream_t stream)
 {
-    afc_retune_kernel<<<(n_ch + 127) / 128, 128, 0, stream>>>(state, n_ch, min_abs_hz, fs_dec, applied);
+    afc_retune_kernel<<<(n_ch + 127) / 128, 128, 0, stream>>>(state, n_ch, min_abs_hz, fs_dec, applied, n_fft);
     return cudaGetLastError();
 }
 

@@ -6,16 +6,17 @@ namespace hbd {
 
 struct FftArgs {
     ChanState* state;
-    const float2* fftbuf;   // [channel][kFftN] frame being collected
-    float2* spectrum;       // [channel][kFftN] last fft-shifted spectrum (getFFT)
-    float* power;           // [channel][kFftN] last power spectrum in dB (getPowerSpectrum)
-    const float2* twiddle;  // [kFftN] exp(-2 pi i e / kFftN), evaluated in float64 on the host
+    const float2* fftbuf;   // [channel][fft_n] frame being collected
+    float2* spectrum;       // [channel][fft_n] last fft-shifted spectrum (getFFT)
+    float* power;           // [channel][fft_n] last power spectrum in dB (getPowerSpectrum)
+    const float2* twiddle;  // [fft_n] exp(-2 pi i e / fft_n), evaluated in float64 on the host
     double fs_dec;
     int ch0;                // first channel of this launch
+    int fft_n;              // 4096 (reference) or 16384
 };
 
 cudaError_t launch_fft_afc(const FftArgs& a, int n_channels, cudaStream_t stream, int* launches);
-cudaError_t launch_afc_reset(ChanState* state, int ch, double corr, double fs_dec, cudaStream_t stream);
-cudaError_t launch_afc_retune(ChanState* state, int n_ch, double min_abs_hz, double fs_dec, double* applied, cudaStream_t stream);
+cudaError_t launch_afc_reset(ChanState* state, int ch, double corr, double fs_dec, int n_fft, cudaStream_t stream);
+cudaError_t launch_afc_retune(ChanState* state, int n_ch, double min_abs_hz, double fs_dec, double* applied, int n_fft, cudaStream_t stream);
 
 } // namespace hbd

@@ -21,7 +21,8 @@ constexpr int kS1Hist       = 320;    // stage-2 history slots (>= T2-1 = 138; d
 constexpr int kLpMaxTaps    = 1025;   // low-pass taps upper bound ((4/trans)|1, trans >= 0.0039)
 constexpr int kLpHist       = 1024;   // low-pass history slots (>= kLpMaxTaps-1)
 constexpr int kLpBatch      = 256;    // Decoder.h:492 batch_size
-constexpr int kFftN         = 4096;   // Decoder.h:163 fft_bins_cnt_
+constexpr int kFftN         = 4096;   // Decoder.h:163 fft_bins_cnt_ (default; hbd_set_fft_size selects 16384)
+constexpr int kFftNMax      = 16384;
 constexpr int kSlicerVent   = 30000;  // SymbolExtractor.h:116 safety vent (3e4)
 constexpr int kBitsCap      = 16384;  // bits the slicer may emit in one call (+ pending UART bits)
 constexpr unsigned kLogCap   = 1u << 20; // decoded-character log entries (ring) between host drains

@@ -141,7 +141,8 @@ tail_kernel(TailArgs a)
     cp_async_commit();
 
     const unsigned fft_have0 = s_st.fft_have;
-    const unsigned fft_take = (fft_have0 < unsigned(kFftN)) ? hbd_min_u(kFftN - fft_have0, n2) : 0u;
+    const unsigned fft_n = unsigned(a.fft_n);
+    const unsigned fft_take = (fft_have0 < fft_n) ? hbd_min_u(fft_n - fft_have0, n2) : 0u;
     const bool dc = s_st.dc_remove != 0;
     float2 carry_prev = make_float2(s_st.demod_last_re, s_st.demod_last_im);
     const bool primed = s_st.demod_primed != 0;
@@ -229,7 +230,7 @@ tail_kernel(TailArgs a)
             for (unsigned k = tid; k < nk; k += kTailThreads) rec[k0 + k] = ynew[k];
         }
         if (k0 < fft_take) {
-            float2* fb = a.fftbuf + (size_t)ch * kFftN + fft_have0;
+            float2* fb = a.fftbuf + (size_t)ch * fft_n + fft_have0;
             for (unsigned k = tid; k < nk && k0 + k < fft_take; k += kTailThreads) fb[k0 + k] = ynew[k];
         }
         have_q += nk;
@@ -344,7 +345,7 @@ tail_kernel(TailArgs a)
             gst.n_filtered = nf;
             if (fft_take) {
                 gst.fft_have = fft_have0 + fft_take;
-                if (fft_have0 + fft_take >= unsigned(kFftN)) gst.fft_ready = 1;
+                if (fft_have0 + fft_take >= fft_n) gst.fft_ready = 1;
             }
             if (nf) {
                 gst.demod_last_re = carry_prev.x;

@@ -16,8 +16,8 @@ struct TailArgs {
     // decimated queue: [kLpHist history slots | pending]
     float2* decq; size_t dq_pitch;
     double fs_dec;
-    // FFT frame buffers [channel][kFftN]
-    float2* fftbuf;
+    // FFT frame buffers [channel][fft_n]
+    float2* fftbuf; int fft_n;
     // low-pass taps [channel][kLpMaxTaps]
     const float* lptaps;
     int max_lp_taps;          // largest lp_ntaps of any channel (sizes the shared-memory queue)

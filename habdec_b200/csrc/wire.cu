@@ -67,8 +67,8 @@ spectrum_frame_kernel(SpectrumFrameArgs a)
     const ChanState& st = a.state[ch];
     unsigned char* out = a.out + size_t(slot) * a.out_pitch;
     if (!st.have_spectrum) { if (tid == 0) a.sizes[slot] = 0; return; }   // getSpectrumInfo: empty vector, no message
-    const float* v = a.power + size_t(ch) * kFftN;
-    const size_t n = kFftN;
+    const size_t n = size_t(a.fft_n);
+    const float* v = a.power + size_t(ch) * n;
     const float zoom = fminf(fmaxf(a.zoom, 0.01f), 0.99f);
     const size_t zb = size_t(__fmul_rn(zoom / 2, float(n)));
     const size_t ze = size_t(__fmul_rn(1.0f - zoom / 2, float(n)));

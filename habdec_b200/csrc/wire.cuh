@@ -9,7 +9,7 @@ constexpr int kDemodHeaderBytes = 20;    // DemodHeader, NetTransport.h:50-57
 
 struct SpectrumFrameArgs {
     const ChanState* state;
-    const float* power;          // [channel][kFftN] dB spectrum
+    const float* power; int fft_n; // [channel][fft_n] dB spectrum
     double fs_dec;
     float zoom; int resolution; int type_size;   // 1: u8, 2: u16, 4: f32
     unsigned char* out; size_t out_pitch;        // [channel slot][out_pitch] bytes

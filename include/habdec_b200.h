@@ -54,6 +54,9 @@ void hbd_destroy(hbd_decoder* h);
 const char* hbd_last_error(hbd_decoder* h);
 /* run all work on this cudaStream_t (default: a private non-blocking stream) */
 int  hbd_set_stream(hbd_decoder* h, void* cuda_stream);
+/* spectrum / AFC FFT size: 4096 (the reference's fft_bins_cnt_, Decoder.h:163; default) or 16384 (the 16k-bin
+ * spectrum of BASELINE configs[1]).  Restarts spectrum collection and the AFC averages of every channel. */
+int  hbd_set_fft_size(hbd_decoder* h, size_t n_bins);
 /* keep per-call stage arrays (decimated IQ, filtered IQ, slicer bits) for hbd_debug_stage(); test use */
 int  hbd_set_record(hbd_decoder* h, int on);
 

@@ -518,7 +518,7 @@ struct Port {
         dec_q.insert(dec_q.end(), work.begin(), work.end());
 
         // FFT frame assembly, Decoder.h:467-489
-        const size_t NFFT = 4096;
+        const size_t NFFT = cfg.fft_bins ? size_t(cfg.fft_bins) : 4096; // Decoder.h:163 (16384: configs[1] extension)
         if (fft_in.size() < NFFT && work.size()) {
             const size_t k = std::min(NFFT - fft_in.size(), work.size());
             fft_in.insert(fft_in.end(), work.begin(), work.begin() + k);

@@ -41,6 +41,8 @@ typedef struct hbo_config {
     int    dec_factor;  /* setupDecimationStagesFactor Decoder.h:268 */
     int    dc_remove;   /* Decoder::dc_remove       Decoder.h:701 */
     int    record;      /* 1: append stage arrays on every call */
+    int    fft_bins;    /* 0 / 4096: the reference's fft_bins_cnt_ (Decoder.h:163); 16384: the 16k-bin extension of
+                           BASELINE configs[1] -- the reference object is run with that member patched at run time */
 } hbo_config;
 
 /* AFC / spectrum scalars after the most recent call */

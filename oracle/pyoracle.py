@@ -21,7 +21,7 @@ STAGE_DECIMATED, STAGE_FILTERED, STAGE_DEMOD, STAGE_FFT, STAGE_POWER, STAGE_LPTA
 class Config(C.Structure):
     _fields_ = [("baud", C.c_double), ("rtty_bits", C.c_int), ("rtty_stops", C.c_float),
                 ("lowpass_bw", C.c_float), ("lowpass_trans", C.c_float), ("dec_factor", C.c_int),
-                ("dc_remove", C.c_int), ("record", C.c_int)]
+                ("dc_remove", C.c_int), ("record", C.c_int), ("fft_bins", C.c_int)]
 
 
 class AfcInfo(C.Structure):
@@ -30,9 +30,9 @@ class AfcInfo(C.Structure):
 
 
 def make_config(baud=300.0, rtty_bits=8, rtty_stops=2.0, lowpass_bw=1500.0, lowpass_trans=0.025,
-                dec_factor=256, dc_remove=False, record=True) -> Config:
+                dec_factor=256, dc_remove=False, record=True, fft_bins=0) -> Config:
     return Config(float(baud), int(rtty_bits), float(rtty_stops), float(lowpass_bw), float(lowpass_trans),
-                  int(dec_factor), int(bool(dc_remove)), int(bool(record)))
+                  int(dec_factor), int(bool(dc_remove)), int(bool(record)), int(fft_bins))
 
 
 def _bind(lib, p):

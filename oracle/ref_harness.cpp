@@ -92,6 +92,11 @@ void configure(habdec::Decoder<float>& D, const hbo_config& c)
     D.lowpass_bw(c.lowpass_bw);
     D.lowpass_trans(c.lowpass_trans);
     D.setupDecimationStagesFactor(size_t(c.dec_factor));
+    if (c.fft_bins && size_t(c.fft_bins) != D.fft_bins_cnt_) {
+        // 16k-bin extension: FFT and AFC classes are size agnostic, only this const member pins 4096.
+        // It is a per-object runtime value (read in process(), Decoder.h:466-506), patched here without touching sources.
+        *const_cast<size_t*>(&D.fft_bins_cnt_) = size_t(c.fft_bins);
+    }
 }
 
 struct Ref {

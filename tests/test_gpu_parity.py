@@ -140,23 +140,30 @@ def test_async_steps_equal_sync_steps():
     assert len(a.getLastSentence(0)) > 10
 
 
-def test_fft_and_afc(oracle_kind):
-    """Spectrum vs a float64 DFT of the same decimated frame; AFC scalars vs the oracle."""
-    fs, baud = 2.048e6, 300.0
-    iq, _ = synth.channel_iq(2, 3, fs, baud, snr_db=-15.0, f_off=60.0)
-    cfg = dict(baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
-    ref = make_oracle(oracle_kind, **cfg).run(iq, fs)
-    dec = api.BatchDecoder(1, record=True, **cfg)
+@pytest.mark.parametrize("fs,baud,bits,n_sent,nfft", [
+    (2.048e6, 300.0, 8, 3, 4096),        # the reference's fft_bins_cnt_
+    (2.5e6, 50.0, 7, 1, 16384),          # BASELINE configs[1]: AirSpy rate, 50 baud 7N2, 16k-bin spectrum
+    (2.048e6, 300.0, 8, 6, 16384),
+])
+def test_fft_and_afc(oracle_kind, fs, baud, bits, n_sent, nfft):
+    """Spectrum vs a float64 DFT of the same decimated frame; AFC scalars vs the oracle (for 16384 bins the oracle is the
+    reference Decoder with its fft_bins_cnt_ member set to 16384 at run time, FFT/AFC classes unchanged)."""
+    iq, _ = synth.channel_iq(2, n_sent, fs, baud, bits, 2, snr_db=-15.0, f_off=60.0)
+    cfg = dict(baud=baud, rtty_bits=bits, rtty_stops=2.0, dec_factor=256)
+    ref = make_oracle(oracle_kind, fft_bins=nfft, **cfg).run(iq, fs)
+    dec = api.BatchDecoder(1, record=True, fft_bins=nfft, **cfg)
+    assert dec.getBinsCount() == nfft
     frames, cur = [], []
     for o in range(0, len(iq), 65536):
         dec.pushSamples(0, iq[o:o + 65536], fs)
         dec.process()
         d = dec.debug_stage(0, api.STAGE_DECIMATED)
         cur.extend(d.tolist())
-        if len(cur) >= 4096:
-            frames.append(np.asarray(cur[:4096], dtype=np.complex64)); cur = []
+        if len(cur) >= nfft:
+            frames.append(np.asarray(cur[:nfft], dtype=np.complex64)); cur = []
+    assert len(frames) >= 2
     spec = dec.getFFT(0)
-    assert spec.shape == (4096,)
+    assert spec.shape == (nfft,)
     want = np.fft.fftshift(np.fft.fft(frames[-1].astype(np.complex128)))
     assert rel_l2(spec, want) <= REL_L2
     assert rel_l2(spec, ref.stage(po.STAGE_FFT)) <= REL_L2
@@ -170,7 +177,8 @@ def test_fft_and_afc(oracle_kind):
     assert dec.getFrequencyCorrection(0) == pytest.approx(a.frequency_correction, abs=1e-9)
     info, power = dec.getSpectrumInfo(0)
     assert info.peak_left_ == abs(a.peak_left) and info.peak_right_ == abs(a.peak_right)
-    assert info.sampling_rate_ == 8000.0
+    assert info.sampling_rate_ == fs / 256 and len(power) == nfft
+    assert dec.poll_chars(0) == ref.chars()
 
 
 # ---- golden fixtures produced by the unmodified reference (tests/golden/make_golden.py) ---------------------

@@ -12,10 +12,10 @@ pytestmark = pytest.mark.gpu
 CHUNK = 65536
 
 
-def _decode_some(n_ch, fs, bauds, n_calls, chunk=CHUNK, accumulate=False, on_call=None):
+def _decode_some(n_ch, fs, bauds, n_calls, chunk=CHUNK, accumulate=False, on_call=None, fft_bins=4096):
     iqs = [synth.channel_iq(c, 4, fs, bauds[c], snr_db=-14.0, f_off=40.0 * c, n_samples=n_calls * chunk)[0] for c in range(n_ch)]
     iq = np.stack(iqs)
-    dec = api.BatchDecoder(n_ch, dec_factor=256)
+    dec = api.BatchDecoder(n_ch, dec_factor=256, fft_bins=fft_bins)
     for c in range(n_ch):
         dec.baud(bauds[c], c)
     if accumulate:
@@ -34,10 +34,11 @@ def _meta(dec, ch):
     return po.SpectrumMeta(nf, nv, dec.getDecimatedSamplingRate(), dec.getShift(ch), pl, pr)
 
 
-def test_spectrum_frames_bit_exact():
+@pytest.mark.parametrize("nfft", [4096, 16384])
+def test_spectrum_frames_bit_exact(nfft):
     fs = 2.048e6
     bauds = [300.0, 300.0, 100.0]
-    dec = _decode_some(3, fs, bauds, 40)
+    dec = _decode_some(3, fs, bauds, 40 if nfft == 4096 else 140, fft_bins=nfft)
     assert dec.spectrum_frame(0, 0.5, 512, 1) != b""
     for zoom, res, ts in [(0.0, 4096, 4), (0.0, 1024, 1), (0.5, 512, 1), (0.5, 512, 2), (0.9, 300, 2), (0.25, 8192, 1), (0.3, 1, 1), (2.0, 77, 4), (0.4, 0, 1)]:
         batch = dec.spectrum_frames(zoom, res, ts)
@@ -46,8 +47,9 @@ def test_spectrum_frames_bit_exact():
             assert dec.spectrum_frame(ch, zoom, res, ts) == want, (zoom, res, ts, ch)
             assert batch[ch] == want, (zoom, res, ts, ch)
     # the peaks made it into the header for a decodable signal
-    hdr = np.frombuffer(dec.spectrum_frame(0, 0.0, 4096, 4)[:52], dtype=np.int32)
-    assert hdr[0] == 52 and hdr[12] == 4055 and hdr[11] == 4      # zoom is clamped to [0.01, 0.99]: 4096 - 2 * 20 bins
+    hdr = np.frombuffer(dec.spectrum_frame(0, 0.0, nfft, 4)[:52], dtype=np.int32)
+    zb, ze = int(np.float32(0.005) * np.float32(nfft)), int(np.float32(0.995) * np.float32(nfft))
+    assert hdr[0] == 52 and hdr[12] == ze - zb and hdr[11] == 4      # zoom is clamped to [0.01, 0.99]
 
 
 def test_no_frame_before_the_first_spectrum():
