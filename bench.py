@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--chunk", type=int, default=65536, help="complex samples per channel per step")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline leg")
+    ap.add_argument("--ssdv", action="store_true", help="diagnostic: run with SSDV packet sync switched on (one more kernel per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true", help="diagnostic: no CUDA events around K1 (no roofline numbers)")
@@ -187,6 +188,8 @@ def run_ours(args):
     dec = api.BatchDecoder(C, device=local_rank, baud=BAUD, rtty_bits=8, rtty_stops=2.0, lowpass_bw=1500.0, lowpass_trans=0.025,
                            dec_factor=FACTOR)
     dec.set_stream(stream.cuda_stream)
+    if args.ssdv:
+        dec.set_ssdv(True)
     base_ptr = ring.data_ptr()
 
     def step(i):

@@ -24,6 +24,12 @@ class SpectrumInfo(C.Structure):
                 ("peak_left_valid_", C.c_int), ("peak_right_valid_", C.c_int)]
 
 
+class SsdvPacketInfo(C.Structure):
+    _fields_ = [("callsign", C.c_char * 8), ("image_id", C.c_int), ("packet_id", C.c_int), ("width", C.c_int),
+                ("height", C.c_int), ("errors", C.c_int), ("set_size", C.c_int)]
+
+
+SSDV_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(SsdvPacketInfo), C.POINTER(C.c_ubyte))
 SENTENCE_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p)
 CHARS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_char), C.c_size_t)
 
@@ -73,6 +79,14 @@ SIGNATURES = {
     "hbd_poll_raw_chars": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_set_sentence_callback": (C.c_int, [_H, SENTENCE_CB, C.c_void_p]),
     "hbd_set_chars_callback": (C.c_int, [_H, CHARS_CB, C.c_void_p]),
+    "hbd_set_ssdv": (C.c_int, [_H, C.c_int]),
+    "hbd_set_ssdv_callback": (C.c_int, [_H, SSDV_CB, C.c_void_p]),
+    "hbd_poll_ssdv_packets": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "hbd_get_ssdv_image": (C.c_size_t, [_H, C.c_int, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_get_ssdv_last_image": (C.c_int, [_H, C.c_int, C.c_char_p, C.POINTER(C.c_int)]),
+    "hbd_ssdv_check_packets": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "hbd_ssdv_host_replay": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "hbd_get_decimation_factor": (C.c_int, [_H]),
     "hbd_get_input_sampling_rate": (C.c_double, [_H]),
     "hbd_get_decimated_sampling_rate": (C.c_double, [_H]),
@@ -138,6 +152,27 @@ def extract_sentence(stream: bytes):
     if not ok:
         return None
     return cs.value, data.value, crc.value, rest.value
+
+
+def ssdv_host_replay(chunks: list[bytes], accepted: list[tuple]):
+    """Host half of the SSDV path alone: chunks = the per-call raw characters, accepted = [(pos, packet256, errors)]
+    ascending.  Returns [(chunk index, callsign, image_id, packet_id, width, height, errors, set_size, packet)]."""
+    lib = load()
+    chars = b"".join(chunks)
+    sizes = (C.c_size_t * max(len(chunks), 1))(*[len(c) for c in chunks])
+    cbuf = (C.c_ubyte * max(len(chars), 1)).from_buffer_copy(chars or b"\0")
+    na = len(accepted)
+    pos = (C.c_uint * max(na, 1))(*[a[0] & 0xFFFFFFFF for a in accepted])
+    pk = (C.c_ubyte * max(256 * na, 1)).from_buffer_copy(b"".join(a[1] for a in accepted) or b"\0")
+    er = (C.c_int * max(na, 1))(*[a[2] for a in accepted])
+    cap = len(chars) // 256 + 1
+    infos = (SsdvPacketInfo * cap)()
+    which = (C.c_uint * cap)()
+    out = (C.c_ubyte * (256 * cap))()
+    n = lib.hbd_ssdv_host_replay(cbuf, sizes, len(chunks), pos, pk, er, na, infos, which, out, cap)
+    raw = bytes(out)
+    return [(which[k], infos[k].callsign.decode(), infos[k].image_id, infos[k].packet_id, infos[k].width, infos[k].height,
+             infos[k].errors, infos[k].set_size, raw[256 * k:256 * k + 256]) for k in range(n)]
 
 
 def crc16(s: bytes) -> bytes:
@@ -271,6 +306,51 @@ class BatchDecoder:
         cb = SENTENCE_CB(lambda user, ch, cs, data, crc: fn(ch, cs, data, crc))
         self._cbs.append(cb)
         self._chk(self._lib.hbd_set_sentence_callback(self._h, cb, None))
+
+    # ---- SSDV packet sync (SSDV_wraper_t::push, ssdv_wrapper.cpp:37-148) ----
+    def set_ssdv(self, on: bool = True): self._chk(self._lib.hbd_set_ssdv(self._h, int(on)))
+
+    def set_ssdv_callback(self, fn):
+        """fn(ch, info_dict, packet_bytes) per accepted packet, like ssdv_callback_ (Decoder.h:631-632)."""
+        def tramp(_user, ch, info, pkt):
+            i = info.contents
+            fn(ch, dict(callsign=i.callsign.decode(), image_id=i.image_id, packet_id=i.packet_id, width=i.width, height=i.height,
+                        errors=i.errors, set_size=i.set_size), bytes(pkt[:256]))
+        self._ssdv_cb = SSDV_CB(tramp) if fn else SSDV_CB()
+        self._chk(self._lib.hbd_set_ssdv_callback(self._h, self._ssdv_cb, None))
+
+    def poll_ssdv_packets(self, ch=0) -> list[tuple]:
+        """[(callsign, image_id, packet_id, width, height, errors, set_size, packet bytes)] since the previous poll."""
+        n = self._lib.hbd_poll_ssdv_packets(self._h, ch, None, None, 0)
+        if not n:
+            return []
+        infos = (SsdvPacketInfo * n)()
+        pk = (C.c_ubyte * (256 * n))()
+        self._lib.hbd_poll_ssdv_packets(self._h, ch, infos, pk, n)
+        raw = bytes(pk)
+        return [(i.callsign.decode(), i.image_id, i.packet_id, i.width, i.height, i.errors, i.set_size, raw[256 * k:256 * k + 256])
+                for k, i in enumerate(infos)]
+
+    def get_ssdv_image(self, ch: int, callsign: str, image_id: int) -> bytes:
+        n = self._lib.hbd_get_ssdv_image(self._h, ch, callsign.encode(), int(image_id), None, 0)
+        buf = (C.c_ubyte * max(n, 1))()
+        self._lib.hbd_get_ssdv_image(self._h, ch, callsign.encode(), int(image_id), buf, n)
+        return bytes(buf[:n])
+
+    def get_ssdv_last_image(self, ch=0):
+        cs = C.create_string_buffer(8)
+        iid = C.c_int(0)
+        self._chk(self._lib.hbd_get_ssdv_last_image(self._h, ch, cs, C.byref(iid)))
+        return cs.value.decode(), iid.value
+
+    def ssdv_check_packets(self, windows: np.ndarray):
+        """Batch packet test on the GPU: windows uint8[n, 256] -> (verdict int32[n], errors int32[n], corrected uint8[n, 256])."""
+        w = np.ascontiguousarray(windows, dtype=np.uint8).reshape(-1, 256).copy()
+        n = w.shape[0]
+        verdict = np.zeros(n, dtype=np.int32)
+        errors = np.zeros(n, dtype=np.int32)
+        self._chk(self._lib.hbd_ssdv_check_packets(self._h, w.ctypes.data, n, verdict.ctypes.data, errors.ctypes.data))
+        return verdict, errors, w
 
     def set_chars_callback(self, fn):
         cb = CHARS_CB(lambda user, ch, p, n: fn(ch, C.string_at(p, n)))

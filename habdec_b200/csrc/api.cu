@@ -19,6 +19,7 @@
 #include "hbd_common.cuh"
 #include "host_tail.h"
 #include "nco.cuh"
+#include "ssdv.cuh"
 #include "tail.cuh"
 #include "wire.cuh"
 
@@ -181,6 +182,15 @@ struct hbd_decoder {
     }
     size_t cap_n_in = 0;     // largest (r + n) the per-call buffers are sized for
 
+    // SSDV packet sync (ssdv.cu + host_tail.cpp SsdvChannel); off until hbd_set_ssdv / hbd_set_ssdv_callback
+    bool ssdv_on = false;
+    unsigned char* d_ssdv_ring = nullptr; unsigned* d_ssdv_total = nullptr; unsigned* d_ssdv_scanned = nullptr;
+    SsdvLogEntry* d_ssdv_log = nullptr; unsigned ssdv_log_tail = 0;
+    std::vector<SsdvLogEntry> h_ssdv_log;
+    std::vector<SsdvChannel> ssdv;
+    hbd_ssdv_cb ssdv_cb = nullptr; void* ssdv_user = nullptr;
+    int enable_ssdv(bool on);
+
     hbd_sentence_cb sentence_cb = nullptr; void* sentence_user = nullptr;
     hbd_chars_cb chars_cb = nullptr; void* chars_user = nullptr;
 
@@ -192,6 +202,15 @@ struct hbd_decoder {
     int collect_locked(unsigned lag);
     void free_all();
 };
+
+static void fill_ssdv_info(hbd_ssdv_packet_info& info, const SsdvEvent& ev)
+{
+    memset(&info, 0, sizeof(info));
+    memcpy(info.callsign, ev.header.callsign, sizeof(info.callsign));
+    info.image_id = ev.header.image_id; info.packet_id = ev.header.packet_id;
+    info.width = ev.header.width; info.height = ev.header.height;
+    info.errors = ev.errors; info.set_size = ev.set_size;
+}
 
 #define HBD_CHECK_H(h)  if (!(h)) return HBD_ERR_ARG
 #define HBD_CHECK_CH(h, ch) if (!(h) || (ch) < 0 || (ch) >= (h)->n_ch) return HBD_ERR_ARG
@@ -244,8 +263,8 @@ int hbd_decoder::alloc_fixed()
     HBD_CUDA_CHECK(dalloc(&d_lptaps, n * kLpMaxTaps));
     HBD_CUDA_CHECK(cudaMemset(d_lptaps, 0, n * kLpMaxTaps * sizeof(float)));
     HBD_CUDA_CHECK(dalloc(&d_log, size_t(kLogCap)));
-    HBD_CUDA_CHECK(dalloc(&d_log_head, 1));
-    HBD_CUDA_CHECK(cudaMemset(d_log_head, 0, sizeof(unsigned)));
+    HBD_CUDA_CHECK(dalloc(&d_log_head, 4));   // [0] character log head, [1] SSDV packet log head, [2] SSDV ring overflow flag
+    HBD_CUDA_CHECK(cudaMemset(d_log_head, 0, 4 * sizeof(unsigned)));
     HBD_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     ev_call.resize(kMaxCallsBetweenCollects * 2);
     for (auto& e : ev_call) HBD_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -313,7 +332,8 @@ void hbd_decoder::free_all()
     if (ev_in) cudaEventDestroy(ev_in);
     void* ptrs[] = {d_state, d_plan, d_carry2[0], d_carry2[1], d_s1x[0], d_s1x[1], d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_log, d_log_head,
                     d_taps1, d_taps2, d_twiddle, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps,
-                    d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage, d_nco, d_wide, d_dacc, d_dacc_n, d_frames, d_frame_sizes};
+                    d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage, d_nco, d_wide, d_dacc, d_dacc_n, d_frames, d_frame_sizes,
+                    d_ssdv_ring, d_ssdv_total, d_ssdv_scanned, d_ssdv_log};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_pinned) cudaFreeHost(h_pinned);
     for (cudaEvent_t e : ev_call) cudaEventDestroy(e);
@@ -515,6 +535,7 @@ int hbd_decoder::process_async_locked()
             ta.max_lp_taps = int(max_lp_taps);
             ta.slicer = d_slicer; ta.slicer_pitch = slicer_pitch; ta.sv_want = sv_want;
             ta.log = d_log; ta.log_head = d_log_head; ta.call_seq = call_seq & 0xffffffu;
+            ta.ssdv_ring = ssdv_on ? d_ssdv_ring : nullptr; ta.ssdv_total = d_ssdv_total;
             ta.demod_last = d_demod; ta.demod_pitch = demod_pitch;
             ta.rec_decimated = record ? d_rec_dec : nullptr; ta.rec_filtered = record ? d_rec_filt : nullptr; ta.rec_pitch = rec_pitch;
             ta.rec_bits = record ? d_rec_bits : nullptr; ta.rec_bits_n = d_rec_bits_n; ta.rec_bits_pitch = rec_bits_pitch;
@@ -523,6 +544,12 @@ int hbd_decoder::process_async_locked()
             fa.state = d_state; fa.fftbuf = d_fftbuf; fa.spectrum = d_spectrum; fa.power = d_power; fa.twiddle = d_twiddle; fa.fs_dec = fs_dec;
             fa.ch0 = c0; fa.fft_n = fft_n;
             HBD_CUDA_CHECK(launch_fft_afc(fa, nc, lo, &nl));
+            if (ssdv_on) {   // test every 0x55-started window the new characters completed
+                SsdvScanArgs sa{};
+                sa.ring = d_ssdv_ring; sa.total = d_ssdv_total; sa.scanned = d_ssdv_scanned; sa.log = d_ssdv_log;
+                sa.log_head = d_log_head + 1; sa.overflow = d_log_head + 2; sa.call_seq = call_seq & 0xffffffu; sa.ch0 = c0;
+                HBD_CUDA_CHECK(launch_ssdv_scan(sa, nc, lo, &nl));
+            }
         }
         if (demod_acc_on && d_demod) { // main.cpp:267-282 runs after EVERY process(), also when nothing new was demodulated
             DemodAccArgs aa{};
@@ -564,9 +591,36 @@ int hbd_decoder::collect_locked(unsigned lag)
     } else {
         HBD_CUDA_CHECK(cudaEventSynchronize(ev_call[(upto - 1) % ev_call.size()]));
     }
-    unsigned head = 0;
-    HBD_CUDA_CHECK(cudaMemcpyAsync(&head, d_log_head, sizeof(unsigned), cudaMemcpyDeviceToHost, copy_stream));
+    unsigned heads[3] = {0, 0, 0};
+    HBD_CUDA_CHECK(cudaMemcpyAsync(heads, d_log_head, sizeof(heads), cudaMemcpyDeviceToHost, copy_stream));
     HBD_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+    const unsigned head = heads[0];
+    const unsigned upto24 = upto & 0xffffffu;
+    if (ssdv_on) {
+        // accepted SSDV packets of the calls being drained go to their channels first: the buffer automaton below
+        // looks a window's verdict up when it reaches it, which is never before the call that completed the window
+        if (heads[2]) { set_error("SSDV character ring overflow: more than 3840 characters in one call, push smaller chunks"); return HBD_ERR_STATE; }
+        const unsigned avail_p = heads[1] - ssdv_log_tail;
+        if (avail_p > kSsdvLogCap) { set_error("SSDV packet log overflow: collect more often"); return HBD_ERR_STATE; }
+        h_ssdv_log.resize(avail_p);
+        if (avail_p) {
+            const unsigned i0 = ssdv_log_tail & (kSsdvLogCap - 1u);
+            const unsigned first = std::min(avail_p, kSsdvLogCap - i0);
+            HBD_CUDA_CHECK(cudaMemcpyAsync(h_ssdv_log.data(), d_ssdv_log + i0, size_t(first) * sizeof(SsdvLogEntry), cudaMemcpyDeviceToHost, copy_stream));
+            if (avail_p > first)
+                HBD_CUDA_CHECK(cudaMemcpyAsync(h_ssdv_log.data() + first, d_ssdv_log, size_t(avail_p - first) * sizeof(SsdvLogEntry), cudaMemcpyDeviceToHost, copy_stream));
+            HBD_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+        }
+        unsigned used = 0;
+        for (; used < avail_p; ++used) {
+            const SsdvLogEntry& e = h_ssdv_log[used];
+            if (((upto24 - e.seq - 1u) & 0xffffffu) >= 0x800000u) break;   // a call still in flight
+            if (e.ch >= unsigned(n_ch)) continue;
+            SsdvVerdict v; v.pos = e.pos; v.errors = e.errors; memcpy(v.data.data(), e.data, 256);
+            ssdv[e.ch].verdicts.push_back(v);
+        }
+        ssdv_log_tail += used;
+    }
     const unsigned avail = head - log_tail;
     if (avail > kLogCap) { set_error("decoded-character log overflow: collect more often"); return HBD_ERR_STATE; }
     h_log.resize(avail);
@@ -587,7 +641,6 @@ int hbd_decoder::collect_locked(unsigned lag)
     std::vector<int> cb_channels;
     // the log is sorted by call; replay call by call, channel by channel
     size_t i = 0;
-    const unsigned upto24 = upto & 0xffffffu;
     while (i < h_log.size()) {
         const unsigned seq = h_log[i].y >> 8;
         if (((upto24 - seq - 1u) & 0xffffffu) >= 0x800000u) break; // seq >= upto: belongs to a call still in flight
@@ -604,6 +657,16 @@ int hbd_decoder::collect_locked(unsigned lag)
             TextChannel& tc = text[size_t(ch)];
             if (chars_cb) { cb_channels.push_back(ch); chars_before.push_back(tc.chars_pending.size()); }
             tc.feed(reinterpret_cast<const unsigned char*>(cc.data()), cc.size(), ch, sink);
+            if (ssdv_on) {   // Decoder.h:573: one SSDV_wraper_t::push per call that decoded characters
+                SsdvEvent ev;
+                if (ssdv[size_t(ch)].push(reinterpret_cast<const unsigned char*>(cc.data()), cc.size(), ev)) {
+                    ssdv[size_t(ch)].events_pending.push_back(ev);
+                    if (ssdv_cb) {   // ssdv_callback_, Decoder.h:631-632
+                        hbd_ssdv_packet_info info; fill_ssdv_info(info, ev);
+                        ssdv_cb(ssdv_user, ch, &info, ev.data.data());
+                    }
+                }
+            }
             if (chars_cb) {
                 const size_t before = chars_before.back();
                 if (tc.chars_pending.size() > before) chars_cb(chars_user, ch, tc.chars_pending.data() + before, tc.chars_pending.size() - before);
@@ -615,6 +678,32 @@ int hbd_decoder::collect_locked(unsigned lag)
     log_tail += unsigned(i);
     calls_collected = upto;
     pending_marks = int(call_seq - calls_collected);
+    return HBD_OK;
+}
+
+// SSDV packet sync on / off.  Switching it on starts from an empty character stream (like a freshly constructed
+// SSDV_wraper_t): every call in flight is drained first, so device ring, scan position and host automaton agree.
+int hbd_decoder::enable_ssdv(bool on)
+{
+    if (on == ssdv_on) return HBD_OK;
+    HBD_CUDA_CHECK(cudaSetDevice(device));
+    { const int rc = collect_locked(0); if (rc) return rc; }
+    const size_t n = size_t(n_ch);
+    if (on) {
+        if (!d_ssdv_ring) {
+            HBD_CUDA_CHECK(dalloc(&d_ssdv_ring, n * kSsdvRing));
+            HBD_CUDA_CHECK(dalloc(&d_ssdv_total, n));
+            HBD_CUDA_CHECK(dalloc(&d_ssdv_scanned, n));
+            HBD_CUDA_CHECK(dalloc(&d_ssdv_log, size_t(kSsdvLogCap)));
+        }
+        HBD_CUDA_CHECK(cudaMemset(d_ssdv_ring, 0, n * kSsdvRing));
+        HBD_CUDA_CHECK(cudaMemset(d_ssdv_total, 0, n * sizeof(unsigned)));
+        HBD_CUDA_CHECK(cudaMemset(d_ssdv_scanned, 0, n * sizeof(unsigned)));
+        HBD_CUDA_CHECK(cudaMemset(d_log_head + 1, 0, 2 * sizeof(unsigned)));
+        ssdv_log_tail = 0;
+        ssdv.assign(n, SsdvChannel());
+    }
+    ssdv_on = on;
     return HBD_OK;
 }
 
@@ -1071,6 +1160,99 @@ int hbd_set_sentence_callback(hbd_decoder* h, hbd_sentence_cb cb, void* user)
 int hbd_set_chars_callback(hbd_decoder* h, hbd_chars_cb cb, void* user)
 {
     HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); h->chars_cb = cb; h->chars_user = user; return HBD_OK;
+}
+
+// ---- SSDV packet sync ---------------------------------------------------------------------------------------
+int hbd_set_ssdv(hbd_decoder* h, int on)
+{
+    HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx);
+    return h->enable_ssdv(on != 0);
+}
+int hbd_set_ssdv_callback(hbd_decoder* h, hbd_ssdv_cb cb, void* user)
+{
+    HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx);
+    h->ssdv_cb = cb; h->ssdv_user = user;
+    return cb ? h->enable_ssdv(true) : HBD_OK;
+}
+size_t hbd_poll_ssdv_packets(hbd_decoder* h, int ch, hbd_ssdv_packet_info* infos, unsigned char* packets, size_t cap_packets)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    if (h->ssdv.empty()) return 0;
+    auto& ev = h->ssdv[size_t(ch)].events_pending;
+    const size_t n = ev.size();
+    for (size_t i = 0; i < std::min(n, cap_packets); ++i) {
+        if (infos) fill_ssdv_info(infos[i], ev[i]);
+        if (packets) memcpy(packets + 256 * i, ev[i].data.data(), 256);
+    }
+    if ((infos || packets) && cap_packets >= n) ev.clear();
+    return n;
+}
+size_t hbd_get_ssdv_image(hbd_decoder* h, int ch, const char* callsign, int image_id, unsigned char* out, size_t cap)
+{
+    if (!h || ch < 0 || ch >= h->n_ch || !callsign) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    if (h->ssdv.empty()) return 0;
+    return h->ssdv[size_t(ch)].image(callsign, image_id, out, cap);
+}
+int hbd_get_ssdv_last_image(hbd_decoder* h, int ch, char callsign[8], int* image_id)
+{
+    HBD_CHECK_CH(h, ch); std::lock_guard<std::mutex> l(h->mtx);
+    if (h->ssdv.empty()) return HBD_ERR_STATE;
+    const auto& k = h->ssdv[size_t(ch)].last_key;
+    if (callsign) { memset(callsign, 0, 8); strncpy(callsign, k.first.c_str(), 7); }
+    if (image_id) *image_id = k.second;
+    return HBD_OK;
+}
+int hbd_ssdv_check_packets(hbd_decoder* h, unsigned char* windows, size_t n, int* verdict, int* errors)
+{
+    HBD_CHECK_H(h);
+    if (!windows || !verdict || !errors) return HBD_ERR_ARG;
+    if (!n) return HBD_OK;
+    std::lock_guard<std::mutex> l(h->mtx);
+    if (cudaSetDevice(h->device) != cudaSuccess) return HBD_ERR_CUDA;
+    unsigned char* d_w = nullptr; int* d_v = nullptr;
+    auto fail = [&](const char* what) { h->set_error(what); if (d_w) cudaFree(d_w); if (d_v) cudaFree(d_v); return HBD_ERR_CUDA; };
+    if (cudaMalloc((void**)&d_w, n * 256) != cudaSuccess || cudaMalloc((void**)&d_v, n * 2 * sizeof(int)) != cudaSuccess) return fail("cudaMalloc (ssdv check)");
+    if (cudaMemcpyAsync(d_w, windows, n * 256, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return fail("cudaMemcpyAsync (ssdv check)");
+    int nl = 0;
+    if (launch_ssdv_check(d_w, int(n), d_v, d_v + n, h->stream, &nl) != cudaSuccess) return fail("ssdv_check_kernel launch");
+    h->launches += unsigned(nl);
+    if (cudaMemcpyAsync(windows, d_w, n * 256, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaMemcpyAsync(verdict, d_v, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaMemcpyAsync(errors, d_v + n, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) return fail("ssdv check read-back");
+    cudaFree(d_w); cudaFree(d_v);
+    return HBD_OK;
+}
+
+// host half of the SSDV path alone (test hook, no GPU): replay SsdvChannel over `n_chunks` pushes of the character
+// stream `chars`, with the accepted windows given by position
+size_t hbd_ssdv_host_replay(const unsigned char* chars, const size_t* chunk_sizes, size_t n_chunks, const unsigned* accepted_pos,
+                            const unsigned char* accepted_packets, const int* accepted_errors, size_t n_accepted,
+                            hbd_ssdv_packet_info* out_infos, unsigned* out_chunk, unsigned char* out_packets, size_t cap)
+{
+    if (!chars || !chunk_sizes) return 0;
+    SsdvChannel sc;
+    for (size_t i = 0; i < n_accepted; ++i) {
+        SsdvVerdict v; v.pos = accepted_pos[i]; v.errors = accepted_errors ? accepted_errors[i] : 0;
+        memcpy(v.data.data(), accepted_packets + 256 * i, 256);
+        sc.verdicts.push_back(v);
+    }
+    size_t off = 0, n_ev = 0;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        SsdvEvent ev;
+        if (chunk_sizes[c] && sc.push(chars + off, chunk_sizes[c], ev)) {
+            if (n_ev < cap) {
+                if (out_infos) fill_ssdv_info(out_infos[n_ev], ev);
+                if (out_chunk) out_chunk[n_ev] = unsigned(c);
+                if (out_packets) memcpy(out_packets + 256 * n_ev, ev.data.data(), 256);
+            }
+            ++n_ev;
+        }
+        off += chunk_sizes[c];
+    }
+    return n_ev;
 }
 
 int hbd_get_decimation_factor(hbd_decoder* h) { return h ? h->factor : 0; }

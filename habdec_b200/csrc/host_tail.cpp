@@ -151,4 +151,79 @@ void TextChannel::feed(const unsigned char* raw, size_t n, int ch, const Sentenc
     if (text_stream.size() > 1000) text_stream.erase(0, text_stream.rfind('$')); // npos => erase everything
 }
 
+// ---- SSDV: header fields the bookkeeping needs (published layout of fsphil/ssdv: [2..5] base-40 callsign, [6] image id,
+// [7..8] packet id, [9] width / 16, [10] height / 16) -----------------------------------------------------------
+SsdvHeader ssdv_decode_header(const unsigned char* pkt)
+{
+    SsdvHeader h;
+    uint32_t code = (uint32_t(pkt[2]) << 24) | (uint32_t(pkt[3]) << 16) | (uint32_t(pkt[4]) << 8) | uint32_t(pkt[5]);
+    if (code <= 0xF423FFFFu) {          // larger codes are not a callsign: the string stays empty
+        int k = 0;
+        for (; code && k < 7; code /= 40) {
+            const unsigned s = code % 40;
+            h.callsign[k++] = s == 0 ? '-' : s < 11 ? char('0' + s - 1) : s < 14 ? '-' : char('A' + s - 14);
+        }
+    }
+    h.image_id = pkt[6];
+    h.packet_id = uint16_t((pkt[7] << 8) | pkt[8]);
+    h.width = uint16_t(pkt[9] << 4);
+    h.height = uint16_t(pkt[10] << 4);
+    return h;
+}
+
+bool SsdvChannel::push(const unsigned char* chars, size_t n, SsdvEvent& ev)
+{
+    buff.insert(buff.end(), chars, chars + n);                               // ssdv_wrapper.cpp:42-45
+    stream_end += uint32_t(n);
+    if (buff.size() < 256) return false;                                     // :47-48
+    auto scan_sync = [this] { while (++packet_begin < long(buff.size()) && buff[size_t(packet_begin)] != 0x55) {} };
+    if (packet_begin == -1) {                                                // :51-61
+        scan_sync();
+        if (packet_begin == long(buff.size())) { buff.clear(); packet_begin = -1; return false; }
+    }
+    if (buff.size() - size_t(packet_begin) < 256) return false;              // :63-64
+    // ssdv_dec_is_packet(buff + packet_begin), :66 -- looked up by stream position
+    const uint32_t pos = stream_end - uint32_t(buff.size() - size_t(packet_begin));
+    while (!verdicts.empty() && int32_t(verdicts.front().pos - pos) < 0) verdicts.pop_front();   // positions only move forward
+    if (verdicts.empty() || verdicts.front().pos != pos) {                   // not a packet, :67-85
+        scan_sync();
+        if (packet_begin == long(buff.size())) { buff.clear(); packet_begin = -1; }
+        else { buff.erase(buff.begin(), buff.begin() + packet_begin); packet_begin = 0; }
+        return false;
+    }
+    const SsdvVerdict v = verdicts.front();
+    verdicts.pop_front();
+    buff.erase(buff.begin() + packet_begin, buff.begin() + packet_begin + 256);   // :89-91
+    packet_begin = -1;
+    Filed f;
+    f.data = v.data;
+    f.header = ssdv_decode_header(v.data.data());                            // :92
+
+    const ImageKey key(f.header.callsign, f.header.image_id);                // :105-141
+    auto it = packets.find(key);
+    if (it == packets.end()) {
+        packets[key][f.header.packet_id] = f;
+    } else {
+        auto& set = it->second;
+        if (!set.empty()) {
+            const Filed& last = set.rbegin()->second;                        // the highest packet id filed so far (:125-126)
+            if (set.count(f.header.packet_id) || last.header.height != f.header.height || last.header.width != f.header.width)
+                set.clear();                                                 // retransmission or a new image under the same id
+        }
+        set[f.header.packet_id] = f;
+    }
+    last_key = key;                                                          // make_jpeg, :171
+    ev.header = f.header; ev.errors = v.errors; ev.set_size = int(packets[key].size()); ev.data = f.data;
+    return true;
+}
+
+size_t SsdvChannel::image(const std::string& callsign, int image_id, unsigned char* out, size_t cap) const
+{
+    auto it = packets.find(ImageKey(callsign, uint16_t(image_id)));
+    if (it == packets.end()) return 0;
+    size_t n = 0;
+    for (const auto& kv : it->second) { if (out && n + 256 <= cap) std::copy(kv.second.data.begin(), kv.second.data.end(), out + n); n += 256; }
+    return n;
+}
+
 } // namespace hbd

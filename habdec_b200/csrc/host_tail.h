@@ -1,7 +1,12 @@
 // Host-side, non data-parallel pieces of the path (see host_tail.cpp)
 #pragma once
+#include <array>
+#include <cstdint>
+#include <deque>
 #include <functional>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace hbd {
@@ -28,6 +33,40 @@ struct TextChannel {
     std::string sentences_pending;  // CRC-valid sentences since the last poll
     std::vector<unsigned char> raw_pending; // raw chars since the last poll (SSDV consumers)
     void feed(const unsigned char* raw, size_t n, int ch, const SentenceSink& sink);
+};
+
+// ---- SSDV packet sync: the buffer automaton and image bookkeeping of SSDV_wraper_t (ssdv_wrapper.cpp:37-148) -------
+// The packet test (ssdv_dec_is_packet, :66) is not evaluated here: the GPU tests every window of 256 consecutive
+// characters that starts at a 0x55 and reports the accepted ones by stream position (ssdv.cu).  That is enough because
+// every window the automaton can ask about is such a window:
+//   * `buff` is always [junk | contiguous stream bytes]: junk (bytes left in front of an extracted packet, :91) holds
+//     no 0x55, since the packet started at the FIRST 0x55 of the buffer (:54) or at offset 0 (:82-83);
+//   * packet_begin always points into the contiguous part, and the 256 bytes from it are contiguous too.
+// The automaton itself -- one packet test per push, the `size < 256` early outs that depend on the junk length, the
+// buffer clears -- is replayed byte for byte, so accepted packets surface on the same call as in the reference.
+struct SsdvHeader {                  // what ssdv_dec_header (fsphil/ssdv, published layout) extracts, :92
+    char callsign[8] = {0};
+    uint16_t image_id = 0, packet_id = 0, width = 0, height = 0;
+};
+SsdvHeader ssdv_decode_header(const unsigned char* pkt);
+
+struct SsdvVerdict { uint32_t pos; int errors; std::array<unsigned char, 256> data; };
+struct SsdvEvent { SsdvHeader header; int errors = 0; int set_size = 0; std::array<unsigned char, 256> data; };
+
+struct SsdvChannel {
+    std::vector<unsigned char> buff;                 // ssdv_wrapper.h:38
+    long packet_begin = -1;                          // :39
+    uint32_t stream_end = 0;                         // stream index one past the last byte of buff (mod 2^32)
+    std::deque<SsdvVerdict> verdicts;                // accepted windows reported by the GPU, ascending position
+    using ImageKey = std::pair<std::string, uint16_t>;
+    struct Filed { SsdvHeader header; std::array<unsigned char, 256> data; };
+    std::map<ImageKey, std::map<uint16_t, Filed>> packets;   // :62; the inner map is the set ordered by packet id (:53-57)
+    ImageKey last_key{"", 0};                        // last_img_k_, :82
+    std::vector<SsdvEvent> events_pending;           // accepted packets since the last poll
+
+    // one SSDV_wraper_t::push(); true (and `ev` filled) when a packet was filed
+    bool push(const unsigned char* chars, size_t n, SsdvEvent& ev);
+    size_t image(const std::string& callsign, int image_id, unsigned char* out, size_t cap) const;
 };
 
 } // namespace hbd

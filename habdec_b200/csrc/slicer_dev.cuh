@@ -241,7 +241,9 @@ struct CharSink {
     unsigned char* buf;   // shared memory, kCharBuf bytes (one warp writes, lane 0 only)
     int n;
     uint2* log; unsigned* log_head; unsigned call_seq; unsigned ch;
+    unsigned char* ring; unsigned ring_total;   // SSDV: the channel's raw-character ring (null: off) and its append count
 };
+constexpr unsigned kRawRingMask = 4096u - 1u;    // == kSsdvRing - 1 (ssdv.cuh)
 constexpr int kCharBuf = 64;
 
 __device__ __forceinline__ void sink_flush(CharSink& s, int lane)
@@ -253,6 +255,10 @@ __device__ __forceinline__ void sink_flush(CharSink& s, int lane)
     pos = __shfl_sync(0xffffffffu, pos, 0);
     __syncwarp();
     for (int i = lane; i < s.n; i += 32) s.log[(pos + unsigned(i)) & (kLogCap - 1u)] = make_uint2(s.ch, (s.call_seq << 8) | unsigned(s.buf[i]));
+    if (s.ring) {
+        for (int i = lane; i < s.n; i += 32) s.ring[(s.ring_total + unsigned(i)) & kRawRingMask] = s.buf[i];
+        s.ring_total += unsigned(s.n);
+    }
     __syncwarp();
     s.n = 0;
 }

@@ -313,7 +313,8 @@ tail_kernel(TailArgs a)
         if (nf) {
             const int n = n_sl;
             const float* v = smem_mode ? s_v : v_g;
-            CharSink sink{s_chars, 0, a.log, a.log_head, a.call_seq, unsigned(ch)};
+            CharSink sink{s_chars, 0, a.log, a.log_head, a.call_seq, unsigned(ch), nullptr, 0u};
+            if (a.ssdv_ring) { sink.ring = a.ssdv_ring + (size_t)ch * (kRawRingMask + 1u); sink.ring_total = a.ssdv_total[ch]; }
             unsigned char* rec_bits = a.rec_bits ? a.rec_bits + (size_t)ch * a.rec_bits_pitch : nullptr;
             unsigned rec_n = a.rec_bits ? a.rec_bits_n[ch] : 0;
             int erase = 0;
@@ -321,6 +322,7 @@ tail_kernel(TailArgs a)
                 erase = slice_channel(v, n, spb, R, smem_mode ? s_maskA : nullptr, smem_mode ? s_maskN : nullptr, s_st.rtty_bits,
                                       s_st.rtty_stops, win, have, sink, rec_bits, rec_n, a.rec_bits_pitch, lane);
             sink_flush(sink, lane);
+            if (sink.ring && lane == 0) a.ssdv_total[ch] = sink.ring_total;
             if (a.rec_bits && lane == 0) a.rec_bits_n[ch] = rec_n;
             // erase consumed samples (SymbolExtractor.h:156-157) / write the queue back
             const int keep = n - erase;

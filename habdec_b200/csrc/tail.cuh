@@ -28,6 +28,8 @@ struct TailArgs {
     // entry = (channel, call_seq << 8 | char).  Kernels of successive calls run in stream order, so the log is
     // sorted by call and, per channel, by time.
     uint2* log; unsigned* log_head; unsigned call_seq;
+    // SSDV packet sync (ssdv.cu): per-channel raw-character ring [channel][kSsdvRing] + append counts; null = off
+    unsigned char* ssdv_ring; unsigned* ssdv_total;
     // last call's discriminator output for getDemodulated() [channel][demod_pitch] (may be null)
     float* demod_last; size_t demod_pitch;
     // optional per-call stage recordings for parity tests [channel][rec_pitch]

@@ -129,6 +129,33 @@ size_t hbd_poll_raw_chars(hbd_decoder* h, int ch, unsigned char* out, size_t cap
 int    hbd_set_sentence_callback(hbd_decoder* h, hbd_sentence_cb cb, void* user);
 int    hbd_set_chars_callback(hbd_decoder* h, hbd_chars_cb cb, void* user);
 
+/* ---- SSDV packet sync (the consumer of the raw characters: SSDV_wraper_t::push, code/Decoder/ssdv_wrapper.cpp:37-148,
+ * fed once per process() that decoded characters, Decoder.h:572-573).  The 0x55 sync scan, the packet test
+ * (CRC-32 + Reed-Solomon(255,223), the published algorithm of fsphil/ssdv's ssdv_dec_is_packet) and the per-image
+ * packet bookkeeping (retransmitted id / changed resolution restart the image, :105-141) run here: the packet test on
+ * the GPU for every channel, the bookkeeping on the host.  JPEG reassembly (ssdv_dec_feed, make_jpeg :151-172) is not
+ * part of this library: hbd_get_ssdv_image returns exactly the packet sequence the reference feeds to it.
+ * Off by default (nothing observable happens in the reference either until ssdv_callback_ is set, Decoder.h:141). */
+typedef struct hbd_ssdv_packet_info {
+    char callsign[8];      /* decoded base-40 callsign, NUL terminated (image key, ssdv_wrapper.cpp:105) */
+    int  image_id, packet_id, width, height;
+    int  errors;           /* symbols corrected by the Reed-Solomon decoder */
+    int  set_size;         /* packets held for (callsign, image_id) now that this one is filed */
+} hbd_ssdv_packet_info;
+/* fires inside hbd_process()/hbd_collect*() once per accepted packet, like ssdv_callback_ (Decoder.h:631-632);
+ * packet = the 256 corrected bytes */
+typedef void (*hbd_ssdv_cb)(void* user, int ch, const hbd_ssdv_packet_info* info, const unsigned char* packet);
+int    hbd_set_ssdv(hbd_decoder* h, int on);                               /* starts from an empty character stream */
+int    hbd_set_ssdv_callback(hbd_decoder* h, hbd_ssdv_cb cb, void* user);  /* a non-NULL callback switches SSDV on */
+/* accepted packets since the previous poll: infos[i], packets[256 * i]; returns the number available */
+size_t hbd_poll_ssdv_packets(hbd_decoder* h, int ch, hbd_ssdv_packet_info* infos, unsigned char* packets, size_t cap_packets);
+/* the packets filed under (callsign, image_id), 256 bytes each in packet-id order (input of make_jpeg); returns bytes */
+size_t hbd_get_ssdv_image(hbd_decoder* h, int ch, const char* callsign, int image_id, unsigned char* out, size_t cap);
+int    hbd_get_ssdv_last_image(hbd_decoder* h, int ch, char callsign[8], int* image_id);   /* last_img_k_, ssdv_wrapper.h:82 */
+/* the packet test alone, batched on the GPU: windows[n][256] (host) are corrected in place where verdict[i] == 0
+ * (packet) and left alone where verdict[i] == -1; errors[i] = corrected symbols */
+int    hbd_ssdv_check_packets(hbd_decoder* h, unsigned char* windows, size_t n, int* verdict, int* errors);
+
 /* ---- info (Decoder.h:98-101) ------------------------------------------------------------------------ */
 int    hbd_get_decimation_factor(hbd_decoder* h);
 double hbd_get_input_sampling_rate(hbd_decoder* h);
@@ -169,6 +196,13 @@ enum { HBD_STAGE_DECIMATED = 0, HBD_STAGE_FILTERED = 1, HBD_STAGE_DEMOD = 2, HBD
        HBD_STAGE_PENDING = 6, HBD_STAGE_BITS = 7 };
 /* arrays of the most recent call (DECIMATED/FILTERED/DEMOD/BITS need hbd_set_record(h,1)); BITS accumulate */
 size_t hbd_debug_stage(hbd_decoder* h, int ch, int stage, float* out, size_t cap_floats);
+/* host half of the SSDV path alone (needs no GPU): the buffer automaton + bookkeeping replayed over n_chunks pushes
+ * (chunk_sizes[i] characters each, empty chunks are skipped like calls without characters) with the accepted windows
+ * given as (stream position, corrected packet, errors), ascending.  Returns the number of events; fills up to `cap`
+ * of out_infos[i], out_chunk[i] (index of the push that filed the packet), out_packets[256 * i]. */
+size_t hbd_ssdv_host_replay(const unsigned char* chars, const size_t* chunk_sizes, size_t n_chunks, const unsigned* accepted_pos,
+                            const unsigned char* accepted_packets, const int* accepted_errors, size_t n_accepted,
+                            hbd_ssdv_packet_info* out_infos, unsigned* out_chunk, unsigned char* out_packets, size_t cap);
 /* low-pass tap design alone (FirFilter::LP_BlackmanHarris, FirFilter.h:173-209); returns the tap count */
 size_t hbd_design_lowpass(float rel_width, float trans, size_t input_size, size_t current_taps, float* out, size_t cap);
 /* sentence layer alone (extractSentence + CRC, sentence_extract.cpp:58-98, CRC.cpp:21-47):

@@ -28,6 +28,8 @@
 #include <thread>
 #include <vector>
 
+#include "ssdv_oracle.h"
+
 #include "decim_taps.inc"
 #include "fftw3.h" // hbd_dft_f64 only
 #include "oracle_abi.h"
@@ -571,6 +573,7 @@ struct Port {
             uart.run(raw);
         }
         if (raw.empty()) return;
+        ssdv.push(reinterpret_cast<const uint8_t*>(raw.data()), raw.size(), n_calls - 1); // Decoder.h:573
         if (cfg.record) for (char c : raw) rec_raw.push_back(float((unsigned char)c));
 
         std::string printable; // Decoder.h:575-580
@@ -592,6 +595,8 @@ struct Port {
     }
 
     bool have_spectrum = false;
+    hbo_ssdv::Port ssdv;     // Decoder.h:193
+    uint32_t n_calls = 0;    // push_process / ssdv_push calls so far
 };
 
 size_t copy_str(const std::string& s, char* out, size_t cap)
@@ -615,8 +620,54 @@ void orc_destroy(void* h) { delete static_cast<Port*>(h); }
 void orc_push_process(void* h, const float* iq, size_t n, double fs)
 {
     Port* p = static_cast<Port*>(h);
+    ++p->n_calls;
     p->push(iq, n, fs);
     p->process();
+}
+
+size_t orc_ssdv_events(void* h, hbo_ssdv_event* out, size_t cap)
+{
+    const auto& ev = static_cast<Port*>(h)->ssdv.events;
+    if (out && cap) memcpy(out, ev.data(), std::min(cap, ev.size()) * sizeof(hbo_ssdv_event));
+    return ev.size();
+}
+void orc_ssdv_push(void* h, const uint8_t* chars, size_t n)
+{
+    Port* p = static_cast<Port*>(h);
+    ++p->n_calls;
+    p->ssdv.push(chars, n, p->n_calls - 1);
+}
+size_t orc_ssdv_image(void* h, const char* callsign, int image_id, uint8_t* out, size_t cap)
+{
+    return static_cast<Port*>(h)->ssdv.image(callsign, image_id, out, cap);
+}
+
+int hbo_ssdv_is_packet(uint8_t pkt[256], int* errors) { return ssdv_dec_is_packet(pkt, errors); }
+
+void hbo_ssdv_make_packet(uint8_t out[256], int type, const char* callsign, int image_id, int packet_id, int width16,
+                          int height16, int flags, int mcu_offset, int mcu_id, const uint8_t* payload)
+{
+    // layout of the published format, see oracle/ssdv_published.h
+    memset(out, 0, 256);
+    out[0] = 0x55; out[1] = uint8_t(0x66 + type);
+    uint32_t code = 0;   // base-40, last character most significant
+    for (int i = int(strlen(callsign)) - 1; i >= 0; --i) {
+        const char c = callsign[i];
+        code *= 40;
+        if (c >= 'A' && c <= 'Z') code += uint32_t(c - 'A' + 14);
+        else if (c >= 'a' && c <= 'z') code += uint32_t(c - 'a' + 14);
+        else if (c >= '0' && c <= '9') code += uint32_t(c - '0' + 1);
+    }
+    out[2] = uint8_t(code >> 24); out[3] = uint8_t(code >> 16); out[4] = uint8_t(code >> 8); out[5] = uint8_t(code);
+    out[6] = uint8_t(image_id); out[7] = uint8_t(packet_id >> 8); out[8] = uint8_t(packet_id);
+    out[9] = uint8_t(width16); out[10] = uint8_t(height16); out[11] = uint8_t(flags); out[12] = uint8_t(mcu_offset);
+    out[13] = uint8_t(mcu_id >> 8); out[14] = uint8_t(mcu_id);
+    const int n_payload = type == 1 ? 237 : 205;
+    memcpy(out + 15, payload, size_t(n_payload));
+    const uint32_t crc = ssdvp_crc32(out + 1, size_t(14 + n_payload));
+    uint8_t* q = out + 15 + n_payload;
+    q[0] = uint8_t(crc >> 24); q[1] = uint8_t(crc >> 16); q[2] = uint8_t(crc >> 8); q[3] = uint8_t(crc);
+    if (type == 0) ssdvp_rs_encode(out + 1, out + 224);
 }
 
 size_t orc_chars(void* h, char* out, size_t cap) { return copy_str(static_cast<Port*>(h)->chars_all, out, cap); }

@@ -55,7 +55,24 @@ typedef struct hbo_afc_info {
     int    peak_right;
 } hbo_afc_info;
 
+/* ---- SSDV packet sync + bookkeeping: SSDV_wraper_t::push, ssdv_wrapper.cpp:37-148 --------
+ * One record per packet the wrapper accepted (== one ssdv_callback_, Decoder.h:631-632), in order. */
+typedef struct hbo_ssdv_event {
+    uint32_t call;        /* index of the push_process / ssdv_push call whose push() returned true */
+    uint16_t image_id, packet_id, width, height;
+    uint16_t set_size;    /* packets filed under (callsign, image_id) once this one is in (ssdv_wrapper.cpp:105-141) */
+    uint16_t reserved;
+    uint32_t set_crc32;   /* CRC-32 of those packets' 256 bytes each, concatenated in packet-id order */
+    char     callsign[8];
+} hbo_ssdv_event;
+
 #define HBO_DECL(P) \
+    /* events so far: returns the count, copies min(cap, count) */ \
+    size_t P##_ssdv_events(void* h, hbo_ssdv_event* out, size_t cap); \
+    /* hand raw characters straight to the decoder's SSDV wrapper (what Decoder.h:572-573 does), one push() */ \
+    void   P##_ssdv_push(void* h, const uint8_t* chars, size_t n); \
+    /* the packets filed under (callsign, image_id), 256 bytes each in packet-id order; returns the byte count */ \
+    size_t P##_ssdv_image(void* h, const char* callsign, int image_id, uint8_t* out, size_t cap); \
     void*  P##_create(const hbo_config* cfg); \
     void   P##_destroy(void* h); \
     /* pushSamples(iq[n] interleaved cf32, fs) followed by operator()() */ \
@@ -99,6 +116,14 @@ typedef struct hbo_spectrum_meta {
     size_t P##_demod_frame(const float* demod, size_t n, int resolution, int type_size, unsigned char* out, size_t cap);
 HBO_WIRE_DECL(ref)
 HBO_WIRE_DECL(orc)
+
+/* the published-algorithm restatement of fsphil/ssdv's packet test (oracle/ssdv_published.h), exported by the port
+ * library: verdict 0 = packet (corrected in place), -1 = not a packet; *errors = corrected symbols */
+int  hbo_ssdv_is_packet(uint8_t pkt[256], int* errors);
+/* test-vector builder: a well-formed packet (type 0 = with FEC, 1 = no FEC); payload bytes are taken from `payload`
+ * (205 / 237 bytes used) */
+void hbo_ssdv_make_packet(uint8_t out[256], int type, const char* callsign, int image_id, int packet_id, int width16,
+                          int height16, int flags, int mcu_offset, int mcu_id, const uint8_t* payload);
 
 /* port only: the sentence layer alone (std::regex, like sentence_extract.cpp:58-98) and the CRC */
 int  orc_extract_sentence(const char* stream, size_t n, char* callsign, char* data, char* crc, size_t cap, size_t* rest_offset);

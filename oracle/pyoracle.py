@@ -24,6 +24,15 @@ class Config(C.Structure):
                 ("dc_remove", C.c_int), ("record", C.c_int), ("fft_bins", C.c_int)]
 
 
+class SsdvEvent(C.Structure):
+    _fields_ = [("call", C.c_uint32), ("image_id", C.c_uint16), ("packet_id", C.c_uint16), ("width", C.c_uint16),
+                ("height", C.c_uint16), ("set_size", C.c_uint16), ("reserved", C.c_uint16), ("set_crc32", C.c_uint32),
+                ("callsign", C.c_char * 8)]
+
+    def astuple(self):
+        return (self.call, self.callsign.decode(), self.image_id, self.packet_id, self.width, self.height, self.set_size, self.set_crc32)
+
+
 class AfcInfo(C.Structure):
     _fields_ = [("frequency_correction", C.c_double), ("shift_hz", C.c_double), ("noise_floor", C.c_double),
                 ("noise_variance", C.c_double), ("peak_left", C.c_int), ("peak_right", C.c_int)]
@@ -48,6 +57,11 @@ def _bind(lib, p):
     f("stage").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     f("afc").argtypes = [C.c_void_p, C.POINTER(AfcInfo)]
     f("reset_frequency_correction").argtypes = [C.c_void_p, C.c_double]
+    f("ssdv_events").restype = C.c_size_t
+    f("ssdv_events").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    f("ssdv_push").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    f("ssdv_image").restype = C.c_size_t
+    f("ssdv_image").argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t]
     f("bench").restype = C.c_double
     f("bench").argtypes = [C.POINTER(Config), C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                            C.c_double, C.c_int, C.POINTER(C.c_uint64)]
@@ -137,6 +151,24 @@ class _Decoder:
     def reset_frequency_correction(self, corr: float):
         self._f("reset_frequency_correction")(self._h, float(corr))
 
+    # ---- SSDV packet sync / bookkeeping (SSDV_wraper_t::push, ssdv_wrapper.cpp:37-148) ----
+    def ssdv_push(self, chars: bytes):
+        """One SSDV_wraper_t::push(chars) on the decoder's wrapper, like Decoder.h:573."""
+        buf = (C.c_ubyte * max(len(chars), 1)).from_buffer_copy(bytes(chars) or b"\0")
+        self._f("ssdv_push")(self._h, buf, len(chars))
+
+    def ssdv_events(self) -> list[tuple]:
+        n = self._f("ssdv_events")(self._h, None, 0)
+        arr = (SsdvEvent * max(n, 1))()
+        self._f("ssdv_events")(self._h, arr, n)
+        return [arr[i].astuple() for i in range(n)]
+
+    def ssdv_image(self, callsign: str, image_id: int) -> bytes:
+        n = self._f("ssdv_image")(self._h, callsign.encode(), int(image_id), None, 0)
+        buf = (C.c_ubyte * max(n, 1))()
+        self._f("ssdv_image")(self._h, callsign.encode(), int(image_id), buf, n)
+        return bytes(buf[:n])
+
 
 class RefDecoder(_Decoder):
     kind = "ref"
@@ -175,6 +207,30 @@ def demod_frame(kind: str, demod: np.ndarray, resolution: int, type_size: int) -
     buf = C.create_string_buffer(max(n, 1))
     fn(demod.ctypes.data, demod.size, resolution, type_size, buf, n)
     return buf.raw[:n]
+
+
+def ssdv_is_packet(pkt: bytes):
+    """Published-algorithm packet test (oracle/ssdv_published.h): (verdict, errors, corrected packet)."""
+    lib = _load("orc")
+    lib.hbo_ssdv_is_packet.restype = C.c_int
+    lib.hbo_ssdv_is_packet.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    buf = (C.c_ubyte * 256).from_buffer_copy(bytes(pkt))
+    err = C.c_int(0)
+    v = lib.hbo_ssdv_is_packet(buf, C.byref(err))
+    return v, err.value, bytes(buf)
+
+
+def ssdv_make_packet(callsign: str, image_id: int, packet_id: int, payload: bytes, fec: bool = True, width16: int = 4,
+                     height16: int = 3, flags: int = 0, mcu_offset: int = 0, mcu_id: int = 0) -> bytes:
+    """A well-formed SSDV packet of the published format (test-vector builder)."""
+    lib = _load("orc")
+    lib.hbo_ssdv_make_packet.argtypes = [C.c_void_p, C.c_int, C.c_char_p] + [C.c_int] * 7 + [C.c_void_p]
+    need = 205 if fec else 237
+    pl = (bytes(payload) + bytes(need))[:need]
+    out = (C.c_ubyte * 256)()
+    src = (C.c_ubyte * need).from_buffer_copy(pl)
+    lib.hbo_ssdv_make_packet(out, 0 if fec else 1, callsign.encode(), image_id, packet_id, width16, height16, flags, mcu_offset, mcu_id, src)
+    return bytes(out)
 
 
 def premix(iq: np.ndarray, fs: float, f_hz: float, phase0: float = 0.0):

@@ -40,6 +40,8 @@
 #undef private
 
 #include "oracle_abi.h"
+#include <stdlib.h>
+#include <unistd.h>
 
 namespace {
 
@@ -106,7 +108,41 @@ struct Ref {
     std::string chars_cb, sentences;
     std::vector<float> decimated, filtered, demod;
     size_t q_in = 0, dec_pending = 0;
+    uint32_t n_calls = 0;
+    std::vector<hbo_ssdv_event> ssdv_events;
+    std::string ssdv_dir;
+    std::map<std::pair<std::string, uint16_t>, std::set<const void*>> ssdv_prev;
 };
+
+// one transcript record per accepted packet, read from the wrapper's own bookkeeping (ssdv_wrapper.h:62,82)
+void record_ssdv_event(Ref* r)
+{
+    auto& W = r->D->ssdv_;
+    const auto key = W.last_img_k_;
+    auto it = W.packets_.find(key);
+    if (it == W.packets_.end() || it->second.empty()) return;
+    hbo_ssdv_event e;
+    memset(&e, 0, sizeof(e));
+    e.call = r->n_calls - 1;
+    // the wrapper does not say which packet it just filed: it is the one object in the set that was not there at the
+    // previous event of this key (the harness keeps that snapshot; the new packet_t is allocated while the old ones
+    // are still alive, ssdv_wrapper.cpp:89 vs :120, so its address is distinct from every one in the snapshot)
+    std::set<const void*>& prev = r->ssdv_prev[key];
+    std::set<const void*> now;
+    std::vector<uint8_t> cat;
+    e.packet_id = 0xFFFF;
+    for (auto& p : it->second) {
+        cat.insert(cat.end(), p->data_.begin(), p->data_.end());
+        now.insert(p.get());
+        if (!prev.count(p.get())) { e.packet_id = p->header_.packet_id; e.width = p->header_.width; e.height = p->header_.height; }
+    }
+    prev.swap(now);
+    e.set_size = uint16_t(it->second.size());
+    e.set_crc32 = ssdvp_crc32(cat.data(), cat.size());
+    e.image_id = uint16_t(key.second);
+    strncpy(e.callsign, key.first.c_str(), sizeof(e.callsign) - 1);
+    r->ssdv_events.push_back(e);
+}
 
 size_t copy_str(const std::string& s, char* out, size_t cap)
 {
@@ -136,6 +172,10 @@ void* ref_create(const hbo_config* cfg)
         r->D->sentence_callback_ = [r](std::string cs, std::string data, std::string crc) {
             r->sentences += cs + "," + data + "*" + crc + "\n";
         };
+        // SSDV_wraper_t::save_jpeg (ssdv_wrapper.cpp:188-215) writes a file per packet: keep them in a scratch directory
+        char tmpl[] = "/tmp/hbd_ref_ssdv_XXXXXX";
+        if (const char* d = mkdtemp(tmpl)) { r->ssdv_dir = d; r->D->ssdvBaseFile(r->ssdv_dir + "/ssdv_"); }
+        r->D->ssdv_callback_ = [r](std::string, int, std::vector<uint8_t>) { record_ssdv_event(r); };
     });
     return r;
 }
@@ -145,6 +185,7 @@ void ref_destroy(void* h)
     Ref* r = static_cast<Ref*>(h);
     if (!r) return;
     r->w->run([r] { r->D.reset(); });
+    if (!r->ssdv_dir.empty()) { std::string cmd = "rm -rf '" + r->ssdv_dir + "'"; if (system(cmd.c_str())) {} }
     delete r;
 }
 
@@ -157,6 +198,7 @@ void ref_push_process(void* h, const float* iq, size_t n, double fs)
         v.samplingRate(fs);
         if (n) memcpy(v.data(), iq, n * sizeof(std::complex<float>));
         auto& D = *r->D;
+        ++r->n_calls;
         D.pushSamples(v);
         D();
         if (!r->cfg.record) return;
@@ -182,6 +224,40 @@ void ref_push_process(void* h, const float* iq, size_t n, double fs)
             r->demod.insert(r->demod.end(), D.demodulated_.begin(), D.demodulated_.end());
         }
     });
+}
+
+size_t ref_ssdv_events(void* h, hbo_ssdv_event* out, size_t cap)
+{
+    Ref* r = static_cast<Ref*>(h);
+    size_t n = 0;
+    r->w->run([&] {
+        n = r->ssdv_events.size();
+        if (out && cap) memcpy(out, r->ssdv_events.data(), std::min(cap, n) * sizeof(hbo_ssdv_event));
+    });
+    return n;
+}
+
+void ref_ssdv_push(void* h, const uint8_t* chars, size_t n)
+{
+    Ref* r = static_cast<Ref*>(h);
+    r->w->run([&] {
+        ++r->n_calls;
+        std::vector<char> v(reinterpret_cast<const char*>(chars), reinterpret_cast<const char*>(chars) + n);
+        if (r->D->ssdv_.push(v)) record_ssdv_event(r);   // what Decoder.h:573,631-632 do
+    });
+}
+
+size_t ref_ssdv_image(void* h, const char* callsign, int image_id, uint8_t* out, size_t cap)
+{
+    Ref* r = static_cast<Ref*>(h);
+    size_t n = 0;
+    r->w->run([&] {
+        auto& W = r->D->ssdv_;
+        auto it = W.packets_.find(std::make_pair(std::string(callsign), uint16_t(image_id)));
+        if (it == W.packets_.end()) return;
+        for (auto& p : it->second) { if (out && n + 256 <= cap) memcpy(out + n, p->data_.data(), 256); n += 256; }
+    });
+    return n;
 }
 
 size_t ref_chars(void* h, char* out, size_t cap)
