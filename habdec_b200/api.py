@@ -29,6 +29,21 @@ class SsdvPacketInfo(C.Structure):
                 ("height", C.c_int), ("errors", C.c_int), ("set_size", C.c_int)]
 
 
+class Telemetry(C.Structure):
+    _fields_ = [("payload_callsign", C.c_char * 64), ("datetime", C.c_char * 40), ("frame", C.c_int), ("lat", C.c_float),
+                ("lon", C.c_float), ("alt", C.c_float)]
+
+
+class GpsDistance(C.Structure):
+    _fields_ = [("dist_line_", C.c_double), ("dist_circle_", C.c_double), ("dist_radians_", C.c_double),
+                ("elevation_", C.c_double), ("bearing_", C.c_double)]
+
+
+class ChannelStats(C.Structure):
+    _fields_ = [("num_ok_", C.c_uint), ("D_", GpsDistance), ("dist_max_", C.c_double), ("elev_min_", C.c_double), ("age_s", C.c_double)]
+
+
+TELEMETRY_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(Telemetry), C.c_char_p)
 SSDV_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(SsdvPacketInfo), C.POINTER(C.c_ubyte))
 SENTENCE_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p)
 CHARS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_char), C.c_size_t)
@@ -108,6 +123,24 @@ SIGNATURES = {
     "hbd_set_demod_accumulate": (C.c_int, [_H, C.c_int]),
     "hbd_get_demod_frame": (C.c_size_t, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_get_demod_frames": (C.c_size_t, [_H, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "hbd_parse_sentence": (C.c_int, [C.c_char_p, C.c_longlong, C.POINTER(Telemetry)]),
+    "hbd_parse_sentence_time": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    "hbd_parse_gps_pos": (C.c_int, [C.c_char_p, C.POINTER(C.c_float)]),
+    "hbd_timestamp_from_hms": (C.c_size_t, [C.c_int, C.c_int, C.c_float, C.c_longlong, C.c_char_p, C.c_size_t]),
+    "hbd_calc_gps_distance": (None, [C.c_double] * 6 + [C.POINTER(GpsDistance)]),
+    "hbd_tracking_telemetry_payload": (C.c_size_t, [C.POINTER(Telemetry), C.c_char_p, C.c_size_t]),
+    "hbd_tracker_create": (C.c_void_p, []),
+    "hbd_tracker_destroy": (None, [C.c_void_p]),
+    "hbd_tracker_set_station": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
+    "hbd_tracker_set_clock": (C.c_int, [C.c_void_p, C.c_longlong]),
+    "hbd_tracker_set_callback": (C.c_int, [C.c_void_p, TELEMETRY_CB, C.c_void_p]),
+    "hbd_tracker_push": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p]),
+    "hbd_tracker_push_sentence": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
+    "hbd_tracker_poll": (C.c_size_t, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_tracker_stats": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ChannelStats)]),
+    "hbd_tracker_stats_payload": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
+    "hbd_tracker_get_sentence": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
+    "hbd_attach_tracker": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "hbd_debug_stage": (C.c_size_t, [_H, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_design_lowpass": (C.c_size_t, [C.c_float, C.c_float, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]),
     "hbd_extract_sentence": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -180,6 +213,107 @@ def crc16(s: bytes) -> bytes:
     out = C.create_string_buffer(5)
     lib.hbd_crc16(s, len(s), out)
     return out.value
+
+
+# ---- telemetry layer (host only; code/common/sentence_parse.cpp, GpsDistance.cpp, websocketServer/main.cpp:292-366) ----
+def parse_sentence(sentence: bytes, now_unix: int = -1):
+    """(status, dict | None): status 1 = parsed, 0 = rejected (empty optional), -1 = the reference throws here."""
+    t = Telemetry()
+    rc = load().hbd_parse_sentence(sentence, int(now_unix), C.byref(t))
+    return rc, (_telemetry_dict(t) if rc == 1 else None)
+
+
+def _telemetry_dict(t: Telemetry) -> dict:
+    return {"payload_callsign": t.payload_callsign, "datetime": t.datetime, "frame": t.frame, "lat": t.lat, "lon": t.lon, "alt": t.alt,
+            "tracking": tracking_payload(t)}
+
+
+def tracking_payload(t: Telemetry) -> bytes:
+    buf = C.create_string_buffer(256)
+    load().hbd_tracking_telemetry_payload(C.byref(t), buf, 256)
+    return buf.value
+
+
+def parse_sentence_time(s: bytes):
+    h, m, sec = C.c_int(), C.c_int(), C.c_float()
+    rc = load().hbd_parse_sentence_time(s, C.byref(h), C.byref(m), C.byref(sec))
+    return rc, ((h.value, m.value, sec.value) if rc == 1 else None)
+
+
+def parse_gps_pos(s: bytes):
+    v = C.c_float()
+    rc = load().hbd_parse_gps_pos(s, C.byref(v))
+    return rc, (v.value if rc == 1 else None)
+
+
+def timestamp_from_hms(h: int, m: int, s: float, now_unix: int = -1) -> bytes:
+    buf = C.create_string_buffer(96)
+    load().hbd_timestamp_from_hms(int(h), int(m), float(s), int(now_unix), buf, 96)
+    return buf.value
+
+
+def calc_gps_distance(lat1, lon1, alt1, lat2, lon2, alt2) -> GpsDistance:
+    g = GpsDistance()
+    load().hbd_calc_gps_distance(lat1, lon1, alt1, lat2, lon2, alt2, C.byref(g))
+    return g
+
+
+class Tracker:
+    """SentenceCallback + GLOBALS::STATS for many channels (hbd_tracker); host only."""
+
+    def __init__(self, station=None, now_unix: int = -1):
+        self._lib = load()
+        self._t = C.c_void_p(self._lib.hbd_tracker_create())
+        self._cb = None
+        if station is not None:
+            self.set_station(*station)
+        if now_unix >= 0:
+            self.set_clock(now_unix)
+
+    def close(self):
+        if self._t:
+            self._lib.hbd_tracker_destroy(self._t)
+            self._t = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self): return self._t
+    def set_station(self, lat, lon, alt): self._lib.hbd_tracker_set_station(self._t, float(lat), float(lon), float(alt))
+    def set_clock(self, now_unix: int): self._lib.hbd_tracker_set_clock(self._t, int(now_unix))
+    def push(self, ch: int, callsign: bytes, data: bytes, crc: bytes) -> int: return self._lib.hbd_tracker_push(self._t, ch, callsign, data, crc)
+    def push_sentence(self, ch: int, sentence: bytes) -> int: return self._lib.hbd_tracker_push_sentence(self._t, ch, sentence)
+
+    def set_callback(self, fn):
+        self._cb = TELEMETRY_CB(lambda user, ch, t, s: fn(ch, _telemetry_dict(t.contents), s)) if fn else C.cast(None, TELEMETRY_CB)
+        self._lib.hbd_tracker_set_callback(self._t, self._cb, None)
+
+    def poll(self, ch: int) -> list[dict]:
+        n = self._lib.hbd_tracker_poll(self._t, ch, None, 0)
+        if not n:
+            return []
+        arr = (Telemetry * n)()
+        self._lib.hbd_tracker_poll(self._t, ch, arr, n)
+        return [_telemetry_dict(t) for t in arr]
+
+    def stats(self, ch: int) -> ChannelStats:
+        st = ChannelStats()
+        self._lib.hbd_tracker_stats(self._t, ch, C.byref(st))
+        return st
+
+    def stats_payload(self, ch: int, with_age: bool = False) -> bytes:
+        buf = C.create_string_buffer(512)
+        self._lib.hbd_tracker_stats_payload(self._t, ch, int(with_age), buf, 512)
+        return buf.value
+
+    def get_sentence(self, ch: int, frame: int) -> bytes:
+        buf = C.create_string_buffer(1200)
+        n = self._lib.hbd_tracker_get_sentence(self._t, ch, int(frame), buf, 1200)
+        return buf.value if n else b""
 
 
 class BatchDecoder:
@@ -301,6 +435,10 @@ class BatchDecoder:
     def poll_raw_chars(self, ch=0) -> bytes: return self._bytes(self._lib.hbd_poll_raw_chars, ch)
     def poll_sentences(self, ch=0) -> list[bytes]:
         return [s for s in self._bytes(self._lib.hbd_poll_sentences, ch).split(b"\n") if s]
+
+    def attach_tracker(self, tracker, ch_offset: int = 0):
+        self._tracker = tracker   # keep it alive
+        self._chk(self._lib.hbd_attach_tracker(self._h, tracker.handle if tracker else None, int(ch_offset)))
 
     def set_sentence_callback(self, fn):
         cb = SENTENCE_CB(lambda user, ch, cs, data, crc: fn(ch, cs, data, crc))

@@ -18,6 +18,7 @@
 #include "fft_afc.cuh"
 #include "hbd_common.cuh"
 #include "host_tail.h"
+#include "telemetry_abi.h"
 #include "nco.cuh"
 #include "ssdv.cuh"
 #include "tail.cuh"
@@ -192,6 +193,7 @@ struct hbd_decoder {
     int enable_ssdv(bool on);
 
     hbd_sentence_cb sentence_cb = nullptr; void* sentence_user = nullptr;
+    hbd_tracker* tracker = nullptr; int tracker_off = 0;   // telemetry layer fed after the sentence callback
     hbd_chars_cb chars_cb = nullptr; void* chars_user = nullptr;
 
     void set_error(const std::string& e) { err = e; }
@@ -633,9 +635,12 @@ int hbd_decoder::collect_locked(unsigned lag)
         HBD_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
     }
     SentenceSink sink;
-    if (sentence_cb) {
-        hbd_sentence_cb cb = sentence_cb; void* user = sentence_user;
-        sink = [cb, user](int ch, const std::string& cs, const std::string& d, const std::string& crc) { cb(user, ch, cs.c_str(), d.c_str(), crc.c_str()); };
+    if (sentence_cb || tracker) {
+        hbd_sentence_cb cb = sentence_cb; void* user = sentence_user; hbd_tracker* trk = tracker; const int off = tracker_off;
+        sink = [cb, user, trk, off](int ch, const std::string& cs, const std::string& d, const std::string& crc) {
+            if (cb) cb(user, ch, cs.c_str(), d.c_str(), crc.c_str());
+            if (trk) tracker_feed(trk, ch + off, cs, d, crc);      // SentenceCallback, websocketServer/main.cpp:292-366
+        };
     }
     std::vector<size_t> chars_before;
     std::vector<int> cb_channels;
@@ -1153,6 +1158,11 @@ size_t hbd_poll_raw_chars(hbd_decoder* h, int ch, unsigned char* out, size_t cap
     if (out && cap >= n) v.clear();
     return n;
 }
+int hbd_attach_tracker(hbd_decoder* h, hbd_tracker* t, int ch_offset)
+{
+    HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); h->tracker = t; h->tracker_off = ch_offset; return HBD_OK;
+}
+
 int hbd_set_sentence_callback(hbd_decoder* h, hbd_sentence_cb cb, void* user)
 {
     HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); h->sentence_cb = cb; h->sentence_user = user; return HBD_OK;

@@ -191,6 +191,54 @@ int    hbd_set_demod_accumulate(hbd_decoder* h, int on);
 size_t hbd_get_demod_frame(hbd_decoder* h, int ch, int resolution, int type_size, unsigned char* out, size_t cap);
 size_t hbd_get_demod_frames(hbd_decoder* h, int resolution, int type_size, unsigned char* out, size_t pitch, unsigned* sizes);
 
+/* ---- telemetry layer (the consumer of the sentence callback: SentenceCallback, code/websocketServer/main.cpp:292-366).
+ * Host only, no GPU involved: a few sentences per second and channel of scalar string work.  Three-way results follow
+ * the reference: 1 = value, 0 = empty optional (too few fields, no GPS fix, unparsable time), -1 = the reference lets a
+ * std::invalid_argument / out_of_range escape here (stoi / stof / string::at).  now_unix < 0 reads the system clock. */
+enum { HBD_PARSE_OK = 1, HBD_PARSE_NONE = 0, HBD_PARSE_THROW = -1, HBD_PARSE_BADARG = -10 /* NULL pointer / malformed input */ };
+typedef struct hbd_telemetry {          /* sondehub::MinTelemetry, code/sondehub/sondehub_uploader.h:12-21 */
+    char  payload_callsign[64];         /* truncated to 63 characters */
+    char  datetime[40];
+    int   frame;
+    float lat, lon, alt;
+} hbd_telemetry;
+typedef struct hbd_gps_distance {       /* habdec::GpsDistance, code/common/GpsDistance.h:7-14 */
+    double dist_line_, dist_circle_, dist_radians_, elevation_, bearing_;
+} hbd_gps_distance;
+typedef struct hbd_channel_stats {      /* GLOBALS::STATS, code/websocketServer/GLOBALS.h:66-73 */
+    unsigned num_ok_;
+    hbd_gps_distance D_;
+    double dist_max_, elev_min_;
+    double age_s;                       /* seconds since last_sentence_timestamp_ */
+} hbd_channel_stats;
+int    hbd_parse_sentence(const char* sentence_without_crc, long long now_unix, hbd_telemetry* out);  /* sentence_parse.cpp:148-199 */
+int    hbd_parse_sentence_time(const char* s, int* hour, int* minute, float* second);                 /* :50-68 */
+int    hbd_parse_gps_pos(const char* s, float* out);                                                  /* :103-145 */
+size_t hbd_timestamp_from_hms(int hour, int minute, float second, long long now_unix, char* out, size_t cap); /* :72-98 */
+void   hbd_calc_gps_distance(double lat1, double lon1, double alt1, double lat2, double lon2, double alt2,
+                             hbd_gps_distance* out);                                                  /* GpsDistance.cpp:21-84 */
+/* "callsign,datetime,lat,lon,alt": what follows "cmd::info:tracking_telemetry=" (main.cpp:326-331) */
+size_t hbd_tracking_telemetry_payload(const hbd_telemetry* t, char* out, size_t cap);
+/* hbd_tracker: SentenceCallback + STATS + sentences_map_ for any number of channels (keys are caller-chosen channel
+ * ids, e.g. global channel numbers on rank 0 after the gather).  Feed it by hand or attach it to a decoder handle. */
+typedef struct hbd_tracker hbd_tracker;
+typedef void (*hbd_telemetry_cb)(void* user, int ch, const hbd_telemetry* t, const char* sentence);
+hbd_tracker* hbd_tracker_create(void);
+void   hbd_tracker_destroy(hbd_tracker* t);
+int    hbd_tracker_set_station(hbd_tracker* t, float lat, float lon, float alt);   /* PARAMS station_lat_/lon_/alt_ */
+int    hbd_tracker_set_clock(hbd_tracker* t, long long now_unix);                  /* >= 0 freezes "today" (tests, replays) */
+int    hbd_tracker_set_callback(hbd_tracker* t, hbd_telemetry_cb cb, void* user);
+int    hbd_tracker_push(hbd_tracker* t, int ch, const char* callsign, const char* data, const char* crc);
+int    hbd_tracker_push_sentence(hbd_tracker* t, int ch, const char* sentence);    /* "callsign,data*crc" as polled */
+size_t hbd_tracker_poll(hbd_tracker* t, int ch, hbd_telemetry* out, size_t cap);   /* records since the previous poll */
+int    hbd_tracker_stats(hbd_tracker* t, int ch, hbd_channel_stats* out);
+/* "cmd::info:stats=ok:..,dist_line:..,...,alt:..[,age:..]" (habdec_ws_protocol.cpp:486-498) */
+size_t hbd_tracker_stats_payload(hbd_tracker* t, int ch, int with_age, char* out, size_t cap);
+size_t hbd_tracker_get_sentence(hbd_tracker* t, int ch, int frame, char* out, size_t cap);   /* sentences_map_[frame] */
+/* every CRC-valid sentence of channel c is pushed to the tracker as channel c + ch_offset, on the processing thread,
+ * after the sentence callback; NULL detaches */
+int    hbd_attach_tracker(hbd_decoder* h, hbd_tracker* t, int ch_offset);
+
 /* ---- test hooks ------------------------------------------------------------------------------------------ */
 enum { HBD_STAGE_DECIMATED = 0, HBD_STAGE_FILTERED = 1, HBD_STAGE_DEMOD = 2, HBD_STAGE_LPTAPS = 5,
        HBD_STAGE_PENDING = 6, HBD_STAGE_BITS = 7 };
