@@ -228,6 +228,10 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     k1_ms, k1_cnt = dec.kernel_timing(0)
     rest_ms, rest_cnt = dec.kernel_timing(1)
+    gaps = {}
+    for name, w in (("k1_end_to_next_k1_start_ms", 2), ("k1_end_to_tail_start_ms", 3), ("tail_end_to_k1_plus2_start_ms", 4)):
+        g_ms, g_cnt = dec.kernel_timing(w)
+        gaps[name] = g_ms / g_cnt if g_cnt else None
     dec.set_kernel_timing(False)
     launches = dec.kernel_launches() - launches0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -293,7 +297,7 @@ def run_ours(args):
                          "traffic_source": "ncu --set full capture of this workload, profiles/r1_k1_decim1_ncu_full_raw.csv (bytes per launch)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_ms, "launches_timed": k1_cnt,
-                         "k1_share_of_step": (k1_ms / ms) if ms else None, "rest_of_step_ms": rest_ms / max(rest_cnt, 1)},
+                         "k1_share_of_step": (k1_ms / ms) if ms else None, "rest_of_step_ms": rest_ms / max(rest_cnt, 1), "pipeline_gaps": gaps},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "host_issue_ms_per_step": host_issue_ms,
             "results": {"channels_gathered": len(gathered) if gathered else 0, "sentences_expected_per_channel_approx": exp_sent,
                         "sentences_min": min(got_sent) if got_sent else None, "sentences_max": max(got_sent) if got_sent else None}}

@@ -101,6 +101,7 @@ struct hbd_decoder {
     std::vector<cudaEvent_t> ev_consumed;   // per group: K1 + carry done (input consumed, stage-1 output ready)
     std::vector<cudaEvent_t> ev_tail;       // per (group, stage-1 buffer): tail done, that buffer may be overwritten by K1
     std::vector<char> tail_pending;
+    bool tail_ev_late = false;              // HBD_TAIL_EV_LATE=1 (measurement hook): record ev_tail after the whole lo-stream sequence
     cudaEvent_t ev_in = nullptr;
     int sync_groups()
     {
@@ -515,6 +516,7 @@ int hbd_decoder::process_async_locked()
     for (int g = 0; g < n_groups; ++g) {
         const int c0 = int((long long)n_ch * g / n_groups), c1 = int((long long)n_ch * (g + 1) / n_groups);
         const int nc = c1 - c0;
+        bool tail_recorded = false;
         // K1 of this group overwrites the group's stage-1 buffer: the previous call's tail must be done with it
         if (tail_pending[size_t(2 * g + s1_cur)]) HBD_CUDA_CHECK(cudaStreamWaitEvent(hi, ev_tail[size_t(2 * g + s1_cur)], 0));
         {   // K1 also writes the next call's carry (even when no channel has a full decimation block yet)
@@ -542,6 +544,9 @@ int hbd_decoder::process_async_locked()
             ta.rec_decimated = record ? d_rec_dec : nullptr; ta.rec_filtered = record ? d_rec_filt : nullptr; ta.rec_pitch = rec_pitch;
             ta.rec_bits = record ? d_rec_bits : nullptr; ta.rec_bits_n = d_rec_bits_n; ta.rec_bits_pitch = rec_bits_pitch;
             HBD_CUDA_CHECK(launch_tail(ta, nc, lo, &nl));
+            // only the tail kernel reads the stage-1 buffer: K1 of the call after next may overwrite it as soon as the
+            // tail is done, without waiting for the FFT / SSDV / demod kernels behind it on this stream
+            if (!tail_ev_late) { HBD_CUDA_CHECK(cudaEventRecord(ev_tail[size_t(2 * g + s1_cur)], lo)); tail_recorded = true; }
             FftArgs fa{};
             fa.state = d_state; fa.fftbuf = d_fftbuf; fa.spectrum = d_spectrum; fa.power = d_power; fa.twiddle = d_twiddle; fa.fs_dec = fs_dec;
             fa.ch0 = c0; fa.fft_n = fft_n;
@@ -560,7 +565,7 @@ int hbd_decoder::process_async_locked()
             HBD_CUDA_CHECK(launch_demod_accumulate(aa, nc, lo, &nl));
         }
         if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
-        HBD_CUDA_CHECK(cudaEventRecord(ev_tail[size_t(2 * g + s1_cur)], lo));
+        if (!tail_recorded) HBD_CUDA_CHECK(cudaEventRecord(ev_tail[size_t(2 * g + s1_cur)], lo));
         tail_pending[size_t(2 * g + s1_cur)] = 1;
     }
     // the caller's stream resumes once every group has consumed the input (it does not wait for the tail kernels)
@@ -733,6 +738,7 @@ int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
     h->own_stream = true;
     {
         if (const char* sv = getenv("HBD_SV_WANT")) h->sv_override = atoi(sv);
+        if (const char* tl = getenv("HBD_TAIL_EV_LATE")) h->tail_ev_late = atoi(tl) != 0;
         const char* env = getenv("HBD_GROUPS");
         // one group: with the stage-1 stream double buffered over calls, K1 of call s+1 already overlaps the tail of call s;
         // more groups only help synchronous callers (hbd_process) that cannot pipeline calls
@@ -1099,9 +1105,25 @@ int hbd_get_kernel_timing(hbd_decoder* h, int which, double* total_ms, unsigned*
     std::lock_guard<std::mutex> l(h->mtx);
     cudaSetDevice(h->device);
     if (h->sync_groups() || cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
+    double tot = 0; unsigned cnt = 0;
+    if (which >= 2) {   // pipeline diagnostics (one channel group): signed gaps between events of different pairs
+        const size_t calls = std::min(h->ev_used_k1, h->ev_used_rest) / 2;
+        for (size_t i = 0; i < calls; ++i) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            if (which == 2 && i + 1 < calls) { a = h->ev_k1[2 * i + 1]; b = h->ev_k1[2 * i + 2]; }        // K1 end -> next K1 start
+            else if (which == 3) { a = h->ev_k1[2 * i + 1]; b = h->ev_rest[2 * i]; }                      // K1 end -> own tail start
+            else if (which == 4 && i + 2 < calls) { a = h->ev_rest[2 * i + 1]; b = h->ev_k1[2 * i + 4]; } // tail end -> K1 start two calls on
+            if (!a) continue;
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) return HBD_ERR_CUDA;
+            tot += ms; ++cnt;
+        }
+        if (total_ms) *total_ms = tot;
+        if (count) *count = cnt;
+        return HBD_OK;
+    }
     const std::vector<cudaEvent_t>& pool = which == 0 ? h->ev_k1 : h->ev_rest;
     const size_t used = which == 0 ? h->ev_used_k1 : h->ev_used_rest;
-    double tot = 0; unsigned cnt = 0;
     for (size_t i = 0; i + 1 < used; i += 2) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, pool[i], pool[i + 1]) != cudaSuccess) return HBD_ERR_CUDA;

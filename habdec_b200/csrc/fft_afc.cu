@@ -1,4 +1,4 @@
-// K4 -- spectrum FFT + AFC, one CTA per channel.
+// K4 -- spectrum FFT + AFC, a small grid of CTAs each owning a strided set of channels.
 //
 //   FFT::operator() + swap_half     code/Decoder/FFT.cpp:77-99   (FFTW3f forward c2c, unnormalised, no window)
 //   FftPower / ComputeVariance / FindPeaks   code/Decoder/AFC.h:225-329
@@ -17,6 +17,7 @@
 // unfused multiplies/adds so that it matches the CPU's arithmetic.
 #include "hbd_common.cuh"
 #include "fft_afc.cuh"
+#include <algorithm>
 
 namespace hbd {
 
@@ -218,13 +219,32 @@ fft_afc_kernel(FftArgs a)
     __shared__ int s_ai[kFftThreads / 32];
     __shared__ int s_bad;
 
-    const int ch = a.ch0 + blockIdx.x, t = threadIdx.x;
+    __shared__ unsigned char s_todo[kFftThreads];
+    const int t = threadIdx.x;
+    // CTA b owns channels b, b + G, b + 2G, ... (G = gridDim.x, at most kFftThreads of them).  Phase A: thread j looks at
+    // the j-th owned channel; a channel without a complete frame only needs the per-call AFC step (the common case:
+    // 15 of 16 calls at 256 decimated samples per call), done here by one thread per channel, all channels in parallel.
+    // Phase B: channels with a complete frame are transformed one after the other by the whole CTA.  A small grid with
+    // in-CTA ownership keeps the number of 50 KB-shared-memory CTAs that must find room next to the resident K1 small.
+    {
+        const int j_ch = int(blockIdx.x) + t * int(gridDim.x);
+        unsigned char todo = 0;
+        if (j_ch < a.n_channels) {
+            ChanState& sj = a.state[a.ch0 + j_ch];
+            if (sj.fft_ready) todo = 1;
+            else if (sj.afc_tick) { afc_step(sj, a.fs_dec, N); sj.afc_tick = 0; }
+        }
+        s_todo[t] = todo;
+    }
+    __syncthreads();
+    for (int j = 0; int(blockIdx.x) + j * int(gridDim.x) < a.n_channels; ++j) {
+    if (!s_todo[j]) continue;
+    const int ch = a.ch0 + int(blockIdx.x) + j * int(gridDim.x);
     ChanState& st = a.state[ch];
-    const bool do_fft = st.fft_ready != 0;
     const bool do_tick = st.afc_tick != 0;
-    if (!do_fft && !do_tick) return;
+    __syncthreads();   // everybody has read the flags thread 0 clears at the end of the previous channel
 
-    if (do_fft) {
+    {
         const float2* x = a.fftbuf + (size_t)ch * N;
         const float2* __restrict__ tw = a.twiddle; // tw[e] = exp(-2 pi i e / N)
         float2* spec = a.spectrum + (size_t)ch * N;
@@ -313,6 +333,7 @@ fft_afc_kernel(FftArgs a)
         afc_step(st, a.fs_dec, N);
         st.afc_tick = 0;
     }
+    }
 }
 
 template <int N>
@@ -326,7 +347,13 @@ static cudaError_t launch_fft_n(const FftArgs& a, int n_channels, cudaStream_t s
         cudaFuncSetAttribute(fft_afc_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
-    fft_afc_kernel<N><<<n_channels, kFftThreads, smem, stream>>>(a);
+    static int n_sms = 0;
+    if (!n_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev); if (n_sms < 1) n_sms = 1; }
+    int grid = std::min(n_channels, 4 * n_sms);
+    grid = std::max(grid, (n_channels + kFftThreads - 1) / kFftThreads);   // a CTA owns at most kFftThreads channels
+    if (grid < 1) return cudaSuccess;
+    FftArgs b = a; b.n_channels = n_channels;
+    fft_afc_kernel<N><<<grid, kFftThreads, smem, stream>>>(b);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -13,6 +13,7 @@ struct FftArgs {
     double fs_dec;
     int ch0;                // first channel of this launch
     int fft_n;              // 4096 (reference) or 16384
+    int n_channels;         // channels of this launch (set by launch_fft_afc)
 };
 
 cudaError_t launch_fft_afc(const FftArgs& a, int n_channels, cudaStream_t stream, int* launches);
