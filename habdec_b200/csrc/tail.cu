@@ -203,9 +203,17 @@ tail_kernel(TailArgs a)
         // stage-2 history for the next call: the last T2-1 stage-1 samples, taken from the last tile's window
         if (M2 > 1 && k0 + nk == n2) {
             const int win = int(nk) * M2 + lead;
+            // The reference runs the stage IN PLACE (Decoder.h:441-446): when Decimator.h:141-143 copies the last T2-1
+            // inputs, the n2 outputs already sit on the head of the same buffer.  For short calls (n1 - (T2-1) < n2,
+            // i.e. n1 < 184 at M2 = 4) the head of the history therefore holds stage-2 OUTPUTS, not stage-1 samples.
+            const int p0 = int(n2) * M2 - (T2 - 1);          // position of history sample 0 in this call's stage-1 stream
+            const bool in_place_overlap = p0 >= 0 && p0 < int(n2);
+            if (in_place_overlap) __syncthreads();            // ynew[] of the (single) tile is complete
             for (int i = tid; i < T2 - 1; i += kTailThreads) {
                 const int w = win - (T2 - 1) + i;
-                s1n[kS1Hist - (T2 - 1) + i] = s_x[M2 == 4 ? pad16(w) : w];
+                float2 v = s_x[M2 == 4 ? pad16(w) : w];
+                if (in_place_overlap && p0 + i < int(n2)) v = ynew[p0 + i];
+                s1n[kS1Hist - (T2 - 1) + i] = v;
             }
         }
         __syncthreads();
