@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline leg")
     ap.add_argument("--ssdv", action="store_true", help="diagnostic: run with SSDV packet sync switched on (one more kernel per step)")
+    ap.add_argument("--collect-every", type=int, default=16, help="drain finished calls every this many steps")
+    ap.add_argument("--collect-lag", type=int, default=8, help="calls left in flight by the periodic drain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true", help="diagnostic: no CUDA events around K1 (no roofline numbers)")
@@ -218,10 +220,12 @@ def run_ours(args):
         t_h = time.perf_counter()
         step(n_done); n_done += 1
         t_issue += time.perf_counter() - t_h
-        if (k + 1) % 16 == 0:
-            dec.collect_ready(8)        # drain finished calls; the newest 8 stay in flight so the GPU never idles
+        if (k + 1) % args.collect_every == 0:
+            dec.collect_ready(args.collect_lag)   # drain finished calls; the newest few stay in flight so the GPU never idles
     host_issue_ms = t_issue * 1e3 / max(args.steps, 1)   # host time to enqueue one step, collects excluded (diagnostic)
+    t_fc = time.perf_counter()
     dec.collect()                       # results drained (D2H + sentence layer) inside the timed region
+    final_collect_ms = (time.perf_counter() - t_fc) * 1e3
     ev1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -298,7 +302,7 @@ def run_ours(args):
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_ms, "launches_timed": k1_cnt,
                          "k1_share_of_step": (k1_ms / ms) if ms else None, "rest_of_step_ms": rest_ms / max(rest_cnt, 1), "pipeline_gaps": gaps},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "host_issue_ms_per_step": host_issue_ms,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "host_issue_ms_per_step": host_issue_ms, "final_collect_ms": final_collect_ms,
             "results": {"channels_gathered": len(gathered) if gathered else 0, "sentences_expected_per_channel_approx": exp_sent,
                         "sentences_min": min(got_sent) if got_sent else None, "sentences_max": max(got_sent) if got_sent else None}}
 

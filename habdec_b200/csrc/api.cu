@@ -591,6 +591,12 @@ int hbd_decoder::collect_locked(unsigned lag)
         return HBD_OK;
     }
     if (call_seq - calls_collected <= lag) return HBD_OK;
+    if (lag == 0 && call_seq - calls_collected > 2) {
+        // a full drain behind a queue of calls: take the finished calls first, in halving steps, so the host's sentence
+        // layer works while the GPU is still busy with the newest calls instead of after it has gone idle
+        for (unsigned l = (call_seq - calls_collected) / 2; l >= 1; l /= 2) { const int rc = collect_locked(l); if (rc) return rc; }
+        if (call_seq == calls_collected) return collect_locked(0);
+    }
     const unsigned upto = call_seq - lag;            // calls [calls_collected, upto) get drained
     if (lag == 0) {
         if (sync_groups()) { set_error("stream sync failed"); return HBD_ERR_CUDA; }
