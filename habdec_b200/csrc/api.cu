@@ -59,6 +59,7 @@ struct HostChan {
     // mirrors of device counters that are pure functions of the push sizes
     unsigned in_r = 0, dec_pending = 0;
     size_t grown1 = 0, grown2 = 0, grown_lp = 0;
+    unsigned fft_have = 0;   // mirror of ChanState::fft_have: tells the host which calls complete an FFT frame (K4 launch)
     size_t lp_input_size = 0, lp_ntaps = 0;
     unsigned pushed = 0;     // samples waiting in the staging row
     unsigned last_nf = 0, last_n2 = 0;
@@ -297,13 +298,15 @@ int hbd_decoder::alloc_fft()
     HBD_CUDA_CHECK(cudaMemset(d_spectrum, 0, n * N * sizeof(float2)));
     HBD_CUDA_CHECK(dalloc(&d_power, n * N));
     HBD_CUDA_CHECK(cudaMemset(d_power, 0, n * N * sizeof(float)));
-    HBD_CUDA_CHECK(dalloc(&d_twiddle, N));
-    std::vector<float2> tw(N);
-    for (size_t e = 0; e < N; ++e) {
-        const double ang = -2.0 * M_PI * double(e) / double(N);
-        tw[e] = make_float2(float(std::cos(ang)), float(std::sin(ang)));
-    }
-    HBD_CUDA_CHECK(cudaMemcpy(d_twiddle, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+    // [0, N): exp(-2 pi i e / N); behind it the twiddles of the 4096-point (sub-)transform in the order its threads read
+    // them: pass 1 [k1][t] = W_4096^(t k1) (16 x 256), pass 2 [j1][m2] = W_256^(m2 j1) (16 x 16); all evaluated in float64
+    HBD_CUDA_CHECK(dalloc(&d_twiddle, N + 4096 + 256));
+    std::vector<float2> tw(N + 4096 + 256);
+    auto w = [](double num, double den) { const double ang = -2.0 * M_PI * num / den; return make_float2(float(std::cos(ang)), float(std::sin(ang))); };
+    for (size_t e = 0; e < N; ++e) tw[e] = w(double(e), double(N));
+    for (size_t k1 = 0; k1 < 16; ++k1) for (size_t t = 0; t < 256; ++t) tw[N + k1 * 256 + t] = w(double(t * k1), 4096.0);
+    for (size_t j1 = 0; j1 < 16; ++j1) for (size_t m2 = 0; m2 < 16; ++m2) tw[N + 4096 + j1 * 16 + m2] = w(double(16 * m2 * j1), 4096.0);
+    HBD_CUDA_CHECK(cudaMemcpy(d_twiddle, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
     return HBD_OK;
 }
 
@@ -413,6 +416,7 @@ int hbd_decoder::process_async_locked()
     auto quiesce = [&]() -> int { if (!groups_idle) { if (sync_groups()) return HBD_ERR_CUDA; groups_idle = true; } return HBD_OK; };
 
     bool cfg_dirty_any = false;
+    bool need_k4 = false;    // some channel completes an FFT frame in this call
     unsigned max_nf = 0;
     std::vector<float> new_taps;
     for (size_t c = 0; c < n; ++c) {
@@ -424,6 +428,10 @@ int hbd_decoder::process_async_locked()
         x.pushed = 0;
         x.last_n2 = p.n2; x.last_nf = 0;
         if (p.flags & 1u) { cfg_dirty_any |= x.cfg_dirty; continue; }
+        if (p.n2 && x.fft_have < unsigned(fft_n)) {   // FFT frame assembly, Decoder.h:467-473 (mirror of K2's arithmetic)
+            x.fft_have += std::min(unsigned(fft_n) - x.fft_have, p.n2);
+            if (x.fft_have >= unsigned(fft_n)) { need_k4 = true; x.fft_have = 0; }   // transformed and cleared in this call
+        }
         // history re-zeroing when the reference's work buffers grow (Decimator.h:74-79)
         if (M1 > 1) {
             const size_t need = size_t(p.consumed) + size_t(T1) + size_t(M1);
@@ -550,7 +558,7 @@ int hbd_decoder::process_async_locked()
             FftArgs fa{};
             fa.state = d_state; fa.fftbuf = d_fftbuf; fa.spectrum = d_spectrum; fa.power = d_power; fa.twiddle = d_twiddle; fa.fs_dec = fs_dec;
             fa.ch0 = c0; fa.fft_n = fft_n;
-            HBD_CUDA_CHECK(launch_fft_afc(fa, nc, lo, &nl));
+            if (need_k4) HBD_CUDA_CHECK(launch_fft_afc(fa, nc, lo, &nl));   // other calls: K2 has stepped the AFC itself
             if (ssdv_on) {   // test every 0x55-started window the new characters completed
                 SsdvScanArgs sa{};
                 sa.ring = d_ssdv_ring; sa.total = d_ssdv_total; sa.scanned = d_ssdv_scanned; sa.log = d_ssdv_log;
@@ -805,6 +813,7 @@ int hbd_set_fft_size(hbd_decoder* h, size_t n_bins)
     // spectrum / AFC state back to a freshly constructed decoder's (Average<T> starts with one 0 sample)
     std::vector<ChanState> st(size_t(h->n_ch));
     if (cudaMemcpy(st.data(), h->d_state, st.size() * sizeof(ChanState), cudaMemcpyDeviceToHost) != cudaSuccess) return HBD_ERR_CUDA;
+    for (auto& x : h->hc) x.fft_have = 0;
     for (auto& s : st) {
         s.fft_have = s.fft_ready = s.have_spectrum = 0;
         s.afc_correction = s.afc_noise_floor = s.afc_noise_var = s.afc_shift_hz = 0;

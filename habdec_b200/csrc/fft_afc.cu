@@ -17,6 +17,7 @@
 // unfused multiplies/adds so that it matches the CPU's arithmetic.
 #include "hbd_common.cuh"
 #include "fft_afc.cuh"
+#include "afc_dev.cuh"
 #include <algorithm>
 
 namespace hbd {
@@ -105,64 +106,13 @@ __device__ void block_argmax(float v, int i, float* sv, int* si, float& ov, int&
     ov = sv[0]; oi = si[0];
 }
 
-// ---- Average<T> (Average.h:39-55) -------------------------------------------------------------------------------
-__device__ __forceinline__ double avg_get_d(double sum, unsigned cnt) { return cnt ? __ddiv_rn(sum, double(cnt)) : sum; }
-__device__ __forceinline__ double avg_add_d(double& sum, unsigned& cnt, unsigned cap, double val)
-{
-    const double g = avg_get_d(sum, cnt);
-    const double diff = __dsub_rn(g, val);
-    if (cnt == cap) sum = __dadd_rn(__dmul_rn(g, double(cap - 1)), val);
-    else { ++cnt; sum = __dadd_rn(sum, val); }
-    return diff;
-}
-__device__ __forceinline__ double avg_get_i(int sum, unsigned cnt) { return cnt ? __ddiv_rn(double(sum), double(cnt)) : double(sum); }
-__device__ __forceinline__ double avg_add_i(int& sum, unsigned& cnt, unsigned cap, int val)
-{
-    const double g = avg_get_i(sum, cnt);
-    const double diff = __dsub_rn(g, double(val));
-    if (cnt == cap) sum = int(__dadd_rn(__dmul_rn(g, double(cap - 1)), double(val))); // truncating assignment
-    else { ++cnt; sum += val; }
-    return diff;
-}
-
-__device__ void afc_step(ChanState& st, double fs_dec, int n_fft)
-{
-    if (!st.have_spectrum || !st.spec_ok) { st.afc_correction = 0; return; } // AFC.h:96-100
-    st.afc_noise_floor = st.spec_nf;
-    st.afc_noise_var = st.spec_nv;
-    avg_add_d(st.nf_sum, st.nf_cnt, 100, st.spec_nf);
-    avg_add_d(st.nv_sum, st.nv_cnt, 100, st.spec_nv);
-    int p1 = st.spec_p1, p2 = st.spec_p2;
-    const float thr = float(__dadd_rn(avg_get_d(st.nf_sum, st.nf_cnt), __dmul_rn(3.0, fabs(avg_get_d(st.nv_sum, st.nv_cnt)))));
-    const bool d1 = st.spec_p1_val > thr, d2 = st.spec_p2_val > thr;
-    bool stable_l = false, stable_r = false;
-    if (d1 && d2) {
-        if (p2 < p1) { const int t = p1; p1 = p2; p2 = t; }
-        if (avg_add_i(st.pl_sum, st.pl_cnt, 4, p1) <= 2.0) stable_l = true;
-        if (avg_add_i(st.pr_sum, st.pr_cnt, 4, p2) <= 2.0) stable_r = true;
-    }
-    const double la = avg_get_i(st.pl_sum, st.pl_cnt), ra = avg_get_i(st.pr_sum, st.pr_cnt);
-    st.gui_left = 0;
-    if (d1) st.gui_left = stable_l ? int(la) : int(-la);
-    st.gui_right = 0;
-    if (d2) st.gui_right = stable_r ? int(ra) : int(-ra);
-    if (stable_l && stable_r) {
-        const int pl = int(round(la)), pr = int(round(ra));
-        const int dist = pr - pl;
-        const double hz_per_bin = __ddiv_rn(fs_dec, double(n_fft));
-        st.afc_shift_hz = __dmul_rn(hz_per_bin, double(dist));
-        const double mid = double(pl + dist / 2);
-        const double err = __dsub_rn(mid, double(n_fft) / 2);
-        if (4 < fabs(err)) st.afc_correction = __dmul_rn(hz_per_bin, err);
-    }
-}
-
 // 4096-point forward DFT of x[stride * n + offset] (n = 0 .. 4095) by 256 threads: three register-resident radix-16
-// passes, two exchanges through s_a (16*16*17 float2).  tw[e * tw_step] = exp(-2 pi i e / 4096).  Bin k is handed
-// to store(k, value).
+// passes, two exchanges through s_a (16*16*17 float2).  tw1 / tw2: the twiddles of pass 1 / 2 in the order the threads
+// read them (host tables behind the N-point table, see alloc_fft).  Bin k is handed
+// to store(j2, k, value) with k = k1 + 16*j1 + 256*j2 and j2 a compile-time constant after unrolling.
 template <typename Store>
-__device__ __forceinline__ void fft4096(const float2* __restrict__ x, int stride, int offset, const float2* __restrict__ tw, int tw_step,
-                                        float2* s_a, Store store)
+__device__ __forceinline__ void fft4096(const float2* __restrict__ x, int stride, int offset, const float2* __restrict__ tw1,
+                                        const float2* __restrict__ tw2, float2* s_a, Store store)
 {
     const int t = threadIdx.x;
     float2 v[16];
@@ -173,7 +123,7 @@ __device__ __forceinline__ void fft4096(const float2* __restrict__ x, int stride
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
         float2 y = v[bin16(k1)];
-        if (k1) y = cmul(y, tw[(t * k1) * tw_step]);
+        if (k1) y = cmul(y, tw1[k1 * 256 + t]);          // W_4096^(t*k1), table laid out [k1][t]: coalesced
         s_a[k1 * 256 + t] = y;
     }
     __syncthreads();
@@ -187,7 +137,7 @@ __device__ __forceinline__ void fft4096(const float2* __restrict__ x, int stride
 #pragma unroll
         for (int j1 = 0; j1 < 16; ++j1) {
             float2 y = v[bin16(j1)];
-            if (j1) y = cmul(y, tw[(16 * m2 * j1) * tw_step]);
+            if (j1) y = cmul(y, tw2[j1 * 16 + m2]);           // W_256^(m2*j1), [j1][m2]
             s_a[k1 * (16 * 17) + j1 * 17 + m2] = y;
         }
     }
@@ -200,7 +150,155 @@ __device__ __forceinline__ void fft4096(const float2* __restrict__ x, int stride
         dft16(v);
         __syncthreads();
 #pragma unroll
-        for (int j2 = 0; j2 < 16; ++j2) store(k1 + 16 * j1 + 256 * j2, v[bin16(j2)]);
+        for (int j2 = 0; j2 < 16; ++j2) store(j2, k1 + 16 * j1 + 256 * j2, v[bin16(j2)]);
+    }
+}
+
+// (sum, arg-max with first-index tie break) over one (double, float, int) triple per thread: one shuffle tree, two
+// barriers; every thread folds the eight warp results itself.  `slot` selects one of two scratch sets so that two
+// reductions in a row need no barrier in between.
+struct RedScratch { double s[2][kFftThreads / 32]; float v[2][kFftThreads / 32]; int i[2][kFftThreads / 32]; };
+__device__ __forceinline__ void block_sum_argmax(double& s, float& v, int& i, RedScratch& r, int slot)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { r.s[slot][w] = s; r.v[slot][w] = v; r.i[slot][w] = i; }
+    __syncthreads();
+    s = r.s[slot][0]; v = r.v[slot][0]; i = r.i[slot][0];
+#pragma unroll
+    for (int k = 1; k < kFftThreads / 32; ++k) {
+        s += r.s[slot][k];
+        const float ov = r.v[slot][k]; const int oi = r.i[slot][k];
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+
+// N = 4096, the reference's size and the one on the decode path: the bins are transposed through the exchange area so
+// that spectrum and power leave as coalesced rows, a thread keeps the dB values of its 16 bins in registers to the end
+// (no power-spectrum staging in shared memory, no re-read), the
+// statistics take two fused block reductions, the channel's state is staged in shared memory while the transform runs
+// and the per-call AFC step is done by thread 0 on that copy while the other warps already load the next channel.
+__global__ void __launch_bounds__(kFftThreads, 3)
+fft_afc4096_kernel(FftArgs a)
+{
+    constexpr int N = 4096;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_a = reinterpret_cast<float2*>(smem_raw);
+    __shared__ unsigned char s_todo[kFftThreads];
+    __shared__ RedScratch s_red;
+    __shared__ ChanState s_cs;
+    const int t = threadIdx.x;
+    {   // phase A: one thread per owned channel (see fft_afc_kernel below)
+        const int j_ch = int(blockIdx.x) + t * int(gridDim.x);
+        unsigned char todo = 0;
+        if (j_ch < a.n_channels) {
+            ChanState& sj = a.state[a.ch0 + j_ch];
+            if (sj.fft_ready) todo = 1;
+            else if (sj.afc_tick) { afc_step(sj, a.fs_dec, N); sj.afc_tick = 0; }
+        }
+        s_todo[t] = todo;
+    }
+    __syncthreads();
+    const double inv_fs = 1.0 / a.fs_dec;
+    const float2* __restrict__ tw = a.twiddle;
+    for (int j = 0; int(blockIdx.x) + j * int(gridDim.x) < a.n_channels; ++j) {
+        if (!s_todo[j]) continue;
+        const int ch = a.ch0 + int(blockIdx.x) + j * int(gridDim.x);
+        ChanState& st = a.state[ch];
+        if (t < 32) {   // stage the channel's state (thread 0 steps the AFC on it at the end); warp 0 only, after its previous use
+            __syncwarp();
+            const unsigned* src = reinterpret_cast<const unsigned*>(&st);
+            unsigned* dst = reinterpret_cast<unsigned*>(&s_cs);
+            for (int i = t; i < int(sizeof(ChanState) / 4); i += 32) dst[i] = src[i];
+        }
+        const float2* x = a.fftbuf + (size_t)ch * N;
+        float2* spec = a.spectrum + (size_t)ch * N;
+        float* pw = a.power + (size_t)ch * N;
+        float pdb[16];
+        int bad = 0;
+        // the last pass leaves bin k = kb + 256*j2 with thread kb's transpose: hand the bins over through the (now free)
+        // exchange area, one pad slot per 16, so that spectrum and power go out as coalesced rows
+        fft4096(x, 1, 0, tw + N, tw + N + 4096, s_a, [&](int, int k, float2 z) { s_a[k + (k >> 4)] = z; });
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            // spectrum out with the halves swapped (FFT.cpp:77-87); FftPower of the bin (AFC.h:236-286)
+            const int i = t + 256 * m, k = (i + N / 2) & (N - 1);
+            const float2 z = s_a[k + (k >> 4)];
+            spec[i] = z;
+            if (z.x != z.x || z.y != z.y || isinf(z.x) || isinf(z.y)) bad = 1;
+            float p = __fadd_rn(__fmul_rn(z.x, z.x), __fmul_rn(z.y, z.y)) / float(N);
+            p = __fmul_rn(p, p);
+            {   // float(double(p) / fs_dec): reciprocal + one residual step (see fft_afc_kernel)
+                const double xd = double(p);
+                double q = xd * inv_fs;
+                const double r = fma(-q, a.fs_dec, xd);
+                if (isfinite(r)) q = fma(r, inv_fs, q);
+                p = float(q);
+            }
+            p = __fmul_rn(10.0f, log10f(p));
+            pw[i] = p;
+            if (p != p || isinf(p)) bad = 1;
+            pdb[m] = p;
+        }
+        const bool ok = !__syncthreads_or(bad);        // any NaN/Inf aborts the update (AFC.h:250-283)
+        if (ok) {
+            // noise floor = mean, "variance" = standard deviation, both float64 (AFC.h:103-104,225-232); FindPeaks (AFC.h:290-329)
+            double s1 = 0;
+            float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {             // ascending shifted index: first maximum wins
+                const float p = pdb[m];
+                s1 += double(p);
+                if (p > bv) { bv = p; bi = t + 256 * m; }
+            }
+            block_sum_argmax(s1, bv, bi, s_red, 0);
+            const double nf = s1 / double(N);
+            const float p1v = bv; const int p1 = bi;
+            const float rel_sep = float(500.0f / a.fs_dec);
+            int sep = int(round(double(rel_sep) * double(N)));
+            sep = max(8, sep);
+            const int lo = max(p1 - 2 * sep, 0), hi = min(p1 + 2 * sep, N);
+            double q = 0;
+            bv = -INFINITY; bi = 0x7fffffff;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const float p = pdb[m];
+                const int i = t + 256 * m;
+                const double d = double(p) - nf;
+                q += d * d;
+                if (i >= lo && i < hi && abs(i - p1) > sep / 2 && p > bv) { bv = p; bi = i; }
+            }
+            block_sum_argmax(q, bv, bi, s_red, 1);
+            if (t == 0) {
+                const double nv = sqrt(q / double(N));
+                const float P0 = pdb[0];               // thread 0 owns bin 0 of the shifted spectrum
+                float p1v_ = p1v, p2v = bv; int p1_ = p1, p2 = bi;
+                if (!(p2v > P0)) { p2 = 0; p2v = P0; } // running best starts at v[0], index 0
+                if (p2 < p1_) { const int ti = p1_; p1_ = p2; p2 = ti; const float tv = p1v_; p1v_ = p2v; p2v = tv; }
+                s_cs.spec_nf = nf; s_cs.spec_nv = nv;
+                s_cs.spec_p1 = p1_; s_cs.spec_p2 = p2; s_cs.spec_p1_val = p1v_; s_cs.spec_p2_val = p2v;
+            }
+        }
+        if (t == 0) {
+            s_cs.spec_ok = ok ? 1 : 0;
+            s_cs.have_spectrum = 1;
+            if (s_cs.afc_tick) afc_step(s_cs, a.fs_dec, N);
+            st.spec_nf = s_cs.spec_nf; st.spec_nv = s_cs.spec_nv;
+            st.spec_p1 = s_cs.spec_p1; st.spec_p2 = s_cs.spec_p2; st.spec_p1_val = s_cs.spec_p1_val; st.spec_p2_val = s_cs.spec_p2_val;
+            st.spec_ok = s_cs.spec_ok;
+            st.have_spectrum = 1;
+            afc_store(st, s_cs);
+            st.afc_tick = 0;
+            st.fft_ready = 0;
+            st.fft_have = 0;
+        }
     }
 }
 
@@ -251,6 +349,7 @@ fft_afc_kernel(FftArgs a)
         float* pw = a.power + (size_t)ch * N;
         if (t == 0) s_bad = 0;
         int bad = 0;
+        const double inv_fs = 1.0 / a.fs_dec;
         // FftPower of one bin (AFC.h:236-286), spectrum out with the halves swapped (FFT.cpp:77-87)
         auto emit = [&](int k, float2 z) {
             const int i = (k + N / 2) & (N - 1);
@@ -258,15 +357,23 @@ fft_afc_kernel(FftArgs a)
             if (z.x != z.x || z.y != z.y || isinf(z.x) || isinf(z.y)) bad = 1;
             float p = __fadd_rn(__fmul_rn(z.x, z.x), __fmul_rn(z.y, z.y)) / float(N);
             p = __fmul_rn(p, p);
-            p = float(__ddiv_rn(double(p), a.fs_dec));
+            {   // float(double(p) / fs_dec) (AFC.h:268): reciprocal + one residual step instead of the ~40-instruction
+                // IEEE division routine (this line alone was 12 % of the kernel's instructions); the quotient is the
+                // correctly rounded one except for double-precision ties that cannot survive the rounding to float
+                const double x = double(p);
+                double q = x * inv_fs;
+                const double r = fma(-q, a.fs_dec, x);
+                if (isfinite(r)) q = fma(r, inv_fs, q);
+                p = float(q);
+            }
             p = __fmul_rn(10.0f, log10f(p));
             if (N == 4096) s_p[i] = p; else pw[i] = p;
         };
         if (N == 4096) {
-            fft4096(x, 1, 0, tw, 1, s_a, emit);
+            fft4096(x, 1, 0, tw + N, tw + N + 4096, s_a, [&](int, int k, float2 z) { emit(k, z); });
         } else {
             for (int r = 0; r < 4; ++r) {
-                fft4096(x, 4, r, tw, 4, s_a, [&](int k, float2 z) { s_f[r * 4096 + k] = z; });
+                fft4096(x, 4, r, tw + N, tw + N + 4096, s_a, [&](int, int k, float2 z) { s_f[r * 4096 + k] = z; });
                 __syncthreads();
             }
             // X[k + 4096 q] = sum_r W_N^(r k) F_r[k] W_4^(r q)
@@ -339,12 +446,14 @@ fft_afc_kernel(FftArgs a)
 template <int N>
 static cudaError_t launch_fft_n(const FftArgs& a, int n_channels, cudaStream_t stream, int* launches)
 {
-    const size_t smem = size_t(16 * 16 * 17) * 8 + (N == 4096 ? size_t(4096) * 4 : size_t(16384) * 8);
+    const size_t smem = size_t(16 * 16 * 17) * 8 + (N == 4096 ? size_t(0) : size_t(16384) * 8);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fft_afc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = N == 4096 ? cudaFuncSetAttribute(fft_afc4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                  : cudaFuncSetAttribute(fft_afc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        cudaFuncSetAttribute(fft_afc_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (N == 4096) cudaFuncSetAttribute(fft_afc4096_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        else cudaFuncSetAttribute(fft_afc_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
     static int n_sms = 0;
@@ -353,7 +462,8 @@ static cudaError_t launch_fft_n(const FftArgs& a, int n_channels, cudaStream_t s
     grid = std::max(grid, (n_channels + kFftThreads - 1) / kFftThreads);   // a CTA owns at most kFftThreads channels
     if (grid < 1) return cudaSuccess;
     FftArgs b = a; b.n_channels = n_channels;
-    fft_afc_kernel<N><<<grid, kFftThreads, smem, stream>>>(b);
+    if (N == 4096) fft_afc4096_kernel<<<grid, kFftThreads, smem, stream>>>(b);
+    else fft_afc_kernel<N><<<grid, kFftThreads, smem, stream>>>(b);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
@@ -361,7 +471,7 @@ static cudaError_t launch_fft_n(const FftArgs& a, int n_channels, cudaStream_t s
 cudaError_t launch_fft_afc(const FftArgs& a, int n_channels, cudaStream_t stream, int* launches)
 {
     if (a.fft_n == 16384) return launch_fft_n<16384>(a, n_channels, stream, launches);
-    return launch_fft_n<4096>(a, n_channels, stream, launches);
+    return launch_fft_n<4096>(a, n_channels, stream, launches);   // fft_afc4096_kernel
 }
 
 // AFC::resetFrequencyCorrection (AFC.h:188-194), one thread per call

@@ -9,7 +9,7 @@ struct FftArgs {
     const float2* fftbuf;   // [channel][fft_n] frame being collected
     float2* spectrum;       // [channel][fft_n] last fft-shifted spectrum (getFFT)
     float* power;           // [channel][fft_n] last power spectrum in dB (getPowerSpectrum)
-    const float2* twiddle;  // [fft_n] exp(-2 pi i e / fft_n), evaluated in float64 on the host
+    const float2* twiddle;  // [fft_n] exp(-2 pi i e / fft_n) + [16][256] pass-1 + [16][16] pass-2 twiddles of the 4096-point transform (float64-evaluated, host)
     double fs_dec;
     int ch0;                // first channel of this launch
     int fft_n;              // 4096 (reference) or 16384

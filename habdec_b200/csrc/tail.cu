@@ -25,6 +25,7 @@
 // The stage-2 window tile is padded by 2 samples every 16 so that the 64-byte thread stride is bank-conflict free.
 #include "hbd_common.cuh"
 #include "slicer_dev.cuh"
+#include "afc_dev.cuh"
 #include "tail.cuh"
 #include <algorithm>
 
@@ -56,7 +57,14 @@ __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kTailThreads)
+// out of line on purpose: the float64 state machine would otherwise raise the register count of the whole kernel
+__device__ __noinline__ void afc_step_staged(ChanState& staged, ChanState& global_state, double fs_dec, int n_fft)
+{
+    afc_step(staged, fs_dec, n_fft);
+    afc_store(global_state, staged);
+}
+
+__global__ void __launch_bounds__(kTailThreads + 32)
 tail_kernel(TailArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -75,7 +83,25 @@ tail_kernel(TailArgs a)
     const float2* s1 = a.s1 + (size_t)ch * a.s1_pitch;
     float2* s1n = a.s1_next + (size_t)ch * a.s1_pitch;
     if (pl.flags & 1u) { // fewer than `factor` samples queued (Decoder.h:429-430): only carry the stage-2 history over
-        if (a.M2 > 1) for (int i = tid; i < a.T2 - 1; i += kTailThreads) s1n[kS1Hist - (a.T2 - 1) + i] = s1[kS1Hist - (a.T2 - 1) + i];
+        if (a.M2 > 1 && tid < kTailThreads) for (int i = tid; i < a.T2 - 1; i += kTailThreads) s1n[kS1Hist - (a.T2 - 1) + i] = s1[kS1Hist - (a.T2 - 1) + i];
+        return;
+    }
+    if (tid >= kTailThreads) {
+        // Warp 4, the AFC warp.  AFC<float>::process on a call that completes no FFT frame (15 of 16 calls at 256 decimated
+        // samples per call): the reference re-runs it on the stale spectrum (Decoder.h:501-509); only the state machine
+        // moves, on the statistics K4 cached for that spectrum.  One thread steps it while the four signal warps run the
+        // FIRs and the slicer, so K4 is not launched at all for such a call.  The warp joins the two barriers of round
+        // trip 1 (the staged state) and retires; barriers after that count the remaining warps only.
+        __syncthreads();
+        cp_async_wait_all();
+        __syncthreads();
+        if (tid == kTailThreads) {
+            const unsigned total = pl.dec_pending + pl.n2;
+            const unsigned have0 = s_st.fft_have, fn = unsigned(a.fft_n);
+            const unsigned take = (have0 < fn) ? hbd_min_u(fn - have0, pl.n2) : 0u;
+            const bool done = take && have0 + take >= fn;
+            if (total >= unsigned(kLpBatch) && !done) afc_step_staged(s_st, a.state[ch], a.fs_dec, a.fft_n);
+        }
         return;
     }
 
@@ -143,6 +169,7 @@ tail_kernel(TailArgs a)
     const unsigned fft_have0 = s_st.fft_have;
     const unsigned fft_n = unsigned(a.fft_n);
     const unsigned fft_take = (fft_have0 < fft_n) ? hbd_min_u(fft_n - fft_have0, n2) : 0u;
+    const bool frame_done = fft_take && fft_have0 + fft_take >= fft_n;   // K4 transforms it (and steps the AFC) in this call
     const bool dc = s_st.dc_remove != 0;
     float2 carry_prev = make_float2(s_st.demod_last_re, s_st.demod_last_im);
     const bool primed = s_st.demod_primed != 0;
@@ -351,7 +378,7 @@ tail_kernel(TailArgs a)
         }
         if (lane == 0) {
             gst.dec_pending = new_pending;
-            gst.afc_tick = tick ? 1u : 0u;
+            gst.afc_tick = (tick && frame_done) ? 1u : 0u;   // with a new frame the step follows the transform, in K4
             gst.n_filtered = nf;
             if (fft_take) {
                 gst.fft_have = fft_have0 + fft_take;
@@ -397,7 +424,7 @@ cudaError_t launch_tail(TailArgs a, int n_channels, cudaStream_t stream, int* la
         cudaFuncSetAttribute(tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured_smem = want;
     }
-    tail_kernel<<<n_channels, kTailThreads, smem, stream>>>(a);
+    tail_kernel<<<n_channels, kTailThreads + 32, smem, stream>>>(a);   // 4 signal warps + the AFC warp
     if (launches) ++*launches;
     return cudaGetLastError();
 }
