@@ -105,10 +105,18 @@ struct Geo {
 constexpr int kStages   = HBD_K1_STAGES; // ring depth per warp
 constexpr int kRedPitch = 36;            // float2 per row: 16-byte aligned rows, 32 B mod 128 B (see reduce_rows)
 
+#ifndef HBD_K1_RED_IN_RING
+#define HBD_K1_RED_IN_RING 1
+#endif
+// NOUT == 1 (the /64 first stage): the reduction tile of a piece lives INSIDE the ring slot being consumed -- row b
+// (288 B) is written after superblock b (512 B) of the slot has been read, so it only ever covers consumed samples, and
+// the tile is summed before the slot is handed back to the TMA.  That takes 27 KB per CTA off K1's footprint, which is
+// what lets a third tail CTA (or a second FFT CTA) co-reside with K1 on an SM.
 template <int M, int T>
 struct WarpSmem {
+    static constexpr bool kRedInRing = HBD_K1_RED_IN_RING && Geo<M, T>::NOUT == 1 && Geo<M, T>::PSB * kRedPitch * 8 <= Geo<M, T>::PSB * 64 * 8;
     alignas(16) unsigned char ring[kStages][Geo<M, T>::PIECE_BYTES];
-    alignas(16) float2 red[Geo<M, T>::RED_ROWS][kRedPitch];
+    alignas(16) float2 red[kRedInRing ? 1 : Geo<M, T>::RED_ROWS][kRedPitch];
     alignas(8) uint64_t full[kStages];
 };
 
@@ -215,6 +223,7 @@ decim1_kernel(DecimArgs a)
             if (lane == 0) {
                 if (hi2 > lo) {
                     const int c_hi = min(hi2, 0), d_lo = max(lo, 0);
+                    if (WarpSmem<M, T>::kRedInRing) fence_proxy_async();   // the slot last held generic-proxy stores (reduction rows)
                     mbar_expect_tx(&sm.full[slot], uint32_t(hi2 - lo) * 8u);
                     if (c_hi > lo) tma_load_1d(dst + (lo - A) * 8, carry + lo, uint32_t(c_hi - lo) * 8u, &sm.full[slot]);
                     if (hi2 > d_lo) tma_load_1d(dst + (d_lo - A) * 8, chunk + d_lo, uint32_t(hi2 - d_lo) * 8u, &sm.full[slot]);
@@ -254,6 +263,7 @@ decim1_kernel(DecimArgs a)
             phase_bits ^= 1u << slot;
             __syncwarp();
             const float2* src = reinterpret_cast<const float2*>(sm.ring[slot]) + odd + lane;
+            float2 (*red)[kRedPitch] = WarpSmem<M, T>::kRedInRing ? reinterpret_cast<float2 (*)[kRedPitch]>(sm.ring[slot]) : sm.red;
 
 #pragma unroll 1
             for (int g = 0; g < G::GROUPS_PER_PIECE; ++g) {
@@ -274,7 +284,8 @@ decim1_kernel(DecimArgs a)
                     for (int j = 0; j < G::NOUT; ++j) {
                         const int r = (j + u * G::NOUT) % G::NLIVE;
                         if (G::NOUT == 1) {
-                            sm.red[g * G::U + u][lane] = acc[r];            // row = superblock within the piece
+                            if (WarpSmem<M, T>::kRedInRing) __syncwarp();     // every lane has read superblock (g*U+u) of the slot
+                            red[g * G::U + u][lane] = acc[r];               // row = superblock within the piece
                         } else {
                             sm.red[staged][lane] = acc[r];
                             if (++staged == 16) { reduce_rows(sm.red, 16, k_next + j - 15, k_lo, k_hi, out, lane); staged = 0; }
@@ -285,7 +296,7 @@ decim1_kernel(DecimArgs a)
                 }
             }
             if (G::NOUT == 1) {
-                reduce_rows(sm.red, G::PSB, k_next, k_lo, k_hi, out, lane);
+                reduce_rows(red, G::PSB, k_next, k_lo, k_hi, out, lane);
                 k_next += G::PSB;
             }
         }

@@ -458,7 +458,7 @@ static cudaError_t launch_fft_n(const FftArgs& a, int n_channels, cudaStream_t s
     }
     static int n_sms = 0;
     if (!n_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev); if (n_sms < 1) n_sms = 1; }
-    int grid = std::min(n_channels, 4 * n_sms);
+    int grid = std::min(n_channels, 3 * n_sms);   // 3 CTAs per SM are resident (80 registers x 256 threads): one wave
     grid = std::max(grid, (n_channels + kFftThreads - 1) / kFftThreads);   // a CTA owns at most kFftThreads channels
     if (grid < 1) return cudaSuccess;
     FftArgs b = a; b.n_channels = n_channels;
