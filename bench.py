@@ -33,8 +33,8 @@ TOTAL_CHANNELS = 4096
 SNR_DB = -15.0
 ALGO_BYTES_PER_SAMPLE_K1 = 8.0 + 8.0 / 64.0   # cf32 read + stage-1 output write
 # DRAM bytes per input sample that K1 really moved in the ncu --set full capture of this exact workload
-# (profiles/r1_k1_decim1_ncu_full_raw.csv: dram__bytes_read.sum 2.1705 GB + dram__bytes_write.sum 0.0468 GB per 2^28 samples)
-NCU_TRAFFIC_BYTES_PER_SAMPLE_K1 = (2.170545e9 + 0.046819e9) / 268435456.0
+# (profiles/r1c_k1_ncu_full_raw.csv: dram__bytes_read.sum 2.170465 GB + dram__bytes_write.sum 0.046897 GB per 2^28 samples)
+NCU_TRAFFIC_BYTES_PER_SAMPLE_K1 = (2.170465e9 + 0.046897e9) / 268435456.0
 METRIC = "aggregate IQ MSamples/s decoded (chars bit-exact)"
 
 
@@ -298,7 +298,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "decim1_kernel<64,348> (K1, stage-1 FIR decimator)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": (NCU_TRAFFIC_BYTES_PER_SAMPLE_K1 * C * args.chunk * args.steps / max(k1_cnt, 1)) if (C == 4096 and args.chunk == 65536) else None,
-                         "traffic_source": "ncu --set full capture of this workload, profiles/r1_k1_decim1_ncu_full_raw.csv (bytes per launch)",
+                         "traffic_source": "ncu --set full capture of this workload, profiles/r1c_k1_ncu_full_raw.csv (bytes per launch)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_ms, "launches_timed": k1_cnt,
                          "k1_share_of_step": (k1_ms / ms) if ms else None, "rest_of_step_ms": rest_ms / max(rest_cnt, 1), "pipeline_gaps": gaps},
