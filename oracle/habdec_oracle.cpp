@@ -617,6 +617,18 @@ extern "C" {
 void* orc_create(const hbo_config* cfg) { Port* p = new Port; p->configure(*cfg); return p; }
 void orc_destroy(void* h) { delete static_cast<Port*>(h); }
 
+void orc_set_param(void* h, int which, double value) // Decoder.h:654-706: plain member updates, nothing pending is touched
+{
+    Port* p = static_cast<Port*>(h);
+    switch (which) {
+    case 0: p->slicer.baud = value; p->cfg.baud = value; break;
+    case 1: p->uart.nbits = size_t(value); p->cfg.rtty_bits = int(value); break;
+    case 2: p->uart.nstops = float(value); p->cfg.rtty_stops = float(value); break;
+    case 3: p->cfg.dc_remove = value != 0; break;
+    default: break;
+    }
+}
+
 void orc_push_process(void* h, const float* iq, size_t n, double fs)
 {
     Port* p = static_cast<Port*>(h);

@@ -57,6 +57,7 @@ def _bind(lib, p):
     f("stage").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     f("afc").argtypes = [C.c_void_p, C.POINTER(AfcInfo)]
     f("reset_frequency_correction").argtypes = [C.c_void_p, C.c_double]
+    f("set_param").argtypes = [C.c_void_p, C.c_int, C.c_double]
     f("ssdv_events").restype = C.c_size_t
     f("ssdv_events").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     f("ssdv_push").argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -147,6 +148,10 @@ class _Decoder:
         a = AfcInfo()
         self._f("afc")(self._h, C.byref(a))
         return a
+
+    def set_param(self, which: str, value: float):
+        """Run-time setter between calls (Decoder.h:654-706): 'baud', 'rtty_bits', 'rtty_stops', 'dc_remove'."""
+        self._f("set_param")(self._h, {"baud": 0, "rtty_bits": 1, "rtty_stops": 2, "dc_remove": 3}[which], float(value))
 
     def reset_frequency_correction(self, corr: float):
         self._f("reset_frequency_correction")(self._h, float(corr))

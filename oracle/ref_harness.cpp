@@ -189,6 +189,21 @@ void ref_destroy(void* h)
     delete r;
 }
 
+void ref_set_param(void* h, int which, double value)
+{
+    Ref* r = static_cast<Ref*>(h);
+    r->w->run([=] {
+        auto& D = *r->D;
+        switch (which) {
+        case 0: D.baud(value); break;
+        case 1: D.rtty_bits(size_t(value)); break;
+        case 2: D.rtty_stops(float(value)); break;
+        case 3: D.dc_remove(value != 0); break;
+        default: break;
+        }
+    });
+}
+
 void ref_push_process(void* h, const float* iq, size_t n, double fs)
 {
     Ref* r = static_cast<Ref*>(h);

@@ -215,3 +215,37 @@ def test_cfg4_full_width_4096_channels(oracle_kind):
         assert dec2.poll_sentences(c) == ref.sentences(), "channel %d" % c
     del ring
     torch.cuda.empty_cache()
+
+
+def test_setters_between_calls(oracle_kind):
+    """Decoder.h:654-706: baud / rtty_bits / rtty_stops / dc_remove changed between two process() calls act on the
+    samples, bits and characters already pending.  Channel 1 of a two-channel batch is re-configured twice while
+    channel 0 keeps its settings."""
+    fs = 2.048e6
+    a, _ = synth.channel_iq(31, 2, fs, 300.0, snr_db=-15.0)
+    b, _ = synth.channel_iq(32, 2, fs, 100.0, nbits=7, nstops=1, snr_db=-15.0)
+    a = a[:len(a) // 65536 * 65536]
+    b = b[:len(b) // 65536 * 65536]
+    iq1 = np.concatenate([a, b, a])
+    iq0 = np.concatenate([a, a, a])[:len(iq1)]
+    if len(iq0) < len(iq1):
+        iq0 = np.concatenate([iq0, np.zeros(len(iq1) - len(iq0), dtype=np.complex64)])
+    n_calls = len(iq1) // 65536
+    marks = {len(a) // 65536: [("baud", 100.0), ("rtty_bits", 7), ("rtty_stops", 1.0), ("dc_remove", 1)],
+             (len(a) + len(b)) // 65536: [("baud", 300.0), ("rtty_bits", 8), ("rtty_stops", 2.0), ("dc_remove", 0)]}
+    dec = api.BatchDecoder(2, baud=300.0, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
+    refs = [make_oracle(oracle_kind, baud=300.0), make_oracle(oracle_kind, baud=300.0)]
+    iq = np.stack([iq0, iq1])
+    for i in range(n_calls):
+        for name, v in marks.get(i, []):
+            getattr(dec, name)(v, 1)
+            refs[1].set_param(name, v)
+        blk = np.ascontiguousarray(iq[:, i * 65536:(i + 1) * 65536])
+        dec.pushSamplesBatch(blk, fs)
+        dec.process()
+        for c in range(2):
+            refs[c].push_process(blk[c], fs)
+    for c in range(2):
+        assert dec.poll_chars(c) == refs[c].chars(), "channel %d" % c
+        assert dec.poll_sentences(c) == refs[c].sentences(), "channel %d" % c
+    assert len(refs[1].sentences()) >= 5

@@ -142,3 +142,28 @@ def test_wire_format_restatement_matches_reference_serialisation():
         live = g.frames("ref")
         for k in gold.files:
             assert live[k].tobytes() == gold[k].tobytes(), k
+
+
+def test_port_equals_reference_with_setters_between_calls():
+    """baud / rtty_bits / rtty_stops / dc_remove changed mid-stream (Decoder.h:654-706): restatement == reference."""
+    if not po.available("ref"):
+        pytest.skip("oracle/_ref not built")
+    fs = 2.048e6
+    a, _ = synth.channel_iq(31, 2, fs, 300.0, snr_db=-15.0)
+    b, _ = synth.channel_iq(32, 2, fs, 100.0, nbits=7, nstops=1, snr_db=-15.0)
+    a = a[:len(a) // 65536 * 65536]
+    b = b[:len(b) // 65536 * 65536]
+    iq = np.concatenate([a, b, a])
+    marks = {len(a) // 65536: [("baud", 100.0), ("rtty_bits", 7), ("rtty_stops", 1.0), ("dc_remove", 1)],
+             (len(a) + len(b)) // 65536: [("baud", 300.0), ("rtty_bits", 8), ("rtty_stops", 2.0), ("dc_remove", 0)]}
+    outs = []
+    for K in (po.RefDecoder, po.PortDecoder):
+        d = K(po.make_config(baud=300.0))
+        for i, o in enumerate(range(0, len(iq), 65536)):
+            for k, v in marks.get(i, []):
+                d.set_param(k, v)
+            d.push_process(iq[o:o + 65536], fs)
+        outs.append((d.chars(), d.sentences(), d.stage(po.STAGE_DEMOD), d.stage(po.STAGE_DECIMATED)))
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+    assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][3], outs[1][3])
+    assert len(outs[0][1]) == 6
