@@ -158,6 +158,13 @@ struct hbd_decoder {
     // input
     float2* d_stage = nullptr; size_t stage_pitch = 0;   // host pushes land here
     const float2* ext = nullptr; size_t ext_pitch = 0; size_t ext_n = 0; // zero-copy device push
+    // fused-NCO parameter ring: pinned host slots + device slots, so a push never waits for the GPU
+    static constexpr unsigned kNcoSlots = 16;
+    NcoChan* h_nco_pin = nullptr; NcoChan* d_nco_ring = nullptr; cudaEvent_t ev_nco[kNcoSlots] = {}; unsigned nco_seq = 0;
+    const NcoChan* ext_nco_ptr = nullptr;
+    bool ext_nco = false;    // ... of RAW samples that K1 mixes through the channels' NCOs itself (fused K0; ext_pitch 0 = wideband row)
+    bool nco_fused = true;   // HBD_NCO_FUSED=0 (measurement / test hook): always pre-mix with K0 into the staging matrix
+    int push_fused_nco(const float2* src, size_t pitch, size_t n);
     float* h_pinned = nullptr; size_t pinned_bytes = 0;  // staging for pageable host memory
 
     // websocket wire formats (wire.cu)
@@ -346,6 +353,9 @@ void hbd_decoder::free_all()
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (cudaEvent_t e : ev_k1) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_rest) cudaEventDestroy(e);
+    if (h_nco_pin) { cudaFreeHost(h_nco_pin); h_nco_pin = nullptr; }
+    if (d_nco_ring) { cudaFree(d_nco_ring); d_nco_ring = nullptr; }
+    for (cudaEvent_t& e : ev_nco) if (e) { cudaEventDestroy(e); e = nullptr; }
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -532,6 +542,7 @@ int hbd_decoder::process_async_locked()
             da.chunk = chunk; da.chunk_pitch = chunk_pitch; da.carry = d_carry2[carry_cur]; da.carry_next = d_carry2[carry_cur ^ 1];
             da.s1 = d_s1x[s1_cur]; da.s1_pitch = s1_pitch; da.s1_hist = kS1Hist;
             da.plan = d_plan; da.taps = d_taps1; da.ch0 = c0; da.n_channels = nc;
+            da.nco = ext_nco ? ext_nco_ptr : nullptr;
             if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), hi));
             HBD_CUDA_CHECK(launch_decim1(da, M1, T1, max_n1, n_sms, hi, &nl));
             if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), hi));
@@ -584,7 +595,7 @@ int hbd_decoder::process_async_locked()
     HBD_CUDA_CHECK(cudaEventRecord(ev_call[call_seq % ev_call.size()], lo)); // everything of this call is done
     ++call_seq;
     ++pending_marks;
-    ext = nullptr; ext_n = 0;
+    ext = nullptr; ext_n = 0; ext_nco = false;
     return HBD_OK;
 }
 
@@ -753,6 +764,7 @@ int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
     {
         if (const char* sv = getenv("HBD_SV_WANT")) h->sv_override = atoi(sv);
         if (const char* tl = getenv("HBD_TAIL_EV_LATE")) h->tail_ev_late = atoi(tl) != 0;
+        if (const char* nf = getenv("HBD_NCO_FUSED")) h->nco_fused = atoi(nf) != 0;
         const char* env = getenv("HBD_GROUPS");
         // one group: with the stage-1 stream double buffered over calls, K1 of call s+1 already overlaps the tail of call s;
         // more groups only help synchronous callers (hbd_process) that cannot pipeline calls
@@ -968,6 +980,36 @@ int hbd_decoder::mix_into_stage(const float2* src, size_t src_pitch, int c0, int
     return HBD_OK;
 }
 
+// Fused form of mix_into_stage for a whole-batch device push with nothing staged: the raw samples stay where they are
+// (src_pitch 0: one wideband row), the per-channel NCO parameters go to the device and K1 mixes while it decimates
+// (decim1.cu, DecimArgs::nco) -- no K0 launch, no 8-byte write + 8-byte read per channel-sample through HBM.
+int hbd_decoder::push_fused_nco(const float2* src, size_t pitch, size_t n)
+{
+    if (!h_nco_pin) {
+        HBD_CUDA_CHECK(cudaHostAlloc((void**)&h_nco_pin, sizeof(NcoChan) * size_t(n_ch) * kNcoSlots, cudaHostAllocDefault));
+        HBD_CUDA_CHECK(dalloc(&d_nco_ring, size_t(n_ch) * kNcoSlots));
+        for (unsigned i = 0; i < kNcoSlots; ++i) HBD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_nco[i], cudaEventDisableTiming));
+    }
+    const unsigned slot = nco_seq % kNcoSlots;
+    if (nco_seq >= kNcoSlots) HBD_CUDA_CHECK(cudaEventSynchronize(ev_nco[slot]));   // the upload that last used this pinned slot (16 pushes ago)
+    ++nco_seq;
+    NcoChan* hp = h_nco_pin + size_t(slot) * size_t(n_ch);
+    for (int c = 0; c < n_ch; ++c) {
+        HostChan& x = hc[size_t(c)];
+        NcoChan& k = hp[c];
+        k.inc = x.nco_freq / fs_in;
+        k.ph0 = x.nco_phase;
+        k.step_re = 1.0; k.step_im = 0.0;   // K0's rotation, unused by K1
+        double ph = x.nco_phase + double(n) * k.inc;
+        x.nco_phase = ph - std::floor(ph);
+    }
+    NcoChan* dp = d_nco_ring + size_t(slot) * size_t(n_ch);
+    HBD_CUDA_CHECK(cudaMemcpyAsync(dp, hp, sizeof(NcoChan) * size_t(n_ch), cudaMemcpyHostToDevice, stream));
+    HBD_CUDA_CHECK(cudaEventRecord(ev_nco[slot], stream));
+    ext = src; ext_pitch = pitch; ext_n = n; ext_nco = true; ext_nco_ptr = dp;
+    return HBD_OK;
+}
+
 int hbd_push_samples(hbd_decoder* h, int ch, const float* iq, size_t n, double fs)
 {
     HBD_CHECK_CH(h, ch);
@@ -1030,8 +1072,6 @@ static int push_wideband(hbd_decoder* h, const float* iq, size_t n, double fs, b
     if (cudaSetDevice(h->device) != cudaSuccess) return HBD_ERR_CUDA;
     const unsigned base = h->hc[0].pushed;
     for (auto& x : h->hc) if (x.pushed != base) { h->set_error("wideband push needs equal queue depth in all channels"); return HBD_ERR_STATE; }
-    const int rc = ensure_stage(h, size_t(base) + n);
-    if (rc) return rc;
     latch_rate(h, fs);
     const float2* src = reinterpret_cast<const float2*>(iq);
     if (!device) {
@@ -1044,6 +1084,13 @@ static int push_wideband(hbd_decoder* h, const float* iq, size_t n, double fs, b
         if (e != cudaSuccess) { h->set_error(cudaGetErrorString(e)); return HBD_ERR_CUDA; }
         src = h->d_wide;
     }
+    if (h->nco_fused && base == 0 && n && decim1_supports_fused_nco(h->M1, h->T1) && !(reinterpret_cast<uintptr_t>(src) & 15)) {
+        // host capture: the caller owns `iq` again on return (Decoder.h:209-213 copies), so the upload has to be complete
+        if (!device && cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
+        return h->push_fused_nco(src, 0, n);
+    }
+    const int rc = ensure_stage(h, size_t(base) + n);
+    if (rc) return rc;
     const int rc2 = h->mix_into_stage(src, 0, 0, h->n_ch, base, n);
     if (rc2) return rc2;
     for (auto& x : h->hc) x.pushed += unsigned(n);
@@ -1072,6 +1119,8 @@ int hbd_push_samples_device(hbd_decoder* h, const float* d_iq, size_t n, size_t 
         if (cudaSetDevice(h->device) != cudaSuccess) return HBD_ERR_CUDA;
         const unsigned base = h->hc[0].pushed;
         for (auto& x : h->hc) if (x.pushed != base) { h->set_error("batch push needs equal queue depth in all channels"); return HBD_ERR_STATE; }
+        if (h->nco_fused && base == 0 && n && decim1_supports_fused_nco(h->M1, h->T1))
+            return h->push_fused_nco(reinterpret_cast<const float2*>(d_iq), pitch, n);   // zero copy after all: K1 mixes
         const int rc = ensure_stage(h, size_t(base) + n);
         if (rc) return rc;
         const int rc2 = h->mix_into_stage(reinterpret_cast<const float2*>(d_iq), pitch, 0, h->n_ch, base, n);

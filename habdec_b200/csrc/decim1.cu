@@ -153,7 +153,51 @@ __device__ __forceinline__ void reduce_rows(const float2 (*red)[kRedPitch], int 
     __syncwarp();
 }
 
-template <int M, int T>
+// ---- fused NCO (K0 inside K1) ---------------------------------------------------------------------------------------
+// phasor(j) = cf32( E[j >> 12] * S1[(j >> 6) & 63] ) (x) cf32( S2[j & 63] ),  E[B] = cis(ph0 + 4096 B inc), S1[a] = cis(64 a inc),
+// S2[b] = cis(b inc), cis(p) = exp(-2 pi i frac(p)): every factor is an exact float64 sincospi, E * S1 is a float64
+// product (once per 64 samples), the last product is float with a fixed operation order, so the value depends on j only
+// (ramp-in overlap of two spans, the carry written for the next call and the samples filtered in this call all see the
+// same number).  It differs from the directly evaluated, once-rounded phasor of the oracle (pyoracle.premix) by at most
+// ~1.5e-7 relative -- the size of the FIR's own float rounding, two orders below the 1e-5 stage tolerance.  (A float64
+// product per sample costs 4 FP64 operations + 2 conversions and made this kernel 2.3x slower than the plain K1.)
+struct NcoWarpSmem {
+    double2 s1[64], s2[64];
+    double2 e[32];        // E[ebase .. ebase+31]
+    float2 pq[16];        // cf32(E * S1) for the 64-sample groups a ring piece touches
+};
+__device__ __forceinline__ double2 nco_cis(double ph)
+{
+    ph -= floor(ph);
+    double sn, cs;
+    sincospi(-2.0 * ph, &sn, &cs);
+    return make_double2(cs, sn);
+}
+__device__ __forceinline__ double2 nco_cmul(double2 a, double2 b)
+{
+    return make_double2(__fma_rn(a.x, b.x, -__dmul_rn(a.y, b.y)), __fma_rn(a.x, b.y, __dmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ float2 nco_f(double2 p) { return make_float2(float(p.x), float(p.y)); }
+__device__ __forceinline__ float2 nco_phasor(float2 p, float2 s) // cf32(E*S1) (x) cf32(S2), fixed operation order
+{
+    return make_float2(__fmaf_rn(p.x, s.x, -__fmul_rn(p.y, s.y)), __fmaf_rn(p.x, s.y, __fmul_rn(p.y, s.x)));
+}
+__device__ __forceinline__ float2 nco_apply(float2 x, float2 ph) // std::complex<float> product, no FMA (like nco.cu)
+{
+    const float pr = ph.x, pi = ph.y;
+    float2 y;
+    y.x = __fsub_rn(__fmul_rn(x.x, pr), __fmul_rn(x.y, pi));
+    y.y = __fadd_rn(__fmul_rn(x.x, pi), __fmul_rn(x.y, pr));
+    return y;
+}
+__device__ __forceinline__ void nco_fill_e(NcoWarpSmem& ns, const NcoChan& nc, int ebase, int lane)
+{
+    __syncwarp();
+    ns.e[lane] = nco_cis(__dadd_rn(nc.ph0, __dmul_rn(double(ebase + lane) * 4096.0, nc.inc)));
+    __syncwarp();
+}
+
+template <int M, int T, bool NCO>
 __global__ void __launch_bounds__(kDecimWarps * 32, 1)
 decim1_kernel(DecimArgs a)
 {
@@ -161,6 +205,7 @@ decim1_kernel(DecimArgs a)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSmem<M, T>& sm = reinterpret_cast<WarpSmem<M, T>*>(smem_raw)[warp];
+    NcoWarpSmem& ns = reinterpret_cast<NcoWarpSmem*>(smem_raw + sizeof(WarpSmem<M, T>) * kDecimWarps)[NCO ? warp : 0];
 
     if (lane == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
@@ -197,6 +242,21 @@ decim1_kernel(DecimArgs a)
         // (b-1)*NOUT < k <= b*NOUT end inside it.  This span owns superblocks [b_lo, b_hi) of the channel.
         const int n1 = int(pl.n1);
         const int n_sb_total = (n1 - 1 + G::NOUT - 1) / G::NOUT + 1;       // superblocks 0 .. ceil((n1-1)/NOUT)
+        NcoChan nc{};
+        bool mixing = false;
+        int ebase = 0;
+        if (NCO) {
+            nc = a.nco[ch];
+            mixing = !(nc.inc == 0.0 && nc.ph0 == 0.0);                     // a channel without an offset is a plain copy (nco.cu)
+            if (mixing) {
+                __syncwarp();
+                for (int k = lane; k < 64; k += 32) {
+                    ns.s1[k] = nco_cis(__dmul_rn(double(64 * k), nc.inc));
+                    ns.s2[k] = nco_cis(__dmul_rn(double(k), nc.inc));
+                }
+                nco_fill_e(ns, nc, ebase, lane);
+            }
+        }
         if (!(pl.flags & 1u) && b_lo < n_sb_total) {
         const int b_hi = min(b_span_hi, n_sb_total);
         const int b_first = b_lo - G::RAMP_GROUPS * G::U;                   // ramp-in: whole groups, outputs discarded
@@ -262,6 +322,45 @@ decim1_kernel(DecimArgs a)
             mbar_wait(&sm.full[slot], (phase_bits >> slot) & 1u);
             phase_bits ^= 1u << slot;
             __syncwarp();
+            if (NCO && mixing) {
+                // mix the piece in place (samples with 0 <= j < n come from the raw chunk; j < 0 is the already mixed carry)
+                const int jp = j0 + p * G::PIECE_SAMPLES;                    // j of this lane-0 sample of superblock 0
+                const int j_last = min(jp + G::PIECE_SAMPLES - 1, j_end - 1);
+                if (j_last >= 0) {
+                    const int b_min = max(jp, 0) >> 12, b_max = j_last >> 12;
+                    if (b_min < ebase || b_max >= ebase + 32) { ebase = b_min; nco_fill_e(ns, nc, ebase, lane); }
+                    const int q0 = jp >> 6;                                   // floor: jp may be negative
+                    if (lane <= G::PSB) {
+                        const int q = q0 + lane;
+                        if (q >= 0 && (q >> 6) < ebase + 32) ns.pq[lane] = nco_f(nco_cmul(ns.e[(q >> 6) - ebase], ns.s1[q & 63]));
+                    }
+                    __syncwarp();
+                    const int c0 = jp & 63;
+                    const int w0 = (c0 + lane) >> 6, w1 = (c0 + lane + 32) >> 6;
+                    const float2 s2a = nco_f(ns.s2[(c0 + lane) & 63]), s2b = nco_f(ns.s2[(c0 + lane + 32) & 63]);
+                    float2* px = reinterpret_cast<float2*>(sm.ring[slot]) + odd + lane;
+                    // batches of 4 superblocks: all loads first, then the arithmetic, then the stores -- a load-mix-store
+                    // loop serialises on shared-memory ordering (each LDS behind the previous STS, ~100 cycles a round)
+                    static_assert(!NCO || G::PSB % 4 == 0, "pre-pass batches");
+#pragma unroll 1
+                    for (int sb0 = 0; sb0 < G::PSB; sb0 += 4) {
+                        float2 xa[4], xb[4], pa[4], pb[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            xa[u] = px[(sb0 + u) * 64]; xb[u] = px[(sb0 + u) * 64 + 32];
+                            pa[u] = ns.pq[sb0 + u + w0]; pb[u] = ns.pq[sb0 + u + w1];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = jp + (sb0 + u) * 64 + lane;
+                            const float2 ya = nco_apply(xa[u], nco_phasor(pa[u], s2a)), yb = nco_apply(xb[u], nco_phasor(pb[u], s2b));
+                            if (j >= 0 && j < j_end) px[(sb0 + u) * 64] = ya;
+                            if (j + 32 >= 0 && j + 32 < j_end) px[(sb0 + u) * 64 + 32] = yb;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
             const float2* src = reinterpret_cast<const float2*>(sm.ring[slot]) + odd + lane;
             float2 (*red)[kRedPitch] = WarpSmem<M, T>::kRedInRing ? reinterpret_cast<float2 (*)[kRedPitch]>(sm.ring[slot]) : sm.red;
 
@@ -311,9 +410,16 @@ decim1_kernel(DecimArgs a)
             const int keep = T - 1 + int(pl.r + pl.n - pl.consumed);       // <= kCarryCap (host checked)
             float2* next = a.carry_next + (size_t)ch * kCarryCap + kCarryCap;
             const int jn = int(pl.n);
+            if (NCO && mixing && jn > 0) {
+                const int b_min = max(jn - keep, 0) >> 12, b_max = (jn - 1) >> 12;
+                if (b_min < ebase || b_max >= ebase + 32) { ebase = b_min; nco_fill_e(ns, nc, ebase, lane); }
+            }
             for (int i = lane; i < keep; i += 32) {
                 const int j = jn - keep + i;
-                next[i - keep] = (j < 0) ? carry[j] : chunk[j];
+                float2 v = (j < 0) ? carry[j] : chunk[j];
+                if (NCO && mixing && j >= 0)   // the carry holds MIXED samples: same phasor as the in-ring mix above
+                    v = nco_apply(v, nco_phasor(nco_f(nco_cmul(ns.e[(j >> 12) - ebase], ns.s1[(j >> 6) & 63])), nco_f(ns.s2[j & 63])));
+                next[i - keep] = v;
             }
         }
     }
@@ -381,18 +487,18 @@ cudaError_t launch_carry(const ChanPlan* plan, const float2* chunk, size_t chunk
 
 constexpr int kMinSpan = 48; // superblocks: keeps the ramp-in below ~12 % when there are few channels
 
-template <int M, int T>
+template <int M, int T, bool NCO = false>
 static cudaError_t launch_fast(DecimArgs a, unsigned max_n1, int n_sms, cudaStream_t stream, int* launches)
 {
     using G = Geo<M, T>;
-    const size_t smem = sizeof(WarpSmem<M, T>) * kDecimWarps;
+    const size_t smem = sizeof(WarpSmem<M, T>) * kDecimWarps + (NCO ? sizeof(NcoWarpSmem) * kDecimWarps : 0);
     static bool configured = false; // one device per process (one process per GPU)
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(decim1_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(decim1_kernel<M, T, NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         // all kernels of the path ask for the same (maximum) shared-memory carve-out so that the low-priority tail kernels
         // can co-reside with K1 on an SM instead of forcing a carve-out reconfiguration
-        cudaFuncSetAttribute(decim1_kernel<M, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(decim1_kernel<M, T, NCO>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
     a.sb_per_channel = max_n1 ? int((max_n1 - 1 + G::NOUT - 1) / G::NOUT + 1) : 1;
@@ -404,13 +510,17 @@ static cudaError_t launch_fast(DecimArgs a, unsigned max_n1, int n_sms, cudaStre
     const long long n_spans = (total_sb + span - 1) / span;
     int grid = (int)std::min<long long>(n_sms, (n_spans + kDecimWarps - 1) / kDecimWarps);
     if (grid < 1) grid = 1;
-    decim1_kernel<M, T><<<grid, kDecimWarps * 32, smem, stream>>>(a);
+    decim1_kernel<M, T, NCO><<<grid, kDecimWarps * 32, smem, stream>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
 
 cudaError_t launch_decim1(DecimArgs a, int M, int T, unsigned max_n1, int n_sms, cudaStream_t stream, int* launches)
 {
+    if (a.nco) {   // fused NCO: only the /64 first stage has it (decim1_supports_fused_nco)
+        if (M == 64 && T == 348) return launch_fast<64, 348, true>(a, max_n1, n_sms, stream, launches);
+        return cudaErrorInvalidValue;
+    }
     if (M == 64 && T == 348) return launch_fast<64, 348>(a, max_n1, n_sms, stream, launches);
     if (M == 32 && T == 174) return launch_fast<32, 174>(a, max_n1, n_sms, stream, launches);
     if (M == 32 && T == 212) return launch_fast<32, 212>(a, max_n1, n_sms, stream, launches);
@@ -427,5 +537,7 @@ cudaError_t launch_decim1(DecimArgs a, int M, int T, unsigned max_n1, int n_sms,
     }
     return launch_carry(a.plan, a.chunk, a.chunk_pitch, a.carry, a.carry_next, T, a.ch0, a.n_channels, stream, launches);
 }
+
+bool decim1_supports_fused_nco(int M, int T) { return M == 64 && T == 348; }
 
 } // namespace hbd

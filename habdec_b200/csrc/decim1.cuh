@@ -1,6 +1,7 @@
 // K1 launch interface (see decim1.cu)
 #pragma once
 #include "hbd_common.cuh"
+#include "nco.cuh"
 
 namespace hbd {
 
@@ -23,11 +24,15 @@ struct DecimArgs {
     float2* carry_next;        // other half of the carry ping-pong pair: K1 writes the next call's carry here
     int sb_per_channel;        // superblock slots per channel (uniform upper bound; set by launch_decim1)
     int span;                  // superblocks per warp (contiguous in the flattened (channel, superblock) plane)
+    const NcoChan* nco;        // non-null: `chunk` holds RAW samples (chunk_pitch 0: one wideband row shared by all channels) and K1
+                               // mixes every channel through its NCO on the fly (fused K0); the carry always holds mixed samples
 };
 
 // M == 1 means "no decimator" (copy).  `launches` is incremented per kernel launched.  Writes the carry of the
 // next call into a.carry_next (inside K1 on the fast path, by carry_kernel otherwise).
 cudaError_t launch_decim1(DecimArgs a, int M, int T, unsigned max_n1, int n_sms, cudaStream_t stream, int* launches);
+// can launch_decim1 mix the channels through their NCOs itself (DecimArgs::nco) for this first stage?
+bool decim1_supports_fused_nco(int M, int T);
 // stage-1 carry (history + unconsumed remainder) for the next call: carry -> carry_next
 cudaError_t launch_carry(const ChanPlan* plan, const float2* chunk, size_t chunk_pitch, const float2* carry, float2* carry_next, int T1, int ch0,
                          int n_channels, cudaStream_t stream, int* launches);

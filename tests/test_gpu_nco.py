@@ -216,3 +216,57 @@ def test_afc_retune_all_channels_on_gpu():
         assert a.poll_chars(c) == b.poll_chars(c)
         assert a.getPeaks(c) == b.getPeaks(c)
         assert a.get_nco(c) == b.get_nco(c)
+
+
+@pytest.mark.parametrize("chunk", [65536, 40000, 262144])
+def test_fused_nco_equals_premix_kernel(oracle_kind, chunk):
+    """The NCO fused into K1 (device / wideband pushes: no K0 launch, no staging matrix) against the K0 + staging path
+    (HBD_NCO_FUSED=0) and against premix + reference: chunks that are not multiples of the factor (mixed remainder in
+    the carry), 262 144-sample chunks (more than 32 blocks of 4096: the E table is refilled) and a retune between calls."""
+    import os
+    fs = 2.5e6
+    offsets, bauds = [-310e3, 55e3, 0.0, 420e3], [300.0, 300.0, 300.0, 600.0]
+    wide, _ = _wideband(fs, offsets, bauds, 1, snr_db=-8.0)
+    n = len(wide) // chunk * chunk
+    n_ch = len(offsets)
+    decs = []
+    for fused in ("1", "0"):
+        os.environ["HBD_NCO_FUSED"] = fused
+        try:
+            d = api.BatchDecoder(n_ch, dec_factor=256, record=True)
+        finally:
+            del os.environ["HBD_NCO_FUSED"]
+        for c in range(n_ch):
+            d.baud(bauds[c], c)
+            d.set_nco(offsets[c], c)
+        decs.append(d)
+    refs = [make_oracle(oracle_kind, baud=bauds[c], rtty_bits=8, rtty_stops=2.0, dec_factor=256) for c in range(n_ch)]
+    phases = [0.0] * n_ch
+    freqs = list(offsets)
+    stages = [[[] for _ in range(n_ch)] for _ in decs]
+    launches0 = [d.kernel_launches() for d in decs]
+    for i, o in enumerate(range(0, n, chunk)):
+        if i == 2:      # retune channel 1 by +37 Hz between two calls (what hbd_afc_retune does)
+            freqs[1] += 37.0
+            for d in decs:
+                d.set_nco(freqs[1], 1)
+        blk = wide[o:o + chunk]
+        for k, d in enumerate(decs):
+            d.pushWideband(blk, fs)
+            d.process()
+            for c in range(n_ch):
+                stages[k][c].append(d.debug_stage(c, api.STAGE_DECIMATED).copy())
+        for c in range(n_ch):
+            mixed, phases[c] = po.premix(blk, fs, freqs[c], phases[c])
+            refs[c].push_process(mixed, fs)
+    # the fused decoder never launched K0: one kernel less per call
+    calls = n // chunk
+    assert (decs[1].kernel_launches() - launches0[1]) - (decs[0].kernel_launches() - launches0[0]) >= calls
+    for c in range(n_ch):
+        fused = np.concatenate(stages[0][c]); k0 = np.concatenate(stages[1][c]); want = refs[c].stage(po.STAGE_DECIMATED)
+        assert fused.shape == k0.shape == want.shape
+        den = max(np.linalg.norm(want.astype(np.complex128)), 1e-30)
+        assert np.linalg.norm(fused.astype(np.complex128) - k0) / den <= 1e-6, "channel %d fused vs K0" % c
+        assert np.linalg.norm(fused.astype(np.complex128) - want) / den <= 1e-5, "channel %d fused vs reference" % c
+        assert decs[0].poll_chars(c) == refs[c].chars(), "channel %d" % c
+        assert decs[0].poll_sentences(c) == refs[c].sentences(), "channel %d" % c
