@@ -91,6 +91,14 @@ def test_varying_chunk_sizes_with_empty_pushes(oracle_kind):
     assert dec.poll_sentences(0) == ref.sentences()
     assert dec.getLastSentence(0) == ref.last_sentence()
     assert len(ref.sentences()) >= 2
+    # FFT frames complete on irregular calls here (the host decides per call whether K4 has to run): spectrum and AFC
+    a = ref.afc()
+    assert rel_l2(dec.getFFT(0), ref.stage(po.STAGE_FFT)) <= REL_L2
+    assert dec.getPeaks(0) == (a.peak_left, a.peak_right)
+    nf, nv = dec.getNoiseFloor(0)
+    assert abs(nf - a.noise_floor) < 1e-3 and abs(nv - a.noise_variance) < 1e-3
+    assert dec.getShift(0) == pytest.approx(a.shift_hz, abs=1e-9)
+    assert dec.getFrequencyCorrection(0) == pytest.approx(a.frequency_correction, abs=1e-9)
 
 
 def test_slicer_vent_after_long_carrier(oracle_kind):
