@@ -257,3 +257,31 @@ def test_setters_between_calls(oracle_kind):
         assert dec.poll_chars(c) == refs[c].chars(), "channel %d" % c
         assert dec.poll_sentences(c) == refs[c].sentences(), "channel %d" % c
     assert len(refs[1].sentences()) >= 5
+
+
+@pytest.mark.parametrize("fs,max_rate,want", [(2.048e6, 8000.0, 256), (2.048e6, 40000.0, 64), (1.024e6, 8000.0, 128),
+                                              (256e3, 9000.0, 32), (64e3, 8000.0, 8), (2.048e6, 1000.0, 0)])
+def test_setup_decimation_stages_bw(oracle_kind, fs, max_rate, want):
+    """Decoder::setupDecimationStagesBW (Decoder.h:336-412): 0 before a sampling rate is latched; then the smallest
+    power of two (2..128, else 256) that brings the rate under the limit, same stage plan as the factor call.
+    Limits that need more than one 256x plan are refused (0) -- the reference would cascade plans."""
+    baud = 300.0
+    iq, _ = synth.channel_iq(4, 1, fs, baud, snr_db=-10.0 if fs > 1e5 else -3.0)
+    chunk = 65536
+    n = len(iq) // chunk * chunk
+    dec = api.BatchDecoder(1, baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=1)
+    assert dec.setupDecimationStagesBW(max_rate) == 0                  # Decoder.h:340-341: no sampling rate yet
+    dec.pushSamples(0, iq[:chunk], fs)
+    got = dec.setupDecimationStagesBW(max_rate)
+    assert got == want
+    if not want:
+        return
+    assert dec.getDecimationFactor() == want and dec.getDecimatedSamplingRate() == fs / want
+    dec.process()
+    for o in range(chunk, n, chunk):
+        dec.pushSamples(0, iq[o:o + chunk], fs)
+        dec.process()
+    ref = make_oracle(oracle_kind, baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=want).run(iq[:n], fs, chunk)
+    assert dec.poll_chars(0) == ref.chars()
+    assert dec.poll_sentences(0) == ref.sentences()     # (not every rate/limit pair decodes in the reference either)
+    assert dec.poll_raw_chars(0) is not None
