@@ -99,7 +99,11 @@ double hbd_get_nco(hbd_decoder* h, int ch);
  * 100 Hz) the NCO is moved by the correction and the AFC is reset; applied[n_channels] (may be NULL) receives the
  * corrections, the return value is the number of channels retuned (< 0: error) */
 int    hbd_afc_retune(hbd_decoder* h, double min_abs_hz, double* applied);
-/* one capture (host / device cf32 row of n_complex samples) pushed to EVERY channel through its NCO */
+/* one capture (host / device cf32 row of n_complex samples) pushed to EVERY channel through its NCO.  With the
+ * /64 first stage (factor 256) and nothing else queued, the mix is fused into the decimator kernel: a DEVICE capture is
+ * then read in place (no staging copy) and, like hbd_push_samples_device, must stay valid and unchanged until the work
+ * enqueued by the next hbd_process()/hbd_process_async() has passed it (work put on the handle's stream afterwards is
+ * ordered behind that automatically).  hbd_push_samples_device with NCOs set is zero copy under the same conditions. */
 int hbd_push_wideband(hbd_decoder* h, const float* iq, size_t n_complex, double sampling_rate);
 int hbd_push_wideband_device(hbd_decoder* h, const float* d_iq, size_t n_complex, double sampling_rate);
 
