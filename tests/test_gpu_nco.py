@@ -218,7 +218,7 @@ def test_afc_retune_all_channels_on_gpu():
         assert a.get_nco(c) == b.get_nco(c)
 
 
-@pytest.mark.parametrize("chunk", [65536, 40000, 262144])
+@pytest.mark.parametrize("chunk", [65536, 40000, 40001, 262144])
 def test_fused_nco_equals_premix_kernel(oracle_kind, chunk):
     """The NCO fused into K1 (device / wideband pushes: no K0 launch, no staging matrix) against the K0 + staging path
     (HBD_NCO_FUSED=0) and against premix + reference: chunks that are not multiples of the factor (mixed remainder in
