@@ -118,3 +118,24 @@ def test_iqsource_file_matches_reference_transcript(tmp_path):
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "iqsource_ref")
     if os.path.exists(ref_bin):
         assert g.transcript(ref_bin, path) == golden
+
+
+def test_cpp_facade_builds_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """include/habdec_b200/Decoder.hpp + IQSource.hpp compile as C++17 against the C ABI library; on a box without a CUDA
+    device the Decoder constructor throws (no CPU fallback, nothing is decoded by other means)."""
+    import subprocess
+    import numpy as np
+    lib_dir = os.path.join(ROOT, "habdec_b200")
+    exe = _build_cpp(tmp_path, os.path.join(ROOT, "tests", "cpp", "decoder_thread.cpp"), "decoder_thread",
+                     extra=("-L", lib_dir, "-lhabdec_b200", "-Wl,-rpath," + lib_dir))
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present: the run itself is covered by tests/test_gpu_cpp_facade.py")
+    except ImportError:
+        pass
+    path = str(tmp_path / "z.cf32")
+    np.zeros(65536, dtype=np.complex64).tofile(path)
+    r = subprocess.run([exe, path, "2048000", "300", "8", "2"], capture_output=True)
+    assert r.returncode != 0
+    assert b"no usable CUDA device" in r.stderr and b"CHARS" not in r.stdout
