@@ -472,9 +472,11 @@ int hbd_decoder::process_async_locked()
         x.lp_dirty = false;
         if (T != x.lp_ntaps) {
             if (T > size_t(kLpMaxTaps)) { set_error("low-pass needs more than kLpMaxTaps taps"); return HBD_ERR_ARG; }
+            const size_t T_old = x.lp_ntaps;
             x.lp_ntaps = T;
             x.cfg_dirty = true;
             if (quiesce()) return HBD_ERR_CUDA;
+            if (T_old > T && d_decq) HBD_CUDA_CHECK(launch_lp_hist_shrink(d_decq + c * dq_pitch, int(T_old), int(T), stream));
             HBD_CUDA_CHECK(cudaMemcpyAsync(d_lptaps + c * kLpMaxTaps, new_taps.data(), 4 * T, cudaMemcpyHostToDevice, stream));
             HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // new_taps is reused
         }
@@ -877,6 +879,10 @@ static int set_lp(hbd_decoder* h, int ch, float bw, float trans, bool set_bw)
         const double fs_dec = h->fs_in / h->factor;
         const size_t T = design_lowpass(float(x.lp_bw / fs_dec), x.lp_trans, x.lp_input_size, x.lp_ntaps, taps);
         if (T != x.lp_ntaps && T <= size_t(kLpMaxTaps)) {
+            if (x.lp_ntaps > T && h->d_decq) {
+                if (launch_lp_hist_shrink(h->d_decq + size_t(c) * h->dq_pitch, int(x.lp_ntaps), int(T), h->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
+            }
             x.lp_ntaps = T; x.cfg_dirty = true;
             if (cudaMemcpy(h->d_lptaps + size_t(c) * kLpMaxTaps, taps.data(), 4 * T, cudaMemcpyHostToDevice) != cudaSuccess) return HBD_ERR_CUDA;
         }

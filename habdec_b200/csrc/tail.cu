@@ -397,6 +397,24 @@ tail_kernel(TailArgs a)
     }
 }
 
+// A SMALLER low-pass (lowpass_trans raised mid-stream): FirFilter keeps its work buffer, whose first T_new-1 entries are
+// the OLDEST part of the previous T_old-1 history samples (FirFilter.h:139-152 copies the new input behind them), so that
+// part becomes the history of the new filter.  One CTA moves it to the end of the history slots.
+__global__ void lp_hist_shrink_kernel(float2* row, int t_old, int t_new)
+{
+    __shared__ float2 s[kLpMaxTaps];
+    const int n = t_new - 1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = row[kLpHist - (t_old - 1) + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) row[kLpHist - n + i] = s[i];
+}
+cudaError_t launch_lp_hist_shrink(float2* decq_row, int t_old, int t_new, cudaStream_t stream)
+{
+    if (t_new < 2 || t_new >= t_old) return cudaSuccess;
+    lp_hist_shrink_kernel<<<1, 256, 0, stream>>>(decq_row, t_old, t_new);
+    return cudaGetLastError();
+}
+
 // shared-memory layout of one launch (all sizes in elements of the respective arrays)
 static void tail_layout(TailArgs& a, size_t* bytes)
 {

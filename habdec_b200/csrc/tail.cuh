@@ -41,4 +41,7 @@ struct TailArgs {
 
 cudaError_t launch_tail(TailArgs a, int n_channels, cudaStream_t stream, int* launches);
 
+// low-pass tap count shrank from t_old to t_new: keep the reference's part of the history (see tail.cu)
+cudaError_t launch_lp_hist_shrink(float2* decq_row, int t_old, int t_new, cudaStream_t stream);
+
 } // namespace hbd

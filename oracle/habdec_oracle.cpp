@@ -625,6 +625,8 @@ void orc_set_param(void* h, int which, double value) // Decoder.h:654-706: plain
     case 1: p->uart.nbits = size_t(value); p->cfg.rtty_bits = int(value); break;
     case 2: p->uart.nstops = float(value); p->cfg.rtty_stops = float(value); break;
     case 3: p->cfg.dc_remove = value != 0; break;
+    case 4: p->lp_bw = float(value); p->lp.design(float(p->lp_bw / p->fs_dec()), p->lp_trans); break;     // Decoder.h:238-243
+    case 5: p->lp_trans = float(value); p->lp.design(float(p->lp_bw / p->fs_dec()), p->lp_trans); break;  // Decoder.h:252-257
     default: break;
     }
 }

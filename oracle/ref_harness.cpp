@@ -199,6 +199,8 @@ void ref_set_param(void* h, int which, double value)
         case 1: D.rtty_bits(size_t(value)); break;
         case 2: D.rtty_stops(float(value)); break;
         case 3: D.dc_remove(value != 0); break;
+        case 4: D.lowpass_bw(float(value)); break;
+        case 5: D.lowpass_trans(float(value)); break;
         default: break;
         }
     });

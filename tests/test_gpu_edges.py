@@ -285,3 +285,33 @@ def test_setup_decimation_stages_bw(oracle_kind, fs, max_rate, want):
     assert dec.poll_chars(0) == ref.chars()
     assert dec.poll_sentences(0) == ref.sentences()     # (not every rate/limit pair decodes in the reference either)
     assert dec.poll_raw_chars(0) is not None
+
+
+def test_lowpass_setters_between_calls(oracle_kind):
+    """Decoder::lowpass_bw / lowpass_trans re-run the design at once (Decoder.h:238-257): a new bandwidth with an unchanged
+    tap count changes nothing (FirFilter.h:193-194); a wider transition gives a SHORTER filter whose history is the oldest
+    part of the previous one (the work buffer is kept, FirFilter.h:139-152).  Both reproduced; filtered stream compared."""
+    fs, baud = 2.048e6, 300.0
+    iq, _ = synth.channel_iq(41, 3, fs, baud, snr_db=-15.0)
+    n = len(iq) // 65536 * 65536
+    cfg = dict(baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
+    dec = api.BatchDecoder(1, record=True, **cfg)
+    ref = make_oracle(oracle_kind, **cfg)
+    filt = []
+    for i, o in enumerate(range(0, n, 65536)):
+        if i == 6:
+            dec.lowpass_bw(900.0, 0); ref.set_param("lowpass_bw", 900.0)
+        if i == 14:
+            dec.lowpass_trans(0.05, 0); ref.set_param("lowpass_trans", 0.05)
+        dec.pushSamples(0, iq[o:o + 65536], fs)
+        dec.process()
+        ref.push_process(iq[o:o + 65536], fs)
+        filt.append(dec.debug_stage(0, api.STAGE_FILTERED).copy())
+    got, want = np.concatenate(filt), ref.stage(po.STAGE_FILTERED)
+    assert got.shape == want.shape and rel_l2(got, want) <= REL_L2
+    # the call right after the shrink is where a wrong history would show: compare it on its own
+    k = 14 * 256
+    assert rel_l2(got[k:k + 256], want[k:k + 256]) <= REL_L2
+    assert np.array_equal(dec.debug_stage(0, api.STAGE_LPTAPS), ref.stage(po.STAGE_LPTAPS)) and len(ref.stage(po.STAGE_LPTAPS)) == 81
+    assert dec.poll_chars(0) == ref.chars()
+    assert dec.poll_sentences(0) == ref.sentences()
