@@ -95,15 +95,18 @@ class ClockSampler:
 
     def _run(self):
         nv = self.nv
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        rs, k = 0, 0
         while not self._stop:
             try:
                 clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                if k % 3 == 0:          # NVML queries can take tens of ms on a busy box: the clock every time, the reasons every third
+                    rs = reasons(self.h)
+                k += 1
                 self.rows.append((clk, rs))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def stop(self):
         self._stop = True
