@@ -1,6 +1,9 @@
 """Multi-GPU plumbing: channels are block-partitioned over ranks (one process per GPU) and never
 exchange signal data; only decoded sentences and per-channel AFC/stat records travel, once per
-batch, to rank 0 (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+batch, to rank 0 (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests).
+The one exception is the wideband channeliser (BASELINE configs[4]): every rank needs the whole
+capture, so the rank that owns the receiver broadcasts each block once (20 MS/s x 8 B = 160 MB/s)
+and every rank cuts its own slice of frequency-offset channels out of it."""
 from __future__ import annotations
 
 import json
@@ -13,6 +16,21 @@ def shard(n_channels: int, world: int, rank: int) -> range:
     base, rem = divmod(n_channels, world)
     lo = rank * base + min(rank, rem)
     return range(lo, lo + base + (1 if rank < rem else 0))
+
+
+def broadcast_capture(block, world: int, src: int = 0):
+    """One block of the wideband capture (float32 tensor [n, 2], interleaved cf32) from rank `src` to all ranks, in
+    place.  NCCL on GPUs (one broadcast over NVLink/NVSwitch per block), gloo on CPU.  Returns the tensor."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.broadcast(block, src=src)
+    return block
+
+
+def wideband_plan(offsets_hz, world: int, rank: int):
+    """Rank `rank`'s slice of the frequency-offset channels of one capture: (first global channel, NCO offsets)."""
+    mine = shard(len(offsets_hz), world, rank)
+    return mine.start, [float(offsets_hz[c]) for c in mine]
 
 
 def collect_local_results(dec, ch0: int) -> dict:

@@ -45,3 +45,35 @@ def test_gather_to_rank0_gloo(world, n_channels):
     assert sorted(merged) == list(range(n_channels))
     for c, v in merged.items():
         assert v["last"] == "C%04d" % c and len(v["sentences"]) == c % 3 and v["afc"][4] == c
+
+
+def _wideband_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(7)
+    block = torch.randn((4096, 2), generator=g) if rank == 0 else torch.zeros((4096, 2))
+    hdist.broadcast_capture(block, world, src=0)
+    offsets = [(c - 5) * 15e3 for c in range(11)]
+    ch0, mine = hdist.wideband_plan(offsets, world, rank)
+    q.put((rank, float(block.double().sum()), ch0, mine))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_wideband_capture_broadcast_and_channel_plan_gloo():
+    """configs[4] on N ranks: every rank ends up with the identical capture block and a disjoint slice of the offsets."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_wideband_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1] != 0.0                       # same samples everywhere
+    assert got[0][2] == 0 and got[1][2] == len(got[0][3])      # block partition
+    assert got[0][3] + got[1][3] == [(c - 5) * 15e3 for c in range(11)]
