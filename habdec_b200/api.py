@@ -145,6 +145,7 @@ SIGNATURES = {
     "hbd_design_lowpass": (C.c_size_t, [C.c_float, C.c_float, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]),
     "hbd_extract_sentence": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "hbd_crc16": (None, [C.c_char_p, C.c_size_t, C.c_char_p]),
+    "hbd_text_replay": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
 }
 
 _lib = None
@@ -206,6 +207,19 @@ def ssdv_host_replay(chunks: list[bytes], accepted: list[tuple]):
     raw = bytes(out)
     return [(which[k], infos[k].callsign.decode(), infos[k].image_id, infos[k].packet_id, infos[k].width, infos[k].height,
              infos[k].errors, infos[k].set_size, raw[256 * k:256 * k + 256]) for k in range(n)]
+
+
+def text_replay(chunks: list[bytes]):
+    """The text layer alone (host only): (CRC-valid sentences, last sentence, remaining text stream) after feeding `chunks`."""
+    lib = load()
+    chars = b"".join(chunks)
+    sizes = (C.c_size_t * max(len(chunks), 1))(*[len(c) for c in chunks])
+    cbuf = (C.c_ubyte * max(len(chars), 1)).from_buffer_copy(chars or b"\0")
+    n = lib.hbd_text_replay(cbuf, sizes, len(chunks), None, 0)
+    out = C.create_string_buffer(max(n, 1))
+    lib.hbd_text_replay(cbuf, sizes, len(chunks), out, n)
+    sent, last, stream = out.raw[:n].split(b"\x1e")
+    return [x for x in sent.split(b"\n") if x], last, stream
 
 
 def crc16(s: bytes) -> bytes:

@@ -5,6 +5,7 @@
 #include "../../include/habdec_b200.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -49,14 +50,10 @@ bool plan_for_factor(size_t factor, std::vector<TapTable>& st)
     }
 }
 
-// host mirror of one channel
-struct HostChan {
-    double baud = 1;         // SymbolExtractor default symbol_rate_ = 1
-    size_t rtty_bits = 0;
-    float rtty_stops = 0;
-    float lp_bw = 1500, lp_trans = 0.025f;
-    bool dc_remove = false;
-    // mirrors of device counters that are pure functions of the push sizes
+// host mirror of one channel, part 1: stream counters that are pure functions of the push sizes (and of the
+// low-pass configuration).  While every channel is fed the same way they are identical for all channels, and only
+// hc[0]'s copy is kept current (hbd_decoder::ctr_uniform / sync_ctrs): a steady-state call costs O(1) host work.
+struct ChanCtr {
     unsigned in_r = 0, dec_pending = 0;
     size_t grown1 = 0, grown2 = 0, grown_lp = 0;
     unsigned fft_have = 0;   // mirror of ChanState::fft_have: tells the host which calls complete an FFT frame (K4 launch)
@@ -64,9 +61,25 @@ struct HostChan {
     unsigned pushed = 0;     // samples waiting in the staging row
     unsigned last_nf = 0, last_n2 = 0;
     unsigned demod_n = 0;    // size of the reference's demodulated_ (last call that produced any; Decoder.h:546-555)
+    unsigned lp_shadow_n = 0;  // inputs of the last low-pass call kept in the shadow of the reference's work buffer
+    bool lp_dirty = true;    // bw / trans / input size changed since the last design attempt
+    bool same(const ChanCtr& o) const
+    {
+        return in_r == o.in_r && dec_pending == o.dec_pending && grown1 == o.grown1 && grown2 == o.grown2 && grown_lp == o.grown_lp &&
+               fft_have == o.fft_have && lp_input_size == o.lp_input_size && lp_ntaps == o.lp_ntaps && pushed == o.pushed &&
+               last_nf == o.last_nf && last_n2 == o.last_n2 && demod_n == o.demod_n && lp_shadow_n == o.lp_shadow_n && lp_dirty == o.lp_dirty;
+    }
+};
+// part 2: configuration (always per channel)
+struct HostChan : ChanCtr {
+    double baud = 1;         // SymbolExtractor default symbol_rate_ = 1
+    size_t rtty_bits = 0;
+    float rtty_stops = 0;
+    float lp_bw = 1500, lp_trans = 0.025f;
+    bool dc_remove = false;
     double nco_freq = 0, nco_phase = 0; // pre-mixer: frequency in Hz, phase (cycles) of the next pushed sample
     bool cfg_dirty = true;
-    bool lp_dirty = true;    // bw / trans / input size changed since the last design attempt
+    ChanCtr& ctr() { return *this; }
 };
 
 constexpr unsigned kMaxCallsBetweenCollects = 256; // process_async forces a drain beyond this (log capacity)
@@ -77,6 +90,7 @@ __global__ void init_cfg_kernel(ChanState* st, const double* baud, const float* 
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= n_ch || !dirty[ch]) return;
     st[ch].baud = baud[ch];
+    if (st[ch].rtty_stops != stops[ch] || st[ch].rtty_bits != bits[ch]) st[ch].uart_rescan = 1;   // RTTY.h:90-134 rescans bits_ under the new framing
     st[ch].rtty_stops = stops[ch];
     st[ch].rtty_bits = bits[ch];
     st[ch].dc_remove = dc[ch];
@@ -84,6 +98,14 @@ __global__ void init_cfg_kernel(ChanState* st, const double* baud, const float* 
 }
 
 } // namespace
+
+// a user callback recorded under the handle's mutex and fired after it is released (a callback may call hbd_* again)
+struct Deferred {
+    enum Kind { kSentence, kChars, kSsdv } kind;
+    int ch;
+    std::string a, b, c;                                   // sentence: callsign, data, crc; chars: a
+    hbd_ssdv_packet_info info; std::array<unsigned char, 256> pkt;
+};
 
 struct hbd_decoder {
     std::mutex mtx;
@@ -95,13 +117,10 @@ struct hbd_decoder {
     // stream and the carry are double buffered over calls, so K1 only ever waits for the tail of call s-1).
     //   hi (high priority): K1 (+ carry) of every call
     //   lo (low priority):  K2 tail / K4 fft_afc; they fill the SM resources K1 leaves free
-    // Optionally the channels are cut into groups (HBD_GROUPS) so that K1 of one group overlaps the tail of the other
-    // inside ONE call; that only helps callers that cannot pipeline calls.
-    int n_groups = 1;
     cudaStream_t hi = nullptr, lo = nullptr;
-    std::vector<cudaEvent_t> ev_consumed;   // per group: K1 + carry done (input consumed, stage-1 output ready)
-    std::vector<cudaEvent_t> ev_tail;       // per (group, stage-1 buffer): tail done, that buffer may be overwritten by K1
-    std::vector<char> tail_pending;
+    cudaEvent_t ev_consumed = nullptr;      // K1 + carry done (input consumed, stage-1 output ready)
+    cudaEvent_t ev_tail[2] = {nullptr, nullptr};   // per stage-1 buffer: tail done, that buffer may be overwritten by K1
+    bool tail_pending[2] = {false, false};
     bool tail_ev_late = false;              // HBD_TAIL_EV_LATE=1 (measurement hook): record ev_tail after the whole lo-stream sequence
     cudaEvent_t ev_in = nullptr;
     int sync_groups()
@@ -118,7 +137,29 @@ struct hbd_decoder {
     int M1 = 1, T1 = 1, M2 = 1, T2 = 1;
     int fft_n = kFftN;       // spectrum size: 4096 like the reference, or 16384 (hbd_set_fft_size)
     int alloc_fft();
-    std::vector<HostChan> hc;        // compact, scanned on every call
+    std::vector<HostChan> hc;        // per-channel configuration + counters (see ChanCtr)
+    // Uniform mode: every channel has been fed the same way since creation (whole-batch pushes only), so all ChanCtr are
+    // equal and only hc[0]'s is stepped per call; hc[1..] lag behind (ctr_stale) until sync_ctrs() copies them.
+    bool ctr_uniform = true, ctr_stale = false;
+    bool lp_cfg_uniform = true;      // lp_bw / lp_trans are the same for all channels (setters with ch == -1 only)
+    bool cfg_dirty_any = true;       // some channel has cfg_dirty set
+    bool derived_dirty = true;       // max_lp_taps_c / max_spb_c need recomputing
+    size_t max_lp_taps_c = 1; double max_spb_c = 1;
+    void sync_ctrs() { if (ctr_stale) { for (size_t c = 1; c < hc.size(); ++c) hc[c].ctr() = hc[0].ctr(); ctr_stale = false; } }
+    void leave_uniform() { sync_ctrs(); ctr_uniform = false; }
+    // staged (host-pushed, not yet processed) samples: the same count in every channel?
+    bool queue_depth_equal(unsigned& base)
+    {
+        base = hc[0].pushed;
+        if (ctr_uniform) return true;
+        for (const auto& x : hc) if (x.pushed != base) return false;
+        return true;
+    }
+    void add_pushed(unsigned n)
+    {
+        if (ctr_uniform) { hc[0].pushed += n; ctr_stale = true; }
+        else for (auto& x : hc) x.pushed += n;
+    }
     std::vector<TextChannel> text;   // sentence layer state, touched only when a channel produced characters
 
     // device state
@@ -136,11 +177,23 @@ struct hbd_decoder {
     float* d_lptaps = nullptr;
     float* d_slicer = nullptr;   size_t slicer_pitch = 0;
     float* d_demod = nullptr;    size_t demod_pitch = 0;
-    uint2* d_log = nullptr;              // decoded-character log (ring, kLogCap entries)
-    unsigned* d_log_head = nullptr;      // monotonic append counter
+    unsigned short* d_uart_runs = nullptr;   // UART backlog [n][kUartRunsCap] (slicer_dev.cuh)
+    // Decoded-character log: ring of log_cap entries appended by the tail kernels (monotonic head in d_log_ctl[0]).
+    // After the kernels of a call the control words are copied to that call's slot of h_heads (pinned), in stream order:
+    // the host only ever reads a COMMITTED head, never the live one (entries below it are completely written).
+    uint2* d_log = nullptr;
+    unsigned log_cap = 0;                // power of two, sized from the channel count
+    unsigned* d_log_ctl = nullptr;       // kCtlWords control words (see LogCtl in hbd_common.cuh)
+    unsigned* h_heads = nullptr;         // pinned, [ev_call.size()][kCtlWords]
+    unsigned* h_tail_pin = nullptr;      // pinned, [2]: char log tail, SSDV log tail (source of the async upload)
     unsigned log_tail = 0;               // host: entries below this index are already processed
     unsigned call_seq = 0;               // calls enqueued so far (24 bits travel in the log entries)
     unsigned calls_collected = 0;        // calls whose characters went through the sentence layer
+    unsigned done_seq = 0;               // calls known to have completed (event queries, see log_pressure)
+    unsigned done_head = 0;              // committed character-log head of call done_seq - 1
+    unsigned per_call_max = 0;           // largest number of characters one completed call appended so far
+    unsigned long long chars_lost = 0;   // characters dropped by log overflows (reported by hbd_collect*)
+    unsigned ovf_seen[3] = {0, 0, 0};    // last seen kCtlSsdvRingOvf / kCtlSsdvOvf / kCtlCharOvf (monotonic counters)
     std::vector<cudaEvent_t> ev_call;    // ring: completion of call (seq % size)
     cudaStream_t copy_stream = nullptr;  // result read-back, independent of the compute streams
     std::vector<uint2> h_log;            // host staging
@@ -177,7 +230,8 @@ struct hbd_decoder {
     // NCO pre-mixer (nco.cu)
     NcoChan* d_nco = nullptr; std::vector<NcoChan> h_nco;
     float2* d_wide = nullptr; size_t wide_cap = 0;       // wideband capture row shared by all channels
-    bool nco_active() const { for (const auto& x : hc) if (x.nco_freq != 0 || x.nco_phase != 0) return true; return false; }
+    bool nco_any = false;    // some channel has (had) a non-zero NCO frequency or phase (set by hbd_set_nco, never cleared)
+    bool nco_active() const { return nco_any; }
     int mix_into_stage(const float2* src, size_t src_pitch, int c0, int nc, size_t dst_off, size_t n);
     int pending_marks = 0;   // async calls since the last collect
     int sv_override = -1;
@@ -204,6 +258,7 @@ struct hbd_decoder {
     hbd_sentence_cb sentence_cb = nullptr; void* sentence_user = nullptr;
     hbd_tracker* tracker = nullptr; int tracker_off = 0;   // telemetry layer fed after the sentence callback
     hbd_chars_cb chars_cb = nullptr; void* chars_user = nullptr;
+    std::vector<Deferred> deferred;  // callbacks recorded by collect_locked, fired by the entry point after unlocking
 
     void set_error(const std::string& e) { err = e; }
     int ensure_call_capacity(size_t n_in_max);
@@ -211,8 +266,44 @@ struct hbd_decoder {
     int upload_taps();
     int process_async_locked();
     int collect_locked(unsigned lag);
+    int log_pressure();
     void free_all();
 };
+
+// Runs `body` (a lambda returning int) under the handle's mutex, then fires the callbacks it recorded with the mutex
+// released -- a callback may call any hbd_* function of the same handle (the reference's getRTTY()/getLastSentence()
+// are callable from sentence_callback_ as well).
+namespace {
+struct CallbackSet { hbd_sentence_cb s; void* su; hbd_chars_cb c; void* cu; hbd_ssdv_cb v; void* vu; hbd_tracker* trk; int off; };
+void fire_deferred(const std::vector<Deferred>& ev, const CallbackSet& cb)
+{
+    for (const Deferred& d : ev) {
+        switch (d.kind) {
+        case Deferred::kSentence:
+            if (cb.s) cb.s(cb.su, d.ch, d.a.c_str(), d.b.c_str(), d.c.c_str());
+            if (cb.trk) tracker_feed(cb.trk, d.ch + cb.off, d.a, d.b, d.c);      // SentenceCallback, websocketServer/main.cpp:292-366
+            break;
+        case Deferred::kChars: if (cb.c) cb.c(cb.cu, d.ch, d.a.data(), d.a.size()); break;
+        case Deferred::kSsdv: if (cb.v) cb.v(cb.vu, d.ch, &d.info, d.pkt.data()); break;
+        }
+    }
+}
+template <typename F>
+int locked_then_fire(hbd_decoder* h, F body)
+{
+    std::vector<Deferred> ev;
+    CallbackSet cb{};
+    int rc;
+    {
+        std::lock_guard<std::mutex> l(h->mtx);
+        rc = body();
+        ev.swap(h->deferred);
+        cb = CallbackSet{h->sentence_cb, h->sentence_user, h->chars_cb, h->chars_user, h->ssdv_cb, h->ssdv_user, h->tracker, h->tracker_off};
+    }
+    if (!ev.empty()) fire_deferred(ev, cb);
+    return rc;
+}
+} // namespace
 
 static void fill_ssdv_info(hbd_ssdv_packet_info& info, const SsdvEvent& ev)
 {
@@ -271,14 +362,22 @@ int hbd_decoder::alloc_fixed()
         HBD_CUDA_CHECK(cudaMemset(d_carry2[i], 0, n * kCarryCap * sizeof(float2)));
     }
     { const int rc = alloc_fft(); if (rc) return rc; }
+    HBD_CUDA_CHECK(dalloc(&d_uart_runs, n * size_t(kUartRunsCap)));
     HBD_CUDA_CHECK(dalloc(&d_lptaps, n * kLpMaxTaps));
     HBD_CUDA_CHECK(cudaMemset(d_lptaps, 0, n * kLpMaxTaps * sizeof(float)));
-    HBD_CUDA_CHECK(dalloc(&d_log, size_t(kLogCap)));
-    HBD_CUDA_CHECK(dalloc(&d_log_head, 4));   // [0] character log head, [1] SSDV packet log head, [2] SSDV ring overflow flag
-    HBD_CUDA_CHECK(cudaMemset(d_log_head, 0, 4 * sizeof(unsigned)));
+    // character log: at least 512 entries per channel (a 600 baud channel decodes ~2 characters per 65 536-sample call,
+    // so that is > 250 calls between drains even when every channel is noise); log_pressure() drains before it fills
+    log_cap = kLogCapMin;
+    while (size_t(log_cap) < 512 * n && log_cap < (1u << 30)) log_cap <<= 1;
+    HBD_CUDA_CHECK(dalloc(&d_log, size_t(log_cap)));
+    HBD_CUDA_CHECK(dalloc(&d_log_ctl, size_t(kCtlWords)));
+    HBD_CUDA_CHECK(cudaMemset(d_log_ctl, 0, kCtlWords * sizeof(unsigned)));
     HBD_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     ev_call.resize(kMaxCallsBetweenCollects * 2);
     for (auto& e : ev_call) HBD_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    HBD_CUDA_CHECK(cudaHostAlloc((void**)&h_heads, ev_call.size() * kCtlWords * sizeof(unsigned), cudaHostAllocDefault));
+    memset(h_heads, 0, ev_call.size() * kCtlWords * sizeof(unsigned));
+    HBD_CUDA_CHECK(cudaHostAlloc((void**)&h_tail_pin, 2 * sizeof(unsigned), cudaHostAllocDefault));
     call_chars.resize(n);
     HBD_CUDA_CHECK(dalloc(&d_taps1, 512));
     HBD_CUDA_CHECK(dalloc(&d_taps2, 512));
@@ -340,15 +439,17 @@ void hbd_decoder::free_all()
     if (stream) cudaStreamSynchronize(stream);
     if (hi) cudaStreamDestroy(hi);
     if (lo) cudaStreamDestroy(lo);
-    for (cudaEvent_t e : ev_consumed) cudaEventDestroy(e);
-    for (cudaEvent_t e : ev_tail) cudaEventDestroy(e);
+    if (ev_consumed) cudaEventDestroy(ev_consumed);
+    for (cudaEvent_t e : ev_tail) if (e) cudaEventDestroy(e);
     if (ev_in) cudaEventDestroy(ev_in);
-    void* ptrs[] = {d_state, d_plan, d_carry2[0], d_carry2[1], d_s1x[0], d_s1x[1], d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_log, d_log_head,
+    void* ptrs[] = {d_state, d_plan, d_carry2[0], d_carry2[1], d_s1x[0], d_s1x[1], d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_uart_runs, d_log, d_log_ctl,
                     d_taps1, d_taps2, d_twiddle, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps,
                     d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage, d_nco, d_wide, d_dacc, d_dacc_n, d_frames, d_frame_sizes,
                     d_ssdv_ring, d_ssdv_total, d_ssdv_scanned, d_ssdv_log};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_pinned) cudaFreeHost(h_pinned);
+    if (h_heads) cudaFreeHost(h_heads);
+    if (h_tail_pin) cudaFreeHost(h_tail_pin);
     for (cudaEvent_t e : ev_call) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (cudaEvent_t e : ev_k1) cudaEventDestroy(e);
@@ -388,110 +489,190 @@ int hbd_decoder::ensure_call_capacity(size_t n_in_max)
     return HBD_OK;
 }
 
+namespace {
+// What one channel's share of a process() call amounts to on the host: the reference's buffer arithmetic
+// (Decoder.h:426-436,492-542) stepped on the channel's counters.  No CUDA calls in here; the caller applies the
+// side effects to that channel's rows -- or, in uniform mode, to the rows of every channel at once.
+struct ChanStep {
+    ChanPlan plan;
+    bool zero_carry = false;       // Decimator.h:74-79: the stage's work buffer grew -> its history is zeroed
+    bool zero_s1hist = false;
+    bool zero_lphist = false;      // FirFilter.h:141-147
+    bool taps_changed = false;     // low-pass redesigned: upload `taps`
+    size_t taps_old = 0, taps_new = 0;
+    bool frame_done = false;       // this call completes an FFT frame (K4 runs)
+    unsigned nf = 0;
+};
+} // namespace
+
+// returns HBD_OK or HBD_ERR_ARG (nothing has been changed in that case)
+static int step_channel(hbd_decoder* h, HostChan& x, unsigned pushed, ChanStep& o, std::vector<float>& taps)
+{
+    const int factor = h->factor, M1 = h->M1, T1 = h->T1, M2 = h->M2, T2 = h->T2, fft_n = h->fft_n;
+    const double fs_dec = h->fs_in / factor;
+    ChanPlan& p = o.plan;
+    p.r = x.in_r; p.n = pushed;
+    p.dec_pending = x.dec_pending; p.lp_ntaps = unsigned(x.lp_ntaps);
+    const unsigned total = x.in_r + pushed;
+    if (int(total) < factor) {            // Decoder.h:429-430
+        p.consumed = 0; p.n1 = p.n2 = 0; p.flags = 1;
+        x.in_r = total; x.pushed = 0; x.last_n2 = 0; x.last_nf = 0;
+        return HBD_OK;
+    }
+    p.consumed = total - total % unsigned(factor);
+    p.n1 = p.consumed / unsigned(M1);
+    p.n2 = p.consumed / unsigned(factor);
+    p.flags = 0;
+    // ---- everything that can fail comes first: the low-pass design (pure) --------------------------------
+    const unsigned total_dec = x.dec_pending + p.n2;
+    const bool gated = total_dec < unsigned(kLpBatch);                 // Decoder.h:494-495
+    const bool cut_off = !gated && fs_dec > 4 * 40e3;                  // Decoder.h:522-527
+    unsigned nf = 0;
+    size_t T = x.lp_ntaps;
+    bool redesign = false;
+    if (!gated && !cut_off) {
+        nf = total_dec - total_dec % unsigned(kLpBatch);
+        const bool dirty = x.lp_dirty || x.lp_input_size != nf;
+        if (dirty) {                                                   // Decoder.h:536-538
+            T = design_lowpass(float(x.lp_bw / fs_dec), x.lp_trans, nf, x.lp_ntaps, taps);
+            if (T > size_t(kLpMaxTaps)) { h->set_error("low-pass needs more than kLpMaxTaps (1025) taps: raise lowpass_trans"); return HBD_ERR_ARG; }
+            redesign = T != x.lp_ntaps;
+        }
+    }
+    // ---- commit ----------------------------------------------------------------------------------------------
+    x.in_r = total - p.consumed;
+    x.pushed = 0;
+    x.last_n2 = p.n2; x.last_nf = 0;
+    if (p.n2 && x.fft_have < unsigned(fft_n)) {   // FFT frame assembly, Decoder.h:467-473 (mirror of K2's arithmetic)
+        x.fft_have += std::min(unsigned(fft_n) - x.fft_have, p.n2);
+        if (x.fft_have >= unsigned(fft_n)) { o.frame_done = true; x.fft_have = 0; }   // transformed and cleared in this call
+    }
+    if (M1 > 1) {   // history re-zeroing when the reference's work buffers grow (Decimator.h:74-79)
+        const size_t need = size_t(p.consumed) + size_t(T1) + size_t(M1);
+        if (x.grown1 < need) { x.grown1 = need; o.zero_carry = true; }
+    }
+    if (M2 > 1) {
+        const size_t need = size_t(p.n1) + size_t(T2) + size_t(M2);
+        if (x.grown2 < need) { x.grown2 = need; o.zero_s1hist = true; }
+    }
+    if (gated) { x.dec_pending = total_dec; return HBD_OK; }
+    if (cut_off) { x.dec_pending = 0; return HBD_OK; }
+    x.dec_pending = total_dec - nf;
+    x.last_nf = nf; x.demod_n = nf; o.nf = nf;
+    x.lp_input_size = nf; x.lp_dirty = false;
+    if (redesign) {
+        o.taps_changed = true; o.taps_old = x.lp_ntaps; o.taps_new = T;
+        x.lp_ntaps = T; x.cfg_dirty = true; h->cfg_dirty_any = true; h->derived_dirty = true;
+    }
+    p.lp_ntaps = unsigned(x.lp_ntaps);
+    const size_t need = size_t(nf) + x.lp_ntaps;
+    if (x.grown_lp < need) { x.grown_lp = need; o.zero_lphist = true; }   // FirFilter.h:141-147
+    return HBD_OK;
+}
+
+// Keep the character / SSDV logs from filling up: look at what the completed calls have appended (their committed
+// heads sit in pinned host memory, so this costs an event query, not a copy) and drain early when the calls still in
+// flight could exhaust the space that is left.
+int hbd_decoder::log_pressure()
+{
+    while (done_seq != call_seq && cudaEventQuery(ev_call[done_seq % ev_call.size()]) == cudaSuccess) {
+        const unsigned head = h_heads[size_t(done_seq % ev_call.size()) * kCtlWords + kCtlCharHead];
+        per_call_max = std::max(per_call_max, head - done_head);
+        done_head = head;
+        ++done_seq;
+    }
+    const unsigned in_flight = call_seq - done_seq + 1u;     // the call about to be enqueued included
+    const unsigned long long worst = (unsigned long long)(done_head - log_tail) + 2ull * in_flight * std::max(per_call_max, unsigned(n_ch));
+    bool drain = worst > log_cap;
+    if (ssdv_on && done_seq) {
+        const unsigned sh = h_heads[size_t((done_seq - 1u) % ev_call.size()) * kCtlWords + kCtlSsdvHead];
+        if (sh - ssdv_log_tail > kSsdvLogCap / 2u) drain = true;
+    }
+    if (call_seq - calls_collected >= ev_call.size() / 2u) drain = true;   // event / head slots are about to be reused
+    if (!drain || call_seq == calls_collected) return HBD_OK;
+    return collect_locked(call_seq - calls_collected > 2u ? 1u : 0u);
+}
+
 int hbd_decoder::process_async_locked()
 {
     if (!fs_in) return HBD_OK; // Decoder.h:418-419: uninitialised -> silently nothing
     HBD_CUDA_CHECK(cudaSetDevice(device));
-    if (call_seq - calls_collected >= kMaxCallsBetweenCollects) { const int rc = collect_locked(0); if (rc) return rc; }
+    { const int rc = log_pressure(); if (rc) return rc; }
     const size_t n = size_t(n_ch);
     const double fs_dec = fs_in / factor;
-
-    // ---- plan: the reference's buffer arithmetic, per channel ------------------------------------------
-    h_plan.resize(n);
-    size_t max_total = 0; unsigned max_n1 = 0;
-    bool any_work = false;
-    for (size_t c = 0; c < n; ++c) {
-        HostChan& x = hc[c];
-        const unsigned pushed = ext ? unsigned(ext_n) : x.pushed;
-        ChanPlan& p = h_plan[c];
-        p.r = x.in_r; p.n = pushed;
-        const unsigned total = x.in_r + pushed;
-        max_total = std::max<size_t>(max_total, total);
-        if (int(total) < factor) { p.consumed = 0; p.n1 = p.n2 = 0; p.flags = 1; }
-        else {
-            p.consumed = total - total % unsigned(factor);
-            p.n1 = p.consumed / unsigned(M1);
-            p.n2 = p.consumed / unsigned(factor);
-            p.flags = 0;
-            any_work = true;
-        }
-        max_n1 = std::max(max_n1, p.n1);
-    }
-    if (max_total > cap_n_in || !d_s1x[0]) { // buffers are about to be reallocated: nothing may be in flight
-        if (sync_groups()) return HBD_ERR_CUDA;
-    }
-    { const int rc = ensure_call_capacity(max_total); if (rc) return rc; }
-    if (demod_acc_on) { const int rc = ensure_dacc(); if (rc) return rc; }
-    bool groups_idle = false; // set once we had to wait for the group streams (rare host-side state changes)
+    bool groups_idle = false; // set once we had to wait for the compute streams (rare host-side state changes)
     auto quiesce = [&]() -> int { if (!groups_idle) { if (sync_groups()) return HBD_ERR_CUDA; groups_idle = true; } return HBD_OK; };
 
-    bool cfg_dirty_any = false;
-    bool need_k4 = false;    // some channel completes an FFT frame in this call
-    unsigned max_nf = 0;
+    // ---- plan ------------------------------------------------------------------------------------------------
+    // uniform mode (whole-batch pushes only, one low-pass setting): channel 0 stands for all of them, O(1) per call
+    const bool uni = ctr_uniform && lp_cfg_uniform;
+    if (!uni) sync_ctrs();
+    size_t max_total = 0; unsigned max_n1 = 0, max_nf = 0;
+    bool any_work = false, need_k4 = false;
     std::vector<float> new_taps;
-    for (size_t c = 0; c < n; ++c) {
-        HostChan& x = hc[c];
-        const ChanPlan& p = h_plan[c];
-        ChanPlan& pw = h_plan[c];
-        pw.dec_pending = x.dec_pending; pw.lp_ntaps = unsigned(x.lp_ntaps);
-        x.in_r = p.r + p.n - p.consumed;
-        x.pushed = 0;
-        x.last_n2 = p.n2; x.last_nf = 0;
-        if (p.flags & 1u) { cfg_dirty_any |= x.cfg_dirty; continue; }
-        if (p.n2 && x.fft_have < unsigned(fft_n)) {   // FFT frame assembly, Decoder.h:467-473 (mirror of K2's arithmetic)
-            x.fft_have += std::min(unsigned(fft_n) - x.fft_have, p.n2);
-            if (x.fft_have >= unsigned(fft_n)) { need_k4 = true; x.fft_have = 0; }   // transformed and cleared in this call
-        }
-        // history re-zeroing when the reference's work buffers grow (Decimator.h:74-79)
-        if (M1 > 1) {
-            const size_t need = size_t(p.consumed) + size_t(T1) + size_t(M1);
-            if (x.grown1 < need) {
-                x.grown1 = need;
-                if (quiesce()) return HBD_ERR_CUDA;
-                HBD_CUDA_CHECK(cudaMemsetAsync(d_carry2[carry_cur] + c * kCarryCap + (kCarryCap - (T1 - 1) - p.r), 0, sizeof(float2) * size_t(T1 - 1), stream));
-            }
-        }
-        if (M2 > 1) {
-            const size_t need = size_t(p.n1) + size_t(T2) + size_t(M2);
-            if (x.grown2 < need) {
-                x.grown2 = need;
-                if (quiesce()) return HBD_ERR_CUDA;
-                HBD_CUDA_CHECK(cudaMemsetAsync(d_s1x[s1_cur] + c * s1_pitch, 0, sizeof(float2) * kS1Hist, stream));
-            }
-        }
-        const unsigned total_dec = x.dec_pending + p.n2;
-        if (total_dec < unsigned(kLpBatch)) { x.dec_pending = total_dec; cfg_dirty_any |= x.cfg_dirty; continue; }
-        if (fs_dec > 4 * 40e3) { x.dec_pending = 0; cfg_dirty_any |= x.cfg_dirty; continue; }
-        const unsigned nf = total_dec - total_dec % unsigned(kLpBatch);
-        x.dec_pending = total_dec - nf;
-        x.last_nf = nf;
-        x.demod_n = nf;
-        // low-pass design, Decoder.h:536-538
-        if (x.lp_input_size != nf) { x.lp_input_size = nf; x.lp_dirty = true; }
-        const size_t T = x.lp_dirty ? design_lowpass(float(x.lp_bw / fs_dec), x.lp_trans, x.lp_input_size, x.lp_ntaps, new_taps) : x.lp_ntaps;
-        x.lp_dirty = false;
-        if (T != x.lp_ntaps) {
-            if (T > size_t(kLpMaxTaps)) { set_error("low-pass needs more than kLpMaxTaps taps"); return HBD_ERR_ARG; }
-            const size_t T_old = x.lp_ntaps;
-            x.lp_ntaps = T;
-            x.cfg_dirty = true;
+    ChanPlan uplan{};
+    if (uni) {
+        ChanStep st;
+        const unsigned pushed = ext ? unsigned(ext_n) : hc[0].pushed;
+        max_total = size_t(hc[0].in_r) + pushed;
+        if (max_total > cap_n_in || !d_s1x[0]) { if (quiesce()) return HBD_ERR_CUDA; }   // buffers are about to be reallocated
+        { const int rc = ensure_call_capacity(max_total); if (rc) return rc; }
+        const int rc = step_channel(this, hc[0], pushed, st, new_taps);
+        if (rc) return rc;   // nothing has been stepped
+        ctr_stale = true;
+        uplan = st.plan;
+        any_work = !(st.plan.flags & 1u); need_k4 = st.frame_done; max_n1 = st.plan.n1; max_nf = st.nf;
+        if (st.zero_carry || st.zero_s1hist || st.zero_lphist || st.taps_changed) {
             if (quiesce()) return HBD_ERR_CUDA;
-            if (T_old > T && d_decq) HBD_CUDA_CHECK(launch_lp_hist_shrink(d_decq + c * dq_pitch, int(T_old), int(T), stream));
-            HBD_CUDA_CHECK(cudaMemcpyAsync(d_lptaps + c * kLpMaxTaps, new_taps.data(), 4 * T, cudaMemcpyHostToDevice, stream));
-            HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // new_taps is reused
+            if (st.zero_carry)
+                HBD_CUDA_CHECK(cudaMemset2DAsync(d_carry2[carry_cur] + (kCarryCap - (T1 - 1) - st.plan.r), kCarryCap * sizeof(float2), 0,
+                                                 sizeof(float2) * size_t(T1 - 1), n, stream));
+            if (st.zero_s1hist) HBD_CUDA_CHECK(cudaMemset2DAsync(d_s1x[s1_cur], s1_pitch * sizeof(float2), 0, sizeof(float2) * kS1Hist, n, stream));
+            if (st.taps_changed) {
+                if (st.taps_old > st.taps_new && d_decq) HBD_CUDA_CHECK(launch_lp_hist_shrink(d_decq, dq_pitch, n_ch, int(st.taps_old), int(st.taps_new), stream));
+                std::vector<float> all(n * st.taps_new);
+                for (size_t c = 0; c < n; ++c) memcpy(all.data() + c * st.taps_new, new_taps.data(), 4 * st.taps_new);
+                HBD_CUDA_CHECK(cudaMemcpy2DAsync(d_lptaps, kLpMaxTaps * sizeof(float), all.data(), st.taps_new * sizeof(float), st.taps_new * sizeof(float), n,
+                                                 cudaMemcpyHostToDevice, stream));
+                HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // `all` goes out of scope
+                for (size_t c = 1; c < n; ++c) hc[c].cfg_dirty = true;   // lp_ntaps travels with the configuration upload
+            }
+            if (st.zero_lphist) HBD_CUDA_CHECK(cudaMemset2DAsync(d_decq, dq_pitch * sizeof(float2), 0, sizeof(float2) * kLpHist, n, stream));
         }
-        pw.lp_ntaps = unsigned(x.lp_ntaps);
-        max_nf = std::max(max_nf, nf);
-        const size_t need = size_t(nf) + x.lp_ntaps;
-        if (x.grown_lp < need) { // FirFilter.h:141-147
-            x.grown_lp = need;
+    } else {
+        h_plan.resize(n);
+        for (size_t c = 0; c < n; ++c) max_total = std::max<size_t>(max_total, size_t(hc[c].in_r) + (ext ? unsigned(ext_n) : hc[c].pushed));
+        if (max_total > cap_n_in || !d_s1x[0]) { if (quiesce()) return HBD_ERR_CUDA; }
+        { const int rc = ensure_call_capacity(max_total); if (rc) return rc; }
+        for (size_t c = 0; c < n; ++c) {
+            HostChan& x = hc[c];
+            ChanStep st;
+            const int rc = step_channel(this, x, ext ? unsigned(ext_n) : x.pushed, st, new_taps);
+            if (rc) return rc;   // channels below c have been stepped: their samples are gone (documented in the header)
+            h_plan[c] = st.plan;
+            any_work |= !(st.plan.flags & 1u); need_k4 |= st.frame_done;
+            max_n1 = std::max(max_n1, st.plan.n1); max_nf = std::max(max_nf, st.nf);
+            if (!(st.zero_carry || st.zero_s1hist || st.zero_lphist || st.taps_changed)) continue;
             if (quiesce()) return HBD_ERR_CUDA;
-            HBD_CUDA_CHECK(cudaMemsetAsync(d_decq + c * dq_pitch, 0, sizeof(float2) * kLpHist, stream));
+            if (st.zero_carry) HBD_CUDA_CHECK(cudaMemsetAsync(d_carry2[carry_cur] + c * kCarryCap + (kCarryCap - (T1 - 1) - st.plan.r), 0, sizeof(float2) * size_t(T1 - 1), stream));
+            if (st.zero_s1hist) HBD_CUDA_CHECK(cudaMemsetAsync(d_s1x[s1_cur] + c * s1_pitch, 0, sizeof(float2) * kS1Hist, stream));
+            if (st.taps_changed) {
+                if (st.taps_old > st.taps_new && d_decq) HBD_CUDA_CHECK(launch_lp_hist_shrink(d_decq + c * dq_pitch, dq_pitch, 1, int(st.taps_old), int(st.taps_new), stream));
+                HBD_CUDA_CHECK(cudaMemcpyAsync(d_lptaps + c * kLpMaxTaps, new_taps.data(), 4 * st.taps_new, cudaMemcpyHostToDevice, stream));
+                HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // new_taps is reused
+            }
+            if (st.zero_lphist) HBD_CUDA_CHECK(cudaMemsetAsync(d_decq + c * dq_pitch, 0, sizeof(float2) * kLpHist, stream));
         }
-        cfg_dirty_any |= x.cfg_dirty;
+        // back to uniform mode as soon as the channels agree again (e.g. after a round of per-channel pushes of one size)
+        bool same = true;
+        for (size_t c = 1; c < n && same; ++c) same = hc[c].same(hc[0]);
+        ctr_uniform = same;
     }
+    if (demod_acc_on) { const int rc = ensure_dacc(); if (rc) return rc; }
+
     if (cfg_dirty_any) {
         if (quiesce()) return HBD_ERR_CUDA;
+        sync_ctrs();
         std::vector<double> b(n); std::vector<float> s(n); std::vector<int> bi(n), dc(n), nt(n); std::vector<unsigned char> d(n);
         for (size_t c = 0; c < n; ++c) {
             b[c] = hc[c].baud; s[c] = hc[c].rtty_stops; bi[c] = int(hc[c].rtty_bits); dc[c] = hc[c].dc_remove; nt[c] = int(hc[c].lp_ntaps);
@@ -506,95 +687,104 @@ int hbd_decoder::process_async_locked()
         init_cfg_kernel<<<(n_ch + 127) / 128, 128, 0, stream>>>(d_state, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps, d_cfg_dirty, n_ch);
         ++launches;
         HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // host vectors go out of scope
+        cfg_dirty_any = false;
     }
-    if (h_plan_uploaded.size() != n || memcmp(h_plan.data(), h_plan_uploaded.data(), n * sizeof(ChanPlan)) != 0) {
-        if (quiesce()) return HBD_ERR_CUDA;
-        HBD_CUDA_CHECK(cudaMemcpyAsync(d_plan, h_plan.data(), n * sizeof(ChanPlan), cudaMemcpyHostToDevice, stream));
-        HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
-        h_plan_uploaded = h_plan;
+    bool plan_uniform = uni;
+    if (!uni) {
+        plan_uniform = true;
+        for (size_t c = 1; c < n && plan_uniform; ++c) plan_uniform = memcmp(&h_plan[c], &h_plan[0], sizeof(ChanPlan)) == 0;
+        uplan = h_plan[0];
+        if (!plan_uniform && (h_plan_uploaded.size() != n || memcmp(h_plan.data(), h_plan_uploaded.data(), n * sizeof(ChanPlan)) != 0)) {
+            if (quiesce()) return HBD_ERR_CUDA;
+            HBD_CUDA_CHECK(cudaMemcpyAsync(d_plan, h_plan.data(), n * sizeof(ChanPlan), cudaMemcpyHostToDevice, stream));
+            HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
+            h_plan_uploaded = h_plan;
+        }
     }
 
     // what the tail kernel stages in shared memory: sized from host-side knowledge of all channels
-    bool plan_uniform = true;
-    size_t max_lp_taps = 1;
-    double max_spb = 1;
-    for (size_t c = 0; c < n; ++c) {
-        if (plan_uniform && c && memcmp(&h_plan[c], &h_plan[0], sizeof(ChanPlan)) != 0) plan_uniform = false;
-        max_lp_taps = std::max(max_lp_taps, hc[c].lp_ntaps);
-        if (hc[c].baud > 0) max_spb = std::max(max_spb, fs_dec / hc[c].baud);
+    if (derived_dirty) {
+        sync_ctrs();
+        max_lp_taps_c = 1; max_spb_c = 1;
+        for (size_t c = 0; c < n; ++c) {
+            max_lp_taps_c = std::max(max_lp_taps_c, hc[c].lp_ntaps);
+            if (hc[c].baud > 0) max_spb_c = std::max(max_spb_c, fs_dec / hc[c].baud);
+        }
+        derived_dirty = false;
     }
     // a channel normally holds < ~12 symbols of pending samples after a slicer pass (plus this call's batch)
-    int sv_want = int(std::min<double>(6144.0, 16.0 * max_spb + double(max_nf) + 64.0));
+    int sv_want = int(std::min<double>(6144.0, 16.0 * max_spb_c + double(max_nf) + 64.0));
     if (sv_override >= 0) sv_want = sv_override;   // test hook (HBD_SV_WANT): 0 forces the slicer's HBM path
 
     const float2* chunk = ext ? ext : d_stage;
     const size_t chunk_pitch = ext ? ext_pitch : stage_pitch;
     int nl = 0;
-    // everything the caller (and the host-side updates above) put on `stream` happens before the groups start
+    // everything the caller (and the host-side updates above) put on `stream` happens before the kernels start
     HBD_CUDA_CHECK(cudaEventRecord(ev_in, stream));
     HBD_CUDA_CHECK(cudaStreamWaitEvent(hi, ev_in, 0));
-    for (int g = 0; g < n_groups; ++g) {
-        const int c0 = int((long long)n_ch * g / n_groups), c1 = int((long long)n_ch * (g + 1) / n_groups);
-        const int nc = c1 - c0;
-        bool tail_recorded = false;
-        // K1 of this group overwrites the group's stage-1 buffer: the previous call's tail must be done with it
-        if (tail_pending[size_t(2 * g + s1_cur)]) HBD_CUDA_CHECK(cudaStreamWaitEvent(hi, ev_tail[size_t(2 * g + s1_cur)], 0));
-        {   // K1 also writes the next call's carry (even when no channel has a full decimation block yet)
-            DecimArgs da{};
-            da.chunk = chunk; da.chunk_pitch = chunk_pitch; da.carry = d_carry2[carry_cur]; da.carry_next = d_carry2[carry_cur ^ 1];
-            da.s1 = d_s1x[s1_cur]; da.s1_pitch = s1_pitch; da.s1_hist = kS1Hist;
-            da.plan = d_plan; da.taps = d_taps1; da.ch0 = c0; da.n_channels = nc;
-            da.nco = ext_nco ? ext_nco_ptr : nullptr;
-            if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), hi));
-            HBD_CUDA_CHECK(launch_decim1(da, M1, T1, max_n1, n_sms, hi, &nl));
-            if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), hi));
-        }
-        HBD_CUDA_CHECK(cudaEventRecord(ev_consumed[size_t(g)], hi)); // input no longer needed by this group; stage-1 output ready
-        HBD_CUDA_CHECK(cudaStreamWaitEvent(lo, ev_consumed[size_t(g)], 0));
-        if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
-        if (any_work) {
-            TailArgs ta{};
-            ta.plan = d_plan; ta.uplan = h_plan[0]; ta.uniform = plan_uniform ? 1 : 0; ta.state = d_state; ta.ch0 = c0;
-            ta.s1 = d_s1x[s1_cur]; ta.s1_next = d_s1x[s1_cur ^ 1]; ta.s1_pitch = s1_pitch; ta.taps2 = d_taps2; ta.M2 = M2; ta.T2 = T2;
-            ta.decq = d_decq; ta.dq_pitch = dq_pitch; ta.fs_dec = fs_dec; ta.fftbuf = d_fftbuf; ta.fft_n = fft_n; ta.lptaps = d_lptaps;
-            ta.max_lp_taps = int(max_lp_taps);
-            ta.slicer = d_slicer; ta.slicer_pitch = slicer_pitch; ta.sv_want = sv_want;
-            ta.log = d_log; ta.log_head = d_log_head; ta.call_seq = call_seq & 0xffffffu;
-            ta.ssdv_ring = ssdv_on ? d_ssdv_ring : nullptr; ta.ssdv_total = d_ssdv_total;
-            ta.demod_last = d_demod; ta.demod_pitch = demod_pitch;
-            ta.rec_decimated = record ? d_rec_dec : nullptr; ta.rec_filtered = record ? d_rec_filt : nullptr; ta.rec_pitch = rec_pitch;
-            ta.rec_bits = record ? d_rec_bits : nullptr; ta.rec_bits_n = d_rec_bits_n; ta.rec_bits_pitch = rec_bits_pitch;
-            HBD_CUDA_CHECK(launch_tail(ta, nc, lo, &nl));
-            // only the tail kernel reads the stage-1 buffer: K1 of the call after next may overwrite it as soon as the
-            // tail is done, without waiting for the FFT / SSDV / demod kernels behind it on this stream
-            if (!tail_ev_late) { HBD_CUDA_CHECK(cudaEventRecord(ev_tail[size_t(2 * g + s1_cur)], lo)); tail_recorded = true; }
-            FftArgs fa{};
-            fa.state = d_state; fa.fftbuf = d_fftbuf; fa.spectrum = d_spectrum; fa.power = d_power; fa.twiddle = d_twiddle; fa.fs_dec = fs_dec;
-            fa.ch0 = c0; fa.fft_n = fft_n;
-            if (need_k4) HBD_CUDA_CHECK(launch_fft_afc(fa, nc, lo, &nl));   // other calls: K2 has stepped the AFC itself
-            if (ssdv_on) {   // test every 0x55-started window the new characters completed
-                SsdvScanArgs sa{};
-                sa.ring = d_ssdv_ring; sa.total = d_ssdv_total; sa.scanned = d_ssdv_scanned; sa.log = d_ssdv_log;
-                sa.log_head = d_log_head + 1; sa.overflow = d_log_head + 2; sa.call_seq = call_seq & 0xffffffu; sa.ch0 = c0;
-                HBD_CUDA_CHECK(launch_ssdv_scan(sa, nc, lo, &nl));
-            }
-        }
-        if (demod_acc_on && d_demod) { // main.cpp:267-282 runs after EVERY process(), also when nothing new was demodulated
-            DemodAccArgs aa{};
-            aa.state = d_state; aa.demod = d_demod; aa.demod_pitch = demod_pitch; aa.acc = d_dacc; aa.acc_pitch = dacc_pitch; aa.acc_n = d_dacc_n;
-            aa.fs_dec = fs_dec; aa.ch0 = c0;
-            HBD_CUDA_CHECK(launch_demod_accumulate(aa, nc, lo, &nl));
-        }
-        if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
-        if (!tail_recorded) HBD_CUDA_CHECK(cudaEventRecord(ev_tail[size_t(2 * g + s1_cur)], lo));
-        tail_pending[size_t(2 * g + s1_cur)] = 1;
+    bool tail_recorded = false;
+    // K1 overwrites the stage-1 buffer: the tail of the call before the previous one must be done with it
+    if (tail_pending[s1_cur]) HBD_CUDA_CHECK(cudaStreamWaitEvent(hi, ev_tail[s1_cur], 0));
+    {   // K1 also writes the next call's carry (even when no channel has a full decimation block yet)
+        DecimArgs da{};
+        da.chunk = chunk; da.chunk_pitch = chunk_pitch; da.carry = d_carry2[carry_cur]; da.carry_next = d_carry2[carry_cur ^ 1];
+        da.s1 = d_s1x[s1_cur]; da.s1_pitch = s1_pitch; da.s1_hist = kS1Hist;
+        da.plan = d_plan; da.uplan = uplan; da.uniform = plan_uniform ? 1 : 0; da.taps = d_taps1; da.ch0 = 0; da.n_channels = n_ch;
+        da.nco = ext_nco ? ext_nco_ptr : nullptr;
+        if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), hi));
+        HBD_CUDA_CHECK(launch_decim1(da, M1, T1, max_n1, n_sms, hi, &nl));
+        if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_k1, ev_used_k1), hi));
     }
-    // the caller's stream resumes once every group has consumed the input (it does not wait for the tail kernels)
-    for (int g = 0; g < n_groups; ++g) HBD_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_consumed[size_t(g)], 0));
+    HBD_CUDA_CHECK(cudaEventRecord(ev_consumed, hi)); // input no longer needed; stage-1 output ready
+    HBD_CUDA_CHECK(cudaStreamWaitEvent(lo, ev_consumed, 0));
+    if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
+    if (any_work) {
+        TailArgs ta{};
+        ta.plan = d_plan; ta.uplan = uplan; ta.uniform = plan_uniform ? 1 : 0; ta.state = d_state; ta.ch0 = 0;
+        ta.s1 = d_s1x[s1_cur]; ta.s1_next = d_s1x[s1_cur ^ 1]; ta.s1_pitch = s1_pitch; ta.taps2 = d_taps2; ta.M2 = M2; ta.T2 = T2;
+        ta.decq = d_decq; ta.dq_pitch = dq_pitch; ta.fs_dec = fs_dec; ta.fftbuf = d_fftbuf; ta.fft_n = fft_n; ta.lptaps = d_lptaps;
+        ta.max_lp_taps = int(max_lp_taps_c);
+        ta.slicer = d_slicer; ta.slicer_pitch = slicer_pitch; ta.sv_want = sv_want;
+        ta.log = d_log; ta.log_ctl = d_log_ctl; ta.log_mask = log_cap - 1u; ta.call_seq = call_seq & 0xffffffu;
+        ta.uart_runs = d_uart_runs;
+        ta.ssdv_ring = ssdv_on ? d_ssdv_ring : nullptr; ta.ssdv_total = d_ssdv_total;
+        ta.demod_last = d_demod; ta.demod_pitch = demod_pitch;
+        ta.rec_decimated = record ? d_rec_dec : nullptr; ta.rec_filtered = record ? d_rec_filt : nullptr; ta.rec_pitch = rec_pitch;
+        ta.rec_bits = record ? d_rec_bits : nullptr; ta.rec_bits_n = d_rec_bits_n; ta.rec_bits_pitch = rec_bits_pitch;
+        HBD_CUDA_CHECK(launch_tail(ta, n_ch, lo, &nl));
+        // only the tail kernel reads the stage-1 buffer: K1 of the call after next may overwrite it as soon as the
+        // tail is done, without waiting for the FFT / SSDV / demod kernels behind it on this stream
+        if (!tail_ev_late) { HBD_CUDA_CHECK(cudaEventRecord(ev_tail[s1_cur], lo)); tail_recorded = true; }
+        FftArgs fa{};
+        fa.state = d_state; fa.fftbuf = d_fftbuf; fa.spectrum = d_spectrum; fa.power = d_power; fa.twiddle = d_twiddle; fa.fs_dec = fs_dec;
+        fa.ch0 = 0; fa.fft_n = fft_n;
+        if (need_k4) HBD_CUDA_CHECK(launch_fft_afc(fa, n_ch, lo, &nl));   // other calls: K2 has stepped the AFC itself
+        if (ssdv_on) {   // test every 0x55-started window the new characters completed
+            SsdvScanArgs sa{};
+            sa.ring = d_ssdv_ring; sa.total = d_ssdv_total; sa.scanned = d_ssdv_scanned; sa.log = d_ssdv_log;
+            sa.ctl = d_log_ctl; sa.call_seq = call_seq & 0xffffffu; sa.ch0 = 0;
+            HBD_CUDA_CHECK(launch_ssdv_scan(sa, n_ch, lo, &nl));
+        }
+    }
+    if (demod_acc_on && d_demod) { // main.cpp:267-282 runs after EVERY process(), also when nothing new was demodulated
+        DemodAccArgs aa{};
+        aa.state = d_state; aa.demod = d_demod; aa.demod_pitch = demod_pitch; aa.acc = d_dacc; aa.acc_pitch = dacc_pitch; aa.acc_n = d_dacc_n;
+        aa.fs_dec = fs_dec; aa.ch0 = 0;
+        HBD_CUDA_CHECK(launch_demod_accumulate(aa, n_ch, lo, &nl));
+    }
+    if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
+    if (!tail_recorded) HBD_CUDA_CHECK(cudaEventRecord(ev_tail[s1_cur], lo));
+    tail_pending[s1_cur] = true;
+    // the caller's stream resumes once the input has been consumed (it does not wait for the tail kernels)
+    HBD_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_consumed, 0));
     carry_cur ^= 1;
     if (any_work) s1_cur ^= 1; // the tail (which moves the stage-2 history to the other buffer) ran
     launches += unsigned(nl);
-    HBD_CUDA_CHECK(cudaEventRecord(ev_call[call_seq % ev_call.size()], lo)); // everything of this call is done
+    // commit: the log control words as they stand after this call, into the call's pinned slot (stream order: every
+    // entry below these heads is completely written when ev_call fires)
+    const size_t slot = call_seq % ev_call.size();
+    HBD_CUDA_CHECK(cudaMemcpyAsync(h_heads + slot * kCtlWords, d_log_ctl, kCtlWords * sizeof(unsigned), cudaMemcpyDeviceToHost, lo));
+    HBD_CUDA_CHECK(cudaEventRecord(ev_call[slot], lo)); // everything of this call is done
     ++call_seq;
     ++pending_marks;
     ext = nullptr; ext_n = 0; ext_nco = false;
@@ -603,7 +793,7 @@ int hbd_decoder::process_async_locked()
 
 // Drain decoded characters of all calls up to (last enqueued - lag) and run the sentence layer on them, call by
 // call like Decoder::process().  lag == 0 waits for everything; lag > 0 leaves the newest calls in flight so the GPU
-// keeps working while the host is busy here.
+// keeps working while the host is busy here.  User callbacks are only RECORDED here (h->deferred).
 int hbd_decoder::collect_locked(unsigned lag)
 {
     HBD_CUDA_CHECK(cudaSetDevice(device));
@@ -615,8 +805,10 @@ int hbd_decoder::collect_locked(unsigned lag)
     if (lag == 0 && call_seq - calls_collected > 2) {
         // a full drain behind a queue of calls: take the finished calls first, in halving steps, so the host's sentence
         // layer works while the GPU is still busy with the newest calls instead of after it has gone idle
-        for (unsigned l = (call_seq - calls_collected) / 2; l >= 1; l /= 2) { const int rc = collect_locked(l); if (rc) return rc; }
-        if (call_seq == calls_collected) return collect_locked(0);
+        int first_rc = HBD_OK;
+        for (unsigned l = (call_seq - calls_collected) / 2; l >= 1; l /= 2) { const int rc = collect_locked(l); if (rc == HBD_ERR_CUDA) return rc; if (rc && !first_rc) first_rc = rc; }
+        const int rc = collect_locked(0);
+        return rc ? rc : first_rc;
     }
     const unsigned upto = call_seq - lag;            // calls [calls_collected, upto) get drained
     if (lag == 0) {
@@ -625,17 +817,27 @@ int hbd_decoder::collect_locked(unsigned lag)
     } else {
         HBD_CUDA_CHECK(cudaEventSynchronize(ev_call[(upto - 1) % ev_call.size()]));
     }
-    unsigned heads[3] = {0, 0, 0};
-    HBD_CUDA_CHECK(cudaMemcpyAsync(heads, d_log_head, sizeof(heads), cudaMemcpyDeviceToHost, copy_stream));
-    HBD_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
-    const unsigned head = heads[0];
+    // the COMMITTED control words of call upto-1 (never the live head: newer calls may be appending right now)
+    unsigned heads[kCtlWords];
+    memcpy(heads, h_heads + size_t((upto - 1) % ev_call.size()) * kCtlWords, sizeof(heads));
+    const unsigned head = heads[kCtlCharHead];
     const unsigned upto24 = upto & 0xffffffu;
+    int result = HBD_OK;
     if (ssdv_on) {
         // accepted SSDV packets of the calls being drained go to their channels first: the buffer automaton below
         // looks a window's verdict up when it reaches it, which is never before the call that completed the window
-        if (heads[2]) { set_error("SSDV character ring overflow: more than 3840 characters in one call, push smaller chunks"); return HBD_ERR_STATE; }
-        const unsigned avail_p = heads[1] - ssdv_log_tail;
-        if (avail_p > kSsdvLogCap) { set_error("SSDV packet log overflow: collect more often"); return HBD_ERR_STATE; }
+        // the overflow words are monotonic counters: a change since the previous drain is reported once, decoding goes on
+        if (heads[kCtlSsdvRingOvf] != ovf_seen[0]) {
+            ovf_seen[0] = heads[kCtlSsdvRingOvf];
+            set_error("SSDV character ring overflow: more than 3840 characters in one call (windows lost); push smaller chunks");
+            result = HBD_ERR_STATE;
+        }
+        if (heads[kCtlSsdvOvf] != ovf_seen[1]) {
+            set_error("SSDV packet log overflow: " + std::to_string(heads[kCtlSsdvOvf] - ovf_seen[1]) + " packet(s) lost; collect more often");
+            ovf_seen[1] = heads[kCtlSsdvOvf];
+            result = HBD_ERR_STATE;
+        }
+        const unsigned avail_p = std::min(heads[kCtlSsdvHead] - ssdv_log_tail, kSsdvLogCap);
         h_ssdv_log.resize(avail_p);
         if (avail_p) {
             const unsigned i0 = ssdv_log_tail & (kSsdvLogCap - 1u);
@@ -645,42 +847,52 @@ int hbd_decoder::collect_locked(unsigned lag)
                 HBD_CUDA_CHECK(cudaMemcpyAsync(h_ssdv_log.data() + first, d_ssdv_log, size_t(avail_p - first) * sizeof(SsdvLogEntry), cudaMemcpyDeviceToHost, copy_stream));
             HBD_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
         }
-        unsigned used = 0;
-        for (; used < avail_p; ++used) {
-            const SsdvLogEntry& e = h_ssdv_log[used];
-            if (((upto24 - e.seq - 1u) & 0xffffffu) >= 0x800000u) break;   // a call still in flight
+        for (unsigned k = 0; k < avail_p; ++k) {
+            const SsdvLogEntry& e = h_ssdv_log[k];
             if (e.ch >= unsigned(n_ch)) continue;
             SsdvVerdict v; v.pos = e.pos; v.errors = e.errors; memcpy(v.data.data(), e.data, 256);
             ssdv[e.ch].verdicts.push_back(v);
         }
-        ssdv_log_tail += used;
+        ssdv_log_tail = heads[kCtlSsdvHead];
+    }
+    if (heads[kCtlCharOvf] != ovf_seen[2]) {
+        // a writer found the ring full and dropped its characters (it never overwrites unread entries).  Which slots of
+        // the range were skipped is not recorded, so the whole range is given up; decoding continues behind it.
+        ovf_seen[2] = heads[kCtlCharOvf];
+        chars_lost += head - log_tail;
+        set_error("decoded-character log overflow: " + std::to_string(head - log_tail) + " characters of calls [" + std::to_string(calls_collected) + ", " +
+                  std::to_string(upto) + ") lost; collect more often");
+        log_tail = head;
+        result = HBD_ERR_STATE;
     }
     const unsigned avail = head - log_tail;
-    if (avail > kLogCap) { set_error("decoded-character log overflow: collect more often"); return HBD_ERR_STATE; }
     h_log.resize(avail);
     if (avail) {
-        const unsigned i0 = log_tail & (kLogCap - 1u);
-        const unsigned first = std::min(avail, kLogCap - i0);
+        const unsigned i0 = log_tail & (log_cap - 1u);
+        const unsigned first = std::min(avail, log_cap - i0);
         HBD_CUDA_CHECK(cudaMemcpyAsync(h_log.data(), d_log + i0, size_t(first) * sizeof(uint2), cudaMemcpyDeviceToHost, copy_stream));
         if (avail > first)
             HBD_CUDA_CHECK(cudaMemcpyAsync(h_log.data() + first, d_log, size_t(avail - first) * sizeof(uint2), cudaMemcpyDeviceToHost, copy_stream));
         HBD_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
     }
+    // the writers may reuse everything below the new tail
+    log_tail = head;
+    h_tail_pin[0] = log_tail; h_tail_pin[1] = ssdv_log_tail;
+    HBD_CUDA_CHECK(cudaMemcpyAsync(d_log_ctl + kCtlCharTail, h_tail_pin, sizeof(unsigned), cudaMemcpyHostToDevice, copy_stream));
+    HBD_CUDA_CHECK(cudaMemcpyAsync(d_log_ctl + kCtlSsdvTail, h_tail_pin + 1, sizeof(unsigned), cudaMemcpyHostToDevice, copy_stream));
+    HBD_CUDA_CHECK(cudaStreamSynchronize(copy_stream));   // h_tail_pin is rewritten by the next drain
+
+    const bool want_sent = sentence_cb || tracker;
     SentenceSink sink;
-    if (sentence_cb || tracker) {
-        hbd_sentence_cb cb = sentence_cb; void* user = sentence_user; hbd_tracker* trk = tracker; const int off = tracker_off;
-        sink = [cb, user, trk, off](int ch, const std::string& cs, const std::string& d, const std::string& crc) {
-            if (cb) cb(user, ch, cs.c_str(), d.c_str(), crc.c_str());
-            if (trk) tracker_feed(trk, ch + off, cs, d, crc);      // SentenceCallback, websocketServer/main.cpp:292-366
+    if (want_sent)
+        sink = [this](int ch, const std::string& cs, const std::string& d, const std::string& crc) {
+            Deferred ev; ev.kind = Deferred::kSentence; ev.ch = ch; ev.a = cs; ev.b = d; ev.c = crc;
+            deferred.push_back(std::move(ev));
         };
-    }
-    std::vector<size_t> chars_before;
-    std::vector<int> cb_channels;
     // the log is sorted by call; replay call by call, channel by channel
     size_t i = 0;
     while (i < h_log.size()) {
         const unsigned seq = h_log[i].y >> 8;
-        if (((upto24 - seq - 1u) & 0xffffffu) >= 0x800000u) break; // seq >= upto: belongs to a call still in flight
         touched.clear();
         size_t j = i;
         for (; j < h_log.size() && (h_log[j].y >> 8) == seq; ++j) {
@@ -692,30 +904,30 @@ int hbd_decoder::collect_locked(unsigned lag)
         for (int ch : touched) {
             std::string& cc = call_chars[size_t(ch)];
             TextChannel& tc = text[size_t(ch)];
-            if (chars_cb) { cb_channels.push_back(ch); chars_before.push_back(tc.chars_pending.size()); }
+            const size_t before = tc.chars_pending.size();
             tc.feed(reinterpret_cast<const unsigned char*>(cc.data()), cc.size(), ch, sink);
+            if (chars_cb && tc.chars_pending.size() > before) {   // character_callback_, Decoder.h:617-629 (not paced by wall clock)
+                Deferred ev; ev.kind = Deferred::kChars; ev.ch = ch; ev.a.assign(tc.chars_pending.data() + before, tc.chars_pending.size() - before);
+                deferred.push_back(std::move(ev));
+            }
             if (ssdv_on) {   // Decoder.h:573: one SSDV_wraper_t::push per call that decoded characters
-                SsdvEvent ev;
-                if (ssdv[size_t(ch)].push(reinterpret_cast<const unsigned char*>(cc.data()), cc.size(), ev)) {
-                    ssdv[size_t(ch)].events_pending.push_back(ev);
+                SsdvEvent sev;
+                if (ssdv[size_t(ch)].push(reinterpret_cast<const unsigned char*>(cc.data()), cc.size(), sev)) {
+                    ssdv[size_t(ch)].events_pending.push_back(sev);
                     if (ssdv_cb) {   // ssdv_callback_, Decoder.h:631-632
-                        hbd_ssdv_packet_info info; fill_ssdv_info(info, ev);
-                        ssdv_cb(ssdv_user, ch, &info, ev.data.data());
+                        Deferred ev; ev.kind = Deferred::kSsdv; ev.ch = ch; fill_ssdv_info(ev.info, sev); ev.pkt = sev.data;
+                        deferred.push_back(std::move(ev));
                     }
                 }
-            }
-            if (chars_cb) {
-                const size_t before = chars_before.back();
-                if (tc.chars_pending.size() > before) chars_cb(chars_user, ch, tc.chars_pending.data() + before, tc.chars_pending.size() - before);
             }
             cc.clear();
         }
         i = j;
     }
-    log_tail += unsigned(i);
+    (void)upto24;
     calls_collected = upto;
     pending_marks = int(call_seq - calls_collected);
-    return HBD_OK;
+    return result;
 }
 
 // SSDV packet sync on / off.  Switching it on starts from an empty character stream (like a freshly constructed
@@ -736,8 +948,10 @@ int hbd_decoder::enable_ssdv(bool on)
         HBD_CUDA_CHECK(cudaMemset(d_ssdv_ring, 0, n * kSsdvRing));
         HBD_CUDA_CHECK(cudaMemset(d_ssdv_total, 0, n * sizeof(unsigned)));
         HBD_CUDA_CHECK(cudaMemset(d_ssdv_scanned, 0, n * sizeof(unsigned)));
-        HBD_CUDA_CHECK(cudaMemset(d_log_head + 1, 0, 2 * sizeof(unsigned)));
-        ssdv_log_tail = 0;
+        // the SSDV log keeps its (monotonic) head: nothing below it is of interest any more
+        ssdv_log_tail = h_heads[size_t((call_seq ? call_seq - 1u : 0u) % ev_call.size()) * kCtlWords + kCtlSsdvHead];
+        h_tail_pin[1] = ssdv_log_tail;
+        HBD_CUDA_CHECK(cudaMemcpy(d_log_ctl + kCtlSsdvTail, h_tail_pin + 1, sizeof(unsigned), cudaMemcpyHostToDevice));
         ssdv.assign(n, SsdvChannel());
     }
     ssdv_on = on;
@@ -767,23 +981,14 @@ int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
         if (const char* sv = getenv("HBD_SV_WANT")) h->sv_override = atoi(sv);
         if (const char* tl = getenv("HBD_TAIL_EV_LATE")) h->tail_ev_late = atoi(tl) != 0;
         if (const char* nf = getenv("HBD_NCO_FUSED")) h->nco_fused = atoi(nf) != 0;
-        const char* env = getenv("HBD_GROUPS");
-        // one group: with the stage-1 stream double buffered over calls, K1 of call s+1 already overlaps the tail of call s;
-        // more groups only help synchronous callers (hbd_process) that cannot pipeline calls
-        int g = env ? atoi(env) : 1;
-        g = std::max(1, std::min(g, std::min(n_channels, 8)));
-        h->n_groups = g;
-        h->ev_consumed.resize(size_t(g)); h->ev_tail.resize(size_t(2 * g)); h->tail_pending.assign(size_t(2 * g), 0);
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); // numerically lower = higher priority
         if (cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
             cudaStreamCreateWithPriority(&h->lo, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { h->free_all(); delete h; return HBD_ERR_CUDA; }
-        for (int i = 0; i < g; ++i) {
-            if (cudaEventCreateWithFlags(&h->ev_consumed[size_t(i)], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&h->ev_tail[size_t(2 * i)], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&h->ev_tail[size_t(2 * i + 1)], cudaEventDisableTiming) != cudaSuccess) { h->free_all(); delete h; return HBD_ERR_CUDA; }
-        }
-        if (cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess) { h->free_all(); delete h; return HBD_ERR_CUDA; }
+        if (cudaEventCreateWithFlags(&h->ev_consumed, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_tail[1], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess) { h->free_all(); delete h; return HBD_ERR_CUDA; }
     }
     const int rc = h->alloc_fixed();
     if (rc) { h->free_all(); delete h; return rc; }
@@ -827,6 +1032,7 @@ int hbd_set_fft_size(hbd_decoder* h, size_t n_bins)
     // spectrum / AFC state back to a freshly constructed decoder's (Average<T> starts with one 0 sample)
     std::vector<ChanState> st(size_t(h->n_ch));
     if (cudaMemcpy(st.data(), h->d_state, st.size() * sizeof(ChanState), cudaMemcpyDeviceToHost) != cudaSuccess) return HBD_ERR_CUDA;
+    h->sync_ctrs();
     for (auto& x : h->hc) x.fft_have = 0;
     for (auto& s : st) {
         s.fft_have = s.fft_ready = s.have_spectrum = 0;
@@ -847,29 +1053,36 @@ int hbd_set_record(hbd_decoder* h, int on)
     return HBD_OK;
 }
 
-#define HBD_SETTER(NAME, TYPE, FIELD, DIRTY)                                         \
+#define HBD_SETTER(NAME, TYPE, FIELD)                                                \
     int hbd_set_##NAME(hbd_decoder* h, int ch, TYPE v)                               \
     {                                                                                \
         if (!h || ch < -1 || ch >= h->n_ch) return HBD_ERR_ARG;                      \
         std::lock_guard<std::mutex> l(h->mtx);                                       \
         for (int c = (ch < 0 ? 0 : ch); c < (ch < 0 ? h->n_ch : ch + 1); ++c) {      \
             h->hc[size_t(c)].FIELD = v;                                              \
-            if (DIRTY) h->hc[size_t(c)].cfg_dirty = true;                            \
+            h->hc[size_t(c)].cfg_dirty = true;                                       \
         }                                                                            \
+        h->cfg_dirty_any = h->derived_dirty = true;                                  \
         return HBD_OK;                                                               \
     }
-HBD_SETTER(baud, double, baud, true)
-HBD_SETTER(rtty_bits, size_t, rtty_bits, true)
-HBD_SETTER(rtty_stops, float, rtty_stops, true)
-HBD_SETTER(dc_remove, int, dc_remove, true)
+HBD_SETTER(baud, double, baud)
+HBD_SETTER(rtty_bits, size_t, rtty_bits)
+HBD_SETTER(rtty_stops, float, rtty_stops)
+HBD_SETTER(dc_remove, int, dc_remove)
 
 // Decoder::lowpass_bw / lowpass_trans re-run the design immediately (Decoder.h:238-257)
 static int set_lp(hbd_decoder* h, int ch, float bw, float trans, bool set_bw)
 {
     if (!h || ch < -1 || ch >= h->n_ch) return HBD_ERR_ARG;
     std::lock_guard<std::mutex> l(h->mtx);
+    // FirFilter::LP_BlackmanHarris takes (size_t)(4 / trans) taps (clipped to the block length); the tap rows hold kLpMaxTaps
+    if (!set_bw && trans != 0.f && !(4.0f / trans <= float(kLpMaxTaps - 1))) {
+        h->set_error("lowpass_trans below 4/1024 needs more than kLpMaxTaps (1025) low-pass taps");
+        return HBD_ERR_ARG;
+    }
     cudaSetDevice(h->device);
     h->sync_groups();
+    h->sync_ctrs();
     std::vector<float> taps;
     for (int c = (ch < 0 ? 0 : ch); c < (ch < 0 ? h->n_ch : ch + 1); ++c) {
         HostChan& x = h->hc[size_t(c)];
@@ -880,24 +1093,37 @@ static int set_lp(hbd_decoder* h, int ch, float bw, float trans, bool set_bw)
         const size_t T = design_lowpass(float(x.lp_bw / fs_dec), x.lp_trans, x.lp_input_size, x.lp_ntaps, taps);
         if (T != x.lp_ntaps && T <= size_t(kLpMaxTaps)) {
             if (x.lp_ntaps > T && h->d_decq) {
-                if (launch_lp_hist_shrink(h->d_decq + size_t(c) * h->dq_pitch, int(x.lp_ntaps), int(T), h->stream) != cudaSuccess ||
+                if (launch_lp_hist_shrink(h->d_decq + size_t(c) * h->dq_pitch, h->dq_pitch, 1, int(x.lp_ntaps), int(T), h->stream) != cudaSuccess ||
                     cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
             }
-            x.lp_ntaps = T; x.cfg_dirty = true;
+            x.lp_ntaps = T; x.cfg_dirty = true; h->cfg_dirty_any = h->derived_dirty = true;
             if (cudaMemcpy(h->d_lptaps + size_t(c) * kLpMaxTaps, taps.data(), 4 * T, cudaMemcpyHostToDevice) != cudaSuccess) return HBD_ERR_CUDA;
         }
     }
+    bool cfg_same = true, ctr_same = true;
+    for (size_t c = 1; c < h->hc.size(); ++c) {
+        cfg_same = cfg_same && h->hc[c].lp_bw == h->hc[0].lp_bw && h->hc[c].lp_trans == h->hc[0].lp_trans;
+        ctr_same = ctr_same && h->hc[c].same(h->hc[0]);
+    }
+    h->lp_cfg_uniform = cfg_same; h->ctr_uniform = ctr_same;
     return HBD_OK;
 }
 int hbd_set_lowpass_bw(hbd_decoder* h, int ch, float bw) { return set_lp(h, ch, bw, 0, true); }
 int hbd_set_lowpass_trans(hbd_decoder* h, int ch, float tr) { return set_lp(h, ch, 0, tr, false); }
 
-double hbd_get_baud(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].baud; }
-size_t hbd_get_rtty_bits(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].rtty_bits; }
-float hbd_get_rtty_stops(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].rtty_stops; }
-float hbd_get_lowpass_bw(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].lp_bw; }
-float hbd_get_lowpass_trans(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].lp_trans; }
-int hbd_get_dc_remove(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].dc_remove; }
+#define HBD_GETTER(NAME, TYPE, FIELD)                                                \
+    TYPE hbd_get_##NAME(hbd_decoder* h, int ch)                                      \
+    {                                                                                \
+        if (!h || ch < 0 || ch >= h->n_ch) return 0;                                 \
+        std::lock_guard<std::mutex> l(h->mtx);                                       \
+        return h->hc[size_t(ch)].FIELD;                                              \
+    }
+HBD_GETTER(baud, double, baud)
+HBD_GETTER(rtty_bits, size_t, rtty_bits)
+HBD_GETTER(rtty_stops, float, rtty_stops)
+HBD_GETTER(lowpass_bw, float, lp_bw)
+HBD_GETTER(lowpass_trans, float, lp_trans)
+HBD_GETTER(dc_remove, int, dc_remove)
 
 static size_t apply_factor(hbd_decoder* h, size_t factor)
 {
@@ -911,6 +1137,7 @@ static size_t apply_factor(hbd_decoder* h, size_t factor)
     h->upload_taps();
     for (int i = 0; i < 2; ++i) cudaMemset(h->d_carry2[i], 0, size_t(h->n_ch) * kCarryCap * sizeof(float2));
     for (int i = 0; i < 2; ++i) if (h->d_s1x[i]) cudaMemset(h->d_s1x[i], 0, size_t(h->n_ch) * h->s1_pitch * sizeof(float2));
+    h->sync_ctrs();
     for (auto& x : h->hc) {
         x.grown1 = x.grown2 = 0;
         // unconsumed input stays queued in the reference (iq_in_buffer_ is untouched); it sits at the end of the carry
@@ -1023,6 +1250,7 @@ int hbd_push_samples(hbd_decoder* h, int ch, const float* iq, size_t n, double f
     std::lock_guard<std::mutex> l(h->mtx);
     if (h->ext) { h->set_error("device push pending"); return HBD_ERR_STATE; }
     if (cudaSetDevice(h->device) != cudaSuccess) return HBD_ERR_CUDA;
+    if (h->n_ch > 1) h->leave_uniform();   // per-channel feeding: the counters are stepped channel by channel from here on
     HostChan& x = h->hc[size_t(ch)];
     const int rc = ensure_stage(h, size_t(x.pushed) + n);
     if (rc) return rc;
@@ -1048,8 +1276,8 @@ int hbd_push_samples_batch(hbd_decoder* h, const float* iq, size_t n, size_t pit
     std::lock_guard<std::mutex> l(h->mtx);
     if (h->ext) { h->set_error("device push pending"); return HBD_ERR_STATE; }
     if (cudaSetDevice(h->device) != cudaSuccess) return HBD_ERR_CUDA;
-    unsigned base = h->hc[0].pushed;
-    for (auto& x : h->hc) if (x.pushed != base) { h->set_error("batch push needs equal queue depth in all channels"); return HBD_ERR_STATE; }
+    unsigned base = 0;
+    if (!h->queue_depth_equal(base)) { h->set_error("batch push needs equal queue depth in all channels"); return HBD_ERR_STATE; }
     const int rc = ensure_stage(h, size_t(base) + n);
     if (rc) return rc;
     if (n) {
@@ -1063,7 +1291,7 @@ int hbd_push_samples_batch(hbd_decoder* h, const float* iq, size_t n, size_t pit
         const int rc2 = h->mix_into_stage(h->d_stage + base, h->stage_pitch, 0, h->n_ch, base, n); // in place
         if (rc2) return rc2;
     }
-    for (auto& x : h->hc) x.pushed += unsigned(n);
+    h->add_pushed(unsigned(n));
     return HBD_OK;
 }
 
@@ -1076,8 +1304,8 @@ static int push_wideband(hbd_decoder* h, const float* iq, size_t n, double fs, b
     std::lock_guard<std::mutex> l(h->mtx);
     if (h->ext) { h->set_error("device push pending"); return HBD_ERR_STATE; }
     if (cudaSetDevice(h->device) != cudaSuccess) return HBD_ERR_CUDA;
-    const unsigned base = h->hc[0].pushed;
-    for (auto& x : h->hc) if (x.pushed != base) { h->set_error("wideband push needs equal queue depth in all channels"); return HBD_ERR_STATE; }
+    unsigned base = 0;
+    if (!h->queue_depth_equal(base)) { h->set_error("wideband push needs equal queue depth in all channels"); return HBD_ERR_STATE; }
     latch_rate(h, fs);
     const float2* src = reinterpret_cast<const float2*>(iq);
     if (!device) {
@@ -1099,7 +1327,7 @@ static int push_wideband(hbd_decoder* h, const float* iq, size_t n, double fs, b
     if (rc) return rc;
     const int rc2 = h->mix_into_stage(src, 0, 0, h->n_ch, base, n);
     if (rc2) return rc2;
-    for (auto& x : h->hc) x.pushed += unsigned(n);
+    h->add_pushed(unsigned(n));
     return HBD_OK;
 }
 int hbd_push_wideband(hbd_decoder* h, const float* iq, size_t n, double fs) { return push_wideband(h, iq, n, fs, false); }
@@ -1110,9 +1338,15 @@ int hbd_set_nco(hbd_decoder* h, int ch, double freq_hz)
     if (!h || ch < -1 || ch >= h->n_ch) return HBD_ERR_ARG;
     std::lock_guard<std::mutex> l(h->mtx);
     for (int c = (ch < 0 ? 0 : ch); c < (ch < 0 ? h->n_ch : ch + 1); ++c) h->hc[size_t(c)].nco_freq = freq_hz;
+    if (freq_hz != 0) h->nco_any = true;
     return HBD_OK;
 }
-double hbd_get_nco(hbd_decoder* h, int ch) { if (!h || ch < 0 || ch >= h->n_ch) return 0; return h->hc[size_t(ch)].nco_freq; }
+double hbd_get_nco(hbd_decoder* h, int ch)
+{
+    if (!h || ch < 0 || ch >= h->n_ch) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    return h->hc[size_t(ch)].nco_freq;
+}
 
 int hbd_push_samples_device(hbd_decoder* h, const float* d_iq, size_t n, size_t pitch, double fs)
 {
@@ -1123,32 +1357,33 @@ int hbd_push_samples_device(hbd_decoder* h, const float* d_iq, size_t n, size_t 
     latch_rate(h, fs);
     if (h->nco_active()) { // zero copy is not possible: the mixed samples go through the staging matrix
         if (cudaSetDevice(h->device) != cudaSuccess) return HBD_ERR_CUDA;
-        const unsigned base = h->hc[0].pushed;
-        for (auto& x : h->hc) if (x.pushed != base) { h->set_error("batch push needs equal queue depth in all channels"); return HBD_ERR_STATE; }
+        unsigned base = 0;
+        if (!h->queue_depth_equal(base)) { h->set_error("batch push needs equal queue depth in all channels"); return HBD_ERR_STATE; }
         if (h->nco_fused && base == 0 && n && decim1_supports_fused_nco(h->M1, h->T1))
             return h->push_fused_nco(reinterpret_cast<const float2*>(d_iq), pitch, n);   // zero copy after all: K1 mixes
         const int rc = ensure_stage(h, size_t(base) + n);
         if (rc) return rc;
         const int rc2 = h->mix_into_stage(reinterpret_cast<const float2*>(d_iq), pitch, 0, h->n_ch, base, n);
         if (rc2) return rc2;
-        for (auto& x : h->hc) x.pushed += unsigned(n);
+        h->add_pushed(unsigned(n));
         return HBD_OK;
     }
-    for (auto& x : h->hc) if (x.pushed) { h->set_error("host push pending"); return HBD_ERR_STATE; }
+    { unsigned base = 0; if (!h->queue_depth_equal(base) || base) { h->set_error("host push pending"); return HBD_ERR_STATE; } }
     h->ext = reinterpret_cast<const float2*>(d_iq); h->ext_pitch = pitch; h->ext_n = n;
     return HBD_OK;
 }
 
-int hbd_process_async(hbd_decoder* h) { HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); return h->process_async_locked(); }
-int hbd_collect(hbd_decoder* h) { HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); return h->collect_locked(0); }
-int hbd_collect_ready(hbd_decoder* h, unsigned lag) { HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); return h->collect_locked(lag); }
+int hbd_process_async(hbd_decoder* h) { HBD_CHECK_H(h); return locked_then_fire(h, [h] { return h->process_async_locked(); }); }
+int hbd_collect(hbd_decoder* h) { HBD_CHECK_H(h); return locked_then_fire(h, [h] { return h->collect_locked(0); }); }
+int hbd_collect_ready(hbd_decoder* h, unsigned lag) { HBD_CHECK_H(h); return locked_then_fire(h, [h, lag] { return h->collect_locked(lag); }); }
 int hbd_process(hbd_decoder* h)
 {
     HBD_CHECK_H(h);
-    std::lock_guard<std::mutex> l(h->mtx);
-    const int rc = h->process_async_locked();
-    if (rc) return rc;
-    return h->collect_locked(0);
+    return locked_then_fire(h, [h] {
+        const int rc = h->process_async_locked();
+        if (rc) return rc;
+        return h->collect_locked(0);
+    });
 }
 int hbd_synchronize(hbd_decoder* h)
 {
@@ -1267,14 +1502,17 @@ int hbd_set_chars_callback(hbd_decoder* h, hbd_chars_cb cb, void* user)
 // ---- SSDV packet sync ---------------------------------------------------------------------------------------
 int hbd_set_ssdv(hbd_decoder* h, int on)
 {
-    HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx);
-    return h->enable_ssdv(on != 0);
+    HBD_CHECK_H(h);
+    return locked_then_fire(h, [h, on] { return h->enable_ssdv(on != 0); });
 }
 int hbd_set_ssdv_callback(hbd_decoder* h, hbd_ssdv_cb cb, void* user)
 {
-    HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx);
-    h->ssdv_cb = cb; h->ssdv_user = user;
-    return cb ? h->enable_ssdv(true) : HBD_OK;
+    HBD_CHECK_H(h);
+    return locked_then_fire(h, [h, cb, user] {
+        const int rc = cb ? h->enable_ssdv(true) : HBD_OK;   // drains the calls in flight (under the previous callback)
+        h->ssdv_cb = cb; h->ssdv_user = user;
+        return rc;
+    });
 }
 size_t hbd_poll_ssdv_packets(hbd_decoder* h, int ch, hbd_ssdv_packet_info* infos, unsigned char* packets, size_t cap_packets)
 {
@@ -1401,6 +1639,7 @@ size_t hbd_get_demodulated(hbd_decoder* h, int ch, float* out, size_t cap)
 {
     if (!h || ch < 0 || ch >= h->n_ch) return 0;
     std::lock_guard<std::mutex> l(h->mtx);
+    h->sync_ctrs();
     const size_t n = h->hc[size_t(ch)].demod_n;   // a call that demodulates nothing leaves the previous block in place
     if (!h->d_demod) return 0;
     return fetch_floats(h, h->d_demod + size_t(ch) * h->demod_pitch, n, out, cap);
@@ -1560,7 +1799,7 @@ int hbd_afc_retune(hbd_decoder* h, double min_abs_hz, double* applied_out)
     if (e != cudaSuccess) { h->set_error(cudaGetErrorString(e)); return HBD_ERR_CUDA; }
     int count = 0;
     for (size_t c = 0; c < n; ++c) {
-        if (applied[c] != 0.0) { h->hc[c].nco_freq += applied[c]; ++count; }
+        if (applied[c] != 0.0) { h->hc[c].nco_freq += applied[c]; h->nco_any = true; ++count; }
         if (applied_out) applied_out[c] = applied[c];
     }
     return count;
@@ -1609,6 +1848,7 @@ size_t hbd_debug_stage(hbd_decoder* h, int ch, int stage, float* out, size_t cap
 {
     if (!h || ch < 0 || ch >= h->n_ch) return 0;
     std::lock_guard<std::mutex> l(h->mtx);
+    h->sync_ctrs();
     const HostChan& x = h->hc[size_t(ch)];
     switch (stage) {
     case HBD_STAGE_DECIMATED:
@@ -1660,6 +1900,19 @@ int hbd_extract_sentence(const char* stream, size_t n, char* callsign, char* dat
     put(callsign, m.callsign); put(data, m.data); put(crc, m.crc);
     if (rest) *rest = m.rest_offset;
     return 1;
+}
+
+// the text layer alone (test hook, no GPU): TextChannel::feed over n_chunks pushes of raw characters; `out` receives
+// "<CRC-valid sentences, one per line>\x1e<last sentence>\x1e<text stream>"; returns the size of that report
+size_t hbd_text_replay(const unsigned char* chars, const size_t* chunk_sizes, size_t n_chunks, char* out, size_t cap)
+{
+    if (!chars || !chunk_sizes) return 0;
+    TextChannel tc;
+    size_t off = 0;
+    for (size_t c = 0; c < n_chunks; ++c) { tc.feed(chars + off, chunk_sizes[c], 0, SentenceSink()); off += chunk_sizes[c]; }
+    const std::string rep = tc.sentences_pending + "\x1e" + tc.last_sentence + "\x1e" + tc.text_stream;
+    if (out && cap) memcpy(out, rep.data(), std::min(cap, rep.size()));
+    return rep.size();
 }
 
 void hbd_crc16(const char* s, size_t n, char out[5])

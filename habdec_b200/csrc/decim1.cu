@@ -235,7 +235,7 @@ decim1_kernel(DecimArgs a)
         const int b_span_hi = int(g_end - g < (long long)(a.sb_per_channel - b_lo) ? b_lo + (g_end - g) : a.sb_per_channel);
         g += b_span_hi - b_lo;
         const int ch = a.ch0 + chl;
-        const ChanPlan pl = a.plan[ch];
+        const ChanPlan pl = a.uniform ? a.uplan : a.plan[ch];
         const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
         const float2* carry = a.carry + (size_t)ch * kCarryCap + kCarryCap; // carry[j] valid for -kCarryCap <= j < 0
         // superblock b covers step-local sample positions x in (64(b-1), 64b]; the outputs k with
@@ -430,7 +430,7 @@ decim1_kernel(DecimArgs a)
 __global__ void decim1_generic_kernel(DecimArgs a, int M, int T)
 {
     const int ch = a.ch0 + blockIdx.y;
-    const ChanPlan pl = a.plan[ch];
+    const ChanPlan pl = a.uniform ? a.uplan : a.plan[ch];
     if (pl.flags & 1u) return;
     const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
     const float2* carry = a.carry + (size_t)ch * kCarryCap + kCarryCap;
@@ -453,7 +453,7 @@ __global__ void decim1_generic_kernel(DecimArgs a, int M, int T)
 __global__ void decim1_copy_kernel(DecimArgs a)
 {
     const int ch = a.ch0 + blockIdx.y;
-    const ChanPlan pl = a.plan[ch];
+    const ChanPlan pl = a.uniform ? a.uplan : a.plan[ch];
     if (pl.flags & 1u) return;
     const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
     float2* out = a.s1 + (size_t)ch * a.s1_pitch + a.s1_hist;
@@ -462,11 +462,11 @@ __global__ void decim1_copy_kernel(DecimArgs a)
 
 // ---- stage-1 carry for the NEXT call when K1 is not the TMA kernel: last (T1-1 + r') samples of [carry | chunk] ----
 __global__ void __launch_bounds__(128)
-carry_kernel(const ChanPlan* __restrict__ plan, const float2* __restrict__ chunk_base, size_t chunk_pitch, const float2* __restrict__ carry_base,
+carry_kernel(const ChanPlan* __restrict__ plan, ChanPlan uplan, int uniform, const float2* __restrict__ chunk_base, size_t chunk_pitch, const float2* __restrict__ carry_base,
              float2* __restrict__ next_base, int T1, int ch0)
 {
     const int ch = ch0 + blockIdx.x;
-    const ChanPlan pl = plan[ch];
+    const ChanPlan pl = uniform ? uplan : plan[ch];
     const int keep = T1 - 1 + int(pl.r + pl.n - pl.consumed);             // <= kCarryCap (host checked)
     const float2* carry = carry_base + (size_t)ch * kCarryCap + kCarryCap;
     float2* next = next_base + (size_t)ch * kCarryCap + kCarryCap;
@@ -477,10 +477,10 @@ carry_kernel(const ChanPlan* __restrict__ plan, const float2* __restrict__ chunk
     }
 }
 
-cudaError_t launch_carry(const ChanPlan* plan, const float2* chunk, size_t chunk_pitch, const float2* carry, float2* carry_next, int T1, int ch0,
+cudaError_t launch_carry(const ChanPlan* plan, ChanPlan uplan, int uniform, const float2* chunk, size_t chunk_pitch, const float2* carry, float2* carry_next, int T1, int ch0,
                          int n_channels, cudaStream_t stream, int* launches)
 {
-    carry_kernel<<<n_channels, 128, 0, stream>>>(plan, chunk, chunk_pitch, carry, carry_next, T1, ch0);
+    carry_kernel<<<n_channels, 128, 0, stream>>>(plan, uplan, uniform, chunk, chunk_pitch, carry, carry_next, T1, ch0);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
@@ -535,7 +535,7 @@ cudaError_t launch_decim1(DecimArgs a, int M, int T, unsigned max_n1, int n_sms,
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    return launch_carry(a.plan, a.chunk, a.chunk_pitch, a.carry, a.carry_next, T, a.ch0, a.n_channels, stream, launches);
+    return launch_carry(a.plan, a.uplan, a.uniform, a.chunk, a.chunk_pitch, a.carry, a.carry_next, T, a.ch0, a.n_channels, stream, launches);
 }
 
 bool decim1_supports_fused_nco(int M, int T) { return M == 64 && T == 348; }

@@ -17,7 +17,9 @@ struct DecimArgs {
     float2* s1;                // stage-1 output stream, [channel][s1_pitch]; outputs start at s1_hist
     size_t s1_pitch;
     int s1_hist;
-    const ChanPlan* plan;      // per channel
+    const ChanPlan* plan;      // per channel (read only when !uniform)
+    ChanPlan uplan;            // the plan of every channel when uniform (kernel argument: no upload, no dependent global load)
+    int uniform;
     const float* taps;         // T floats (device)
     int ch0;                   // first channel of this launch
     int n_channels;            // channels in this launch
@@ -34,7 +36,7 @@ cudaError_t launch_decim1(DecimArgs a, int M, int T, unsigned max_n1, int n_sms,
 // can launch_decim1 mix the channels through their NCOs itself (DecimArgs::nco) for this first stage?
 bool decim1_supports_fused_nco(int M, int T);
 // stage-1 carry (history + unconsumed remainder) for the next call: carry -> carry_next
-cudaError_t launch_carry(const ChanPlan* plan, const float2* chunk, size_t chunk_pitch, const float2* carry, float2* carry_next, int T1, int ch0,
+cudaError_t launch_carry(const ChanPlan* plan, ChanPlan uplan, int uniform, const float2* chunk, size_t chunk_pitch, const float2* carry, float2* carry_next, int T1, int ch0,
                          int n_channels, cudaStream_t stream, int* launches);
 
 } // namespace hbd

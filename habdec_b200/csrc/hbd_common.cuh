@@ -25,7 +25,20 @@ constexpr int kFftN         = 4096;   // Decoder.h:163 fft_bins_cnt_ (default; h
 constexpr int kFftNMax      = 16384;
 constexpr int kSlicerVent   = 30000;  // SymbolExtractor.h:116 safety vent (3e4)
 constexpr int kBitsCap      = 16384;  // bits the slicer may emit in one call (+ pending UART bits)
-constexpr unsigned kLogCap   = 1u << 20; // decoded-character log entries (ring) between host drains
+constexpr unsigned kUartRunsCap = 2048; // UART backlog entries per channel (slicer runs since the last decoded character)
+constexpr unsigned kLogCapMin = 1u << 20; // decoded-character log entries (ring) between host drains: max(this, 512 per channel)
+
+// control words of the result logs (one device array, copied to a pinned per-call slot after the kernels of every call)
+enum LogCtl {
+    kCtlCharHead = 0,     // monotonic append counter of the character log
+    kCtlSsdvHead = 1,     // ... of the SSDV packet log
+    kCtlSsdvRingOvf = 2,  // a call appended more raw characters than a channel's SSDV ring holds
+    kCtlCharTail = 3,     // entries below this index have been consumed by the host (uploaded after every drain)
+    kCtlCharOvf = 4,      // characters a writer had to DROP because the ring was full (never overwrites unread entries)
+    kCtlSsdvTail = 5,
+    kCtlSsdvOvf = 6,      // SSDV packets dropped for the same reason
+    kCtlWords = 8
+};
 
 // ---- per-channel persistent state (device resident, one struct per channel) -----------------------
 struct ChanState {
@@ -49,6 +62,10 @@ struct ChanState {
     unsigned slicer_n;      // pending slicer samples
     unsigned uart_n;        // pending UART bits (< one frame)
     unsigned long long uart_win; // those bits, LSB = oldest
+    unsigned uart_runs_n;   // entries of the channel's UART backlog (slicer_dev.cuh: bits since the last decoded character)
+    unsigned uart_ovf;      // the backlog outgrew its buffer
+    unsigned uart_rescan;   // rtty_bits / rtty_stops changed: the backlog is re-evaluated when the next bit arrives
+    unsigned pad0_;
 
     // AFC (AFC.h:72-90): two Average<double>(100), two Average<int>(4)
     double   afc_correction, afc_noise_floor, afc_noise_var, afc_shift_hz;

@@ -71,7 +71,7 @@ std::string crc16_hex(const std::string& s)
 //     .*?(\$+)([\w,\-,\s]+?),(.+?)(\*|\$)(\w\w\w\w).*
 // on the stream with '\n' replaced by ' '.  std::regex costs tens of microseconds per call, which
 // would make the host the bottleneck at GPU decode rates, so the same match is found directly.
-// Equivalence (also fuzz-tested against std::regex in tests/test_host_tail.py):
+// Equivalence (also fuzz-tested against std::regex in tests/test_host_side.py):
 //  * `.*?` lazy  => the earliest start position with a '$' from which the rest can match; a start
 //    inside a run of '$' behaves like the start of that run (`\$+` must swallow the rest of the
 //    run, because '$' is not in the callsign class), so runs are tried left to right.
@@ -124,29 +124,44 @@ void TextChannel::feed(const unsigned char* raw, size_t n, int ch, const Sentenc
 {
     if (!n) return; // the reference returns before touching the streams when no char was decoded (:568-569)
     raw_pending.insert(raw_pending.end(), raw, raw + n);
-    size_t added = 0;
+    const size_t old_len = text_stream.size();
     for (size_t i = 0; i < n; ++i) {
         const char c = char(raw[i]);
         if ((std::isprint((unsigned char)c) && (unsigned char)c < 0x80) || c == '\n') { // isprint(char) in the "C" locale
             text_stream.push_back(c);
             chars_pending.push_back(c);
-            ++added;
         }
     }
-    (void)added;
     if (text_stream.size() > 20) {
-        SentenceMatch m;
-        while (extract_sentence(text_stream, m)) {
-            std::string rest = text_stream.substr(m.rest_offset);
-            std::replace(rest.begin(), rest.end(), '\n', ' ');    // the reference keeps the space-substituted copy (:599)
-            text_stream.swap(rest);
-            last_sentence = m.callsign + "," + m.data + "*" + m.crc;
-            if (m.crc == crc16_hex(m.callsign + "," + m.data)) {
-                sentences_pending += last_sentence;
-                sentences_pending.push_back('\n');
-                if (sink) sink(ch, m.callsign, m.data, m.crc);
+        // The scan loop below leaves a stream without a match (scan_clean).  New characters can only complete a match
+        // whose CRC group ends among them -- the pattern's trailing `.*` swallows everything behind the CRC, so a match that
+        // ends earlier would have been found before -- i.e. some new position i with [*$] at i-4 and \w at i-3..i.
+        // One more way: extractSentence refuses any stream without a '*' (sentence_extract.cpp:74), so a new '*' anywhere can
+        // wake a match that ends in "$" + CRC further left.  Without either, the whole scan (a copy of the stream + a pass
+        // over it, per call and channel) is skipped.
+        bool candidate = !scan_clean;
+        for (size_t i = old_len; !candidate && i < text_stream.size(); ++i) {
+            const char* p = text_stream.data() + i;
+            candidate = p[0] == '*' || (i >= 4 && (p[-4] == '*' || p[-4] == '$') && is_word((unsigned char)p[-3]) && is_word((unsigned char)p[-2]) &&
+                                        is_word((unsigned char)p[-1]) && is_word((unsigned char)p[0]));
+        }
+        if (candidate) {
+            SentenceMatch m;
+            while (extract_sentence(text_stream, m)) {
+                std::string rest = text_stream.substr(m.rest_offset);
+                std::replace(rest.begin(), rest.end(), '\n', ' ');    // the reference keeps the space-substituted copy (:599)
+                text_stream.swap(rest);
+                last_sentence = m.callsign + "," + m.data + "*" + m.crc;
+                if (m.crc == crc16_hex(m.callsign + "," + m.data)) {
+                    sentences_pending += last_sentence;
+                    sentences_pending.push_back('\n');
+                    if (sink) sink(ch, m.callsign, m.data, m.crc);
+                }
             }
         }
+        scan_clean = true;
+    } else if (text_stream.size() != old_len) {
+        scan_clean = false;   // a short stream is not scanned (Decoder.h:591): it may hold a complete sentence already
     }
     if (text_stream.size() > 1000) text_stream.erase(0, text_stream.rfind('$')); // npos => erase everything
 }

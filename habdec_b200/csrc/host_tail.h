@@ -32,6 +32,7 @@ struct TextChannel {
     std::string chars_pending;      // printable chars since the last poll / callback
     std::string sentences_pending;  // CRC-valid sentences since the last poll
     std::vector<unsigned char> raw_pending; // raw chars since the last poll (SSDV consumers)
+    bool scan_clean = true;         // text_stream is known to hold no extractable sentence (see feed)
     void feed(const unsigned char* raw, size_t n, int ch, const SentenceSink& sink);
 };
 

@@ -18,9 +18,7 @@
 // The long segment sum only decides a sign, so it is summed in parallel and re-done
 // sequentially only when the parallel sum is too close to zero to be certain.
 //
-// UART: the reference rescans its whole bit vector on every call; verdicts for positions
-// whose frame was fully available never change, so the same characters come out of a
-// shift-register automaton that carries < one frame of bits between calls (bounded state).
+// UART: see uart_feed_run / uart_replay below (shift register + run-length coded backlog).
 //
 // `v` is a generic pointer: the pending samples normally sit in shared memory (staged by the
 // tail kernel), and in global memory only when a channel has more pending samples than the
@@ -240,7 +238,7 @@ __device__ __forceinline__ bool segment_mean_positive(const float* __restrict__ 
 struct CharSink {
     unsigned char* buf;   // shared memory, kCharBuf bytes (one warp writes, lane 0 only)
     int n;
-    uint2* log; unsigned* log_head; unsigned call_seq; unsigned ch;
+    uint2* log; unsigned* ctl; unsigned log_mask; unsigned call_seq; unsigned ch;   // ctl: LogCtl words
     unsigned char* ring; unsigned ring_total;   // SSDV: the channel's raw-character ring (null: off) and its append count
 };
 constexpr unsigned kRawRingMask = 4096u - 1u;    // == kSsdvRing - 1 (ssdv.cuh)
@@ -250,11 +248,21 @@ __device__ __forceinline__ void sink_flush(CharSink& s, int lane)
 {
     // warp-uniform: s.n is kept identical in all lanes
     if (s.n == 0) return;
-    unsigned pos = 0;
-    if (lane == 0) pos = atomicAdd(s.log_head, unsigned(s.n));
+    unsigned pos = 0, tail = 0;
+    if (lane == 0) {
+        pos = atomicAdd(s.ctl + kCtlCharHead, unsigned(s.n));
+        tail = *reinterpret_cast<volatile unsigned*>(s.ctl + kCtlCharTail);
+    }
     pos = __shfl_sync(0xffffffffu, pos, 0);
+    tail = __shfl_sync(0xffffffffu, tail, 0);
     __syncwarp();
-    for (int i = lane; i < s.n; i += 32) s.log[(pos + unsigned(i)) & (kLogCap - 1u)] = make_uint2(s.ch, (s.call_seq << 8) | unsigned(s.buf[i]));
+    // never overwrite entries the host has not read yet: a full ring drops the characters and counts them
+    // (the host reports the loss, api.cu collect_locked; it drains early enough that this does not happen, log_pressure)
+    if (pos + unsigned(s.n) - tail > s.log_mask + 1u) {
+        if (lane == 0) atomicAdd(s.ctl + kCtlCharOvf, unsigned(s.n));
+    } else {
+        for (int i = lane; i < s.n; i += 32) s.log[(pos + unsigned(i)) & s.log_mask] = make_uint2(s.ch, (s.call_seq << 8) | unsigned(s.buf[i]));
+    }
     if (s.ring) {
         for (int i = lane; i < s.n; i += 32) s.ring[(s.ring_total + unsigned(i)) & kRawRingMask] = s.buf[i];
         s.ring_total += unsigned(s.n);
@@ -273,20 +281,91 @@ __device__ __forceinline__ bool slicer_geometry(int n, double fs, double baud, i
     return true;
 }
 
+// ---- UART deframer (RTTY<bool>::operator(), RTTY.h:77-137) -----------------------------------------------------------
+// The reference keeps every bit since the last decoded character (bits_) and rescans all of them on every call with the
+// framing in force at that moment.  While the framing does not change, the verdict of a position whose frame was
+// completely available never changes, so the same characters come out of a shift register that holds the undecided
+// suffix only (win / have, < one frame).  What the shift register cannot reproduce is a framing CHANGE (rtty_bits /
+// rtty_stops setters between calls, or the step from "not configured" to configured): the reference then re-evaluates
+// the whole backlog under the new framing.  So the backlog is kept as well, run-length coded in HBM (one entry per
+// slicer run; after a decode it shrinks to what the reference keeps: nothing, or the one stop bit a fractional stop
+// count leaves behind), and replayed through the shift register when the host flags a change (ChanState::uart_rescan).
+struct UartFraming {
+    bool on;        // false: nbits == 0 && nstops == 0 (RTTY.h:79-80), or a frame that does not fit the 64-bit window
+    int nbits, stop_chk, need, adv;
+};
+__device__ __forceinline__ UartFraming uart_framing(int nbits, float nstops)
+{
+    UartFraming f;
+    f.on = (nbits != 0 || nstops != 0.f) && nbits >= 0 && nbits <= 16 && nstops >= 0.f && nstops <= 8.f;
+    f.nbits = nbits;
+    f.stop_chk = int(ceilf(nstops));          // stop bits inspected: s = 0 .. while s < nstops
+    f.need = 1 + nbits + f.stop_chk;          // bits that must be available at a position
+    f.adv = 1 + nbits + int(nstops);          // i += nstops_ truncates (size_t += float)
+    return f;
+}
+struct UartState {
+    unsigned long long win; int have;         // undecided suffix of the bit stream, LSB = oldest
+    unsigned short* runs; unsigned n_runs;    // backlog since the last decoded character: (count << 1 | bit) per slicer run
+    unsigned ovf;                             // the backlog outgrew kUartRunsCap (its newest part is missing)
+};
+
+// feed `cnt` copies of `bit` (warp-uniform scalar code; lane 0 commits the side effects)
+__device__ __forceinline__ void uart_feed_run(UartState& u, const UartFraming& f, bool bit, int cnt, CharSink& sink, int lane)
+{
+    int keep = cnt;                            // bits of this run that stay in the backlog
+    if (f.on) {
+        for (int c = 0; c < cnt; ++c) {
+            u.win |= (unsigned long long)(bit ? 1u : 0u) << u.have;
+            ++u.have;
+            while (u.have >= f.need) {
+                const unsigned stops = unsigned(u.win >> (1 + f.nbits)) & ((1u << f.stop_chk) - 1u);
+                const bool ok = ((u.win & 1ull) == 0ull) && stops == ((1u << f.stop_chk) - 1u);
+                if (ok) {
+                    const unsigned char cc = (unsigned char)((u.win >> 1) & ((1ull << f.nbits) - 1ull));
+                    if (lane == 0) sink.buf[sink.n] = cc;
+                    if (++sink.n == kCharBuf) sink_flush(sink, lane);
+                    u.win >>= f.adv; u.have -= f.adv;
+                    // RTTY.h:133-134: everything up to the last stop bit of this character is erased.  What is left in the
+                    // window (0 or 1 bit: the last inspected stop bit when nstops is fractional) is the bit just fed.
+                    u.n_runs = 0; u.ovf = 0;
+                    keep = cnt - c - 1 + u.have;
+                } else {
+                    u.win >>= 1; u.have -= 1;
+                }
+            }
+        }
+    }
+    if (keep > 0) {
+        if (u.n_runs < kUartRunsCap) { if (lane == 0) u.runs[u.n_runs] = (unsigned short)((min(keep, 32767) << 1) | (bit ? 1 : 0)); ++u.n_runs; }
+        else u.ovf = 1;
+    }
+}
+
+// the framing changed: re-evaluate the backlog from its start, as the reference's next rtty_() does.  In place: every
+// replayed run is read before it is fed, and feeding it appends at most one entry.
+__device__ __forceinline__ void uart_replay(UartState& u, const UartFraming& f, CharSink& sink, int lane)
+{
+    const unsigned n_old = u.n_runs;
+    const unsigned was_ovf = u.ovf;
+    u.n_runs = 0; u.win = 0ull; u.have = 0;
+    for (unsigned r = 0; r < n_old; ++r) {
+        const unsigned e = u.runs[r];          // same address in every lane
+        __syncwarp();
+        uart_feed_run(u, f, (e & 1u) != 0u, int(e >> 1), sink, lane);
+        __syncwarp();
+    }
+    if (was_ovf) { u.win = 0ull; u.have = 0; u.ovf = 1; }   // a gap follows the kept part: start afresh behind it
+}
+
 // One warp slices the pending samples v[0..n) of a channel.  Returns the number of samples to erase from the
-// front (0 if no flip point was found).  UART state goes through win/have; characters go to `sink`.
+// front (0 if no flip point was found).  UART state goes through `u`; characters go to `sink`.
 // maskA/maskN: position masks from slicer_build_masks, or null (scan on the fly).
 __device__ __forceinline__ int slice_channel(const float* __restrict__ v, int n, int spb, int R, const unsigned* maskA, const unsigned* maskN,
-                                             int nbits, float nstops, unsigned long long& win, int& have, CharSink& sink,
+                                             int nbits, float nstops, UartState& u, bool& rescan, CharSink& sink,
                                              unsigned char* rec_bits, unsigned& rec_n, unsigned rec_cap, int lane)
 {
-
-    // UART automaton (RTTY.h:77-137, see header)
-    const bool uart_on = (nbits != 0 || nstops != 0.f) && nbits <= 16 && nstops <= 8.f;
-    const int stop_chk = int(ceilf(nstops));               // stop bits inspected: s = 0 .. while s < nstops
-    const int need = 1 + nbits + stop_chk;                  // bits that must be available at a position
-    const int adv = 1 + nbits + int(nstops);                // i += nstops_ truncates (size_t += float)
-
+    const UartFraming f = uart_framing(nbits, nstops);
     int last = 0, off = 0;
     for (;;) {
         const int flip = maskA ? next_flip_masked(v, maskA, maskN, n, off, spb, R, lane) : next_flip(v, n, off, spb, R, lane);
@@ -294,25 +373,10 @@ __device__ __forceinline__ int slice_channel(const float* __restrict__ v, int n,
         const bool bit = segment_mean_positive(v, last, flip, lane);
         const int cnt = int(size_t(roundf(__fdiv_rn(float(flip - last), float(spb)))));
         last = off = flip;
-        // feed `cnt` copies of `bit` (warp-uniform scalar code; lane 0 commits the side effects)
-        for (int c = 0; c < cnt; ++c) {
-            if (rec_bits) { if (lane == 0 && rec_n < rec_cap) rec_bits[rec_n] = bit; ++rec_n; }
-            if (!uart_on) continue;
-            win |= (unsigned long long)(bit ? 1u : 0u) << have;
-            ++have;
-            while (have >= need) {
-                const unsigned stops = unsigned(win >> (1 + nbits)) & ((1u << stop_chk) - 1u);
-                const bool ok = ((win & 1ull) == 0ull) && stops == ((1u << stop_chk) - 1u);
-                if (ok) {
-                    const unsigned char cc = (unsigned char)((win >> 1) & ((1ull << nbits) - 1ull));
-                    if (lane == 0) sink.buf[sink.n] = cc;
-                    if (++sink.n == kCharBuf) sink_flush(sink, lane);
-                    win >>= adv; have -= adv;
-                } else {
-                    win >>= 1; have -= 1;
-                }
-            }
-        }
+        if (cnt <= 0) continue;
+        if (rec_bits) { for (int c = 0; c < cnt; ++c) { if (lane == 0 && rec_n < rec_cap) rec_bits[rec_n] = bit; ++rec_n; } }
+        if (rescan) { uart_replay(u, f, sink, lane); rescan = false; }   // Decoder.h:562-566: rtty_() runs when new symbols arrive
+        uart_feed_run(u, f, bit, cnt, sink, lane);
     }
     return min(last, n);
 }

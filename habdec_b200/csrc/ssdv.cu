@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kSsdvWarps * 32) ssdv_scan_kernel(SsdvScanArgs
     SsdvScratch& w = scratch[warp];
     const unsigned end = total - (kSsdvPkt - 1u);     // window starts in [from, end) are complete
     if (total - from > kSsdvRing) {                    // the ring no longer holds [from, total)
-        if (lane == 0) *a.overflow = 1u;
+        if (lane == 0) atomicAdd(a.ctl + kCtlSsdvRingOvf, 1u);
         from = total - kSsdvRing;
     }
     for (unsigned base = from; int(end - base) > 0; base += 32u) {
@@ -260,14 +260,19 @@ __global__ void __launch_bounds__(kSsdvWarps * 32) ssdv_scan_kernel(SsdvScanArgs
             __syncwarp();
             int errors = 0;
             if (is_packet_warp(tab, w, errors, lane)) {
-                unsigned at = 0;
-                if (lane == 0) at = atomicAdd(a.log_head, 1u);
+                unsigned at = 0, tail = 0;
+                if (lane == 0) { at = atomicAdd(a.ctl + kCtlSsdvHead, 1u); tail = *reinterpret_cast<volatile unsigned*>(a.ctl + kCtlSsdvTail); }
                 at = __shfl_sync(0xffffffffu, at, 0);
-                SsdvLogEntry& e = a.log[at & (kSsdvLogCap - 1u)];
-                if (lane == 0) { e.ch = unsigned(ch); e.seq = a.call_seq; e.pos = q; e.errors = errors; }
-                __syncwarp();
-                for (int i = lane; i < int(kSsdvPkt / 4); i += 32)
-                    reinterpret_cast<unsigned*>(e.data)[i] = reinterpret_cast<const unsigned*>(w.pkt)[i];
+                tail = __shfl_sync(0xffffffffu, tail, 0);
+                if (at - tail >= kSsdvLogCap) {        // full: never overwrite an entry the host has not read (counted, reported)
+                    if (lane == 0) atomicAdd(a.ctl + kCtlSsdvOvf, 1u);
+                } else {
+                    SsdvLogEntry& e = a.log[at & (kSsdvLogCap - 1u)];
+                    if (lane == 0) { e.ch = unsigned(ch); e.seq = a.call_seq; e.pos = q; e.errors = errors; }
+                    __syncwarp();
+                    for (int i = lane; i < int(kSsdvPkt / 4); i += 32)
+                        reinterpret_cast<unsigned*>(e.data)[i] = reinterpret_cast<const unsigned*>(w.pkt)[i];
+                }
             }
             __syncwarp();
         }

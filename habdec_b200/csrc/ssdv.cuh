@@ -21,8 +21,8 @@ struct SsdvScanArgs {
     const unsigned char* ring;   // [channel][kSsdvRing]
     const unsigned* total;       // [channel] raw characters appended so far (written by the tail kernel)
     unsigned* scanned;           // [channel] window starts below this index have been examined
-    SsdvLogEntry* log; unsigned* log_head;   // accepted packets, monotonic head
-    unsigned* overflow;          // set to 1 when a call appended more characters than the ring can hold
+    SsdvLogEntry* log;           // accepted packets (ring of kSsdvLogCap entries)
+    unsigned* ctl;               // LogCtl words: kCtlSsdvHead (monotonic), kCtlSsdvTail, kCtlSsdvOvf, kCtlSsdvRingOvf
     unsigned call_seq;
     int ch0;
 };

@@ -343,19 +343,19 @@ tail_kernel(TailArgs a)
     }
     if (tid < 32) {
         unsigned slicer_n = s_st.slicer_n;
-        unsigned long long win = s_st.uart_win;
-        int have = int(s_st.uart_n);
+        UartState us{s_st.uart_win, int(s_st.uart_n), a.uart_runs + (size_t)ch * kUartRunsCap, s_st.uart_runs_n, s_st.uart_ovf};
+        bool rescan = s_st.uart_rescan != 0;
         if (nf) {
             const int n = n_sl;
             const float* v = smem_mode ? s_v : v_g;
-            CharSink sink{s_chars, 0, a.log, a.log_head, a.call_seq, unsigned(ch), nullptr, 0u};
+            CharSink sink{s_chars, 0, a.log, a.log_ctl, a.log_mask, a.call_seq, unsigned(ch), nullptr, 0u};
             if (a.ssdv_ring) { sink.ring = a.ssdv_ring + (size_t)ch * (kRawRingMask + 1u); sink.ring_total = a.ssdv_total[ch]; }
             unsigned char* rec_bits = a.rec_bits ? a.rec_bits + (size_t)ch * a.rec_bits_pitch : nullptr;
             unsigned rec_n = a.rec_bits ? a.rec_bits_n[ch] : 0;
             int erase = 0;
             if (slicing)
                 erase = slice_channel(v, n, spb, R, smem_mode ? s_maskA : nullptr, smem_mode ? s_maskN : nullptr, s_st.rtty_bits,
-                                      s_st.rtty_stops, win, have, sink, rec_bits, rec_n, a.rec_bits_pitch, lane);
+                                      s_st.rtty_stops, us, rescan, sink, rec_bits, rec_n, a.rec_bits_pitch, lane);
             sink_flush(sink, lane);
             if (sink.ring && lane == 0) a.ssdv_total[ch] = sink.ring_total;
             if (a.rec_bits && lane == 0) a.rec_bits_n[ch] = rec_n;
@@ -390,8 +390,11 @@ tail_kernel(TailArgs a)
                 gst.demod_primed = 1;
                 gst.demod_n = nf;
                 gst.slicer_n = slicer_n;
-                gst.uart_win = win;
-                gst.uart_n = unsigned(have);
+                gst.uart_win = us.win;
+                gst.uart_n = unsigned(us.have);
+                gst.uart_runs_n = us.n_runs;
+                gst.uart_ovf = us.ovf;
+                gst.uart_rescan = rescan ? 1u : 0u;
             }
         }
     }
@@ -400,18 +403,19 @@ tail_kernel(TailArgs a)
 // A SMALLER low-pass (lowpass_trans raised mid-stream): FirFilter keeps its work buffer, whose first T_new-1 entries are
 // the OLDEST part of the previous T_old-1 history samples (FirFilter.h:139-152 copies the new input behind them), so that
 // part becomes the history of the new filter.  One CTA moves it to the end of the history slots.
-__global__ void lp_hist_shrink_kernel(float2* row, int t_old, int t_new)
+__global__ void lp_hist_shrink_kernel(float2* rows, size_t pitch, int t_old, int t_new)
 {
     __shared__ float2 s[kLpMaxTaps];
+    float2* row = rows + size_t(blockIdx.x) * pitch;
     const int n = t_new - 1;
     for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = row[kLpHist - (t_old - 1) + i];
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) row[kLpHist - n + i] = s[i];
 }
-cudaError_t launch_lp_hist_shrink(float2* decq_row, int t_old, int t_new, cudaStream_t stream)
+cudaError_t launch_lp_hist_shrink(float2* decq_rows, size_t pitch, int n_rows, int t_old, int t_new, cudaStream_t stream)
 {
-    if (t_new < 2 || t_new >= t_old) return cudaSuccess;
-    lp_hist_shrink_kernel<<<1, 256, 0, stream>>>(decq_row, t_old, t_new);
+    if (t_new < 2 || t_new >= t_old || n_rows < 1) return cudaSuccess;
+    lp_hist_shrink_kernel<<<n_rows, 256, 0, stream>>>(decq_rows, pitch, t_old, t_new);
     return cudaGetLastError();
 }
 

@@ -24,10 +24,11 @@ struct TailArgs {
     // slicer pending samples [channel][slicer_pitch]
     float* slicer; size_t slicer_pitch;
     int sv_want;              // slicer samples to stage in shared memory (channels with more run from HBM)
-    // decoded characters go to one device-wide append log (ring of kLogCap entries, monotonic head):
-    // entry = (channel, call_seq << 8 | char).  Kernels of successive calls run in stream order, so the log is
-    // sorted by call and, per channel, by time.
-    uint2* log; unsigned* log_head; unsigned call_seq;
+    // decoded characters go to one device-wide append log (ring of log_mask + 1 entries, monotonic head in
+    // log_ctl[kCtlCharHead]): entry = (channel, call_seq << 8 | char).  Kernels of successive calls run in stream order,
+    // so the log is sorted by call and, per channel, by time.
+    uint2* log; unsigned* log_ctl; unsigned log_mask; unsigned call_seq;
+    unsigned short* uart_runs;   // UART backlog [channel][kUartRunsCap] (slicer_dev.cuh)
     // SSDV packet sync (ssdv.cu): per-channel raw-character ring [channel][kSsdvRing] + append counts; null = off
     unsigned char* ssdv_ring; unsigned* ssdv_total;
     // last call's discriminator output for getDemodulated() [channel][demod_pitch] (may be null)
@@ -42,6 +43,6 @@ struct TailArgs {
 cudaError_t launch_tail(TailArgs a, int n_channels, cudaStream_t stream, int* launches);
 
 // low-pass tap count shrank from t_old to t_new: keep the reference's part of the history (see tail.cu)
-cudaError_t launch_lp_hist_shrink(float2* decq_row, int t_old, int t_new, cudaStream_t stream);
+cudaError_t launch_lp_hist_shrink(float2* decq_rows, size_t pitch, int n_rows, int t_old, int t_new, cudaStream_t stream);
 
 } // namespace hbd

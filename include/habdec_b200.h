@@ -262,6 +262,9 @@ size_t hbd_design_lowpass(float rel_width, float trans, size_t input_size, size_
  * returns 1 and fills the fields if a sentence was found; *rest_offset = start of the remaining stream */
 int    hbd_extract_sentence(const char* stream, size_t n, char* callsign, char* data, char* crc, size_t cap, size_t* rest_offset);
 void   hbd_crc16(const char* s, size_t n, char out[5]);
+/* the text layer alone (printable filter + sentence scan + trims, Decoder.h:572-613,635-636; needs no GPU): n_chunks pushes of
+ * raw characters; out = "<CRC-valid sentences, one per line>\x1e<last sentence>\x1e<text stream>"; returns its size */
+size_t hbd_text_replay(const unsigned char* chars, const size_t* chunk_sizes, size_t n_chunks, char* out, size_t cap);
 
 #ifdef __cplusplus
 }

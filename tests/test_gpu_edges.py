@@ -259,6 +259,40 @@ def test_setters_between_calls(oracle_kind):
     assert len(refs[1].sentences()) >= 5
 
 
+@pytest.mark.parametrize("first,snr", [((0, 0.0), -15.0), ((7, 1.0), -15.0), ((8, 1.5), -22.0), ((5, 2.0), -24.0)])
+def test_uart_backlog_is_rescanned_after_a_framing_change(oracle_kind, first, snr):
+    """RTTY::operator() keeps every bit since the last decoded character and rescans ALL of them under the framing in
+    force at the next call (RTTY.h:90-134).  Start with the framing unset (bits accumulate, nothing decodes) or wrong
+    (garbage decodes, rejected positions stay), then switch to 8N2 mid-stream: the characters the reference digs out of
+    the backlog have to come out here as well.  Channel 0 keeps 8N2 throughout; channels 2/3 switch at other calls."""
+    fs, baud = 2.048e6, 300.0
+    sigs = [synth.channel_iq(60 + c, 2, fs, baud, snr_db=snr)[0] for c in range(4)]
+    n = min(len(x) for x in sigs) // 65536 * 65536
+    iq = np.stack([x[:n] for x in sigs])
+    n_calls = n // 65536
+    switch = {1: 7, 2: 11, 3: n_calls // 2}
+    dec = api.BatchDecoder(4, baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
+    refs = [make_oracle(oracle_kind, baud=baud) for _ in range(4)]
+    for c in switch:
+        dec.rtty_bits(first[0], c); dec.rtty_stops(first[1], c)
+        refs[c].set_param("rtty_bits", first[0]); refs[c].set_param("rtty_stops", first[1])
+    for i in range(n_calls):
+        for c, at in switch.items():
+            if i == at:
+                dec.rtty_bits(8, c); dec.rtty_stops(2.0, c)
+                refs[c].set_param("rtty_bits", 8); refs[c].set_param("rtty_stops", 2.0)
+        blk = np.ascontiguousarray(iq[:, i * 65536:(i + 1) * 65536])
+        dec.pushSamplesBatch(blk, fs)
+        dec.process()
+        for c in range(4):
+            refs[c].push_process(blk[c], fs)
+    for c in range(4):
+        assert dec.poll_chars(c) == refs[c].chars(), "channel %d" % c
+        assert dec.poll_sentences(c) == refs[c].sentences(), "channel %d" % c
+    if first == (0, 0.0):   # everything sent before the switch sat in the backlog: no character is lost
+        assert len(refs[3].sentences()) == len(refs[0].sentences()) >= 2
+
+
 @pytest.mark.parametrize("fs,max_rate,want", [(2.048e6, 8000.0, 256), (2.048e6, 40000.0, 64), (1.024e6, 8000.0, 128),
                                               (256e3, 9000.0, 32), (64e3, 8000.0, 8), (2.048e6, 1000.0, 0)])
 def test_setup_decimation_stages_bw(oracle_kind, fs, max_rate, want):

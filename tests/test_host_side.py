@@ -71,6 +71,52 @@ def test_sentence_matcher_equals_std_regex_on_fuzz():
     assert matched > 300 and checked == 6000
 
 
+def _text_layer_model(chunks):
+    """Decoder.h:572-613,635-636 with the restatement's std::regex extraction (the reference's extractSentence)."""
+    stream, last, sentences = b"", b"", []
+    for raw in chunks:
+        if not raw:
+            continue
+        stream += bytes(c for c in raw if (32 <= c < 127) or c == 10)
+        if len(stream) > 20:
+            while True:
+                m = po.port_extract_sentence(stream)
+                if m is None:
+                    break
+                cs, data, crc, rest = m
+                stream = stream[rest:].replace(b"\n", b" ")
+                last = cs + b"," + data + b"*" + crc
+                if crc == po.port_crc16(cs + b"," + data):
+                    sentences.append(last)
+        if len(stream) > 1000:
+            k = stream.rfind(b"$")
+            stream = stream[k:] if k >= 0 else b""
+    return sentences, last, stream
+
+
+def test_text_layer_incremental_scan_equals_full_scan_on_fuzz():
+    """TextChannel::feed skips the sentence scan unless the new characters can complete a CRC group; the result has to be
+    what rescanning the whole stream after every push gives (the reference's behaviour), for any chunking."""
+    rng = random.Random(11)
+    n_sent = 0
+    for it in range(300):
+        parts = []
+        for k in range(rng.randint(1, 6)):
+            body = "C%d,%d" % (rng.randint(0, 99), rng.randint(0, 999)) + "".join(rng.choice(",.12ab$ ") for _ in range(rng.randint(0, 5)))
+            crc = api.crc16(body.encode()).decode() if rng.random() < 0.7 else "".join(rng.choice("0123ABC_#") for _ in range(rng.randint(0, 5)))
+            parts.append("".join(rng.choice("$*,ab1 \n\x00\xff#") for _ in range(rng.randint(0, 12))) + "$" * rng.randint(1, 3) + body + rng.choice("**$") + crc + rng.choice(["\n", "", "x"]))
+        text = "".join(parts).encode("latin1")
+        chunks, o = [], 0
+        while o < len(text):
+            k = rng.choice([0, 1, 1, 2, 3, 5, 8, 30])
+            chunks.append(text[o:o + k]); o += k
+        got = api.text_replay(chunks)
+        want = _text_layer_model(chunks)
+        assert (got[0], got[1], got[2]) == (want[0], want[1], want[2]), repr(text)
+        n_sent += len(want[0])
+    assert n_sent > 300
+
+
 def test_sentence_matcher_real_sentences():
     s = synth.make_sentence(12, 3)
     stream = ("noise" + s + s[:20]).encode()
