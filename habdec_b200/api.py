@@ -43,6 +43,16 @@ class ChannelStats(C.Structure):
     _fields_ = [("num_ok_", C.c_uint), ("D_", GpsDistance), ("dist_max_", C.c_double), ("elev_min_", C.c_double), ("age_s", C.c_double)]
 
 
+class ResultRecord(C.Structure):
+    """hbd_result_record: the 768-byte wire format of the multi-GPU result gather (include/habdec_b200.h)."""
+    _fields_ = [("channel", C.c_uint32), ("n_chars", C.c_uint32), ("n_sentences", C.c_uint32), ("sentence_bytes", C.c_uint32),
+                ("flags", C.c_uint32), ("peak_left", C.c_int32), ("peak_right", C.c_int32), ("frequency_correction", C.c_float),
+                ("shift", C.c_float), ("noise_floor", C.c_float), ("noise_variance", C.c_float), ("reserved", C.c_uint32),
+                ("chars", C.c_char * 256), ("sentences", C.c_char * 464)]
+
+
+RECORD_BYTES = C.sizeof(ResultRecord)
+
 TELEMETRY_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(Telemetry), C.c_char_p)
 SSDV_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(SsdvPacketInfo), C.POINTER(C.c_ubyte))
 SENTENCE_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p)
@@ -92,6 +102,7 @@ SIGNATURES = {
     "hbd_poll_chars": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_poll_sentences": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_poll_raw_chars": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_set_raw_chars": (C.c_int, [_H, C.c_int]),
     "hbd_set_sentence_callback": (C.c_int, [_H, SENTENCE_CB, C.c_void_p]),
     "hbd_set_chars_callback": (C.c_int, [_H, CHARS_CB, C.c_void_p]),
     "hbd_set_ssdv": (C.c_int, [_H, C.c_int]),
@@ -123,6 +134,23 @@ SIGNATURES = {
     "hbd_set_demod_accumulate": (C.c_int, [_H, C.c_int]),
     "hbd_get_demod_frame": (C.c_size_t, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_get_demod_frames": (C.c_size_t, [_H, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "hbd_record_set": (None, [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "hbd_pack_results": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_set_stats_snapshot": (C.c_int, [_H, C.c_int]),
+    "hbd_sink_create": (C.c_void_p, [C.c_int]),
+    "hbd_sink_destroy": (None, [C.c_void_p]),
+    "hbd_sink_feed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "hbd_sink_poll_chars": (C.c_size_t, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_sink_poll_sentences": (C.c_size_t, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "hbd_sink_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hbd_sink_totals": (None, [C.c_void_p] + [C.POINTER(C.c_ulonglong)] * 4),
+    "hbd_sink_hash": (C.c_uint64, [C.c_void_p]),
+    "hbd_dist_unique_id": (C.c_int, [C.c_void_p]),
+    "hbd_dist_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
+    "hbd_dist_use_comm": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
+    "hbd_dist_finalize": (C.c_int, [_H]),
+    "hbd_dist_total_channels": (C.c_int, [_H]),
+    "hbd_gather_results": (C.c_int, [_H, C.c_void_p]),
     "hbd_parse_sentence": (C.c_int, [C.c_char_p, C.c_longlong, C.POINTER(Telemetry)]),
     "hbd_parse_sentence_time": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "hbd_parse_gps_pos": (C.c_int, [C.c_char_p, C.POINTER(C.c_float)]),
@@ -270,6 +298,80 @@ def calc_gps_distance(lat1, lon1, alt1, lat2, lon2, alt2) -> GpsDistance:
     g = GpsDistance()
     load().hbd_calc_gps_distance(lat1, lon1, alt1, lat2, lon2, alt2, C.byref(g))
     return g
+
+
+def make_records(channel0: int, chars: list[bytes], sentences: list[bytes], stats=None) -> np.ndarray:
+    """Host-only packer (hbd_record_set): one record per channel from the HEADS of its character / sentence streams.
+    Returns (records uint8[n, 768], chars_used[n], sentence_bytes_used[n])."""
+    lib = load()
+    n = len(chars)
+    recs = np.zeros((n, RECORD_BYTES), dtype=np.uint8)
+    cu, su = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        st = np.asarray(stats[i] if stats is not None else np.zeros(6), dtype=np.float64)
+        lib.hbd_record_set(recs[i].ctypes.data, channel0 + i, chars[i], len(chars[i]), sentences[i], len(sentences[i]), st.ctypes.data, C.byref(a), C.byref(b))
+        cu[i], su[i] = a.value, b.value
+    return recs, cu, su
+
+
+class ResultSink:
+    """Rank-0 side of the result gather (hbd_result_sink, host only): fed with records, polled like a decoder."""
+
+    def __init__(self, total_channels: int):
+        self._lib = load()
+        self._s = C.c_void_p(self._lib.hbd_sink_create(int(total_channels)))
+        self.total_channels = total_channels
+
+    def close(self):
+        if self._s:
+            self._lib.hbd_sink_destroy(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self): return self._s
+
+    def feed(self, records: np.ndarray) -> int:
+        r = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1, RECORD_BYTES)
+        return self._lib.hbd_sink_feed(self._s, r.ctypes.data, r.shape[0])
+
+    def _take(self, fn, ch):
+        n = fn(self._s, ch, None, 0)
+        if not n:
+            return b""
+        buf = C.create_string_buffer(n)
+        fn(self._s, ch, buf, n)
+        return buf.raw[:n]
+
+    def poll_chars(self, ch: int) -> bytes: return self._take(self._lib.hbd_sink_poll_chars, ch)
+    def poll_sentences(self, ch: int) -> list[bytes]:
+        return [x for x in self._take(self._lib.hbd_sink_poll_sentences, ch).split(b"\n") if x]
+
+    def stats(self, ch: int):
+        out = np.zeros(6, dtype=np.float64)
+        return out if self._lib.hbd_sink_stats(self._s, ch, out.ctypes.data) == HBD_OK else None
+
+    def totals(self) -> dict:
+        v = [C.c_ulonglong(0) for _ in range(4)]
+        self._lib.hbd_sink_totals(self._s, *[C.byref(x) for x in v])
+        return {"chars": v[0].value, "sentences": v[1].value, "sentences_min": v[2].value, "records": v[3].value}
+
+    def hash(self) -> int: return int(self._lib.hbd_sink_hash(self._s))
+
+
+def dist_unique_id() -> bytes:
+    """128 bytes that rank 0 hands to every other rank before hbd_dist_init (ncclGetUniqueId)."""
+    buf = (C.c_ubyte * 128)()
+    rc = load().hbd_dist_unique_id(buf)
+    if rc != HBD_OK:
+        raise HbdError("hbd_dist_unique_id failed (%d): NCCL could not be loaded" % rc)
+    return bytes(buf)
 
 
 class Tracker:
@@ -447,6 +549,7 @@ class BatchDecoder:
     def getLastSentence(self, ch=0) -> bytes: return self._bytes(self._lib.hbd_get_last_sentence, ch)
     def poll_chars(self, ch=0) -> bytes: return self._bytes(self._lib.hbd_poll_chars, ch)
     def poll_raw_chars(self, ch=0) -> bytes: return self._bytes(self._lib.hbd_poll_raw_chars, ch)
+    def set_raw_chars(self, on: bool): self._chk(self._lib.hbd_set_raw_chars(self._h, int(on)))
     def poll_sentences(self, ch=0) -> list[bytes]:
         return [s for s in self._bytes(self._lib.hbd_poll_sentences, ch).split(b"\n") if s]
 
@@ -567,6 +670,30 @@ class BatchDecoder:
 
     def demod_frames(self, resolution: int, type_size: int) -> list[bytes]:
         return self._frames(self._lib.hbd_get_demod_frames, resolution, type_size)
+
+    # ---- multi-GPU result gather
+    def pack_results(self, ch_offset: int = 0) -> np.ndarray:
+        """uint8[n_channels, 768]: one hbd_result_record per channel; consumes the pending characters / sentences."""
+        recs = np.zeros((self.n_channels, RECORD_BYTES), dtype=np.uint8)
+        n = self._lib.hbd_pack_results(self._h, int(ch_offset), recs.ctypes.data, self.n_channels)
+        if n != self.n_channels:
+            raise HbdError("hbd_pack_results failed: %s" % (self._lib.hbd_last_error(self._h) or b"").decode())
+        return recs
+
+    def set_stats_snapshot(self, on: bool = True): self._chk(self._lib.hbd_set_stats_snapshot(self._h, int(on)))
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes | None):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id) if unique_id else None
+        self._chk(self._lib.hbd_dist_init(self._h, int(rank), int(world), buf))
+
+    def dist_finalize(self): self._chk(self._lib.hbd_dist_finalize(self._h))
+    def dist_total_channels(self) -> int: return self._lib.hbd_dist_total_channels(self._h)
+
+    def gather_results(self, sink: "ResultSink | None") -> int:
+        rc = self._lib.hbd_gather_results(self._h, sink.handle if sink is not None else None)
+        if rc < 0:
+            self._chk(rc)
+        return rc
 
     def stats_all(self) -> np.ndarray:
         """[n_channels, 6] float64: frequency correction, shift, noise floor, noise variance, peak left, peak right."""

@@ -20,6 +20,7 @@
 #include "hbd_common.cuh"
 #include "host_tail.h"
 #include "telemetry_abi.h"
+#include "api_internal.h"
 #include "nco.cuh"
 #include "ssdv.cuh"
 #include "tail.cuh"
@@ -95,6 +96,17 @@ __global__ void init_cfg_kernel(ChanState* st, const double* baud, const float* 
     st[ch].rtty_bits = bits[ch];
     st[ch].dc_remove = dc[ch];
     st[ch].lp_ntaps = ntaps[ch];
+}
+
+// the per-channel scalars that travel with the gathered results (hbd_result_record), packed after every call
+__global__ void stats_snap_kernel(const ChanState* __restrict__ st, float* __restrict__ out, int n_ch)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_ch) return;
+    const ChanState& s = st[ch];
+    float* o = out + size_t(ch) * 6;
+    o[0] = float(s.afc_correction); o[1] = float(s.afc_shift_hz); o[2] = float(s.afc_noise_floor); o[3] = float(s.afc_noise_var);
+    o[4] = float(s.gui_left); o[5] = float(s.gui_right);
 }
 
 } // namespace
@@ -198,7 +210,10 @@ struct hbd_decoder {
     cudaStream_t copy_stream = nullptr;  // result read-back, independent of the compute streams
     std::vector<uint2> h_log;            // host staging
     std::vector<std::string> call_chars; // per channel: raw chars of the call being replayed
-    std::vector<int> touched;
+    std::vector<unsigned> seg_start;     // collect_locked: first log entry of every (call, channel) segment
+    std::vector<int> split_channels;     // channels whose characters of the call being replayed span several segments
+    static constexpr int kCharBufHost = 64;   // == kCharBuf (slicer_dev.cuh): characters per device-side flush
+    bool keep_raw = true;                // hbd_set_raw_chars: retain the raw (unfiltered) characters for hbd_poll_raw_chars
     float* d_taps1 = nullptr; float* d_taps2 = nullptr;
     float2* d_twiddle = nullptr;
     // config upload scratch
@@ -259,6 +274,15 @@ struct hbd_decoder {
     hbd_tracker* tracker = nullptr; int tracker_off = 0;   // telemetry layer fed after the sentence callback
     hbd_chars_cb chars_cb = nullptr; void* chars_user = nullptr;
     std::vector<Deferred> deferred;  // callbacks recorded by collect_locked, fired by the entry point after unlocking
+    // result gather (gather.cpp / dist.cu): AFC scalars of every channel snapshotted after each call into a small device
+    // ring, so that a drain can read the values that belong to the calls it drains without stopping the pipeline
+    static constexpr unsigned kSnapSlots = 32;
+    bool snap_on = false;
+    float* d_snap = nullptr;         // [kSnapSlots][n][6]
+    float* h_snap = nullptr;         // pinned, [n][6]: snapshot of the newest drained call
+    bool h_snap_valid = false;
+    void* dist_ctx = nullptr;        // dist.cu
+    int enable_snap();
 
     void set_error(const std::string& e) { err = e; }
     int ensure_call_capacity(size_t n_in_max);
@@ -448,6 +472,9 @@ void hbd_decoder::free_all()
                     d_ssdv_ring, d_ssdv_total, d_ssdv_scanned, d_ssdv_log};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_pinned) cudaFreeHost(h_pinned);
+    if (dist_ctx) { internal_free_dist(dist_ctx); dist_ctx = nullptr; }
+    if (d_snap) cudaFree(d_snap);
+    if (h_snap) cudaFreeHost(h_snap);
     if (h_heads) cudaFreeHost(h_heads);
     if (h_tail_pin) cudaFreeHost(h_tail_pin);
     for (cudaEvent_t e : ev_call) cudaEventDestroy(e);
@@ -780,6 +807,10 @@ int hbd_decoder::process_async_locked()
     carry_cur ^= 1;
     if (any_work) s1_cur ^= 1; // the tail (which moves the stage-2 history to the other buffer) ran
     launches += unsigned(nl);
+    if (snap_on) {
+        stats_snap_kernel<<<(n_ch + 127) / 128, 128, 0, lo>>>(d_state, d_snap + size_t(call_seq % kSnapSlots) * n * 6, n_ch);
+        ++launches;
+    }
     // commit: the log control words as they stand after this call, into the call's pinned slot (stream order: every
     // entry below these heads is completely written when ev_call fires)
     const size_t slot = call_seq % ev_call.size();
@@ -865,6 +896,11 @@ int hbd_decoder::collect_locked(unsigned lag)
         log_tail = head;
         result = HBD_ERR_STATE;
     }
+    if (snap_on && call_seq - (upto - 1u) < kSnapSlots - 1u) {   // the slot of call upto-1 has not been reused yet
+        HBD_CUDA_CHECK(cudaMemcpyAsync(h_snap, d_snap + size_t((upto - 1u) % kSnapSlots) * size_t(n_ch) * 6, sizeof(float) * 6 * size_t(n_ch),
+                                       cudaMemcpyDeviceToHost, copy_stream));
+        h_snap_valid = true;
+    }
     const unsigned avail = head - log_tail;
     h_log.resize(avail);
     if (avail) {
@@ -889,40 +925,69 @@ int hbd_decoder::collect_locked(unsigned lag)
             Deferred ev; ev.kind = Deferred::kSentence; ev.ch = ch; ev.a = cs; ev.b = d; ev.c = crc;
             deferred.push_back(std::move(ev));
         };
-    // the log is sorted by call; replay call by call, channel by channel
-    size_t i = 0;
-    while (i < h_log.size()) {
-        const unsigned seq = h_log[i].y >> 8;
-        touched.clear();
-        size_t j = i;
-        for (; j < h_log.size() && (h_log[j].y >> 8) == seq; ++j) {
-            const int ch = int(h_log[j].x);
-            if (ch < 0 || ch >= n_ch) continue;
-            if (call_chars[size_t(ch)].empty()) touched.push_back(ch);
-            call_chars[size_t(ch)].push_back(char(h_log[j].y & 0xffu));
+    // The log is sorted by call, and within a call a channel's characters form ONE contiguous segment (one reservation per
+    // flush; only a channel that decodes more than kCharBuf = 64 characters in a call flushes twice).  Replay segment by
+    // segment: one TextChannel::feed per channel and call, like one Decoder::process().  The per-channel state is
+    // scattered over the heap, so the loop is bound by cache misses: the next segments' states are prefetched.
+    auto feed_channel = [&](int ch, const unsigned char* chars, size_t n_chars) {
+        TextChannel& tc = text[size_t(ch)];
+        const size_t before = tc.chars_pending.size();
+        tc.feed(chars, n_chars, ch, sink, keep_raw);
+        if (chars_cb && tc.chars_pending.size() > before) {   // character_callback_, Decoder.h:617-629 (not paced by wall clock)
+            Deferred ev; ev.kind = Deferred::kChars; ev.ch = ch; ev.a.assign(tc.chars_pending.data() + before, tc.chars_pending.size() - before);
+            deferred.push_back(std::move(ev));
         }
-        for (int ch : touched) {
-            std::string& cc = call_chars[size_t(ch)];
-            TextChannel& tc = text[size_t(ch)];
-            const size_t before = tc.chars_pending.size();
-            tc.feed(reinterpret_cast<const unsigned char*>(cc.data()), cc.size(), ch, sink);
-            if (chars_cb && tc.chars_pending.size() > before) {   // character_callback_, Decoder.h:617-629 (not paced by wall clock)
-                Deferred ev; ev.kind = Deferred::kChars; ev.ch = ch; ev.a.assign(tc.chars_pending.data() + before, tc.chars_pending.size() - before);
-                deferred.push_back(std::move(ev));
-            }
-            if (ssdv_on) {   // Decoder.h:573: one SSDV_wraper_t::push per call that decoded characters
-                SsdvEvent sev;
-                if (ssdv[size_t(ch)].push(reinterpret_cast<const unsigned char*>(cc.data()), cc.size(), sev)) {
-                    ssdv[size_t(ch)].events_pending.push_back(sev);
-                    if (ssdv_cb) {   // ssdv_callback_, Decoder.h:631-632
-                        Deferred ev; ev.kind = Deferred::kSsdv; ev.ch = ch; fill_ssdv_info(ev.info, sev); ev.pkt = sev.data;
-                        deferred.push_back(std::move(ev));
-                    }
+        if (ssdv_on) {   // Decoder.h:573: one SSDV_wraper_t::push per call that decoded characters
+            SsdvEvent sev;
+            if (ssdv[size_t(ch)].push(chars, n_chars, sev)) {
+                ssdv[size_t(ch)].events_pending.push_back(sev);
+                if (ssdv_cb) {   // ssdv_callback_, Decoder.h:631-632
+                    Deferred ev; ev.kind = Deferred::kSsdv; ev.ch = ch; fill_ssdv_info(ev.info, sev); ev.pkt = sev.data;
+                    deferred.push_back(std::move(ev));
                 }
             }
-            cc.clear();
         }
+    };
+    const size_t n_log = h_log.size();
+    // segment boundaries first (sequential pass over the copied log), then the scattered per-channel work
+    seg_start.clear();
+    for (size_t i = 0; i < n_log;) {
+        size_t j = i + 1;
+        while (j < n_log && h_log[j].x == h_log[i].x && (h_log[j].y >> 8) == (h_log[i].y >> 8)) ++j;
+        seg_start.push_back(unsigned(i));
         i = j;
+    }
+    seg_start.push_back(unsigned(n_log));
+    const size_t n_seg = seg_start.size() - 1;
+    unsigned char seg_chars[kCharBufHost];
+    for (size_t k = 0; k < n_seg; ++k) {
+        if (k + 8 < n_seg) { const unsigned c8 = h_log[seg_start[k + 8]].x; if (c8 < unsigned(n_ch)) __builtin_prefetch(&text[c8]); }
+        if (k + 4 < n_seg) { const unsigned c4 = h_log[seg_start[k + 4]].x; if (c4 < unsigned(n_ch)) text[c4].prefetch_tails(); }
+        const size_t i0 = seg_start[k], i1 = seg_start[k + 1];
+        const int ch = int(h_log[i0].x);
+        if (ch < 0 || ch >= n_ch) continue;
+        const unsigned seq = h_log[i0].y >> 8;
+        const size_t len = i1 - i0;
+        // a full buffer means the channel flushed more than once in this call: join the pieces (rare: > 64 characters of
+        // one channel in one call); they need not be adjacent in the log
+        bool joined = len >= size_t(kCharBufHost);
+        if (!joined && !split_channels.empty()) joined = std::find(split_channels.begin(), split_channels.end(), ch) != split_channels.end();
+        if (joined) {
+            if (call_chars[size_t(ch)].empty()) split_channels.push_back(ch);
+            for (size_t i = i0; i < i1; ++i) call_chars[size_t(ch)].push_back(char(h_log[i].y & 0xffu));
+        } else {
+            for (size_t i = 0; i < len; ++i) seg_chars[i] = (unsigned char)(h_log[i0 + i].y & 0xffu);
+            feed_channel(ch, seg_chars, len);
+        }
+        // end of this call's entries: feed the joined channels
+        if (!split_channels.empty() && (k + 1 == n_seg || (h_log[seg_start[k + 1]].y >> 8) != seq)) {
+            for (int sc : split_channels) {
+                std::string& cc = call_chars[size_t(sc)];
+                feed_channel(sc, reinterpret_cast<const unsigned char*>(cc.data()), cc.size());
+                cc.clear();
+            }
+            split_channels.clear();
+        }
     }
     (void)upto24;
     calls_collected = upto;
@@ -958,8 +1023,70 @@ int hbd_decoder::enable_ssdv(bool on)
     return HBD_OK;
 }
 
+int hbd_decoder::enable_snap()
+{
+    if (snap_on) return HBD_OK;
+    HBD_CUDA_CHECK(cudaSetDevice(device));
+    if (!d_snap) {
+        HBD_CUDA_CHECK(dalloc(&d_snap, size_t(kSnapSlots) * size_t(n_ch) * 6));
+        HBD_CUDA_CHECK(cudaMemset(d_snap, 0, sizeof(float) * size_t(kSnapSlots) * size_t(n_ch) * 6));
+        HBD_CUDA_CHECK(cudaHostAlloc((void**)&h_snap, sizeof(float) * 6 * size_t(n_ch), cudaHostAllocDefault));
+        memset(h_snap, 0, sizeof(float) * 6 * size_t(n_ch));
+    }
+    snap_on = true;
+    return HBD_OK;
+}
+
+namespace hbd {
+int internal_device(hbd_decoder* h) { return h->device; }
+void internal_set_error(hbd_decoder* h, const std::string& what) { std::lock_guard<std::mutex> l(h->mtx); h->set_error(what); }
+void** internal_dist_slot(hbd_decoder* h) { return &h->dist_ctx; }
+}
+
 // =====================================================================================================
 extern "C" {
+
+// One record per channel with what the sentence layer has produced since the previous pack (printable characters, CRC-valid
+// sentences; what does not fit a record stays for the next one) and the AFC scalars as of the newest drained call.
+size_t hbd_pack_results(hbd_decoder* h, int ch_offset, hbd_result_record* out, size_t cap_records)
+{
+    if (!h) return 0;
+    std::lock_guard<std::mutex> l(h->mtx);
+    const size_t n = size_t(h->n_ch);
+    if (!out || cap_records < n) return n;
+    std::vector<double> st(6 * n, 0.0);
+    if (h->snap_on && h->h_snap_valid) {
+        for (size_t i = 0; i < 6 * n; ++i) st[i] = h->h_snap[i];
+    } else {   // no snapshot yet: read the live state (waits for the calls in flight)
+        if (h->enable_snap() != HBD_OK) return 0;
+        cudaSetDevice(h->device);
+        h->sync_groups();
+        cudaStreamSynchronize(h->stream);
+        std::vector<ChanState> cs(n);
+        if (cudaMemcpy(cs.data(), h->d_state, n * sizeof(ChanState), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+        for (size_t c = 0; c < n; ++c) {
+            st[6 * c + 0] = cs[c].afc_correction; st[6 * c + 1] = cs[c].afc_shift_hz; st[6 * c + 2] = cs[c].afc_noise_floor;
+            st[6 * c + 3] = cs[c].afc_noise_var; st[6 * c + 4] = cs[c].gui_left; st[6 * c + 5] = cs[c].gui_right;
+        }
+    }
+    for (size_t c = 0; c < n; ++c) {
+        TextChannel& tc = h->text[c];
+        size_t cu = 0, su = 0;
+        hbd_record_set(out + c, uint32_t(ch_offset + int(c)), tc.chars_pending.data(), tc.chars_pending.size(), tc.sentences_pending.data(),
+                       tc.sentences_pending.size(), st.data() + 6 * c, &cu, &su);
+        if (cu) tc.chars_pending.erase(0, cu);
+        if (su) tc.sentences_pending.erase(0, su);
+    }
+    return n;
+}
+int hbd_set_stats_snapshot(hbd_decoder* h, int on)
+{
+    HBD_CHECK_H(h);
+    std::lock_guard<std::mutex> l(h->mtx);
+    if (on) return h->enable_snap();
+    h->snap_on = false; h->h_snap_valid = false;
+    return HBD_OK;
+}
 
 int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
 {
@@ -1485,6 +1612,10 @@ size_t hbd_poll_raw_chars(hbd_decoder* h, int ch, unsigned char* out, size_t cap
     if (out && cap >= n) v.clear();
     return n;
 }
+int hbd_set_raw_chars(hbd_decoder* h, int on)
+{
+    HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); h->keep_raw = on != 0; return HBD_OK;
+}
 int hbd_attach_tracker(hbd_decoder* h, hbd_tracker* t, int ch_offset)
 {
     HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); h->tracker = t; h->tracker_off = ch_offset; return HBD_OK;
@@ -1909,7 +2040,7 @@ size_t hbd_text_replay(const unsigned char* chars, const size_t* chunk_sizes, si
     if (!chars || !chunk_sizes) return 0;
     TextChannel tc;
     size_t off = 0;
-    for (size_t c = 0; c < n_chunks; ++c) { tc.feed(chars + off, chunk_sizes[c], 0, SentenceSink()); off += chunk_sizes[c]; }
+    for (size_t c = 0; c < n_chunks; ++c) { tc.feed(chars + off, chunk_sizes[c], 0, SentenceSink(), true); off += chunk_sizes[c]; }
     const std::string rep = tc.sentences_pending + "\x1e" + tc.last_sentence + "\x1e" + tc.text_stream;
     if (out && cap) memcpy(out, rep.data(), std::min(cap, rep.size()));
     return rep.size();

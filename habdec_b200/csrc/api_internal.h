@@ -1,0 +1,10 @@
+// internal hooks between the translation units of libhabdec_b200.so (not part of the ABI)
+#pragma once
+#include <string>
+struct hbd_decoder;
+namespace hbd {
+int internal_device(hbd_decoder* h);
+void internal_set_error(hbd_decoder* h, const std::string& what);
+void** internal_dist_slot(hbd_decoder* h);     // opaque per-handle context of dist.cu
+void internal_free_dist(void* ctx);            // implemented in dist.cu, called by hbd_destroy
+}

@@ -120,10 +120,10 @@ bool extract_sentence(const std::string& stream_in, SentenceMatch& m)
 }
 
 // ---- per-channel text state: Decoder.h:572-613,635-636 ------------------------------------------------------
-void TextChannel::feed(const unsigned char* raw, size_t n, int ch, const SentenceSink& sink)
+void TextChannel::feed(const unsigned char* raw, size_t n, int ch, const SentenceSink& sink, bool keep_raw)
 {
     if (!n) return; // the reference returns before touching the streams when no char was decoded (:568-569)
-    raw_pending.insert(raw_pending.end(), raw, raw + n);
+    if (keep_raw) raw_pending.insert(raw_pending.end(), raw, raw + n);
     const size_t old_len = text_stream.size();
     for (size_t i = 0; i < n; ++i) {
         const char c = char(raw[i]);

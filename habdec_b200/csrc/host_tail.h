@@ -33,7 +33,13 @@ struct TextChannel {
     std::string sentences_pending;  // CRC-valid sentences since the last poll
     std::vector<unsigned char> raw_pending; // raw chars since the last poll (SSDV consumers)
     bool scan_clean = true;         // text_stream is known to hold no extractable sentence (see feed)
-    void feed(const unsigned char* raw, size_t n, int ch, const SentenceSink& sink);
+    void feed(const unsigned char* raw, size_t n, int ch, const SentenceSink& sink, bool keep_raw);
+    // pull the ends of the two strings feed() appends to into the cache (the drain loop knows its next channels)
+    void prefetch_tails() const
+    {
+        __builtin_prefetch(text_stream.data() + text_stream.size());
+        __builtin_prefetch(chars_pending.data() + chars_pending.size());
+    }
 };
 
 // ---- SSDV packet sync: the buffer automaton and image bookkeeping of SSDV_wraper_t (ssdv_wrapper.cpp:37-148) -------

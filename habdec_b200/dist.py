@@ -1,12 +1,12 @@
 """Multi-GPU plumbing: channels are block-partitioned over ranks (one process per GPU) and never
-exchange signal data; only decoded sentences and per-channel AFC/stat records travel, once per
-batch, to rank 0 (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests).
+exchange signal data; only fixed-size result records (decoded characters, sentences, AFC scalars:
+hbd_result_record, include/habdec_b200.h) travel, once per batch, to rank 0 -- inside the library over
+NCCL (csrc/dist.cu: hbd_dist_init / hbd_gather_results), or through torch.distributed with
+gather_records() below (gloo in the CPU tests).
 The one exception is the wideband channeliser (BASELINE configs[4]): every rank needs the whole
 capture, so the rank that owns the receiver broadcasts each block once (20 MS/s x 8 B = 160 MB/s)
 and every rank cuts its own slice of frequency-offset channels out of it."""
 from __future__ import annotations
-
-import json
 
 import numpy as np
 
@@ -33,38 +33,26 @@ def wideband_plan(offsets_hz, world: int, rank: int):
     return mine.start, [float(offsets_hz[c]) for c in mine]
 
 
-def collect_local_results(dec, ch0: int) -> dict:
-    """Drain one BatchDecoder: {global_channel: {"sentences": [...], "last": str, "afc": [corr, shift, nf, nv, pl, pr]}}."""
-    stats = dec.stats_all()
-    out = {}
-    for c in range(dec.n_channels):
-        out[ch0 + c] = {"sentences": [s.decode("latin1") for s in dec.poll_sentences(c)],
-                        "last": dec.getLastSentence(c).decode("latin1"),
-                        "afc": [float(x) for x in stats[c]]}
-    return out
-
-
-def gather_to_rank0(local: dict, world: int, rank: int, device) -> dict | None:
-    """All ranks call this; rank 0 gets the merged dict, the others None.  Two collectives: sizes, then one
-    padded uint8 all_gather (fixed-size records are latency bound, so one message per rank per batch)."""
-    if world == 1:
-        return {int(k): v for k, v in local.items()}
+def gather_records(records, world: int, rank: int, device):
+    """hbd_result_record blocks (uint8 [n_local, 768], the output of BatchDecoder.pack_results / api.make_records) of
+    all ranks, in rank order, through torch.distributed (gloo in the CPU tests; any backend).  Ranks may own different
+    numbers of channels.  Rank 0 gets uint8 [n_total, 768] (to be fed to a ResultSink), the others None.
+    On GPUs the library moves the records itself over NCCL (hbd_dist_init / hbd_gather_results, csrc/dist.cu); this is
+    the same gather for transports the library does not know."""
+    import numpy as np
     import torch
     import torch.distributed as dist
-    payload = np.frombuffer(json.dumps(local).encode(), dtype=np.uint8)
-    size = torch.tensor([payload.size], dtype=torch.int64, device=device)
-    sizes = [torch.zeros_like(size) for _ in range(world)]
-    dist.all_gather(sizes, size)
-    max_len = int(max(int(s.item()) for s in sizes))
-    buf = torch.zeros(max_len, dtype=torch.uint8, device=device)
-    buf[:payload.size] = torch.from_numpy(payload.copy()).to(device)
+    recs = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1, records.shape[-1])
+    if world == 1:
+        return recs
+    n = torch.tensor([recs.shape[0]], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    buf = torch.zeros((max(counts), recs.shape[1]), dtype=torch.uint8, device=device)
+    buf[:recs.shape[0]] = torch.from_numpy(recs).to(device)
     bufs = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(bufs, buf)
     if rank != 0:
         return None
-    merged = {}
-    for r in range(world):
-        raw = bytes(bufs[r][:int(sizes[r].item())].cpu().numpy())
-        for k, v in json.loads(raw.decode()).items():
-            merged[int(k)] = v
-    return merged
+    return np.concatenate([bufs[r][:counts[r]].cpu().numpy() for r in range(world)], axis=0)

@@ -8,7 +8,11 @@
  *
  * Threading model follows the reference (Decoder.h:146-196): one thread feeds
  * and processes, other threads may call getters/setters; all entry points take
- * the handle's mutex.
+ * the handle's mutex.  Callbacks fire on the thread that called hbd_process() /
+ * hbd_collect*() AFTER the mutex has been released, so a callback may call any
+ * hbd_* function of the same handle (like the reference's callbacks may call
+ * getRTTY()/getLastSentence()).  hbd_last_error() returns a pointer that the next
+ * failing call on the handle overwrites.
  *
  * Batch-wide by design: the input sampling rate and the decimation plan are
  * shared by all channels of a handle (they are channels of one capture / one
@@ -131,6 +135,9 @@ size_t hbd_poll_chars(hbd_decoder* h, int ch, char* out, size_t cap);
 size_t hbd_poll_sentences(hbd_decoder* h, int ch, char* out, size_t cap);
 /* raw UART characters (what the reference hands to SSDV_wraper_t::push, Decoder.h:572-573) since the previous poll */
 size_t hbd_poll_raw_chars(hbd_decoder* h, int ch, unsigned char* out, size_t cap);
+/* retain raw characters for hbd_poll_raw_chars (default on; the reference itself keeps none, a caller that never polls
+ * them switches it off) */
+int    hbd_set_raw_chars(hbd_decoder* h, int on);
 int    hbd_set_sentence_callback(hbd_decoder* h, hbd_sentence_cb cb, void* user);
 int    hbd_set_chars_callback(hbd_decoder* h, hbd_chars_cb cb, void* user);
 
@@ -182,6 +189,58 @@ size_t hbd_get_spectrum_info(hbd_decoder* h, int ch, hbd_spectrum_info* info, fl
 /* the per-channel record that is gathered to rank 0: out[6*ch + 0..5] = frequency correction, shift, noise floor,
  * noise variance, peak left, peak right (one device->host copy for all channels); returns 6*n_channels */
 size_t hbd_get_stats_batch(hbd_decoder* h, double* out, size_t cap_doubles);
+
+/* ---- multi-GPU result gather -------------------------------------------------------------------------
+ * Channels are block-partitioned over ranks (one process per GPU, one hbd_decoder each) and never exchange signal data.
+ * What travels, once per batch of calls, is one fixed-size record per channel with what the reference's callbacks and
+ * getters would have delivered since the previous gather: character_callback_ / sentence_callback_ payloads
+ * (Decoder.h:135-138) and getFrequencyCorrection / getShift / getNoiseFloor / getPeaks (Decoder.h:108-113).
+ * Rank 0 feeds the records into a host-only hbd_result_sink, which a server polls like a decoder.  The records can
+ * travel over any transport (hbd_pack_results + hbd_sink_feed); hbd_dist_* / hbd_gather_results move them over NCCL
+ * (bound at run time with dlopen: the library does not link against it). */
+typedef struct hbd_result_record {          /* wire format, 768 bytes, little endian */
+    uint32_t channel;                       /* global channel number */
+    uint32_t n_chars;                       /* printable characters in chars[] */
+    uint32_t n_sentences;                   /* CRC-valid sentences in sentences[], "callsign,data*crc\n" each */
+    uint32_t sentence_bytes;
+    uint32_t flags;                         /* 1: more characters wait for the next record, 2: more sentences wait, 4: a sentence was cut */
+    int32_t  peak_left, peak_right;
+    float    frequency_correction, shift, noise_floor, noise_variance;
+    uint32_t reserved;
+    char     chars[256];
+    char     sentences[464];
+} hbd_result_record;
+/* fill one record from the heads of a character stream and a sentence stream (whole sentences only); *_used = taken */
+void   hbd_record_set(hbd_result_record* r, uint32_t channel, const char* chars, size_t n_chars, const char* sentences, size_t sentence_bytes,
+                      const double stats[6], size_t* chars_used, size_t* sentence_bytes_used);
+/* one record per local channel (channel = ch_offset + local index) with what hbd_poll_chars / hbd_poll_sentences would
+ * return (and consumes it like they do) plus the AFC scalars as of the newest drained call; returns n_channels */
+size_t hbd_pack_results(hbd_decoder* h, int ch_offset, hbd_result_record* out, size_t cap_records);
+/* keep a per-call snapshot of the AFC scalars on the device so that hbd_pack_results never waits for calls in flight
+ * (switched on by hbd_dist_init and by the first hbd_pack_results) */
+int    hbd_set_stats_snapshot(hbd_decoder* h, int on);
+typedef struct hbd_result_sink hbd_result_sink;
+hbd_result_sink* hbd_sink_create(int total_channels);
+void   hbd_sink_destroy(hbd_result_sink* s);
+int    hbd_sink_feed(hbd_result_sink* s, const hbd_result_record* recs, size_t n);
+size_t hbd_sink_poll_chars(hbd_result_sink* s, int ch, char* out, size_t cap);
+size_t hbd_sink_poll_sentences(hbd_result_sink* s, int ch, char* out, size_t cap);
+int    hbd_sink_stats(hbd_result_sink* s, int ch, double out[6]);   /* correction, shift, noise floor, noise variance, peak l, peak r */
+void   hbd_sink_totals(hbd_result_sink* s, unsigned long long* chars, unsigned long long* sentences, unsigned long long* min_sentences,
+                       unsigned long long* records);
+/* FNV-1a over every channel's character and sentence STREAMS: independent of the sharding and of the gather cadence, so
+ * the same channels decoded on 1, 2, 4 or 8 GPUs give the same value (the correctness check of SURVEY 8e) */
+uint64_t hbd_sink_hash(hbd_result_sink* s);
+/* NCCL transport.  Rank 0 draws an id (hbd_dist_unique_id) and hands the 128 bytes to the other ranks by any means; every
+ * rank then calls hbd_dist_init (ncclCommInitRank on the handle's device), or adopts an ncclComm_t it already has. */
+int    hbd_dist_unique_id(unsigned char out[128]);
+int    hbd_dist_init(hbd_decoder* h, int rank, int world, const unsigned char id[128]);
+int    hbd_dist_use_comm(hbd_decoder* h, void* nccl_comm, int rank, int world);
+int    hbd_dist_finalize(hbd_decoder* h);
+int    hbd_dist_total_channels(hbd_decoder* h);
+/* every rank, at the same points of its call sequence: pack, ncclSend to rank 0 / ncclRecv there, feed `sink` (rank 0 only;
+ * ignored elsewhere).  Global channel = channels of the lower ranks + local index.  Returns the records moved, < 0 on error */
+int    hbd_gather_results(hbd_decoder* h, hbd_result_sink* sink);
 
 /* ---- websocket wire formats, produced on the GPU (the step after the path) -----------------------------------
  * PWR_ payload of "cmd::power:res=R,zoom=Z" (habdec_ws_protocol.cpp:353-404): SpectrumInfoHeader (NetTransport.h:29-47)
