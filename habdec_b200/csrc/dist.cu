@@ -144,7 +144,8 @@ static int dist_attach(hbd_decoder* h, int rank, int world, ncclComm comm, bool 
     if (*slot) { free_ctx(static_cast<DistCtx*>(*slot)); *slot = nullptr; }
     DistCtx* c = new DistCtx;
     c->rank = rank; c->world = world; c->comm = comm; c->own_comm = own;
-    const int rc = setup(h, c);
+    int rc = setup(h, c);
+    if (!rc) rc = hbd_set_stats_snapshot(h, 1);   // a gather never waits for calls in flight
     if (rc) { free_ctx(c); return rc; }
     *slot = c;
     return HBD_OK;
@@ -221,7 +222,10 @@ int hbd_gather_results(hbd_decoder* h, hbd_result_sink* sink)
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(h, "gather: transfer failed");
     }
     ++c->gathers;
-    if (c->rank != 0) return mine;
+    if (c->rank != 0) {   // a sink on another rank mirrors that rank's own channels (same global numbering)
+        if (sink) { const int rc = hbd_sink_feed(sink, c->h_send, size_t(mine)); if (rc) return rc; }
+        return mine;
+    }
     int rc = hbd_sink_feed(sink, c->h_send, size_t(mine));
     if (c->world > 1 && !rc) rc = hbd_sink_feed(sink, c->h_recv + mine, size_t(c->total - mine));
     return rc ? rc : c->total;

@@ -71,7 +71,7 @@ constexpr uint64_t kFnvInit = 0xcbf29ce484222325ull;
 struct SinkChan {
     std::string chars, sentences;            // since the previous poll
     uint64_t h_chars = kFnvInit, h_sent = kFnvInit, n_chars = 0, n_sent = 0;
-    hbd_result_record last{};                 // scalars of the newest record (text fields unused)
+    float stats[4] = {0, 0, 0, 0}; int32_t peaks[2] = {0, 0};   // scalars of the newest record
     bool seen = false;
 };
 } // namespace
@@ -104,7 +104,8 @@ int hbd_sink_feed(hbd_result_sink* s, const hbd_result_record* recs, size_t n)
         c.sentences.append(r.sentences, r.sentence_bytes);
         c.h_chars = fnv1a(c.h_chars, r.chars, r.n_chars); c.n_chars += r.n_chars;
         c.h_sent = fnv1a(c.h_sent, r.sentences, r.sentence_bytes); c.n_sent += r.n_sentences;
-        c.last = r; c.seen = true;
+        c.stats[0] = r.frequency_correction; c.stats[1] = r.shift; c.stats[2] = r.noise_floor; c.stats[3] = r.noise_variance;
+        c.peaks[0] = r.peak_left; c.peaks[1] = r.peak_right; c.seen = true;
         ++s->records;
     }
     return rc;
@@ -133,8 +134,8 @@ int hbd_sink_stats(hbd_result_sink* s, int ch, double out[6])
     if (!s || !out || ch < 0 || size_t(ch) >= s->ch.size()) return HBD_ERR_ARG;
     const SinkChan& c = s->ch[size_t(ch)];
     if (!c.seen) return HBD_ERR_STATE;
-    out[0] = c.last.frequency_correction; out[1] = c.last.shift; out[2] = c.last.noise_floor; out[3] = c.last.noise_variance;
-    out[4] = c.last.peak_left; out[5] = c.last.peak_right;
+    for (int i = 0; i < 4; ++i) out[i] = c.stats[i];
+    out[4] = c.peaks[0]; out[5] = c.peaks[1];
     return HBD_OK;
 }
 // totals over all channels (what was ever fed, polled or not)

@@ -70,17 +70,19 @@ def channel_iq(channel: int, n_sentences: int, fs: float, baud: float, nbits: in
 
 # ---------------------------------------------------------------------------------------------------
 # Periodic "ring" workload for bench.py (BASELINE.json configs[3]: 300 baud 8N2, many channels).
-# One ring = 192 bit periods = 17 UART characters + 5 idle bits; at fs = 2.048 MS/s and 300 baud that is
-# exactly 1 310 720 samples (3 bits == 20 480 samples), i.e. 5 chunks of 262 144 or 20 of 65 536.
+# One ring = 240 bit periods = 21 UART characters (one CRC-valid sentence) + 9 idle bits; at fs = 2.048 MS/s and
+# 300 baud that is exactly 1 638 400 samples (3 bits == 20 480 samples), i.e. 25 chunks of 65 536.
+# The sentence has 21 characters because the reference only scans its text stream for sentences once it holds more
+# than 20 (Decoder.h:591): every ring pass then yields one extracted sentence per channel.
 # A sub-Hz frequency trim makes the phase wrap exactly, so replaying the ring is an endless,
-# continuous-phase RTTY stream that repeats one CRC-valid sentence per pass.
+# continuous-phase RTTY stream.
 # ---------------------------------------------------------------------------------------------------
-RING_BITS = 192
+RING_BITS = 240
 
 
 def ring_sentence(channel: int) -> str:
-    body = "C%04d,%03d" % (channel % 10000, (channel * 7 + 123) % 1000)
-    return "$$" + body + "*" + crc16_ccitt(body.encode()) + "\n"      # 17 characters
+    body = "C%04d,%03d,%03d" % (channel % 10000, (channel * 7 + 123) % 1000, (channel * 13 + 7) % 1000)
+    return "$$" + body + "*" + crc16_ccitt(body.encode()) + "\n"      # 21 characters
 
 
 def ring_bits(channel: int, nbits: int = 8, nstops: int = 2) -> np.ndarray:
@@ -120,17 +122,20 @@ def ring_iq_numpy(channel: int, fs: float = 2.048e6, baud: float = 300.0, shift:
 def ring_iq_torch(ch0: int, n_ch: int, device, fs: float = 2.048e6, baud: float = 300.0, shift: float = 425.0,
                   snr_db: float | None = -15.0, slice_channels: int = 32):
     """Channels ch0..ch0+n_ch-1 of the ring workload generated on `device`: float32 tensor [n_ch, L, 2]
-    (interleaved cf32, row pitch L samples).  Same construction as ring_iq_numpy (different noise stream)."""
+    (interleaved cf32, row pitch L samples).  Same construction as ring_iq_numpy (different noise stream).  The noise
+    generator is re-seeded for every slice of 32 channels from the slice's first GLOBAL channel number, so channel c gets
+    the same samples whether it is generated as part of a 512- or a 4096-channel block (strong-scaling invariance)."""
     import torch
     L = ring_length(fs, baud)
     out = torch.empty((n_ch, L, 2), dtype=torch.float32, device=device)
     n = torch.arange(L, dtype=torch.float64, device=device)
     bi = torch.clamp((n * (baud / fs)).to(torch.int64), max=RING_BITS - 1)
     gen = torch.Generator(device=device)
-    gen.manual_seed(424242 + ch0)
     sigma = None if snr_db is None else 10.0 ** (-snr_db / 20.0) / np.sqrt(2.0)
+    assert ch0 % slice_channels == 0, "channel blocks start on a multiple of %d (the noise is seeded per slice)" % slice_channels
     for s in range(0, n_ch, slice_channels):
         e = min(n_ch, s + slice_channels)
+        gen.manual_seed(424242 + ch0 + s)      # a channel's samples depend on its GLOBAL number only, not on the sharding
         bits = torch.from_numpy(np.stack([ring_bits(ch0 + c) for c in range(s, e)])).to(device)
         f = torch.where(bits[:, bi] > 0, 0.5 * shift, -0.5 * shift).to(torch.float64)
         total = 2.0 * np.pi * f.sum(dim=1, keepdim=True) / fs

@@ -238,8 +238,9 @@ int    hbd_dist_init(hbd_decoder* h, int rank, int world, const unsigned char id
 int    hbd_dist_use_comm(hbd_decoder* h, void* nccl_comm, int rank, int world);
 int    hbd_dist_finalize(hbd_decoder* h);
 int    hbd_dist_total_channels(hbd_decoder* h);
-/* every rank, at the same points of its call sequence: pack, ncclSend to rank 0 / ncclRecv there, feed `sink` (rank 0 only;
- * ignored elsewhere).  Global channel = channels of the lower ranks + local index.  Returns the records moved, < 0 on error */
+/* every rank, at the same points of its call sequence: pack, ncclSend to rank 0 / ncclRecv there, feed `sink`: on rank 0
+ * (required) with the records of ALL channels; on other ranks (optional, may be NULL) with the rank's own records, a local
+ * mirror.  Global channel = channels of the lower ranks + local index.  Returns the records moved, < 0 on error */
 int    hbd_gather_results(hbd_decoder* h, hbd_result_sink* sink);
 
 /* ---- websocket wire formats, produced on the GPU (the step after the path) -----------------------------------

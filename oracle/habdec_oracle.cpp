@@ -768,4 +768,30 @@ double orc_bench(const hbo_config* cfg, int n_threads, const float* iq, size_t n
     return *std::max_element(secs.begin(), secs.end());
 }
 
+void orc_run_ring(const hbo_config* cfg, int n_threads, const float* iq, size_t n_channels, size_t stride, size_t ring_n, size_t chunk,
+                  size_t first_chunk, size_t n_chunks, double fs, char* chars_out, size_t chars_pitch, uint32_t* chars_len,
+                  char* sent_out, size_t sent_pitch, uint32_t* sent_len)
+{
+    std::atomic<size_t> next{0};
+    const size_t slices = ring_n / chunk;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < std::max(1, n_threads); ++t)
+        pool.emplace_back([&] {
+            for (size_t c; (c = next.fetch_add(1)) < n_channels;) {
+                Port P;
+                hbo_config cc = *cfg; cc.record = 0;
+                P.configure(cc);
+                const float* src = iq + 2 * c * stride;
+                for (size_t k = 0; k < n_chunks; ++k) {
+                    P.push(src + 2 * (((first_chunk + k) % slices) * chunk), chunk, fs);
+                    P.process();
+                }
+                chars_len[c] = uint32_t(P.chars_all.size()); sent_len[c] = uint32_t(P.sentences.size());
+                memcpy(chars_out + c * chars_pitch, P.chars_all.data(), std::min(P.chars_all.size(), chars_pitch));
+                memcpy(sent_out + c * sent_pitch, P.sentences.data(), std::min(P.sentences.size(), sent_pitch));
+            }
+        });
+    for (auto& x : pool) x.join();
+}
+
 } // extern "C"

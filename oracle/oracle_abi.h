@@ -97,7 +97,14 @@ typedef struct hbo_ssdv_event {
        passes; returns wall seconds of the slowest thread, total printable \
        chars decoded in *o_chars */ \
     double P##_bench(const hbo_config* cfg, int n_threads, const float* iq, size_t n_complex, \
-                     size_t stride_complex, size_t chunk, double fs, int reps, uint64_t* o_chars);
+                     size_t stride_complex, size_t chunk, double fs, int reps, uint64_t* o_chars); \
+    /* parity checker for whole batches: n_channels decoders (each on its OWN fresh OS thread, n_threads at a time), \
+       channel c decodes the periodic stream iq + c*stride_complex (period ring_n samples) in `chunk`-sized pushes, \
+       chunks first_chunk .. first_chunk+n_chunks-1 of the stream; chars_out + c*pitch receives the printable \
+       characters (count in chars_len[c], truncated to pitch), sent_out likewise the '\n'-joined CRC-valid sentences */ \
+    void   P##_run_ring(const hbo_config* cfg, int n_threads, const float* iq, size_t n_channels, size_t stride_complex, \
+                        size_t ring_n, size_t chunk, size_t first_chunk, size_t n_chunks, double fs, \
+                        char* chars_out, size_t chars_pitch, uint32_t* chars_len, char* sent_out, size_t sent_pitch, uint32_t* sent_len);
 
 HBO_DECL(ref)
 HBO_DECL(orc)

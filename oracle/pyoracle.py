@@ -68,6 +68,10 @@ def _bind(lib, p):
                            C.c_double, C.c_int, C.POINTER(C.c_uint64)]
 
 
+    f("run_ring").argtypes = [C.POINTER(Config), C.c_int, C.c_void_p] + [C.c_size_t] * 6 + [C.c_double, C.c_void_p, C.c_size_t, C.c_void_p,
+                              C.c_void_p, C.c_size_t, C.c_void_p]
+
+
 _libs = {}
 
 
@@ -271,6 +275,24 @@ def bench(kind: str, cfg: Config, iq: np.ndarray, n_threads: int, fs: float, chu
     secs = getattr(lib, kind + "_bench")(C.byref(cfg), n_threads, iq.ctypes.data, n, stride, chunk, float(fs), reps,
                                          C.byref(chars))
     return secs, chars.value
+
+
+def run_ring(kind: str, cfg: Config, iq: np.ndarray, n_threads: int, fs: float, chunk: int, first_chunk: int, n_chunks: int,
+             pitch: int = 4096):
+    """Whole-batch parity checker: iq complex64 [n_channels, ring_n] (periodic streams); every channel is decoded by its
+    own decoder on a fresh OS thread, `n_threads` at a time, over chunks first_chunk .. first_chunk+n_chunks-1.
+    Returns ([printable chars per channel], [CRC-valid sentences per channel])."""
+    lib = _load(kind)
+    iq = np.ascontiguousarray(iq, dtype=np.complex64)
+    n_ch, ring_n = iq.shape
+    chars = np.zeros((n_ch, pitch), dtype=np.uint8)
+    sents = np.zeros((n_ch, pitch), dtype=np.uint8)
+    cl, sl = np.zeros(n_ch, dtype=np.uint32), np.zeros(n_ch, dtype=np.uint32)
+    getattr(lib, kind + "_run_ring")(C.byref(cfg), int(n_threads), iq.ctypes.data, n_ch, ring_n, ring_n, int(chunk), int(first_chunk),
+                                     int(n_chunks), float(fs), chars.ctypes.data, pitch, cl.ctypes.data, sents.ctypes.data, pitch, sl.ctypes.data)
+    assert int(cl.max(initial=0)) <= pitch and int(sl.max(initial=0)) <= pitch, "run_ring: output pitch too small"
+    return ([chars[c, :cl[c]].tobytes() for c in range(n_ch)],
+            [[x for x in sents[c, :sl[c]].tobytes().split(b"\n") if x] for c in range(n_ch)])
 
 
 def port_extract_sentence(stream: bytes):

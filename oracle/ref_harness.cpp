@@ -394,4 +394,40 @@ double ref_bench(const hbo_config* cfg, int n_threads, const float* iq, size_t n
     return *std::max_element(secs.begin(), secs.end());
 }
 
+void ref_run_ring(const hbo_config* cfg, int n_threads, const float* iq, size_t n_channels, size_t stride, size_t ring_n, size_t chunk,
+                  size_t first_chunk, size_t n_chunks, double fs, char* chars_out, size_t chars_pitch, uint32_t* chars_len,
+                  char* sent_out, size_t sent_pitch, uint32_t* sent_len)
+{
+    std::atomic<size_t> next{0};
+    const size_t slices = ring_n / chunk;
+    auto one_channel = [&](size_t c) {
+        habdec::Decoder<float> D;
+        configure(D, *cfg);
+        std::string chars, sentences;
+        D.character_callback_ = [&](std::string s) { chars += s; };
+        D.sentence_callback_ = [&](std::string cs, std::string data, std::string crc) { sentences += cs + "," + data + "*" + crc + "\n"; };
+        habdec::IQVector<float> v;
+        v.samplingRate(fs);
+        const std::complex<float>* src = reinterpret_cast<const std::complex<float>*>(iq) + c * stride;
+        for (size_t k = 0; k < n_chunks; ++k) {
+            const size_t o = ((first_chunk + k) % slices) * chunk;
+            v.resize(chunk);
+            memcpy(v.data(), src + o, chunk * sizeof(std::complex<float>));
+            D.pushSamples(v);
+            D();
+        }
+        chars += D.chr_callback_stream_;
+        chars_len[c] = uint32_t(chars.size()); sent_len[c] = uint32_t(sentences.size());
+        memcpy(chars_out + c * chars_pitch, chars.data(), std::min(chars.size(), chars_pitch));
+        memcpy(sent_out + c * sent_pitch, sentences.data(), std::min(sentences.size(), sent_pitch));
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < std::max(1, n_threads); ++t)
+        pool.emplace_back([&] {
+            // a fresh OS thread per Decoder: FSK2_Demod's carry and the callback timer are thread_local statics
+            for (size_t c; (c = next.fetch_add(1)) < n_channels;) std::thread(one_channel, c).join();
+        });
+    for (auto& x : pool) x.join();
+}
+
 } // extern "C"

@@ -178,49 +178,56 @@ def test_noise_only_and_silence(oracle_kind):
 
 def test_cfg4_full_width_4096_channels(oracle_kind):
     """BASELINE configs[3] at full size on one GPU: 4096 channels x 2.048 MS/s, 300 baud 8N2, 65 536-sample chunks,
-    zero-copy device pushes, pipelined calls.  Size-independent properties over ALL channels (every channel decodes
-    its own CRC-valid ring sentence, nothing leaks between channels) and exact parity with the oracle on a sample."""
+    zero-copy device pushes, pipelined calls, results taken through the gather path (hbd_gather_results -> sink) while
+    calls are in flight.  EVERY channel is compared with the oracle (one reference Decoder per channel on the host
+    threads): characters and sentences exact; plus the size-independent properties (each channel decodes its own
+    CRC-valid ring sentence, nothing leaks between channels)."""
+    import os
     import torch
     fs, baud, chunk, n_ch = 2.048e6, 300.0, 65536, 4096
     L = synth.ring_length(fs, baud)
-    passes = 2
+    slices = L // chunk
+    steps = 2 * slices + 7
     dev = torch.device("cuda", 0)
-    ring = synth.ring_iq_torch(0, n_ch, dev, fs, baud, snr_db=-15.0)      # [n_ch, L, 2] f32 resident in HBM (43 GB)
+    ring = synth.ring_iq_torch(0, n_ch, dev, fs, baud, snr_db=-15.0)      # [n_ch, L, 2] f32 resident in HBM (54 GB)
     torch.cuda.synchronize()
     dec = api.BatchDecoder(n_ch, baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
     dec.set_stream(torch.cuda.current_stream().cuda_stream)
-    steps = passes * L // chunk
+    dec.dist_init(0, 1, None)
+    sink = api.ResultSink(n_ch)
     for i in range(steps):
-        dec.pushSamplesDevice(ring.data_ptr() + (i % (L // chunk)) * chunk * 8, chunk, L, fs)
+        dec.pushSamplesDevice(ring.data_ptr() + (i % slices) * chunk * 8, chunk, L, fs)
         dec.process_async()
         if (i + 1) % 16 == 0:
             dec.collect_ready(4)
+            assert dec.gather_results(sink) == n_ch
     dec.collect()
-    n_sent = 0
+    while True:                      # records hold 256 characters: a second round only if some channel had more pending
+        assert dec.gather_results(sink) == n_ch
+        if all(not dec.poll_chars(c) for c in (0, n_ch // 2, n_ch - 1)):
+            break
+    got_chars = [sink.poll_chars(c) for c in range(n_ch)]
+    got_sents = [sink.poll_sentences(c) for c in range(n_ch)]
     for c in range(n_ch):
-        want = synth.ring_sentence(c).strip().lstrip("$").encode()       # "Cxxxx,yyy*CRC"
-        sents = dec.poll_sentences(c)
-        assert 1 <= len(sents) <= passes, "channel %d decoded %d sentences" % (c, len(sents))
-        assert all(s == want for s in sents), "channel %d: %r != %r" % (c, sents, want)
+        want = synth.ring_sentence(c).strip().lstrip("$").encode()       # "Cxxxx,yyy,zzz*CRC"
+        assert len(got_sents[c]) == 2 and all(s == want for s in got_sents[c]), "channel %d: %r" % (c, got_sents[c])
         body, crc = want.split(b"*")
         assert synth.crc16_ccitt(body).encode() == crc
-        n_sent += len(sents)
-    assert n_sent >= n_ch * (passes - 1)
-    # exact parity on a sample of channels (first, last, span boundaries of K1's warps, a few random ones)
-    rng = np.random.default_rng(17)
-    sample = sorted(set([0, 1, 2, 3, 4, 2047, 2048, n_ch - 2, n_ch - 1] + [int(x) for x in rng.integers(0, n_ch, 7)]))
-    dec2 = api.BatchDecoder(n_ch, baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256)   # fresh state: text stream this time
-    dec2.set_stream(torch.cuda.current_stream().cuda_stream)
-    for i in range(steps):
-        dec2.pushSamplesDevice(ring.data_ptr() + (i % (L // chunk)) * chunk * 8, chunk, L, fs)
-        dec2.process_async()
-    dec2.collect()
-    for c in sample:
-        iq = ring[c].cpu().numpy().view(np.complex64).reshape(-1)
-        ref = make_oracle(oracle_kind, baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
-        ref.run(np.concatenate([iq] * passes), fs, chunk)
-        assert dec2.poll_chars(c) == ref.chars(), "channel %d" % c
-        assert dec2.poll_sentences(c) == ref.sentences(), "channel %d" % c
+    assert sink.totals()["sentences_min"] == 2
+    # the oracle on ALL channels, in slabs that fit host memory
+    cfg = po.make_config(baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256, record=False)
+    threads = os.cpu_count() or 4
+    bad = []
+    for c0 in range(0, n_ch, 256):
+        iq = ring[c0:c0 + 256].cpu().numpy().view(np.complex64).reshape(256, L)
+        ref_chars, ref_sents = po.run_ring(oracle_kind, cfg, iq, threads, fs, chunk, 0, steps)
+        for k in range(256):
+            if got_chars[c0 + k] != ref_chars[k] or got_sents[c0 + k] != ref_sents[k]:
+                bad.append(c0 + k)
+    assert not bad, "%d of %d channels differ from the %s oracle, first: %r" % (len(bad), n_ch, oracle_kind, bad[:8])
+    # AFC scalars travelled with the records
+    st = sink.stats(7)
+    assert st is not None and abs(st[2] - dec.getNoiseFloor(7)[0]) < 1e-3
     del ring
     torch.cuda.empty_cache()
 

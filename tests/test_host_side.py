@@ -134,9 +134,9 @@ def test_block_partition():
 
 def test_ring_workload_properties():
     L = synth.ring_length(2.048e6, 300.0)
-    assert L == 1310720 and L % 65536 == 0 and L % 262144 == 0
+    assert L == 1638400 and L % 65536 == 0
     s = synth.ring_sentence(77)
-    assert len(s) == 17 and s.startswith("$$C0077,")
+    assert len(s) == 21 and s.startswith("$$C0077,")      # > 20 characters: the reference scans its stream once per pass (Decoder.h:591)
     assert len(synth.ring_bits(77)) == synth.RING_BITS
 
 
