@@ -339,12 +339,33 @@ def parity_check(D: Dist, args, leg, n_local, ch0):
     except Exception:
         threads = os.cpu_count() or 1
     sink, ring, L = leg["sink"], leg["ring"], leg["L"]
+    torch = D.torch
     t0 = time.time()
     bad, n_chars, n_sent, sent_min = [], 0, 0, None
     slab = 128
-    for c0 in range(0, n_local, slab):
+    # the ring goes back to the host slab by slab through two pinned buffers; the copy of the next slab runs while the
+    # host threads decode the current one
+    bufs = [torch.empty((slab, L, 2), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    events = [None, None]
+
+    def fetch(i):
+        c0 = i * slab
         c1 = min(n_local, c0 + slab)
-        iq = ring[c0:c1].cpu().numpy().view(np.complex64).reshape(c1 - c0, L)
+        with torch.cuda.stream(copy_stream):
+            bufs[i % 2][:c1 - c0].copy_(ring[c0:c1], non_blocking=True)
+            events[i % 2] = torch.cuda.Event()
+            events[i % 2].record(copy_stream)
+
+    n_slabs = (n_local + slab - 1) // slab
+    fetch(0)
+    for i in range(n_slabs):
+        c0 = i * slab
+        c1 = min(n_local, c0 + slab)
+        events[i % 2].synchronize()
+        if i + 1 < n_slabs:
+            fetch(i + 1)
+        iq = bufs[i % 2][:c1 - c0].numpy().view(np.complex64).reshape(c1 - c0, L)
         ref_chars, ref_sents = po.run_ring(kind, cfg, iq, threads, FS, args.chunk, 0, leg["chunks_decoded"])
         for k in range(c1 - c0):
             g = ch0 + c0 + k
@@ -353,6 +374,7 @@ def parity_check(D: Dist, args, leg, n_local, ch0):
             sent_min = len(got_s) if sent_min is None else min(sent_min, len(got_s))
             if got_c != ref_chars[k] or got_s != ref_sents[k]:
                 bad.append(g)
+    del bufs
     checked = D.sum_int(n_local)
     mism = D.sum_int(len(bad))
     smin = int(min(D.all_values(float(sent_min or 0))))

@@ -44,11 +44,11 @@ class ChannelStats(C.Structure):
 
 
 class ResultRecord(C.Structure):
-    """hbd_result_record: the 768-byte wire format of the multi-GPU result gather (include/habdec_b200.h)."""
-    _fields_ = [("channel", C.c_uint32), ("n_chars", C.c_uint32), ("n_sentences", C.c_uint32), ("sentence_bytes", C.c_uint32),
-                ("flags", C.c_uint32), ("peak_left", C.c_int32), ("peak_right", C.c_int32), ("frequency_correction", C.c_float),
+    """hbd_result_record: the 256-byte wire format of the multi-GPU result gather (include/habdec_b200.h)."""
+    _fields_ = [("channel", C.c_uint32), ("n_chars", C.c_uint16), ("sentence_bytes", C.c_uint16), ("n_sentences", C.c_uint16),
+                ("flags", C.c_uint16), ("peak_left", C.c_int32), ("peak_right", C.c_int32), ("frequency_correction", C.c_float),
                 ("shift", C.c_float), ("noise_floor", C.c_float), ("noise_variance", C.c_float), ("reserved", C.c_uint32),
-                ("chars", C.c_char * 256), ("sentences", C.c_char * 464)]
+                ("chars", C.c_char * 88), ("sentences", C.c_char * 128)]
 
 
 RECORD_BYTES = C.sizeof(ResultRecord)
@@ -188,6 +188,8 @@ def load():
                                "(habdec_b200 has no CPU or pure-Python compute path)")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if os.environ.get("HBD_LIB") and not hasattr(lib, name):
+                continue              # an older tuning / comparison build (tools/ab_step.py)
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
@@ -302,7 +304,7 @@ def calc_gps_distance(lat1, lon1, alt1, lat2, lon2, alt2) -> GpsDistance:
 
 def make_records(channel0: int, chars: list[bytes], sentences: list[bytes], stats=None) -> np.ndarray:
     """Host-only packer (hbd_record_set): one record per channel from the HEADS of its character / sentence streams.
-    Returns (records uint8[n, 768], chars_used[n], sentence_bytes_used[n])."""
+    Returns (records uint8[n, 256], chars_used[n], sentence_bytes_used[n])."""
     lib = load()
     n = len(chars)
     recs = np.zeros((n, RECORD_BYTES), dtype=np.uint8)
@@ -673,7 +675,7 @@ class BatchDecoder:
 
     # ---- multi-GPU result gather
     def pack_results(self, ch_offset: int = 0) -> np.ndarray:
-        """uint8[n_channels, 768]: one hbd_result_record per channel; consumes the pending characters / sentences."""
+        """uint8[n_channels, 256]: one hbd_result_record per channel; consumes the pending characters / sentences."""
         recs = np.zeros((self.n_channels, RECORD_BYTES), dtype=np.uint8)
         n = self._lib.hbd_pack_results(self._h, int(ch_offset), recs.ctypes.data, self.n_channels)
         if n != self.n_channels:

@@ -173,6 +173,8 @@ struct hbd_decoder {
         else for (auto& x : hc) x.pushed += n;
     }
     std::vector<TextChannel> text;   // sentence layer state, touched only when a channel produced characters
+    bool spill_free = true;                // no channel holds spilled (beyond-the-slot) pending bytes: hbd_pack_results stays sequential
+    std::vector<hbd_result_record> pend;   // per channel: characters / sentence bytes waiting for a poll or the next gather (host_tail.h)
 
     // device state
     ChanState* d_state = nullptr;
@@ -931,10 +933,12 @@ int hbd_decoder::collect_locked(unsigned lag)
     // scattered over the heap, so the loop is bound by cache misses: the next segments' states are prefetched.
     auto feed_channel = [&](int ch, const unsigned char* chars, size_t n_chars) {
         TextChannel& tc = text[size_t(ch)];
-        const size_t before = tc.chars_pending.size();
-        tc.feed(chars, n_chars, ch, sink, keep_raw);
-        if (chars_cb && tc.chars_pending.size() > before) {   // character_callback_, Decoder.h:617-629 (not paced by wall clock)
-            Deferred ev; ev.kind = Deferred::kChars; ev.ch = ch; ev.a.assign(tc.chars_pending.data() + before, tc.chars_pending.size() - before);
+        hbd_result_record& pr = pend[size_t(ch)];
+        const size_t before = chars_cb ? tc.chars_size(pr) : 0;
+        tc.feed(chars, n_chars, ch, sink, keep_raw, pr);
+        if (!tc.chars_spill.empty() || !tc.sent_spill.empty()) spill_free = false;
+        if (chars_cb && tc.chars_size(pr) > before) {   // character_callback_, Decoder.h:617-629 (not paced by wall clock)
+            Deferred ev; ev.kind = Deferred::kChars; ev.ch = ch; ev.a = tc.chars_from(pr, before);
             deferred.push_back(std::move(ev));
         }
         if (ssdv_on) {   // Decoder.h:573: one SSDV_wraper_t::push per call that decoded characters
@@ -961,7 +965,7 @@ int hbd_decoder::collect_locked(unsigned lag)
     const size_t n_seg = seg_start.size() - 1;
     unsigned char seg_chars[kCharBufHost];
     for (size_t k = 0; k < n_seg; ++k) {
-        if (k + 8 < n_seg) { const unsigned c8 = h_log[seg_start[k + 8]].x; if (c8 < unsigned(n_ch)) __builtin_prefetch(&text[c8]); }
+        if (k + 8 < n_seg) { const unsigned c8 = h_log[seg_start[k + 8]].x; if (c8 < unsigned(n_ch)) { __builtin_prefetch(&text[c8]); __builtin_prefetch(&pend[c8]); } }
         if (k + 4 < n_seg) { const unsigned c4 = h_log[seg_start[k + 4]].x; if (c4 < unsigned(n_ch)) text[c4].prefetch_tails(); }
         const size_t i0 = seg_start[k], i1 = seg_start[k + 1];
         const int ch = int(h_log[i0].x);
@@ -1069,14 +1073,28 @@ size_t hbd_pack_results(hbd_decoder* h, int ch_offset, hbd_result_record* out, s
             st[6 * c + 3] = cs[c].afc_noise_var; st[6 * c + 4] = cs[c].gui_left; st[6 * c + 5] = cs[c].gui_right;
         }
     }
+    // the pending slots ARE the records: copy, stamp, reset (and move spilled bytes up)
+    bool any_left = false;
     for (size_t c = 0; c < n; ++c) {
-        TextChannel& tc = h->text[c];
-        size_t cu = 0, su = 0;
-        hbd_record_set(out + c, uint32_t(ch_offset + int(c)), tc.chars_pending.data(), tc.chars_pending.size(), tc.sentences_pending.data(),
-                       tc.sentences_pending.size(), st.data() + 6 * c, &cu, &su);
-        if (cu) tc.chars_pending.erase(0, cu);
-        if (su) tc.sentences_pending.erase(0, su);
+        hbd_result_record& pr = h->pend[c];
+        hbd_result_record& o = out[c];
+        o = pr;
+        o.channel = uint32_t(ch_offset + int(c));
+        const double* sc = st.data() + 6 * c;
+        o.frequency_correction = float(sc[0]); o.shift = float(sc[1]); o.noise_floor = float(sc[2]); o.noise_variance = float(sc[3]);
+        o.peak_left = int32_t(sc[4]); o.peak_right = int32_t(sc[5]);
+        o.n_sentences = pr.sentence_bytes ? uint16_t(std::count(pr.sentences, pr.sentences + pr.sentence_bytes, '\n')) : uint16_t(0);
+        pr.n_chars = 0; pr.sentence_bytes = 0;
+        uint16_t fl = 0;
+        if (__builtin_expect(!h->spill_free, 0)) {
+            TextChannel& tc = h->text[c];
+            if (!tc.chars_spill.empty()) { fl |= 1u; TextChannel::refill(pr.chars, pr.n_chars, sizeof(pr.chars), tc.chars_spill); }
+            if (!tc.sent_spill.empty()) { fl |= 2u; TextChannel::refill(pr.sentences, pr.sentence_bytes, sizeof(pr.sentences), tc.sent_spill); }
+            any_left = any_left || !tc.chars_spill.empty() || !tc.sent_spill.empty();
+        }
+        o.flags = fl;
     }
+    if (!h->spill_free) h->spill_free = !any_left;
     return n;
 }
 int hbd_set_stats_snapshot(hbd_decoder* h, int on)
@@ -1102,6 +1120,7 @@ int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
     if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) h->n_sms = prop.multiProcessorCount;
     h->hc.resize(size_t(n_channels));
     h->text.resize(size_t(n_channels));
+    { hbd_result_record z; memset(&z, 0, sizeof(z)); h->pend.assign(size_t(n_channels), z); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return HBD_ERR_CUDA; }
     h->own_stream = true;
     {
@@ -1528,6 +1547,11 @@ int hbd_set_kernel_timing(hbd_decoder* h, int on)
     std::lock_guard<std::mutex> l(h->mtx);
     h->timing = on != 0;
     h->ev_used_k1 = h->ev_used_rest = 0;
+    if (on) {   // events are created here, not on the issue path of the calls being measured
+        cudaSetDevice(h->device);
+        for (auto* pool : {&h->ev_k1, &h->ev_rest})
+            while (pool->size() < 1024) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return HBD_ERR_CUDA; pool->push_back(e); }
+    }
     return HBD_OK;
 }
 
@@ -1588,18 +1612,22 @@ size_t hbd_poll_chars(hbd_decoder* h, int ch, char* out, size_t cap)
 {
     if (!h || ch < 0 || ch >= h->n_ch) return 0;
     std::lock_guard<std::mutex> l(h->mtx);
-    std::string& s = h->text[size_t(ch)].chars_pending;
-    const size_t n = copy_out(s, out, cap);
-    if (out && cap >= n) s.clear();
+    TextChannel& tc = h->text[size_t(ch)];
+    hbd_result_record& pr = h->pend[size_t(ch)];
+    const size_t n = tc.chars_size(pr);
+    if (out && cap && n) { const std::string s = tc.chars_from(pr, 0); memcpy(out, s.data(), std::min(cap, n)); }
+    if (out && cap >= n) tc.clear_chars(pr);
     return n;
 }
 size_t hbd_poll_sentences(hbd_decoder* h, int ch, char* out, size_t cap)
 {
     if (!h || ch < 0 || ch >= h->n_ch) return 0;
     std::lock_guard<std::mutex> l(h->mtx);
-    std::string& s = h->text[size_t(ch)].sentences_pending;
-    const size_t n = copy_out(s, out, cap);
-    if (out && cap >= n) s.clear();
+    TextChannel& tc = h->text[size_t(ch)];
+    hbd_result_record& pr = h->pend[size_t(ch)];
+    const size_t n = tc.sent_size(pr);
+    if (out && cap && n) { const std::string s = tc.sentences_all(pr); memcpy(out, s.data(), std::min(cap, n)); }
+    if (out && cap >= n) tc.clear_sentences(pr);
     return n;
 }
 size_t hbd_poll_raw_chars(hbd_decoder* h, int ch, unsigned char* out, size_t cap)
@@ -2039,9 +2067,10 @@ size_t hbd_text_replay(const unsigned char* chars, const size_t* chunk_sizes, si
 {
     if (!chars || !chunk_sizes) return 0;
     TextChannel tc;
+    hbd_result_record pr; memset(&pr, 0, sizeof(pr));
     size_t off = 0;
-    for (size_t c = 0; c < n_chunks; ++c) { tc.feed(chars + off, chunk_sizes[c], 0, SentenceSink(), true); off += chunk_sizes[c]; }
-    const std::string rep = tc.sentences_pending + "\x1e" + tc.last_sentence + "\x1e" + tc.text_stream;
+    for (size_t c = 0; c < n_chunks; ++c) { tc.feed(chars + off, chunk_sizes[c], 0, SentenceSink(), true, pr); off += chunk_sizes[c]; }
+    const std::string rep = tc.sentences_all(pr) + "\x1e" + tc.last_sentence + "\x1e" + tc.text_stream;
     if (out && cap) memcpy(out, rep.data(), std::min(cap, rep.size()));
     return rep.size();
 }

@@ -13,12 +13,12 @@
 #include <string>
 #include <vector>
 
-static_assert(sizeof(hbd_result_record) == 768, "hbd_result_record is a wire format: 768 bytes");
+static_assert(sizeof(hbd_result_record) == 256, "hbd_result_record is a wire format: 256 bytes");
 
 extern "C" {
 
-// Fill one record from the head of a character stream and a '\n'-terminated sentence stream.  Whole sentences only.
-// Returns through *chars_used / *sentence_bytes_used how much was taken; the rest waits for the next record.
+// Fill one record from the heads of a character stream and of a sentence stream ('\n'-terminated sentences; the
+// streams are cut wherever the record is full).  *chars_used / *sentence_bytes_used = bytes taken.
 void hbd_record_set(hbd_result_record* r, uint32_t channel, const char* chars, size_t n_chars, const char* sentences, size_t sentence_bytes,
                     const double stats[6], size_t* chars_used, size_t* sentence_bytes_used)
 {
@@ -26,35 +26,19 @@ void hbd_record_set(hbd_result_record* r, uint32_t channel, const char* chars, s
     r->channel = channel;
     const size_t nc = std::min(n_chars, sizeof(r->chars));
     if (nc) memcpy(r->chars, chars, nc);
-    r->n_chars = uint32_t(nc);
+    r->n_chars = uint16_t(nc);
     if (nc < n_chars) r->flags |= 1u;
-    size_t used = 0; uint32_t ns = 0;
-    while (used < sentence_bytes) {
-        const void* nl = memchr(sentences + used, '\n', sentence_bytes - used);
-        const size_t len = nl ? size_t(static_cast<const char*>(nl) - (sentences + used)) + 1 : sentence_bytes - used;
-        if (used + len > sizeof(r->sentences)) {
-            if (used == 0 && len > sizeof(r->sentences)) {   // a single sentence longer than the slot: cut it (never stall the stream)
-                memcpy(r->sentences, sentences, sizeof(r->sentences) - 1);
-                r->sentences[sizeof(r->sentences) - 1] = '\n';
-                r->sentence_bytes = uint32_t(sizeof(r->sentences)); ns = 1; used = len; r->flags |= 4u;
-                if (used < sentence_bytes) r->flags |= 2u;
-                goto done;
-            }
-            r->flags |= 2u;
-            break;
-        }
-        memcpy(r->sentences + used, sentences + used, len);
-        used += len; ++ns;
-    }
-    r->sentence_bytes = uint32_t(used);
-done:
-    r->n_sentences = ns;
+    const size_t nsb = std::min(sentence_bytes, sizeof(r->sentences));
+    if (nsb) memcpy(r->sentences, sentences, nsb);
+    r->sentence_bytes = uint16_t(nsb);
+    r->n_sentences = uint16_t(std::count(r->sentences, r->sentences + nsb, '\n'));
+    if (nsb < sentence_bytes) r->flags |= 2u;
     if (stats) {
         r->frequency_correction = float(stats[0]); r->shift = float(stats[1]); r->noise_floor = float(stats[2]); r->noise_variance = float(stats[3]);
         r->peak_left = int32_t(stats[4]); r->peak_right = int32_t(stats[5]);
     }
     if (chars_used) *chars_used = nc;
-    if (sentence_bytes_used) *sentence_bytes_used = used;
+    if (sentence_bytes_used) *sentence_bytes_used = nsb;
 }
 
 } // extern "C"
@@ -97,6 +81,11 @@ int hbd_sink_feed(hbd_result_sink* s, const hbd_result_record* recs, size_t n)
     if (!s || (!recs && n)) return HBD_ERR_ARG;
     int rc = HBD_OK;
     for (size_t i = 0; i < n; ++i) {
+        if (i + 8 < n && recs[i + 8].channel < s->ch.size()) {   // the per-channel strings are scattered over the heap
+            const SinkChan& nx = s->ch[recs[i + 8].channel];
+            __builtin_prefetch(nx.chars.data() + nx.chars.size());
+            __builtin_prefetch(nx.sentences.data() + nx.sentences.size());
+        }
         const hbd_result_record& r = recs[i];
         if (r.channel >= s->ch.size() || r.n_chars > sizeof(r.chars) || r.sentence_bytes > sizeof(r.sentences)) { rc = HBD_ERR_ARG; continue; }
         SinkChan& c = s->ch[r.channel];

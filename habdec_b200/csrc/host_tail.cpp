@@ -120,7 +120,7 @@ bool extract_sentence(const std::string& stream_in, SentenceMatch& m)
 }
 
 // ---- per-channel text state: Decoder.h:572-613,635-636 ------------------------------------------------------
-void TextChannel::feed(const unsigned char* raw, size_t n, int ch, const SentenceSink& sink, bool keep_raw)
+void TextChannel::feed(const unsigned char* raw, size_t n, int ch, const SentenceSink& sink, bool keep_raw, hbd_result_record& pend)
 {
     if (!n) return; // the reference returns before touching the streams when no char was decoded (:568-569)
     if (keep_raw) raw_pending.insert(raw_pending.end(), raw, raw + n);
@@ -129,9 +129,10 @@ void TextChannel::feed(const unsigned char* raw, size_t n, int ch, const Sentenc
         const char c = char(raw[i]);
         if ((std::isprint((unsigned char)c) && (unsigned char)c < 0x80) || c == '\n') { // isprint(char) in the "C" locale
             text_stream.push_back(c);
-            chars_pending.push_back(c);
         }
     }
+    if (text_stream.size() > old_len)   // chr_callback_stream_ (:581) == what waits for hbd_poll_chars / the next gather
+        append(pend.chars, pend.n_chars, sizeof(pend.chars), chars_spill, text_stream.data() + old_len, text_stream.size() - old_len);
     if (text_stream.size() > 20) {
         // The scan loop below leaves a stream without a match (scan_clean).  New characters can only complete a match
         // whose CRC group ends among them -- the pattern's trailing `.*` swallows everything behind the CRC, so a match that
@@ -153,8 +154,8 @@ void TextChannel::feed(const unsigned char* raw, size_t n, int ch, const Sentenc
                 text_stream.swap(rest);
                 last_sentence = m.callsign + "," + m.data + "*" + m.crc;
                 if (m.crc == crc16_hex(m.callsign + "," + m.data)) {
-                    sentences_pending += last_sentence;
-                    sentences_pending.push_back('\n');
+                    const std::string line = last_sentence + "\n";
+                    append(pend.sentences, pend.sentence_bytes, sizeof(pend.sentences), sent_spill, line.data(), line.size());
                     if (sink) sink(ch, m.callsign, m.data, m.crc);
                 }
             }

@@ -2,12 +2,16 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <cstring>
+#include <algorithm>
 #include <deque>
 #include <functional>
 #include <map>
 #include <string>
 #include <utility>
 #include <vector>
+
+#include "../../include/habdec_b200.h"
 
 namespace hbd {
 
@@ -25,21 +29,49 @@ bool extract_sentence(const std::string& stream, SentenceMatch& m);
 
 using SentenceSink = std::function<void(int ch, const std::string& callsign, const std::string& data, const std::string& crc)>;
 
-// text side of one channel (Decoder.h:188-200: rtty_char_stream_, last_sentence_, chr_callback_stream_)
+// text side of one channel (Decoder.h:188-200: rtty_char_stream_, last_sentence_, chr_callback_stream_).
+// What waits to be polled / gathered -- printable characters and CRC-valid sentences since the last poll -- lives in the
+// channel's slot of ONE array of hbd_result_record (hbd_decoder::pend): hbd_pack_results is then a sequential copy of that
+// array, and the drain loop touches one cache line of it per channel instead of two scattered heap strings.  What does
+// not fit a slot (88 characters / 128 sentence bytes) spills into the strings below and moves up when the slot is emptied.
 struct TextChannel {
     std::string text_stream;        // getRTTY()
     std::string last_sentence;      // getLastSentence()
-    std::string chars_pending;      // printable chars since the last poll / callback
-    std::string sentences_pending;  // CRC-valid sentences since the last poll
+    std::string chars_spill, sent_spill;
     std::vector<unsigned char> raw_pending; // raw chars since the last poll (SSDV consumers)
     bool scan_clean = true;         // text_stream is known to hold no extractable sentence (see feed)
-    void feed(const unsigned char* raw, size_t n, int ch, const SentenceSink& sink, bool keep_raw);
-    // pull the ends of the two strings feed() appends to into the cache (the drain loop knows its next channels)
-    void prefetch_tails() const
+    void feed(const unsigned char* raw, size_t n, int ch, const SentenceSink& sink, bool keep_raw, hbd_result_record& pend);
+    // pull the end of the string feed() appends to into the cache (the drain loop knows its next channels)
+    void prefetch_tails() const { __builtin_prefetch(text_stream.data() + text_stream.size()); }
+
+    static void append(char* slot, uint16_t& used, size_t cap, std::string& spill, const char* p, size_t n)
     {
-        __builtin_prefetch(text_stream.data() + text_stream.size());
-        __builtin_prefetch(chars_pending.data() + chars_pending.size());
+        if (spill.empty()) {
+            const size_t k = std::min(n, cap - used);
+            memcpy(slot + used, p, k);
+            used = uint16_t(used + k); p += k; n -= k;
+        }
+        if (n) spill.append(p, n);
     }
+    static void refill(char* slot, uint16_t& used, size_t cap, std::string& spill)   // the slot has just been emptied
+    {
+        const size_t k = std::min(cap, spill.size());
+        if (k) { memcpy(slot, spill.data(), k); spill.erase(0, k); }
+        used = uint16_t(k);
+    }
+    size_t chars_size(const hbd_result_record& r) const { return r.n_chars + chars_spill.size(); }
+    size_t sent_size(const hbd_result_record& r) const { return r.sentence_bytes + sent_spill.size(); }
+    std::string chars_from(const hbd_result_record& r, size_t from) const   // pending characters [from, end)
+    {
+        std::string out;
+        if (from < r.n_chars) out.assign(r.chars + from, r.n_chars - from);
+        const size_t sf = from > r.n_chars ? from - r.n_chars : 0;
+        if (sf < chars_spill.size()) out.append(chars_spill, sf, std::string::npos);
+        return out;
+    }
+    std::string sentences_all(const hbd_result_record& r) const { return std::string(r.sentences, r.sentence_bytes) + sent_spill; }
+    void clear_chars(hbd_result_record& r) { r.n_chars = 0; chars_spill.clear(); }
+    void clear_sentences(hbd_result_record& r) { r.sentence_bytes = 0; sent_spill.clear(); }
 };
 
 // ---- SSDV packet sync: the buffer automaton and image bookkeeping of SSDV_wraper_t (ssdv_wrapper.cpp:37-148) -------

@@ -34,9 +34,9 @@ def wideband_plan(offsets_hz, world: int, rank: int):
 
 
 def gather_records(records, world: int, rank: int, device):
-    """hbd_result_record blocks (uint8 [n_local, 768], the output of BatchDecoder.pack_results / api.make_records) of
+    """hbd_result_record blocks (uint8 [n_local, 256], the output of BatchDecoder.pack_results / api.make_records) of
     all ranks, in rank order, through torch.distributed (gloo in the CPU tests; any backend).  Ranks may own different
-    numbers of channels.  Rank 0 gets uint8 [n_total, 768] (to be fed to a ResultSink), the others None.
+    numbers of channels.  Rank 0 gets uint8 [n_total, 256] (to be fed to a ResultSink), the others None.
     On GPUs the library moves the records itself over NCCL (hbd_dist_init / hbd_gather_results, csrc/dist.cu); this is
     the same gather for transports the library does not know."""
     import numpy as np

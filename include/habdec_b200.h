@@ -192,25 +192,26 @@ size_t hbd_get_stats_batch(hbd_decoder* h, double* out, size_t cap_doubles);
 
 /* ---- multi-GPU result gather -------------------------------------------------------------------------
  * Channels are block-partitioned over ranks (one process per GPU, one hbd_decoder each) and never exchange signal data.
- * What travels, once per batch of calls, is one fixed-size record per channel with what the reference's callbacks and
- * getters would have delivered since the previous gather: character_callback_ / sentence_callback_ payloads
+ * What travels, once per batch of calls, is one fixed-size record per channel with (the next piece of) what the reference's
+ * callbacks and getters would have delivered since the previous gather: character_callback_ / sentence_callback_ payloads
  * (Decoder.h:135-138) and getFrequencyCorrection / getShift / getNoiseFloor / getPeaks (Decoder.h:108-113).
  * Rank 0 feeds the records into a host-only hbd_result_sink, which a server polls like a decoder.  The records can
  * travel over any transport (hbd_pack_results + hbd_sink_feed); hbd_dist_* / hbd_gather_results move them over NCCL
  * (bound at run time with dlopen: the library does not link against it). */
-typedef struct hbd_result_record {          /* wire format, 768 bytes, little endian */
+typedef struct hbd_result_record {          /* wire format, 256 bytes, little endian */
     uint32_t channel;                       /* global channel number */
-    uint32_t n_chars;                       /* printable characters in chars[] */
-    uint32_t n_sentences;                   /* CRC-valid sentences in sentences[], "callsign,data*crc\n" each */
-    uint32_t sentence_bytes;
-    uint32_t flags;                         /* 1: more characters wait for the next record, 2: more sentences wait, 4: a sentence was cut */
+    uint16_t n_chars;                       /* bytes used in chars[]: the next printable characters of the channel */
+    uint16_t sentence_bytes;                /* bytes used in sentences[]: the next bytes of the channel's stream of CRC-valid
+                                               sentences, "callsign,data*crc\n" each (a sentence may continue in the next record) */
+    uint16_t n_sentences;                   /* '\n' terminators among them = sentences completed by this record */
+    uint16_t flags;                         /* 1: more characters wait for the next record, 2: more sentence bytes wait */
     int32_t  peak_left, peak_right;
     float    frequency_correction, shift, noise_floor, noise_variance;
     uint32_t reserved;
-    char     chars[256];
-    char     sentences[464];
+    char     chars[88];
+    char     sentences[128];
 } hbd_result_record;
-/* fill one record from the heads of a character stream and a sentence stream (whole sentences only); *_used = taken */
+/* fill one record from the heads of a character stream and a sentence stream; *_used = bytes taken */
 void   hbd_record_set(hbd_result_record* r, uint32_t channel, const char* chars, size_t n_chars, const char* sentences, size_t sentence_bytes,
                       const double stats[6], size_t* chars_used, size_t* sentence_bytes_used);
 /* one record per local channel (channel = ch_offset + local index) with what hbd_poll_chars / hbd_poll_sentences would

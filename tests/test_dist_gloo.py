@@ -64,7 +64,7 @@ def _worker(rank, world, port, n_channels, q):
 @pytest.mark.parametrize("world,n_channels", [(2, 10), (2, 7)])
 def test_result_records_gather_to_rank0_gloo(world, n_channels):
     """the gathered output is identical however the channels are sharded.  Two gloo ranks pack their block of
-    channels into hbd_result_records (several rounds: some streams exceed one record), rank 0 feeds its sink; contents and
+    channels into hbd_result_records (several rounds: most streams exceed one record), rank 0 feeds its sink; contents and
     the sharding-invariant hash have to equal what ONE process gets for all channels."""
     from habdec_b200 import api
     ctx = mp.get_context("spawn")
@@ -89,7 +89,7 @@ def test_result_records_gather_to_rank0_gloo(world, n_channels):
     # a different stream anywhere changes the hash
     other = api.ResultSink(n_channels)
     recs = _rounds(list(range(n_channels)), 0)
-    recs[0][n_channels - 1, 48] ^= 1
+    recs[0][n_channels - 1, 40] ^= 1
     for r in recs:
         other.feed(r)
     assert other.hash() != h or totals["chars"] == 0
