@@ -6,12 +6,15 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <sched.h>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "decim1.cuh"
@@ -119,6 +122,9 @@ struct Deferred {
     hbd_ssdv_packet_info info; std::array<unsigned char, 256> pkt;
 };
 
+// what one thread of the drain records for its channel range (collect_locked)
+struct ReplayPart { std::vector<std::pair<unsigned, Deferred>> events; bool spilled = false; };
+
 struct hbd_decoder {
     std::mutex mtx;
     std::string err;
@@ -213,8 +219,9 @@ struct hbd_decoder {
     std::vector<uint2> h_log;            // host staging
     std::vector<std::string> call_chars; // per channel: raw chars of the call being replayed
     std::vector<unsigned> seg_start;     // collect_locked: first log entry of every (call, channel) segment
-    std::vector<int> split_channels;     // channels whose characters of the call being replayed span several segments
     static constexpr int kCharBufHost = 64;   // == kCharBuf (slicer_dev.cuh): characters per device-side flush
+    double drain_host_ms = 0; unsigned drain_calls = 0;   // host time of the replay part of the drains (hbd_get_kernel_timing which = 5)
+    int host_threads = 1;                // threads the drain may use (hbd_set_host_threads; default: min(4, cores this process may run on))
     bool keep_raw = true;                // hbd_set_raw_chars: retain the raw (unfiltered) characters for hbd_poll_raw_chars
     float* d_taps1 = nullptr; float* d_taps2 = nullptr;
     float2* d_twiddle = nullptr;
@@ -920,42 +927,13 @@ int hbd_decoder::collect_locked(unsigned lag)
     HBD_CUDA_CHECK(cudaMemcpyAsync(d_log_ctl + kCtlSsdvTail, h_tail_pin + 1, sizeof(unsigned), cudaMemcpyHostToDevice, copy_stream));
     HBD_CUDA_CHECK(cudaStreamSynchronize(copy_stream));   // h_tail_pin is rewritten by the next drain
 
-    const bool want_sent = sentence_cb || tracker;
-    SentenceSink sink;
-    if (want_sent)
-        sink = [this](int ch, const std::string& cs, const std::string& d, const std::string& crc) {
-            Deferred ev; ev.kind = Deferred::kSentence; ev.ch = ch; ev.a = cs; ev.b = d; ev.c = crc;
-            deferred.push_back(std::move(ev));
-        };
     // The log is sorted by call, and within a call a channel's characters form ONE contiguous segment (one reservation per
     // flush; only a channel that decodes more than kCharBuf = 64 characters in a call flushes twice).  Replay segment by
-    // segment: one TextChannel::feed per channel and call, like one Decoder::process().  The per-channel state is
-    // scattered over the heap, so the loop is bound by cache misses: the next segments' states are prefetched.
-    auto feed_channel = [&](int ch, const unsigned char* chars, size_t n_chars) {
-        TextChannel& tc = text[size_t(ch)];
-        hbd_result_record& pr = pend[size_t(ch)];
-        const size_t before = chars_cb ? tc.chars_size(pr) : 0;
-        tc.feed(chars, n_chars, ch, sink, keep_raw, pr);
-        if (!tc.chars_spill.empty() || !tc.sent_spill.empty()) spill_free = false;
-        if (chars_cb && tc.chars_size(pr) > before) {   // character_callback_, Decoder.h:617-629 (not paced by wall clock)
-            Deferred ev; ev.kind = Deferred::kChars; ev.ch = ch; ev.a = tc.chars_from(pr, before);
-            deferred.push_back(std::move(ev));
-        }
-        if (ssdv_on) {   // Decoder.h:573: one SSDV_wraper_t::push per call that decoded characters
-            SsdvEvent sev;
-            if (ssdv[size_t(ch)].push(chars, n_chars, sev)) {
-                ssdv[size_t(ch)].events_pending.push_back(sev);
-                if (ssdv_cb) {   // ssdv_callback_, Decoder.h:631-632
-                    Deferred ev; ev.kind = Deferred::kSsdv; ev.ch = ch; fill_ssdv_info(ev.info, sev); ev.pkt = sev.data;
-                    deferred.push_back(std::move(ev));
-                }
-            }
-        }
-    };
+    // segment: one TextChannel::feed per channel and call, like one Decoder::process().
+    const auto t_replay0 = std::chrono::steady_clock::now();
     const size_t n_log = h_log.size();
-    // segment boundaries first (sequential pass over the copied log), then the scattered per-channel work
     seg_start.clear();
-    for (size_t i = 0; i < n_log;) {
+    for (size_t i = 0; i < n_log;) {           // segment boundaries: one sequential pass over the copied log
         size_t j = i + 1;
         while (j < n_log && h_log[j].x == h_log[i].x && (h_log[j].y >> 8) == (h_log[i].y >> 8)) ++j;
         seg_start.push_back(unsigned(i));
@@ -963,37 +941,113 @@ int hbd_decoder::collect_locked(unsigned lag)
     }
     seg_start.push_back(unsigned(n_log));
     const size_t n_seg = seg_start.size() - 1;
-    unsigned char seg_chars[kCharBufHost];
-    for (size_t k = 0; k < n_seg; ++k) {
-        if (k + 8 < n_seg) { const unsigned c8 = h_log[seg_start[k + 8]].x; if (c8 < unsigned(n_ch)) { __builtin_prefetch(&text[c8]); __builtin_prefetch(&pend[c8]); } }
-        if (k + 4 < n_seg) { const unsigned c4 = h_log[seg_start[k + 4]].x; if (c4 < unsigned(n_ch)) text[c4].prefetch_tails(); }
-        const size_t i0 = seg_start[k], i1 = seg_start[k + 1];
-        const int ch = int(h_log[i0].x);
-        if (ch < 0 || ch >= n_ch) continue;
-        const unsigned seq = h_log[i0].y >> 8;
-        const size_t len = i1 - i0;
-        // a full buffer means the channel flushed more than once in this call: join the pieces (rare: > 64 characters of
-        // one channel in one call); they need not be adjacent in the log
-        bool joined = len >= size_t(kCharBufHost);
-        if (!joined && !split_channels.empty()) joined = std::find(split_channels.begin(), split_channels.end(), ch) != split_channels.end();
-        if (joined) {
-            if (call_chars[size_t(ch)].empty()) split_channels.push_back(ch);
-            for (size_t i = i0; i < i1; ++i) call_chars[size_t(ch)].push_back(char(h_log[i].y & 0xffu));
-        } else {
-            for (size_t i = 0; i < len; ++i) seg_chars[i] = (unsigned char)(h_log[i0 + i].y & 0xffu);
-            feed_channel(ch, seg_chars, len);
-        }
-        // end of this call's entries: feed the joined channels
-        if (!split_channels.empty() && (k + 1 == n_seg || (h_log[seg_start[k + 1]].y >> 8) != seq)) {
-            for (int sc : split_channels) {
-                std::string& cc = call_chars[size_t(sc)];
-                feed_channel(sc, reinterpret_cast<const unsigned char*>(cc.data()), cc.size());
-                cc.clear();
+    // Channels are independent, so the replay is cut by CHANNEL RANGE over a few host threads (the caller's included):
+    // every thread walks all segments in log order and takes the ones of its channels -- per channel the order of the
+    // calls is kept, and the callbacks the threads record are merged back into log order afterwards.
+    const bool want_sent = sentence_cb || tracker;
+    int n_thr = std::max(1, std::min(host_threads, int(n_seg / 1024)));
+    n_thr = std::min(n_thr, n_ch);
+    std::vector<ReplayPart> parts;
+    parts.resize(size_t(n_thr));
+    auto replay = [&](int t) {
+        ReplayPart& part = parts[size_t(t)];
+        const int c_lo = int((long long)n_ch * t / n_thr), c_hi = int((long long)n_ch * (t + 1) / n_thr);
+        unsigned cur_seg = 0;
+        SentenceSink sink;
+        if (want_sent)
+            sink = [&part, &cur_seg](int ch, const std::string& cs, const std::string& d, const std::string& crc) {
+                Deferred ev; ev.kind = Deferred::kSentence; ev.ch = ch; ev.a = cs; ev.b = d; ev.c = crc;
+                part.events.emplace_back(cur_seg, std::move(ev));
+            };
+        auto feed_channel = [&](int ch, const unsigned char* chars, size_t n_chars) {
+            TextChannel& tc = text[size_t(ch)];
+            hbd_result_record& pr = pend[size_t(ch)];
+            const size_t before = chars_cb ? tc.chars_size(pr) : 0;
+            tc.feed(chars, n_chars, ch, sink, keep_raw, pr);
+            if (!tc.chars_spill.empty() || !tc.sent_spill.empty()) part.spilled = true;
+            if (chars_cb && tc.chars_size(pr) > before) {   // character_callback_, Decoder.h:617-629 (not paced by wall clock)
+                Deferred ev; ev.kind = Deferred::kChars; ev.ch = ch; ev.a = tc.chars_from(pr, before);
+                part.events.emplace_back(cur_seg, std::move(ev));
             }
-            split_channels.clear();
+            if (ssdv_on) {   // Decoder.h:573: one SSDV_wraper_t::push per call that decoded characters
+                SsdvEvent sev;
+                if (ssdv[size_t(ch)].push(chars, n_chars, sev)) {
+                    ssdv[size_t(ch)].events_pending.push_back(sev);
+                    if (ssdv_cb) {   // ssdv_callback_, Decoder.h:631-632
+                        Deferred ev; ev.kind = Deferred::kSsdv; ev.ch = ch; fill_ssdv_info(ev.info, sev); ev.pkt = sev.data;
+                        part.events.emplace_back(cur_seg, std::move(ev));
+                    }
+                }
+            }
+        };
+        std::vector<int> split;                    // channels of this range whose characters of the current call span several segments
+        unsigned char seg_chars[kCharBufHost];
+        // the per-channel state is scattered over the heap: a short look-ahead queue of this range's next segments feeds prefetches
+        size_t look = 0;
+        unsigned ahead[8]; int n_ahead = 0, head = 0;
+        auto refill = [&] {
+            while (n_ahead < 8 && look < n_seg) {
+                const unsigned c = h_log[seg_start[look]].x;
+                if (c >= unsigned(c_lo) && c < unsigned(c_hi)) {
+                    ahead[(head + n_ahead) & 7] = unsigned(look); ++n_ahead;
+                    __builtin_prefetch(&text[c]); __builtin_prefetch(&pend[c]);
+                }
+                ++look;
+            }
+        };
+        refill();
+        while (n_ahead) {
+            const size_t k = ahead[head]; head = (head + 1) & 7; --n_ahead;
+            refill();
+            if (n_ahead >= 4) text[h_log[seg_start[ahead[(head + 3) & 7]]].x].prefetch_tails();
+            cur_seg = unsigned(k);
+            const size_t i0 = seg_start[k], i1 = seg_start[k + 1];
+            const int ch = int(h_log[i0].x);
+            const unsigned seq = h_log[i0].y >> 8;
+            const size_t len = i1 - i0;
+            // a full buffer means the channel flushed more than once in this call: join the pieces (rare: > 64 characters of
+            // one channel in one call); they need not be adjacent in the log
+            bool joined = len >= size_t(kCharBufHost);
+            if (!joined && !split.empty()) joined = std::find(split.begin(), split.end(), ch) != split.end();
+            if (joined) {
+                if (call_chars[size_t(ch)].empty()) split.push_back(ch);
+                for (size_t i = i0; i < i1; ++i) call_chars[size_t(ch)].push_back(char(h_log[i].y & 0xffu));
+            } else {
+                for (size_t i = 0; i < len; ++i) seg_chars[i] = (unsigned char)(h_log[i0 + i].y & 0xffu);
+                feed_channel(ch, seg_chars, len);
+            }
+            // end of this call's entries (for this range): feed the joined channels
+            if (!split.empty() && (!n_ahead || (h_log[seg_start[ahead[head]]].y >> 8) != seq)) {
+                for (int sc : split) {
+                    std::string& cc = call_chars[size_t(sc)];
+                    feed_channel(sc, reinterpret_cast<const unsigned char*>(cc.data()), cc.size());
+                    cc.clear();
+                }
+                split.clear();
+            }
+        }
+    };
+    if (n_thr == 1) replay(0);
+    else {
+        std::vector<std::thread> workers;
+        for (int t = 1; t < n_thr; ++t) workers.emplace_back(replay, t);
+        replay(0);
+        for (auto& w : workers) w.join();
+    }
+    {   // callbacks back into log order (stable: a channel's events keep the order they were recorded in)
+        size_t total = 0;
+        for (const ReplayPart& pt : parts) { total += pt.events.size(); if (pt.spilled) spill_free = false; }
+        if (total) {
+            std::vector<std::pair<unsigned, Deferred>> all;
+            all.reserve(total);
+            for (ReplayPart& pt : parts) for (auto& e : pt.events) all.push_back(std::move(e));
+            if (n_thr > 1) std::stable_sort(all.begin(), all.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+            for (auto& e : all) deferred.push_back(std::move(e.second));
         }
     }
     (void)upto24;
+    drain_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_replay0).count();
+    drain_calls += upto - calls_collected;
     calls_collected = upto;
     pending_marks = int(call_seq - calls_collected);
     return result;
@@ -1127,6 +1181,13 @@ int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
         if (const char* sv = getenv("HBD_SV_WANT")) h->sv_override = atoi(sv);
         if (const char* tl = getenv("HBD_TAIL_EV_LATE")) h->tail_ev_late = atoi(tl) != 0;
         if (const char* nf = getenv("HBD_NCO_FUSED")) h->nco_fused = atoi(nf) != 0;
+        {
+            cpu_set_t set;
+            int cores = int(std::thread::hardware_concurrency());
+            if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+            h->host_threads = std::max(1, std::min(4, cores));
+            if (const char* ht = getenv("HBD_HOST_THREADS")) h->host_threads = std::max(1, atoi(ht));
+        }
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); // numerically lower = higher priority
         if (cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
@@ -1547,6 +1608,7 @@ int hbd_set_kernel_timing(hbd_decoder* h, int on)
     std::lock_guard<std::mutex> l(h->mtx);
     h->timing = on != 0;
     h->ev_used_k1 = h->ev_used_rest = 0;
+    h->drain_host_ms = 0; h->drain_calls = 0;
     if (on) {   // events are created here, not on the issue path of the calls being measured
         cudaSetDevice(h->device);
         for (auto* pool : {&h->ev_k1, &h->ev_rest})
@@ -1562,6 +1624,11 @@ int hbd_get_kernel_timing(hbd_decoder* h, int which, double* total_ms, unsigned*
     cudaSetDevice(h->device);
     if (h->sync_groups() || cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
     double tot = 0; unsigned cnt = 0;
+    if (which == 5) {   // host time spent replaying drained calls through the sentence layer (wall clock of the caller's thread)
+        if (total_ms) *total_ms = h->drain_host_ms;
+        if (count) *count = h->drain_calls;
+        return HBD_OK;
+    }
     if (which >= 2) {   // pipeline diagnostics (one channel group): signed gaps between events of different pairs
         const size_t calls = std::min(h->ev_used_k1, h->ev_used_rest) / 2;
         for (size_t i = 0; i < calls; ++i) {
@@ -1639,6 +1706,10 @@ size_t hbd_poll_raw_chars(hbd_decoder* h, int ch, unsigned char* out, size_t cap
     if (out && cap) memcpy(out, v.data(), std::min(cap, n));
     if (out && cap >= n) v.clear();
     return n;
+}
+int hbd_set_host_threads(hbd_decoder* h, int n)
+{
+    HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); h->host_threads = std::max(1, std::min(n, 64)); return HBD_OK;
 }
 int hbd_set_raw_chars(hbd_decoder* h, int on)
 {

@@ -53,13 +53,43 @@ size_t design_lowpass(float rel_width, float trans, size_t input_size, size_t cu
 }
 
 // ---- CRC16-CCITT-FALSE, 4 upper-case hex digits --------------------------------------------------------
+namespace {
+struct CrcTable {
+    uint16_t t[256];
+    CrcTable()
+    {
+        for (unsigned b = 0; b < 256; ++b) {
+            unsigned crc = b << 8;
+            for (int j = 0; j < 8; ++j) crc = (crc & 0x8000) ? ((crc << 1) ^ 0x1021) : (crc << 1);
+            t[b] = uint16_t(crc);
+        }
+    }
+};
+const CrcTable kCrc;
+// character classes of the sentence pattern in the "C" locale (what std::regex's \w and \s and isprint() give the reference)
+struct CharClass {
+    unsigned char t[256];   // bit 0: \w, bit 1: callsign class [\w,\-,\s], bit 2: printable or '\n' (Decoder.h:575-577)
+    CharClass()
+    {
+        for (int c = 0; c < 256; ++c) {
+            const bool w = (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_';
+            const bool sp = c == ' ' || (c >= 9 && c <= 13);
+            t[c] = (unsigned char)((w ? 1 : 0) | ((w || c == ',' || c == '-' || sp) ? 2 : 0) | (((c >= 0x20 && c < 0x7f) || c == '\n') ? 4 : 0));
+        }
+    }
+};
+const CharClass kCls;
+} // namespace
+
+// the bitwise loop of CRC.cpp:21-47 (init 0xFFFF, poly 0x1021, MSB first), one table step per byte
+static unsigned crc16_raw(const char* p, size_t n, unsigned crc = 0xffff)
+{
+    for (size_t i = 0; i < n; ++i) crc = ((crc << 8) ^ kCrc.t[((crc >> 8) ^ (unsigned char)p[i]) & 0xff]) & 0xffff;
+    return crc;
+}
 std::string crc16_hex(const std::string& s)
 {
-    unsigned crc = 0xffff;
-    for (char ch : s) {
-        crc ^= (unsigned(int(ch)) << 8);
-        for (int j = 0; j < 8; ++j) crc = (crc & 0x8000) ? ((crc << 1) ^ 0x1021) : (crc << 1);
-    }
+    const unsigned crc = crc16_raw(s.data(), s.size());
     static const char hex[] = "0123456789ABCDEF";
     std::string r(4, '0');
     r[0] = hex[(crc >> 12) & 15]; r[1] = hex[(crc >> 8) & 15]; r[2] = hex[(crc >> 4) & 15]; r[3] = hex[crc & 15];
@@ -79,16 +109,17 @@ std::string crc16_hex(const std::string& s)
 //    in the class); a later ',' can only shrink the set of possible data ends, so if the first one
 //    fails the run fails.
 //  * data `(.+?)` lazy, >= 1 char => the first '*' or '$' at >= comma+2 followed by four \w.
-static inline bool is_word(unsigned char c) { return std::isalnum(c) || c == '_'; }
-static inline bool is_callsign_char(unsigned char c) { return is_word(c) || c == ',' || c == '-' || std::isspace(c); }
+static inline bool is_word(unsigned char c) { return kCls.t[c] & 1; }
+static inline bool is_callsign_char(unsigned char c) { return kCls.t[c] & 2; }   // '\n' (== ' ' after the substitution) is in \s either way
 
 bool extract_sentence(const std::string& stream_in, SentenceMatch& m)
 {
     m.ok = false;
     const size_t n = stream_in.size();
-    if (stream_in.find('*') == std::string::npos) return false;  // sentence_extract.cpp:74
-    std::string s(stream_in);
-    std::replace(s.begin(), s.end(), '\n', ' ');
+    if (!memchr(stream_in.data(), '*', n)) return false;  // sentence_extract.cpp:74
+    // the reference matches on a copy with '\n' replaced by ' ' (:70-71); both are in \s and in neither of the other classes the
+    // pattern uses, so the match positions are the same on the stream itself and only the extracted fields need the replacement
+    const std::string& s = stream_in;
     size_t p = 0;
     while (p < n) {
         if (s[p] != '$') { ++p; continue; }
@@ -106,9 +137,11 @@ bool extract_sentence(const std::string& stream_in, SentenceMatch& m)
                 if ((s[e] == '*' || s[e] == '$') && is_word((unsigned char)s[e + 1]) && is_word((unsigned char)s[e + 2]) &&
                     is_word((unsigned char)s[e + 3]) && is_word((unsigned char)s[e + 4])) {
                     m.ok = true;
-                    m.callsign = s.substr(q, c - q);
-                    m.data = s.substr(c + 1, e - (c + 1));
-                    m.crc = s.substr(e + 1, 4);
+                    m.callsign.assign(s, q, c - q);
+                    m.data.assign(s, c + 1, e - (c + 1));
+                    m.crc.assign(s, e + 1, 4);
+                    std::replace(m.callsign.begin(), m.callsign.end(), '\n', ' ');
+                    std::replace(m.data.begin(), m.data.end(), '\n', ' ');
                     m.rest_offset = std::min(n, e + 4);           // sentence_extract.cpp:86-87 (keeps the last CRC char)
                     return true;
                 }
@@ -127,9 +160,7 @@ void TextChannel::feed(const unsigned char* raw, size_t n, int ch, const Sentenc
     const size_t old_len = text_stream.size();
     for (size_t i = 0; i < n; ++i) {
         const char c = char(raw[i]);
-        if ((std::isprint((unsigned char)c) && (unsigned char)c < 0x80) || c == '\n') { // isprint(char) in the "C" locale
-            text_stream.push_back(c);
-        }
+        if (kCls.t[(unsigned char)c] & 4) text_stream.push_back(c);   // isprint(char) in the "C" locale, or '\n' (Decoder.h:575-577)
     }
     if (text_stream.size() > old_len)   // chr_callback_stream_ (:581) == what waits for hbd_poll_chars / the next gather
         append(pend.chars, pend.n_chars, sizeof(pend.chars), chars_spill, text_stream.data() + old_len, text_stream.size() - old_len);
@@ -137,32 +168,39 @@ void TextChannel::feed(const unsigned char* raw, size_t n, int ch, const Sentenc
         // The scan loop below leaves a stream without a match (scan_clean).  New characters can only complete a match
         // whose CRC group ends among them -- the pattern's trailing `.*` swallows everything behind the CRC, so a match that
         // ends earlier would have been found before -- i.e. some new position i with [*$] at i-4 and \w at i-3..i.
-        // One more way: extractSentence refuses any stream without a '*' (sentence_extract.cpp:74), so a new '*' anywhere can
-        // wake a match that ends in "$" + CRC further left.  Without either, the whole scan (a copy of the stream + a pass
-        // over it, per call and channel) is skipped.
+        // One more way: extractSentence refuses any stream without a '*' (sentence_extract.cpp:74), so a match that ends in
+        // "$" + CRC stays latent until a '*' shows up anywhere.  `latent` remembers that a scan was cut short by that rule;
+        // only then does a new '*' by itself call for a scan.  Without either, the whole scan is skipped.
         bool candidate = !scan_clean;
         for (size_t i = old_len; !candidate && i < text_stream.size(); ++i) {
             const char* p = text_stream.data() + i;
-            candidate = p[0] == '*' || (i >= 4 && (p[-4] == '*' || p[-4] == '$') && is_word((unsigned char)p[-3]) && is_word((unsigned char)p[-2]) &&
-                                        is_word((unsigned char)p[-1]) && is_word((unsigned char)p[0]));
+            candidate = (p[0] == '*' && latent) || (i >= 4 && (p[-4] == '*' || p[-4] == '$') && is_word((unsigned char)p[-3]) &&
+                                                   is_word((unsigned char)p[-2]) && is_word((unsigned char)p[-1]) && is_word((unsigned char)p[0]));
         }
         if (candidate) {
+            latent = !memchr(text_stream.data(), '*', text_stream.size());   // the scan below gives up at once: the groups seen so far stay latent
             SentenceMatch m;
             while (extract_sentence(text_stream, m)) {
                 std::string rest = text_stream.substr(m.rest_offset);
                 std::replace(rest.begin(), rest.end(), '\n', ' ');    // the reference keeps the space-substituted copy (:599)
                 text_stream.swap(rest);
-                last_sentence = m.callsign + "," + m.data + "*" + m.crc;
-                if (m.crc == crc16_hex(m.callsign + "," + m.data)) {
-                    const std::string line = last_sentence + "\n";
-                    append(pend.sentences, pend.sentence_bytes, sizeof(pend.sentences), sent_spill, line.data(), line.size());
+                last_sentence.clear();
+                last_sentence.reserve(m.callsign.size() + m.data.size() + 7);
+                last_sentence += m.callsign; last_sentence += ','; last_sentence += m.data;
+                unsigned crc = crc16_raw(last_sentence.data(), last_sentence.size());   // CRC of "callsign,data" (Decoder.h:603-604)
+                last_sentence += '*'; last_sentence += m.crc;
+                static const char hex[] = "0123456789ABCDEF";
+                const char want[4] = {hex[(crc >> 12) & 15], hex[(crc >> 8) & 15], hex[(crc >> 4) & 15], hex[crc & 15]};
+                if (m.crc.size() == 4 && memcmp(m.crc.data(), want, 4) == 0) {
+                    append(pend.sentences, pend.sentence_bytes, sizeof(pend.sentences), sent_spill, last_sentence.data(), last_sentence.size());
+                    append(pend.sentences, pend.sentence_bytes, sizeof(pend.sentences), sent_spill, "\n", 1);
                     if (sink) sink(ch, m.callsign, m.data, m.crc);
                 }
             }
         }
         scan_clean = true;
     } else if (text_stream.size() != old_len) {
-        scan_clean = false;   // a short stream is not scanned (Decoder.h:591): it may hold a complete sentence already
+        scan_clean = false; latent = true;   // a short stream is not scanned (Decoder.h:591): it may hold a complete sentence already
     }
     if (text_stream.size() > 1000) text_stream.erase(0, text_stream.rfind('$')); // npos => erase everything
 }

@@ -40,6 +40,7 @@ struct TextChannel {
     std::string chars_spill, sent_spill;
     std::vector<unsigned char> raw_pending; // raw chars since the last poll (SSDV consumers)
     bool scan_clean = true;         // text_stream is known to hold no extractable sentence (see feed)
+    bool latent = false;            // ... except one that only waits for a '*' to appear in the stream (see feed)
     void feed(const unsigned char* raw, size_t n, int ch, const SentenceSink& sink, bool keep_raw, hbd_result_record& pend);
     // pull the end of the string feed() appends to into the cache (the drain loop knows its next channels)
     void prefetch_tails() const { __builtin_prefetch(text_stream.data() + text_stream.size()); }

@@ -122,7 +122,8 @@ int hbd_synchronize(hbd_decoder* h);
 unsigned long long hbd_kernel_launches(hbd_decoder* h);
 /* measurement hook: record CUDA events around every K1 (stage-1 decimator) launch and around the rest of the
  * step; `which` 0 = K1, 1 = rest; 2..4 = signed pipeline gaps (K1 end -> next K1 start, K1 end -> own tail start,
- * tail end -> K1 start two calls later).  Calling set (on or off) clears the accumulated samples. */
+ * tail end -> K1 start two calls later); 5 = host time of the drains' sentence-layer replay (count = calls drained).
+ * Calling set (on or off) clears the accumulated samples. */
 int hbd_set_kernel_timing(hbd_decoder* h, int on);
 int hbd_get_kernel_timing(hbd_decoder* h, int which, double* total_ms, unsigned* count);
 
@@ -138,6 +139,9 @@ size_t hbd_poll_raw_chars(hbd_decoder* h, int ch, unsigned char* out, size_t cap
 /* retain raw characters for hbd_poll_raw_chars (default on; the reference itself keeps none, a caller that never polls
  * them switches it off) */
 int    hbd_set_raw_chars(hbd_decoder* h, int on);
+/* host threads hbd_collect* may use for the sentence layer of many channels (the caller's included); default min(4, cores
+ * the process may run on).  Results and callback order do not depend on it. */
+int    hbd_set_host_threads(hbd_decoder* h, int n);
 int    hbd_set_sentence_callback(hbd_decoder* h, hbd_sentence_cb cb, void* user);
 int    hbd_set_chars_callback(hbd_decoder* h, hbd_chars_cb cb, void* user);
 
