@@ -75,6 +75,25 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  : "memory");
 }
 
+// The same copy with an L2 eviction-priority hint.  K1 streams 2 GB per call through a 126 MB L2 exactly once; marked
+// evict-first, those lines go before the ~150 MB the tail kernel re-reads a moment later (stage-1 outputs, low-pass
+// queue, slicer queue, channel state), which then mostly hit L2 instead of competing with K1 for HBM.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+#ifndef HBD_K1_EVICT_FIRST
+#define HBD_K1_EVICT_FIRST 1
+#endif
+
 // ---- compile-time geometry of one (M, T) decimator ---------------------------------------------------------
 #ifndef HBD_K1_STAGES
 #define HBD_K1_STAGES 3
@@ -221,6 +240,9 @@ decim1_kernel(DecimArgs a)
         h1[j] = tap_for<M, T>(a.taps, j + 1, lane + 32);
     }
 
+    // streamed-once input (not the wideband capture row that every channel re-reads through its NCO)
+    constexpr bool kHint = HBD_K1_EVICT_FIRST && !NCO;
+    const uint64_t l2_first = kHint ? l2_policy_evict_first() : 0ull;
     uint32_t phase_bits = 0; // parity per ring slot
     // Work = the (channel, superblock) plane flattened; every warp takes ONE contiguous span of it, so the
     // ramp-in (RAMP superblocks whose outputs are discarded) is paid once per span and once per channel start
@@ -286,7 +308,10 @@ decim1_kernel(DecimArgs a)
                     if (WarpSmem<M, T>::kRedInRing) fence_proxy_async();   // the slot last held generic-proxy stores (reduction rows)
                     mbar_expect_tx(&sm.full[slot], uint32_t(hi2 - lo) * 8u);
                     if (c_hi > lo) tma_load_1d(dst + (lo - A) * 8, carry + lo, uint32_t(c_hi - lo) * 8u, &sm.full[slot]);
-                    if (hi2 > d_lo) tma_load_1d(dst + (d_lo - A) * 8, chunk + d_lo, uint32_t(hi2 - d_lo) * 8u, &sm.full[slot]);
+                    if (hi2 > d_lo) {
+                        if (kHint) tma_load_1d_hint(dst + (d_lo - A) * 8, chunk + d_lo, uint32_t(hi2 - d_lo) * 8u, &sm.full[slot], l2_first);
+                        else tma_load_1d(dst + (d_lo - A) * 8, chunk + d_lo, uint32_t(hi2 - d_lo) * 8u, &sm.full[slot]);
+                    }
                 } else {
                     mbar_arrive(&sm.full[slot]);
                 }
