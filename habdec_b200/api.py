@@ -141,6 +141,7 @@ SIGNATURES = {
     "hbd_sink_create": (C.c_void_p, [C.c_int]),
     "hbd_sink_destroy": (None, [C.c_void_p]),
     "hbd_sink_feed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "hbd_sink_set_threads": (C.c_int, [C.c_void_p, C.c_int]),
     "hbd_sink_poll_chars": (C.c_size_t, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_sink_poll_sentences": (C.c_size_t, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_sink_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

@@ -1,7 +1,7 @@
 // Multi-GPU result gather: channels are block-partitioned over ranks and never exchange signal data; what
 // travels -- once per batch of calls, to rank 0 -- is one fixed-size hbd_result_record per channel: the characters and
 // CRC-valid sentences decoded since the previous gather plus the AFC scalars.  This file holds the transport-independent
-// half (record packing, the rank-0 sink, the sharding-invariant hash); gather_nccl.cu moves the records over NCCL.
+// half (record packing, the rank-0 sink, the sharding-invariant hash); dist.cu moves the records over NCCL.
 //
 // The reference has no counterpart (one Decoder, one process); the records carry exactly what its callbacks and getters
 // deliver: character_callback_ / sentence_callback_ payloads (Decoder.h:135-138,604-606,625-626) and
@@ -10,7 +10,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <sched.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 static_assert(sizeof(hbd_result_record) == 256, "hbd_result_record is a wire format: 256 bytes");
@@ -45,6 +47,43 @@ void hbd_record_set(hbd_result_record* r, uint32_t channel, const char* chars, s
 
 // ---- rank-0 sink ---------------------------------------------------------------------------------------------------
 namespace {
+// Streaming CRC-32C of the per-channel character / sentence streams: the state carries over record boundaries, so the
+// value does not depend on how a stream was cut into records.  Hardware instruction where the CPU has it (same value).
+struct Crc32cTable {
+    uint32_t t[256];
+    Crc32cTable()
+    {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+            t[i] = c;
+        }
+    }
+};
+const Crc32cTable kCrcTab;
+inline uint32_t crc32c_sw(uint32_t crc, const unsigned char* p, size_t n)
+{
+    for (size_t i = 0; i < n; ++i) crc = kCrcTab.t[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    return crc;
+}
+#if defined(__x86_64__)
+__attribute__((target("sse4.2"))) inline uint32_t crc32c_hw(uint32_t crc, const unsigned char* p, size_t n)
+{
+    uint64_t c = crc;
+    for (; n >= 8; n -= 8, p += 8) { uint64_t v; memcpy(&v, p, 8); c = __builtin_ia32_crc32di(c, v); }
+    uint32_t c32 = uint32_t(c);
+    for (; n; --n, ++p) c32 = __builtin_ia32_crc32qi(c32, *p);
+    return c32;
+}
+const bool kHaveCrcHw = __builtin_cpu_supports("sse4.2");
+#else
+inline uint32_t crc32c_hw(uint32_t crc, const unsigned char* p, size_t n) { return crc32c_sw(crc, p, n); }
+const bool kHaveCrcHw = false;
+#endif
+inline uint32_t crc32c(uint32_t crc, const void* p, size_t n)
+{
+    return kHaveCrcHw ? crc32c_hw(crc, static_cast<const unsigned char*>(p), n) : crc32c_sw(crc, static_cast<const unsigned char*>(p), n);
+}
 inline uint64_t fnv1a(uint64_t h, const void* p, size_t n)
 {
     const unsigned char* b = static_cast<const unsigned char*>(p);
@@ -54,7 +93,8 @@ inline uint64_t fnv1a(uint64_t h, const void* p, size_t n)
 constexpr uint64_t kFnvInit = 0xcbf29ce484222325ull;
 struct SinkChan {
     std::string chars, sentences;            // since the previous poll
-    uint64_t h_chars = kFnvInit, h_sent = kFnvInit, n_chars = 0, n_sent = 0;
+    uint32_t h_chars = ~0u, h_sent = ~0u;    // running CRC-32C of everything ever fed
+    uint64_t n_chars = 0, n_sent = 0;
     float stats[4] = {0, 0, 0, 0}; int32_t peaks[2] = {0, 0};   // scalars of the newest record
     bool seen = false;
 };
@@ -63,6 +103,7 @@ struct SinkChan {
 struct hbd_result_sink {
     std::vector<SinkChan> ch;
     unsigned long long records = 0;
+    int threads = 1;
 };
 
 extern "C" {
@@ -71,32 +112,69 @@ hbd_result_sink* hbd_sink_create(int total_channels)
 {
     if (total_channels < 1) return nullptr;
     hbd_result_sink* s = new (std::nothrow) hbd_result_sink;
-    if (s) s->ch.resize(size_t(total_channels));
+    if (s) {
+        s->ch.resize(size_t(total_channels));
+        cpu_set_t set;
+        int cores = int(std::thread::hardware_concurrency());
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+        s->threads = std::max(1, std::min(4, cores));
+    }
     return s;
 }
 void hbd_sink_destroy(hbd_result_sink* s) { delete s; }
+int hbd_sink_set_threads(hbd_result_sink* s, int n) { if (!s) return HBD_ERR_ARG; s->threads = std::max(1, std::min(n, 64)); return HBD_OK; }
 
-int hbd_sink_feed(hbd_result_sink* s, const hbd_result_record* recs, size_t n)
+// Records of channels in [c_lo, c_hi) only: feeds of many thousand records are cut by channel range over a few threads
+// (the per-channel strings are scattered over the heap, the work is cache-miss bound).
+static int feed_range(hbd_result_sink* s, const hbd_result_record* recs, size_t n, size_t c_lo, size_t c_hi, unsigned long long* fed)
 {
-    if (!s || (!recs && n)) return HBD_ERR_ARG;
     int rc = HBD_OK;
+    unsigned long long cnt = 0;
+    const bool all = c_lo == 0 && c_hi >= s->ch.size();
     for (size_t i = 0; i < n; ++i) {
-        if (i + 8 < n && recs[i + 8].channel < s->ch.size()) {   // the per-channel strings are scattered over the heap
+        if (all && i + 8 < n && recs[i + 8].channel < s->ch.size()) {
             const SinkChan& nx = s->ch[recs[i + 8].channel];
             __builtin_prefetch(nx.chars.data() + nx.chars.size());
             __builtin_prefetch(nx.sentences.data() + nx.sentences.size());
         }
         const hbd_result_record& r = recs[i];
-        if (r.channel >= s->ch.size() || r.n_chars > sizeof(r.chars) || r.sentence_bytes > sizeof(r.sentences)) { rc = HBD_ERR_ARG; continue; }
+        if (r.channel >= s->ch.size() || r.n_chars > sizeof(r.chars) || r.sentence_bytes > sizeof(r.sentences)) { if (c_lo == 0) rc = HBD_ERR_ARG; continue; }
+        if (r.channel < c_lo || r.channel >= c_hi) continue;
         SinkChan& c = s->ch[r.channel];
-        c.chars.append(r.chars, r.n_chars);
-        c.sentences.append(r.sentences, r.sentence_bytes);
-        c.h_chars = fnv1a(c.h_chars, r.chars, r.n_chars); c.n_chars += r.n_chars;
-        c.h_sent = fnv1a(c.h_sent, r.sentences, r.sentence_bytes); c.n_sent += r.n_sentences;
+        if (r.n_chars) { c.chars.append(r.chars, r.n_chars); c.h_chars = crc32c(c.h_chars, r.chars, r.n_chars); c.n_chars += r.n_chars; }
+        if (r.sentence_bytes) { c.sentences.append(r.sentences, r.sentence_bytes); c.h_sent = crc32c(c.h_sent, r.sentences, r.sentence_bytes); c.n_sent += r.n_sentences; }
         c.stats[0] = r.frequency_correction; c.stats[1] = r.shift; c.stats[2] = r.noise_floor; c.stats[3] = r.noise_variance;
         c.peaks[0] = r.peak_left; c.peaks[1] = r.peak_right; c.seen = true;
-        ++s->records;
+        ++cnt;
     }
+    *fed = cnt;
+    return rc;
+}
+
+int hbd_sink_feed(hbd_result_sink* s, const hbd_result_record* recs, size_t n)
+{
+    if (!s || (!recs && n)) return HBD_ERR_ARG;
+    const int n_thr = std::max(1, std::min(s->threads, int(n / 4096)));
+    if (n_thr == 1) {
+        unsigned long long fed = 0;
+        const int rc = feed_range(s, recs, n, 0, s->ch.size(), &fed);
+        s->records += fed;
+        return rc;
+    }
+    std::vector<unsigned long long> fed(size_t(n_thr), 0);
+    std::vector<int> rcs(size_t(n_thr), HBD_OK);
+    // the records arrive in channel order: ranges of the channels present, so the threads get equal shares
+    uint32_t lo = ~0u, hi = 0;
+    for (size_t i = 0; i < n; ++i) { lo = std::min(lo, recs[i].channel); hi = std::max(hi, recs[i].channel); }
+    hi = std::min<uint64_t>(uint64_t(hi) + 1, s->ch.size());
+    lo = std::min(lo, hi);
+    auto bound = [&](int t) { return t == 0 ? size_t(0) : t == n_thr ? s->ch.size() : size_t(lo + (uint64_t(hi - lo) * t) / n_thr); };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_thr; ++t) th.emplace_back([&, t] { rcs[size_t(t)] = feed_range(s, recs, n, bound(t), bound(t + 1), &fed[size_t(t)]); });
+    rcs[0] = feed_range(s, recs, n, bound(0), bound(1), &fed[0]);
+    for (auto& x : th) x.join();
+    int rc = HBD_OK;
+    for (int t = 0; t < n_thr; ++t) { s->records += fed[size_t(t)]; if (rcs[size_t(t)]) rc = rcs[size_t(t)]; }
     return rc;
 }
 
@@ -145,7 +223,7 @@ uint64_t hbd_sink_hash(hbd_result_sink* s)
     if (!s) return h;
     for (size_t c = 0; c < s->ch.size(); ++c) {
         const SinkChan& x = s->ch[c];
-        const uint64_t rec[5] = {uint64_t(c), x.h_chars, x.h_sent, x.n_chars, x.n_sent};
+        const uint64_t rec[5] = {uint64_t(c), uint64_t(x.h_chars), uint64_t(x.h_sent), x.n_chars, x.n_sent};
         h = fnv1a(h, rec, sizeof(rec));
     }
     return h;

@@ -228,12 +228,13 @@ typedef struct hbd_result_sink hbd_result_sink;
 hbd_result_sink* hbd_sink_create(int total_channels);
 void   hbd_sink_destroy(hbd_result_sink* s);
 int    hbd_sink_feed(hbd_result_sink* s, const hbd_result_record* recs, size_t n);
+int    hbd_sink_set_threads(hbd_result_sink* s, int n);   /* host threads a large feed may use (default min(4, cores)) */
 size_t hbd_sink_poll_chars(hbd_result_sink* s, int ch, char* out, size_t cap);
 size_t hbd_sink_poll_sentences(hbd_result_sink* s, int ch, char* out, size_t cap);
 int    hbd_sink_stats(hbd_result_sink* s, int ch, double out[6]);   /* correction, shift, noise floor, noise variance, peak l, peak r */
 void   hbd_sink_totals(hbd_result_sink* s, unsigned long long* chars, unsigned long long* sentences, unsigned long long* min_sentences,
                        unsigned long long* records);
-/* FNV-1a over every channel's character and sentence STREAMS: independent of the sharding and of the gather cadence, so
+/* a hash over every channel's character and sentence STREAMS (running CRC-32C per stream): independent of the sharding and of the gather cadence, so
  * the same channels decoded on 1, 2, 4 or 8 GPUs give the same value (the correctness check of SURVEY 8e) */
 uint64_t hbd_sink_hash(hbd_result_sink* s);
 /* NCCL transport.  Rank 0 draws an id (hbd_dist_unique_id) and hands the 128 bytes to the other ranks by any means; every

@@ -182,6 +182,6 @@ def test_cpp_facade_builds_links_and_fails_loudly_without_a_gpu(tmp_path):
         pass
     path = str(tmp_path / "z.cf32")
     np.zeros(65536, dtype=np.complex64).tofile(path)
-    r = subprocess.run([exe, path, "2048000", "300", "8", "2"], capture_output=True)
+    r = subprocess.run([exe, path, "2048000", "300", "8", "2", "256"], capture_output=True)
     assert r.returncode != 0
     assert b"no usable CUDA device" in r.stderr and b"CHARS" not in r.stdout
