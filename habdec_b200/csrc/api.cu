@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "decim1.cuh"
+#include "mid.cuh"
 #include "decim_taps.inc"
 #include "fft_afc.cuh"
 #include "hbd_common.cuh"
@@ -54,12 +55,15 @@ bool plan_for_factor(size_t factor, std::vector<TapTable>& st)
     }
 }
 
+constexpr int kMaxMidStages = 6;   // a cascaded plan has at most 8 stages: K1's, up to six in the middle, the tail kernel's
+
 // host mirror of one channel, part 1: stream counters that are pure functions of the push sizes (and of the
 // low-pass configuration).  While every channel is fed the same way they are identical for all channels, and only
 // hc[0]'s copy is kept current (hbd_decoder::ctr_uniform / sync_ctrs): a steady-state call costs O(1) host work.
 struct ChanCtr {
     unsigned in_r = 0, dec_pending = 0;
     size_t grown1 = 0, grown2 = 0, grown_lp = 0;
+    size_t grown_mid[kMaxMidStages] = {0, 0, 0, 0, 0, 0};   // work-buffer sizes of the middle stages of a cascaded plan
     unsigned fft_have = 0;   // mirror of ChanState::fft_have: tells the host which calls complete an FFT frame (K4 launch)
     size_t lp_input_size = 0, lp_ntaps = 0;
     unsigned pushed = 0;     // samples waiting in the staging row
@@ -69,6 +73,7 @@ struct ChanCtr {
     bool lp_dirty = true;    // bw / trans / input size changed since the last design attempt
     bool same(const ChanCtr& o) const
     {
+        for (int k = 0; k < kMaxMidStages; ++k) if (grown_mid[k] != o.grown_mid[k]) return false;
         return in_r == o.in_r && dec_pending == o.dec_pending && grown1 == o.grown1 && grown2 == o.grown2 && grown_lp == o.grown_lp &&
                fft_have == o.fft_have && lp_input_size == o.lp_input_size && lp_ntaps == o.lp_ntaps && pushed == o.pushed &&
                last_nf == o.last_nf && last_n2 == o.last_n2 && demod_n == o.demod_n && lp_shadow_n == o.lp_shadow_n && lp_dirty == o.lp_dirty;
@@ -152,7 +157,15 @@ struct hbd_decoder {
 
     double fs_in = 0;
     int factor = 1;
-    int M1 = 1, T1 = 1, M2 = 1, T2 = 1;
+    int M1 = 1, T1 = 1, M2 = 1, T2 = 1;   // first stage (K1) and last stage (tail kernel; M2 == 1: the plan has one stage)
+    std::vector<TapTable> stages;         // the whole plan (Decoder.h:286-320, cascaded by setupDecimationStagesBW :350-399)
+    struct MidStage { int M = 1, T = 1; unsigned div_in = 1; float* d_taps = nullptr; float2* d_out = nullptr; size_t pitch = 0; };
+    std::vector<MidStage> mids;           // stages[1 .. size-2]
+    float2* d_midlast[2] = {nullptr, nullptr}; size_t midlast_pitch = 0, midlast_pitch_b = 0;   // output of the last middle stage = the tail kernel's
+                                          // input, ping-pong over calls like d_s1x
+    unsigned div_last_in = 1;             // samples entering the last stage per call = consumed / div_last_in
+    int carry_cap = kCarryCapMin;
+    int set_plan(const std::vector<TapTable>& st, size_t total_factor);
     int fft_n = kFftN;       // spectrum size: 4096 like the reference, or 16384 (hbd_set_fft_size)
     int alloc_fft();
     std::vector<HostChan> hc;        // per-channel configuration + counters (see ChanCtr)
@@ -296,7 +309,6 @@ struct hbd_decoder {
     void set_error(const std::string& e) { err = e; }
     int ensure_call_capacity(size_t n_in_max);
     int alloc_fixed();
-    int upload_taps();
     int process_async_locked();
     int collect_locked(unsigned lag);
     int log_pressure();
@@ -391,8 +403,8 @@ int hbd_decoder::alloc_fixed()
     }
     HBD_CUDA_CHECK(dalloc(&d_plan, n));
     for (int i = 0; i < 2; ++i) {
-        HBD_CUDA_CHECK(dalloc(&d_carry2[i], n * kCarryCap));
-        HBD_CUDA_CHECK(cudaMemset(d_carry2[i], 0, n * kCarryCap * sizeof(float2)));
+        HBD_CUDA_CHECK(dalloc(&d_carry2[i], n * size_t(carry_cap)));
+        HBD_CUDA_CHECK(cudaMemset(d_carry2[i], 0, n * size_t(carry_cap) * sizeof(float2)));
     }
     { const int rc = alloc_fft(); if (rc) return rc; }
     HBD_CUDA_CHECK(dalloc(&d_uart_runs, n * size_t(kUartRunsCap)));
@@ -449,19 +461,61 @@ int hbd_decoder::alloc_fft()
     return HBD_OK;
 }
 
-int hbd_decoder::upload_taps()
+// Install a decimation plan (a list of (M, taps) stages with the given total factor): K1 runs stages[0], the tail kernel the
+// last stage, mid.cu the ones in between.  A new plan starts from fresh decimators (Decoder.h:283-284,347-348:
+// decimation_stages_.clear()); unconsumed input stays queued (iq_in_buffer_ is untouched) -- it sits at the end of the carry.
+int hbd_decoder::set_plan(const std::vector<TapTable>& st, size_t total_factor)
 {
-    std::vector<TapTable> st;
-    plan_for_factor(size_t(factor), st);
+    HBD_CUDA_CHECK(cudaSetDevice(device));
+    if (sync_groups()) return HBD_ERR_CUDA;
+    HBD_CUDA_CHECK(cudaStreamSynchronize(stream));
+    const size_t n = size_t(n_ch);
+    sync_ctrs();
+    const int old_cap = carry_cap;
+    stages = st;
+    factor = int(total_factor);
     M1 = T1 = M2 = T2 = 1;
-    if (st.size() >= 1) {
+    if (!st.empty()) {
         M1 = st[0].M; T1 = st[0].len;
         HBD_CUDA_CHECK(cudaMemcpy(d_taps1, st[0].bits, 4 * size_t(T1), cudaMemcpyHostToDevice));
     }
     if (st.size() >= 2) {
-        M2 = st[1].M; T2 = st[1].len;
-        HBD_CUDA_CHECK(cudaMemcpy(d_taps2, st[1].bits, 4 * size_t(T2), cudaMemcpyHostToDevice));
+        M2 = st.back().M; T2 = st.back().len;
+        HBD_CUDA_CHECK(cudaMemcpy(d_taps2, st.back().bits, 4 * size_t(T2), cudaMemcpyHostToDevice));
     }
+    for (MidStage& m : mids) { if (m.d_taps) cudaFree(m.d_taps); if (m.d_out) cudaFree(m.d_out); }
+    mids.clear();
+    for (int i = 0; i < 2; ++i) { if (d_midlast[i]) cudaFree(d_midlast[i]); d_midlast[i] = nullptr; }
+    midlast_pitch = midlast_pitch_b = 0;
+    unsigned div = unsigned(M1);
+    for (size_t k = 1; k + 1 < st.size(); ++k) {
+        MidStage m;
+        m.M = st[k].M; m.T = st[k].len; m.div_in = div;
+        HBD_CUDA_CHECK(dalloc(&m.d_taps, size_t(m.T)));
+        HBD_CUDA_CHECK(cudaMemcpy(m.d_taps, st[k].bits, 4 * size_t(m.T), cudaMemcpyHostToDevice));
+        mids.push_back(m);
+        div *= unsigned(m.M);
+    }
+    div_last_in = div;
+    // the carry holds T1-1 samples of history plus the unconsumed remainder (< total factor).  Fresh, zeroed rows (new
+    // decimators have an empty history); the remainder queued under the old plan stays queued, as in the reference
+    unsigned max_r = 0;
+    for (const auto& x : hc) max_r = std::max(max_r, x.in_r);
+    carry_cap = std::max(kCarryCapMin, int((size_t(T1) + std::max<size_t>(total_factor, max_r) + 64 + 63) & ~size_t(63)));
+    float2* fresh[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) {
+        HBD_CUDA_CHECK(cudaMalloc((void**)&fresh[i], n * size_t(carry_cap) * sizeof(float2)));
+        HBD_CUDA_CHECK(cudaMemset(fresh[i], 0, n * size_t(carry_cap) * sizeof(float2)));
+    }
+    for (size_t c = 0; c < n; ++c)
+        if (hc[c].in_r)
+            HBD_CUDA_CHECK(cudaMemcpy(fresh[carry_cur] + c * size_t(carry_cap) + size_t(carry_cap) - hc[c].in_r,
+                                      d_carry2[carry_cur] + c * size_t(old_cap) + size_t(old_cap) - hc[c].in_r, sizeof(float2) * hc[c].in_r, cudaMemcpyDeviceToDevice));
+    for (int i = 0; i < 2; ++i) { cudaFree(d_carry2[i]); d_carry2[i] = fresh[i]; }
+    for (int i = 0; i < 2; ++i) if (d_s1x[i]) HBD_CUDA_CHECK(cudaMemset(d_s1x[i], 0, n * s1_pitch * sizeof(float2)));
+    for (auto& x : hc) { x.grown1 = x.grown2 = 0; for (size_t& g : x.grown_mid) g = 0; }
+    cap_n_in = 0;
+    h_plan_uploaded.clear();
     return HBD_OK;
 }
 
@@ -481,6 +535,8 @@ void hbd_decoder::free_all()
                     d_ssdv_ring, d_ssdv_total, d_ssdv_scanned, d_ssdv_log};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_pinned) cudaFreeHost(h_pinned);
+    for (MidStage& m : mids) { if (m.d_taps) cudaFree(m.d_taps); if (m.d_out) cudaFree(m.d_out); }
+    for (int i = 0; i < 2; ++i) if (d_midlast[i]) cudaFree(d_midlast[i]);
     if (dist_ctx) { internal_free_dist(dist_ctx); dist_ctx = nullptr; }
     if (d_snap) cudaFree(d_snap);
     if (h_snap) cudaFreeHost(h_snap);
@@ -505,6 +561,14 @@ int hbd_decoder::ensure_call_capacity(size_t n_in_max)
     const size_t n1_max = grow_to / size_t(M1) + 2, n2_max = grow_to / size_t(factor) + 2;
     HBD_CUDA_CHECK(grow_rows(&d_s1x[0], &s1_pitch, (kS1Hist + n1_max + 15) & ~size_t(15), n, kS1Hist, stream));
     HBD_CUDA_CHECK(grow_rows(&d_s1x[1], &s1_pitch_b, (kS1Hist + n1_max + 15) & ~size_t(15), n, kS1Hist, stream));
+    for (size_t k = 0; k < mids.size(); ++k) {   // cascaded plan: the buffers between the stages
+        const size_t n_out_max = grow_to / (size_t(mids[k].div_in) * size_t(mids[k].M)) + 2;
+        if (k + 1 < mids.size()) HBD_CUDA_CHECK(grow_rows(&mids[k].d_out, &mids[k].pitch, (kMidHist + n_out_max + 15) & ~size_t(15), n, kMidHist, stream));
+        else {
+            HBD_CUDA_CHECK(grow_rows(&d_midlast[0], &midlast_pitch, (kS1Hist + n_out_max + 15) & ~size_t(15), n, kS1Hist, stream));
+            HBD_CUDA_CHECK(grow_rows(&d_midlast[1], &midlast_pitch_b, (kS1Hist + n_out_max + 15) & ~size_t(15), n, kS1Hist, stream));
+        }
+    }
     HBD_CUDA_CHECK(grow_rows(&d_decq, &dq_pitch, (kLpHist + kLpBatch + n2_max + 15) & ~size_t(15), n, kLpHist + kLpBatch, stream));
     HBD_CUDA_CHECK(grow_rows(&d_slicer, &slicer_pitch, (size_t(kSlicerVent) + 1 + kLpBatch + n2_max + 15) & ~size_t(15), n,
                              slicer_pitch, stream));
@@ -532,7 +596,8 @@ namespace {
 struct ChanStep {
     ChanPlan plan;
     bool zero_carry = false;       // Decimator.h:74-79: the stage's work buffer grew -> its history is zeroed
-    bool zero_s1hist = false;
+    bool zero_s1hist = false;      // ... of the LAST stage (the tail kernel's input buffer)
+    unsigned zero_mid = 0;         // bit k: ... of middle stage k (cascaded plans)
     bool zero_lphist = false;      // FirFilter.h:141-147
     bool taps_changed = false;     // low-pass redesigned: upload `taps`
     size_t taps_old = 0, taps_new = 0;
@@ -587,8 +652,14 @@ static int step_channel(hbd_decoder* h, HostChan& x, unsigned pushed, ChanStep& 
         const size_t need = size_t(p.consumed) + size_t(T1) + size_t(M1);
         if (x.grown1 < need) { x.grown1 = need; o.zero_carry = true; }
     }
+    size_t n_in = p.n1;            // samples entering the next stage
+    for (size_t k = 0; k < h->mids.size(); ++k) {
+        const size_t need = n_in + size_t(h->mids[k].T) + size_t(h->mids[k].M);
+        if (x.grown_mid[k] < need) { x.grown_mid[k] = need; o.zero_mid |= 1u << k; }
+        n_in /= size_t(h->mids[k].M);
+    }
     if (M2 > 1) {
-        const size_t need = size_t(p.n1) + size_t(T2) + size_t(M2);
+        const size_t need = n_in + size_t(T2) + size_t(M2);
         if (x.grown2 < need) { x.grown2 = need; o.zero_s1hist = true; }
     }
     if (gated) { x.dec_pending = total_dec; return HBD_OK; }
@@ -658,12 +729,20 @@ int hbd_decoder::process_async_locked()
         ctr_stale = true;
         uplan = st.plan;
         any_work = !(st.plan.flags & 1u); need_k4 = st.frame_done; max_n1 = st.plan.n1; max_nf = st.nf;
-        if (st.zero_carry || st.zero_s1hist || st.zero_lphist || st.taps_changed) {
+        if (st.zero_carry || st.zero_s1hist || st.zero_mid || st.zero_lphist || st.taps_changed) {
             if (quiesce()) return HBD_ERR_CUDA;
             if (st.zero_carry)
-                HBD_CUDA_CHECK(cudaMemset2DAsync(d_carry2[carry_cur] + (kCarryCap - (T1 - 1) - st.plan.r), kCarryCap * sizeof(float2), 0,
+                HBD_CUDA_CHECK(cudaMemset2DAsync(d_carry2[carry_cur] + (carry_cap - (T1 - 1) - int(st.plan.r)), size_t(carry_cap) * sizeof(float2), 0,
                                                  sizeof(float2) * size_t(T1 - 1), n, stream));
-            if (st.zero_s1hist) HBD_CUDA_CHECK(cudaMemset2DAsync(d_s1x[s1_cur], s1_pitch * sizeof(float2), 0, sizeof(float2) * kS1Hist, n, stream));
+            for (size_t k = 0; k < mids.size(); ++k)
+                if (st.zero_mid & (1u << k)) {
+                    if (k == 0) HBD_CUDA_CHECK(cudaMemset2DAsync(d_s1x[s1_cur], s1_pitch * sizeof(float2), 0, sizeof(float2) * kS1Hist, n, stream));
+                    else HBD_CUDA_CHECK(cudaMemset2DAsync(mids[k - 1].d_out, mids[k - 1].pitch * sizeof(float2), 0, sizeof(float2) * kMidHist, n, stream));
+                }
+            if (st.zero_s1hist) {
+                if (mids.empty()) HBD_CUDA_CHECK(cudaMemset2DAsync(d_s1x[s1_cur], s1_pitch * sizeof(float2), 0, sizeof(float2) * kS1Hist, n, stream));
+                else HBD_CUDA_CHECK(cudaMemset2DAsync(d_midlast[s1_cur], midlast_pitch * sizeof(float2), 0, sizeof(float2) * kS1Hist, n, stream));
+            }
             if (st.taps_changed) {
                 if (st.taps_old > st.taps_new && d_decq) HBD_CUDA_CHECK(launch_lp_hist_shrink(d_decq, dq_pitch, n_ch, int(st.taps_old), int(st.taps_new), stream));
                 std::vector<float> all(n * st.taps_new);
@@ -688,10 +767,18 @@ int hbd_decoder::process_async_locked()
             h_plan[c] = st.plan;
             any_work |= !(st.plan.flags & 1u); need_k4 |= st.frame_done;
             max_n1 = std::max(max_n1, st.plan.n1); max_nf = std::max(max_nf, st.nf);
-            if (!(st.zero_carry || st.zero_s1hist || st.zero_lphist || st.taps_changed)) continue;
+            if (!(st.zero_carry || st.zero_s1hist || st.zero_mid || st.zero_lphist || st.taps_changed)) continue;
             if (quiesce()) return HBD_ERR_CUDA;
-            if (st.zero_carry) HBD_CUDA_CHECK(cudaMemsetAsync(d_carry2[carry_cur] + c * kCarryCap + (kCarryCap - (T1 - 1) - st.plan.r), 0, sizeof(float2) * size_t(T1 - 1), stream));
-            if (st.zero_s1hist) HBD_CUDA_CHECK(cudaMemsetAsync(d_s1x[s1_cur] + c * s1_pitch, 0, sizeof(float2) * kS1Hist, stream));
+            if (st.zero_carry) HBD_CUDA_CHECK(cudaMemsetAsync(d_carry2[carry_cur] + c * size_t(carry_cap) + (carry_cap - (T1 - 1) - int(st.plan.r)), 0, sizeof(float2) * size_t(T1 - 1), stream));
+            for (size_t k = 0; k < mids.size(); ++k)
+                if (st.zero_mid & (1u << k)) {
+                    if (k == 0) HBD_CUDA_CHECK(cudaMemsetAsync(d_s1x[s1_cur] + c * s1_pitch, 0, sizeof(float2) * kS1Hist, stream));
+                    else HBD_CUDA_CHECK(cudaMemsetAsync(mids[k - 1].d_out + c * mids[k - 1].pitch, 0, sizeof(float2) * kMidHist, stream));
+                }
+            if (st.zero_s1hist) {
+                if (mids.empty()) HBD_CUDA_CHECK(cudaMemsetAsync(d_s1x[s1_cur] + c * s1_pitch, 0, sizeof(float2) * kS1Hist, stream));
+                else HBD_CUDA_CHECK(cudaMemsetAsync(d_midlast[s1_cur] + c * midlast_pitch, 0, sizeof(float2) * kS1Hist, stream));
+            }
             if (st.taps_changed) {
                 if (st.taps_old > st.taps_new && d_decq) HBD_CUDA_CHECK(launch_lp_hist_shrink(d_decq + c * dq_pitch, dq_pitch, 1, int(st.taps_old), int(st.taps_new), stream));
                 HBD_CUDA_CHECK(cudaMemcpyAsync(d_lptaps + c * kLpMaxTaps, new_taps.data(), 4 * st.taps_new, cudaMemcpyHostToDevice, stream));
@@ -763,7 +850,7 @@ int hbd_decoder::process_async_locked()
     if (tail_pending[s1_cur]) HBD_CUDA_CHECK(cudaStreamWaitEvent(hi, ev_tail[s1_cur], 0));
     {   // K1 also writes the next call's carry (even when no channel has a full decimation block yet)
         DecimArgs da{};
-        da.chunk = chunk; da.chunk_pitch = chunk_pitch; da.carry = d_carry2[carry_cur]; da.carry_next = d_carry2[carry_cur ^ 1];
+        da.chunk = chunk; da.chunk_pitch = chunk_pitch; da.carry = d_carry2[carry_cur]; da.carry_next = d_carry2[carry_cur ^ 1]; da.carry_cap = carry_cap;
         da.s1 = d_s1x[s1_cur]; da.s1_pitch = s1_pitch; da.s1_hist = kS1Hist;
         da.plan = d_plan; da.uplan = uplan; da.uniform = plan_uniform ? 1 : 0; da.taps = d_taps1; da.ch0 = 0; da.n_channels = n_ch;
         da.nco = ext_nco ? ext_nco_ptr : nullptr;
@@ -775,9 +862,22 @@ int hbd_decoder::process_async_locked()
     HBD_CUDA_CHECK(cudaStreamWaitEvent(lo, ev_consumed, 0));
     if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
     if (any_work) {
+        // cascaded plan: the stages between K1's and the tail kernel's (1/64 of the input rate or less)
+        for (size_t k = 0; k < mids.size(); ++k) {
+            MidArgs ma{};
+            ma.plan = d_plan; ma.uplan = uplan; ma.uniform = plan_uniform ? 1 : 0;
+            if (k == 0) { ma.in = d_s1x[s1_cur]; ma.in_next = d_s1x[s1_cur ^ 1]; ma.in_pitch = s1_pitch; ma.in_hist = kS1Hist; }
+            else { ma.in = mids[k - 1].d_out; ma.in_next = mids[k - 1].d_out; ma.in_pitch = mids[k - 1].pitch; ma.in_hist = kMidHist; }
+            if (k + 1 < mids.size()) { ma.out = mids[k].d_out; ma.out_pitch = mids[k].pitch; ma.out_hist = kMidHist; }
+            else { ma.out = d_midlast[s1_cur]; ma.out_pitch = midlast_pitch; ma.out_hist = kS1Hist; }
+            ma.taps = mids[k].d_taps; ma.M = mids[k].M; ma.T = mids[k].T; ma.div_in = mids[k].div_in;
+            HBD_CUDA_CHECK(launch_mid_stage(ma, n_ch, lo, &nl));
+        }
         TailArgs ta{};
         ta.plan = d_plan; ta.uplan = uplan; ta.uniform = plan_uniform ? 1 : 0; ta.state = d_state; ta.ch0 = 0;
-        ta.s1 = d_s1x[s1_cur]; ta.s1_next = d_s1x[s1_cur ^ 1]; ta.s1_pitch = s1_pitch; ta.taps2 = d_taps2; ta.M2 = M2; ta.T2 = T2;
+        if (mids.empty()) { ta.s1 = d_s1x[s1_cur]; ta.s1_next = d_s1x[s1_cur ^ 1]; ta.s1_pitch = s1_pitch; }
+        else { ta.s1 = d_midlast[s1_cur]; ta.s1_next = d_midlast[s1_cur ^ 1]; ta.s1_pitch = midlast_pitch; }
+        ta.taps2 = d_taps2; ta.M2 = M2; ta.T2 = T2;
         ta.decq = d_decq; ta.dq_pitch = dq_pitch; ta.fs_dec = fs_dec; ta.fftbuf = d_fftbuf; ta.fft_n = fft_n; ta.lptaps = d_lptaps;
         ta.max_lp_taps = int(max_lp_taps_c);
         ta.slicer = d_slicer; ta.slicer_pitch = slicer_pitch; ta.sv_want = sv_want;
@@ -1332,54 +1432,39 @@ HBD_GETTER(lowpass_bw, float, lp_bw)
 HBD_GETTER(lowpass_trans, float, lp_trans)
 HBD_GETTER(dc_remove, int, dc_remove)
 
-static size_t apply_factor(hbd_decoder* h, size_t factor)
-{
-    // a new plan starts from fresh decimators (Decoder.h:283-284: decimation_stages_.clear())
-    std::vector<TapTable> st;
-    if (!plan_for_factor(factor, st)) { h->factor = 1; factor = 0; }
-    else h->factor = int(factor);
-    cudaSetDevice(h->device);
-    h->sync_groups();
-    cudaStreamSynchronize(h->stream);
-    h->upload_taps();
-    for (int i = 0; i < 2; ++i) cudaMemset(h->d_carry2[i], 0, size_t(h->n_ch) * kCarryCap * sizeof(float2));
-    for (int i = 0; i < 2; ++i) if (h->d_s1x[i]) cudaMemset(h->d_s1x[i], 0, size_t(h->n_ch) * h->s1_pitch * sizeof(float2));
-    h->sync_ctrs();
-    for (auto& x : h->hc) {
-        x.grown1 = x.grown2 = 0;
-        // unconsumed input stays queued in the reference (iq_in_buffer_ is untouched); it sits at the end of the carry
-    }
-    h->cap_n_in = 0;
-    h->h_plan_uploaded.clear();
-    return factor;
-}
-
 size_t hbd_setup_decimation_factor(hbd_decoder* h, size_t factor)
 {
     if (!h) return 0;
     std::lock_guard<std::mutex> l(h->mtx);
     if (factor < 1 || factor > 256) return size_t(h->factor);
-    return apply_factor(h, factor);
+    std::vector<TapTable> st;
+    if (!plan_for_factor(factor, st)) { h->set_plan(st, 1); return 0; }   // Decoder.h:283-284,317-319: stages cleared, factor 1, returns 0
+    return h->set_plan(st, factor) == HBD_OK ? factor : 0;
 }
 
+// Decoder::setupDecimationStagesBW (Decoder.h:336-412): while the rate is above the limit, divide by the smallest power of
+// two below 256 that gets under it -- or by 256 when none does -- and append that factor's stages.  Limits far below the
+// input rate therefore cascade several plans (20 MS/s -> 5 kHz: /256 then /16 = (64,348t)(4,139t)(8,54t)(2,69t)).
 size_t hbd_setup_decimation_bw(hbd_decoder* h, double max_rate)
 {
     if (!h) return 0;
     std::lock_guard<std::mutex> l(h->mtx);
     if (!h->fs_in) return 0;
-    // Decoder.h:350-402 loops "divide by the smallest power of two that gets under the limit" -- with div < 256
-    // in the inner loop the first iteration can take 256 only through the fall-through; the product of the
-    // chosen divisors is what matters for this implementation, which only supports single-plan factors.
     double rate = h->fs_in;
     size_t total = 1;
+    std::vector<TapTable> plan, st;
     while (rate > max_rate) {
         int div;
         for (div = 2; div < 256; div *= 2) if (rate / div <= max_rate) break;
         rate /= div; total *= size_t(div);
-        if (total > 256) break;
+        plan_for_factor(size_t(div), st);
+        plan.insert(plan.end(), st.begin(), st.end());
+        if (total > 65536 || plan.size() > size_t(kMaxMidStages + 2)) {
+            h->set_error("setup_decimation_bw: more than 8 stages / a total factor above 65536 is not supported");
+            return 0;
+        }
     }
-    if (total > 256) { h->set_error("setup_decimation_bw: cascades beyond one 256x plan are not supported"); return 0; }
-    return apply_factor(h, total);
+    return h->set_plan(plan, total) == HBD_OK ? total : 0;
 }
 
 static int latch_rate(hbd_decoder* h, double fs)

@@ -259,7 +259,7 @@ decim1_kernel(DecimArgs a)
         const int ch = a.ch0 + chl;
         const ChanPlan pl = a.uniform ? a.uplan : a.plan[ch];
         const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
-        const float2* carry = a.carry + (size_t)ch * kCarryCap + kCarryCap; // carry[j] valid for -kCarryCap <= j < 0
+        const float2* carry = a.carry + (size_t)ch * a.carry_cap + a.carry_cap; // carry[j] valid for -carry_cap <= j < 0
         // superblock b covers step-local sample positions x in (64(b-1), 64b]; the outputs k with
         // (b-1)*NOUT < k <= b*NOUT end inside it.  This span owns superblocks [b_lo, b_hi) of the channel.
         const int n1 = int(pl.n1);
@@ -291,7 +291,7 @@ decim1_kernel(DecimArgs a)
         // everything below is relative to the first sample of the walk, jw = j - j0 >= 0
         const int j0 = 64 * (b_first - 1) + 1 - int(pl.r);
         const int odd = j0 & 1;                // ring sample s holds j = (j0 - odd) + p*PIECE_SAMPLES + s
-        const int j_cap_lo = -kCarryCap, j_end = int(pl.n);
+        const int j_cap_lo = -a.carry_cap, j_end = int(pl.n);
 
         // ---- producer: copy piece p into its ring slot ----------------------------------------------------
         auto issue_piece = [&](int p) {
@@ -432,8 +432,8 @@ decim1_kernel(DecimArgs a)
         // [carry | chunk], r' = r + n - consumed.  It goes to the other half of a ping-pong pair because spans
         // of the same channel owned by other warps may still be reading the current carry.
         if (b_span_hi == a.sb_per_channel) {
-            const int keep = T - 1 + int(pl.r + pl.n - pl.consumed);       // <= kCarryCap (host checked)
-            float2* next = a.carry_next + (size_t)ch * kCarryCap + kCarryCap;
+            const int keep = T - 1 + int(pl.r + pl.n - pl.consumed);       // <= carry_cap (host sized)
+            float2* next = a.carry_next + (size_t)ch * a.carry_cap + a.carry_cap;
             const int jn = int(pl.n);
             if (NCO && mixing && jn > 0) {
                 const int b_min = max(jn - keep, 0) >> 12, b_max = (jn - 1) >> 12;
@@ -458,7 +458,7 @@ __global__ void decim1_generic_kernel(DecimArgs a, int M, int T)
     const ChanPlan pl = a.uniform ? a.uplan : a.plan[ch];
     if (pl.flags & 1u) return;
     const float2* chunk = a.chunk + (size_t)ch * a.chunk_pitch;
-    const float2* carry = a.carry + (size_t)ch * kCarryCap + kCarryCap;
+    const float2* carry = a.carry + (size_t)ch * a.carry_cap + a.carry_cap;
     float2* out = a.s1 + (size_t)ch * a.s1_pitch + a.s1_hist;
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < pl.n1; k += gridDim.x * blockDim.x) {
         const long long j_first = (long long)k * M - (T - 1) - (long long)pl.r;
@@ -488,13 +488,13 @@ __global__ void decim1_copy_kernel(DecimArgs a)
 // ---- stage-1 carry for the NEXT call when K1 is not the TMA kernel: last (T1-1 + r') samples of [carry | chunk] ----
 __global__ void __launch_bounds__(128)
 carry_kernel(const ChanPlan* __restrict__ plan, ChanPlan uplan, int uniform, const float2* __restrict__ chunk_base, size_t chunk_pitch, const float2* __restrict__ carry_base,
-             float2* __restrict__ next_base, int T1, int ch0)
+             float2* __restrict__ next_base, int T1, int ch0, int carry_cap)
 {
     const int ch = ch0 + blockIdx.x;
     const ChanPlan pl = uniform ? uplan : plan[ch];
-    const int keep = T1 - 1 + int(pl.r + pl.n - pl.consumed);             // <= kCarryCap (host checked)
-    const float2* carry = carry_base + (size_t)ch * kCarryCap + kCarryCap;
-    float2* next = next_base + (size_t)ch * kCarryCap + kCarryCap;
+    const int keep = T1 - 1 + int(pl.r + pl.n - pl.consumed);             // <= carry_cap (host sized)
+    const float2* carry = carry_base + (size_t)ch * carry_cap + carry_cap;
+    float2* next = next_base + (size_t)ch * carry_cap + carry_cap;
     const float2* chunk = chunk_base + (size_t)ch * chunk_pitch;
     for (int i = threadIdx.x; i < keep; i += 128) {
         const long long j = (long long)pl.n - keep + i;
@@ -503,9 +503,9 @@ carry_kernel(const ChanPlan* __restrict__ plan, ChanPlan uplan, int uniform, con
 }
 
 cudaError_t launch_carry(const ChanPlan* plan, ChanPlan uplan, int uniform, const float2* chunk, size_t chunk_pitch, const float2* carry, float2* carry_next, int T1, int ch0,
-                         int n_channels, cudaStream_t stream, int* launches)
+                         int n_channels, int carry_cap, cudaStream_t stream, int* launches)
 {
-    carry_kernel<<<n_channels, 128, 0, stream>>>(plan, uplan, uniform, chunk, chunk_pitch, carry, carry_next, T1, ch0);
+    carry_kernel<<<n_channels, 128, 0, stream>>>(plan, uplan, uniform, chunk, chunk_pitch, carry, carry_next, T1, ch0, carry_cap);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
@@ -560,7 +560,7 @@ cudaError_t launch_decim1(DecimArgs a, int M, int T, unsigned max_n1, int n_sms,
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    return launch_carry(a.plan, a.uplan, a.uniform, a.chunk, a.chunk_pitch, a.carry, a.carry_next, T, a.ch0, a.n_channels, stream, launches);
+    return launch_carry(a.plan, a.uplan, a.uniform, a.chunk, a.chunk_pitch, a.carry, a.carry_next, T, a.ch0, a.n_channels, a.carry_cap, stream, launches);
 }
 
 bool decim1_supports_fused_nco(int M, int T) { return M == 64 && T == 348; }

@@ -13,7 +13,8 @@ constexpr int kDecimWarps = HBD_K1_WARPS; // warps per CTA; each warp runs its o
 struct DecimArgs {
     const float2* chunk;       // pushed samples, [channel][chunk_pitch] cf32, chunk[j] for j in [0, n)
     size_t chunk_pitch;        // in samples, even (16-byte rows)
-    const float2* carry;       // [channel][kCarryCap], right aligned: sample j (< 0) at carry[kCarryCap + j]
+    const float2* carry;       // [channel][carry_cap], right aligned: sample j (< 0) at carry[carry_cap + j]
+    int carry_cap;             // row length of the carry buffers (>= T1 - 1 + total factor: history + unconsumed remainder)
     float2* s1;                // stage-1 output stream, [channel][s1_pitch]; outputs start at s1_hist
     size_t s1_pitch;
     int s1_hist;
@@ -37,6 +38,6 @@ cudaError_t launch_decim1(DecimArgs a, int M, int T, unsigned max_n1, int n_sms,
 bool decim1_supports_fused_nco(int M, int T);
 // stage-1 carry (history + unconsumed remainder) for the next call: carry -> carry_next
 cudaError_t launch_carry(const ChanPlan* plan, ChanPlan uplan, int uniform, const float2* chunk, size_t chunk_pitch, const float2* carry, float2* carry_next, int T1, int ch0,
-                         int n_channels, cudaStream_t stream, int* launches);
+                         int n_channels, int carry_cap, cudaStream_t stream, int* launches);
 
 } // namespace hbd

@@ -16,7 +16,8 @@
 namespace hbd {
 
 // ---- capacities (per channel) ------------------------------------------------------------------
-constexpr int kCarryCap     = 1024;   // stage-1 carry: (T1-1) history + (<factor) unconsumed + walk-in margin
+constexpr int kCarryCapMin  = 1024;   // stage-1 carry row: (T1-1) history + (< total factor) unconsumed + margin; grows with cascaded plans
+constexpr int kMidHist      = 352;    // history slots of the buffers between cascaded decimator stages (>= 348 - 1)
 constexpr int kS1Hist       = 320;    // stage-2 history slots (>= T2-1 = 138; doubles as the single-stage carry)
 constexpr int kLpMaxTaps    = 1025;   // low-pass taps upper bound ((4/trans)|1, trans >= 0.0039)
 constexpr int kLpHist       = 1024;   // low-pass history slots (>= kLpMaxTaps-1)

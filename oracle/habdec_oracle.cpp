@@ -627,6 +627,20 @@ void orc_set_param(void* h, int which, double value) // Decoder.h:654-706: plain
     case 3: p->cfg.dc_remove = value != 0; break;
     case 4: p->lp_bw = float(value); p->lp.design(float(p->lp_bw / p->fs_dec()), p->lp_trans); break;     // Decoder.h:238-243
     case 5: p->lp_trans = float(value); p->lp.design(float(p->lp_bw / p->fs_dec()), p->lp_trans); break;  // Decoder.h:252-257
+    case 6: {   // setupDecimationStagesBW, Decoder.h:336-412: plans of <= 256 each are appended until the rate is under the limit
+        if (!p->fs_in) break;
+        double rate = p->fs_in;
+        p->stages.clear(); p->factor = 1;
+        while (rate > value) {
+            int div;
+            for (div = 2; div < 256; div *= 2) if (rate / div <= value) break;
+            rate /= div; p->factor *= div;
+            std::vector<TapTable> plan;
+            decimation_plan(div, plan);
+            for (auto& t : plan) { p->stages.emplace_back(); p->stages.back().setup(t); }
+        }
+        break;
+    }
     default: break;
     }
 }

@@ -90,7 +90,7 @@ typedef struct hbo_ssdv_event {
     void   P##_afc(void* h, hbo_afc_info* out); \
     void   P##_reset_frequency_correction(void* h, double corr); \
     /* run-time setter between two calls: which = 0 baud(double), 1 rtty_bits(size_t), 2 rtty_stops(float), 3 dc_remove(bool), \
-       4 lowpass_bw(float), 5 lowpass_trans(float) (Decoder.h:238-257, 654-706) */ \
+       4 lowpass_bw(float), 5 lowpass_trans(float) (Decoder.h:238-257, 654-706), 6 setupDecimationStagesBW(double) (:336-412) */ \
     void   P##_set_param(void* h, int which, double value); \
     /* CPU baseline: n_threads decoders, one per OS thread, each decoding \
        iq + t*stride_complex .. (+n_complex) in `chunk`-sized pushes, `reps` \

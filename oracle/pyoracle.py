@@ -154,8 +154,9 @@ class _Decoder:
         return a
 
     def set_param(self, which: str, value: float):
-        """Run-time setter between calls (Decoder.h:654-706): 'baud', 'rtty_bits', 'rtty_stops', 'dc_remove', 'lowpass_bw', 'lowpass_trans'."""
-        self._f("set_param")(self._h, {"baud": 0, "rtty_bits": 1, "rtty_stops": 2, "dc_remove": 3, "lowpass_bw": 4, "lowpass_trans": 5}[which], float(value))
+        """Run-time setter between calls (Decoder.h:654-706): 'baud', 'rtty_bits', 'rtty_stops', 'dc_remove', 'lowpass_bw', 'lowpass_trans';
+        'decimation_bw' = setupDecimationStagesBW(value) (Decoder.h:336-412; after the first push)."""
+        self._f("set_param")(self._h, {"baud": 0, "rtty_bits": 1, "rtty_stops": 2, "dc_remove": 3, "lowpass_bw": 4, "lowpass_trans": 5, "decimation_bw": 6}[which], float(value))
 
     def reset_frequency_correction(self, corr: float):
         self._f("reset_frequency_correction")(self._h, float(corr))

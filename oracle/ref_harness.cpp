@@ -201,6 +201,7 @@ void ref_set_param(void* h, int which, double value)
         case 3: D.dc_remove(value != 0); break;
         case 4: D.lowpass_bw(float(value)); break;
         case 5: D.lowpass_trans(float(value)); break;
+        case 6: D.setupDecimationStagesBW(value); break;     // Decoder.h:336-412 (needs a latched sampling rate: after the first push)
         default: break;
         }
     });

@@ -301,11 +301,11 @@ def test_uart_backlog_is_rescanned_after_a_framing_change(oracle_kind, first, sn
 
 
 @pytest.mark.parametrize("fs,max_rate,want", [(2.048e6, 8000.0, 256), (2.048e6, 40000.0, 64), (1.024e6, 8000.0, 128),
-                                              (256e3, 9000.0, 32), (64e3, 8000.0, 8), (2.048e6, 1000.0, 0)])
+                                              (256e3, 9000.0, 32), (64e3, 8000.0, 8)])
 def test_setup_decimation_stages_bw(oracle_kind, fs, max_rate, want):
     """Decoder::setupDecimationStagesBW (Decoder.h:336-412): 0 before a sampling rate is latched; then the smallest
     power of two (2..128, else 256) that brings the rate under the limit, same stage plan as the factor call.
-    Limits that need more than one 256x plan are refused (0) -- the reference would cascade plans."""
+    (Limits that need more than one plan: test_setup_decimation_stages_bw_cascade.)"""
     baud = 300.0
     iq, _ = synth.channel_iq(4, 1, fs, baud, snr_db=-10.0 if fs > 1e5 else -3.0)
     chunk = 65536
@@ -326,6 +326,41 @@ def test_setup_decimation_stages_bw(oracle_kind, fs, max_rate, want):
     assert dec.poll_chars(0) == ref.chars()
     assert dec.poll_sentences(0) == ref.sentences()     # (not every rate/limit pair decodes in the reference either)
     assert dec.poll_raw_chars(0) is not None
+
+
+@pytest.mark.parametrize("max_rate,want,stages,baud,chunk", [(1000.0, 2048, "64,4,8", 50.0, 131072), (3000.0, 1024, "64,4,4", 100.0, 65536),
+                                                             (600.0, 4096, "64,4,8,2", 25.0, 262144)])
+def test_setup_decimation_stages_bw_cascade(oracle_kind, max_rate, want, stages, baud, chunk):
+    """Decoder.h:350-399: the while loop keeps appending plans of up to 256 until the rate is under the limit, so a limit far
+    below the input rate cascades three or four decimators (K1, the middle-stage kernel(s), the tail kernel).  Same call
+    sequence on both sides: one process() at factor 1 (it latches the rate), then the cascade; decimated / filtered /
+    demodulated streams within 1e-5, characters and sentences exact."""
+    fs = 2.048e6
+    iq, _ = synth.channel_iq(5, 1, fs, baud, snr_db=-20.0)
+    n = len(iq) // chunk * chunk
+    cfg = dict(baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=1)
+    dec = api.BatchDecoder(1, record=True, **cfg)
+    ref = make_oracle(oracle_kind, **cfg)
+    got = {"dec": [], "filt": [], "demod": []}
+    for i, o in enumerate(range(0, n, chunk)):
+        dec.pushSamples(0, iq[o:o + chunk], fs)
+        dec.process()
+        ref.push_process(iq[o:o + chunk], fs)
+        # (the reference harness cannot record the undecimated block of the factor-1 call: Decoder.h:522-527 clears it)
+        if i or oracle_kind != "ref":
+            got["dec"].append(dec.debug_stage(0, api.STAGE_DECIMATED).copy())
+        got["filt"].append(dec.debug_stage(0, api.STAGE_FILTERED).copy())
+        got["demod"].append(dec.debug_stage(0, api.STAGE_DEMOD).copy())
+        if i == 0:
+            assert dec.setupDecimationStagesBW(max_rate) == want
+            ref.set_param("decimation_bw", max_rate)
+            assert dec.getDecimationFactor() == want and dec.getDecimatedSamplingRate() == fs / want
+    check_stages({k: np.concatenate(v) for k, v in got.items()}, ref)
+    assert dec.poll_chars(0) == ref.chars()
+    assert dec.poll_sentences(0) == ref.sentences()
+    assert len(ref.sentences()) >= 1, "the %s plan decodes nothing in the reference either: pick another signal" % stages
+    a = ref.afc()
+    assert dec.getPeaks(0) == (a.peak_left, a.peak_right)
 
 
 def test_lowpass_setters_between_calls(oracle_kind):
