@@ -69,14 +69,13 @@ struct ChanCtr {
     unsigned pushed = 0;     // samples waiting in the staging row
     unsigned last_nf = 0, last_n2 = 0;
     unsigned demod_n = 0;    // size of the reference's demodulated_ (last call that produced any; Decoder.h:546-555)
-    unsigned lp_shadow_n = 0;  // inputs of the last low-pass call kept in the shadow of the reference's work buffer
     bool lp_dirty = true;    // bw / trans / input size changed since the last design attempt
     bool same(const ChanCtr& o) const
     {
         for (int k = 0; k < kMaxMidStages; ++k) if (grown_mid[k] != o.grown_mid[k]) return false;
         return in_r == o.in_r && dec_pending == o.dec_pending && grown1 == o.grown1 && grown2 == o.grown2 && grown_lp == o.grown_lp &&
                fft_have == o.fft_have && lp_input_size == o.lp_input_size && lp_ntaps == o.lp_ntaps && pushed == o.pushed &&
-               last_nf == o.last_nf && last_n2 == o.last_n2 && demod_n == o.demod_n && lp_shadow_n == o.lp_shadow_n && lp_dirty == o.lp_dirty;
+               last_nf == o.last_nf && last_n2 == o.last_n2 && demod_n == o.demod_n && lp_dirty == o.lp_dirty;
     }
 };
 // part 2: configuration (always per channel)
@@ -744,7 +743,6 @@ int hbd_decoder::process_async_locked()
                 else HBD_CUDA_CHECK(cudaMemset2DAsync(d_midlast[s1_cur], midlast_pitch * sizeof(float2), 0, sizeof(float2) * kS1Hist, n, stream));
             }
             if (st.taps_changed) {
-                if (st.taps_old > st.taps_new && d_decq) HBD_CUDA_CHECK(launch_lp_hist_shrink(d_decq, dq_pitch, n_ch, int(st.taps_old), int(st.taps_new), stream));
                 std::vector<float> all(n * st.taps_new);
                 for (size_t c = 0; c < n; ++c) memcpy(all.data() + c * st.taps_new, new_taps.data(), 4 * st.taps_new);
                 HBD_CUDA_CHECK(cudaMemcpy2DAsync(d_lptaps, kLpMaxTaps * sizeof(float), all.data(), st.taps_new * sizeof(float), st.taps_new * sizeof(float), n,
@@ -752,7 +750,7 @@ int hbd_decoder::process_async_locked()
                 HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // `all` goes out of scope
                 for (size_t c = 1; c < n; ++c) hc[c].cfg_dirty = true;   // lp_ntaps travels with the configuration upload
             }
-            if (st.zero_lphist) HBD_CUDA_CHECK(cudaMemset2DAsync(d_decq, dq_pitch * sizeof(float2), 0, sizeof(float2) * kLpHist, n, stream));
+            if (st.zero_lphist) HBD_CUDA_CHECK(cudaMemset2DAsync(d_decq, dq_pitch * sizeof(float2), 0, sizeof(float2) * std::min<size_t>(hc[0].lp_ntaps, kLpHist), n, stream));
         }
     } else {
         h_plan.resize(n);
@@ -780,11 +778,10 @@ int hbd_decoder::process_async_locked()
                 else HBD_CUDA_CHECK(cudaMemsetAsync(d_midlast[s1_cur] + c * midlast_pitch, 0, sizeof(float2) * kS1Hist, stream));
             }
             if (st.taps_changed) {
-                if (st.taps_old > st.taps_new && d_decq) HBD_CUDA_CHECK(launch_lp_hist_shrink(d_decq + c * dq_pitch, dq_pitch, 1, int(st.taps_old), int(st.taps_new), stream));
                 HBD_CUDA_CHECK(cudaMemcpyAsync(d_lptaps + c * kLpMaxTaps, new_taps.data(), 4 * st.taps_new, cudaMemcpyHostToDevice, stream));
                 HBD_CUDA_CHECK(cudaStreamSynchronize(stream)); // new_taps is reused
             }
-            if (st.zero_lphist) HBD_CUDA_CHECK(cudaMemsetAsync(d_decq + c * dq_pitch, 0, sizeof(float2) * kLpHist, stream));
+            if (st.zero_lphist) HBD_CUDA_CHECK(cudaMemsetAsync(d_decq + c * dq_pitch, 0, sizeof(float2) * std::min<size_t>(x.lp_ntaps, kLpHist), stream));
         }
         // back to uniform mode as soon as the channels agree again (e.g. after a round of per-channel pushes of one size)
         bool same = true;
@@ -1399,10 +1396,6 @@ static int set_lp(hbd_decoder* h, int ch, float bw, float trans, bool set_bw)
         const double fs_dec = h->fs_in / h->factor;
         const size_t T = design_lowpass(float(x.lp_bw / fs_dec), x.lp_trans, x.lp_input_size, x.lp_ntaps, taps);
         if (T != x.lp_ntaps && T <= size_t(kLpMaxTaps)) {
-            if (x.lp_ntaps > T && h->d_decq) {
-                if (launch_lp_hist_shrink(h->d_decq + size_t(c) * h->dq_pitch, h->dq_pitch, 1, int(x.lp_ntaps), int(T), h->stream) != cudaSuccess ||
-                    cudaStreamSynchronize(h->stream) != cudaSuccess) return HBD_ERR_CUDA;
-            }
             x.lp_ntaps = T; x.cfg_dirty = true; h->cfg_dirty_any = h->derived_dirty = true;
             if (cudaMemcpy(h->d_lptaps + size_t(c) * kLpMaxTaps, taps.data(), 4 * T, cudaMemcpyHostToDevice) != cudaSuccess) return HBD_ERR_CUDA;
         }

@@ -116,9 +116,10 @@ tail_kernel(TailArgs a)
     const int lead = (M2 == 4) ? ((T2 - 1 + 3) & ~3) : (T2 - 1);
     const int skew2 = lead - (T2 - 1);
     const int n_blocks = (skew2 + T2 + 3) / 4;
-    // low-pass geometry: s_q[i] = q[qbase - qskew + i]; history starts at s_q[qskew]
-    const long long qbase = (long long)kLpHist - hist;
-    const int qskew = int(qbase & 1);
+    // Low-pass queue in HBM (one row per channel): slots [0, kLpHist) mirror the head of the reference's work buffer
+    // (FirFilter.h:139-160: [T-1 history | the inputs of the last call]), the samples waiting for a 256-batch follow at
+    // kLpHist.  In shared memory: s_q[qskew ..] = history, then the queue; qskew keeps the LDS.128 of the filter aligned.
+    const int qskew = (T > 0 && (hist & 1)) ? 1 : 0;
     const int n_pairs = (qskew + T + 2) / 2;
 
     // ---- round trip 1 -------------------------------------------------------------------------------------
@@ -138,7 +139,7 @@ tail_kernel(TailArgs a)
         }
     };
     load_window(0, hbd_min_u(kTile, n2));
-    for (int i = tid; i < hist + int(dec_pending); i += kTailThreads) cp_async8(&s_q[qskew + i], &dq[qbase + i]);
+    for (int i = tid; i < hist + int(dec_pending); i += kTailThreads) cp_async8(&s_q[qskew + i], &dq[i < hist ? i : kLpHist + (i - hist)]);
     cp_async_commit();
     if (M2 == 4) { for (int u = tid; u < 4 * n_blocks; u += kTailThreads) s_h2[u] = (u >= skew2 && u - skew2 < T2) ? a.taps2[u - skew2] : 0.f; }
     else if (M2 > 1) { for (int i = tid; i < T2; i += kTailThreads) s_h2[i] = a.taps2[i]; }
@@ -304,6 +305,14 @@ tail_kernel(TailArgs a)
                 a.rec_filtered[(size_t)ch * a.rec_pitch + produced + o] = acc0;
                 a.rec_filtered[(size_t)ch * a.rec_pitch + produced + o + 1] = acc1;
             }
+            // the reference leaves this call's inputs behind the history in its work buffer (FirFilter.h:149-152); a later,
+            // LONGER filter takes them for history (:139-147 do not clear a buffer that is large enough), so they are kept too
+            {
+                const int mi = hist + int(produced) + o;
+                const float2* qin = s_q + qpos + hist;
+                if (mi < kLpHist) dq[mi] = qin[o];
+                if (mi + 1 < kLpHist) dq[mi + 1] = qin[o + 1];
+            }
             carry_prev = s_f[kTile]; // last filtered sample of this batch (same value in every thread)
             produced += kLpBatch;
             have_q -= kLpBatch;
@@ -328,7 +337,7 @@ tail_kernel(TailArgs a)
     // ---- persist: low-pass history + unfiltered remainder (write only) ---------------------------------------
     if (!(tick && nf == 0)) { // the >160 kS/s cut-off drops the queue and leaves the history alone
         const int n_keep = hist + int(have_q);
-        for (int m = tid; m < n_keep; m += kTailThreads) dq[kLpHist - hist + m] = s_q[qpos + m];
+        for (int m = tid; m < n_keep; m += kTailThreads) dq[m < hist ? m : kLpHist + (m - hist)] = s_q[qpos + m];
     }
 
     // ---- slicer: position masks by all threads, then the sequential search + UART on warp 0 ----------------------
@@ -398,25 +407,6 @@ tail_kernel(TailArgs a)
             }
         }
     }
-}
-
-// A SMALLER low-pass (lowpass_trans raised mid-stream): FirFilter keeps its work buffer, whose first T_new-1 entries are
-// the OLDEST part of the previous T_old-1 history samples (FirFilter.h:139-152 copies the new input behind them), so that
-// part becomes the history of the new filter.  One CTA moves it to the end of the history slots.
-__global__ void lp_hist_shrink_kernel(float2* rows, size_t pitch, int t_old, int t_new)
-{
-    __shared__ float2 s[kLpMaxTaps];
-    float2* row = rows + size_t(blockIdx.x) * pitch;
-    const int n = t_new - 1;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = row[kLpHist - (t_old - 1) + i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) row[kLpHist - n + i] = s[i];
-}
-cudaError_t launch_lp_hist_shrink(float2* decq_rows, size_t pitch, int n_rows, int t_old, int t_new, cudaStream_t stream)
-{
-    if (t_new < 2 || t_new >= t_old || n_rows < 1) return cudaSuccess;
-    lp_hist_shrink_kernel<<<n_rows, 256, 0, stream>>>(decq_rows, pitch, t_old, t_new);
-    return cudaGetLastError();
 }
 
 // shared-memory layout of one launch (all sizes in elements of the respective arrays)

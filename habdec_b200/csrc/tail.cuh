@@ -13,7 +13,8 @@ struct TailArgs {
     // stage 2
     float2* s1; float2* s1_next; size_t s1_pitch;  // this call's stage-1 stream; the next call's buffer (receives the stage-2 history)
     const float* taps2; int M2, T2;
-    // decimated queue: [kLpHist history slots | pending]
+    // decimated queue: [kLpHist slots mirroring the head of the reference's low-pass work buffer: history, then the last
+    // call's inputs | samples pending in front of the low-pass]
     float2* decq; size_t dq_pitch;
     double fs_dec;
     // FFT frame buffers [channel][fft_n]
@@ -42,7 +43,5 @@ struct TailArgs {
 
 cudaError_t launch_tail(TailArgs a, int n_channels, cudaStream_t stream, int* launches);
 
-// low-pass tap count shrank from t_old to t_new: keep the reference's part of the history (see tail.cu)
-cudaError_t launch_lp_hist_shrink(float2* decq_rows, size_t pitch, int n_rows, int t_old, int t_new, cudaStream_t stream);
 
 } // namespace hbd

@@ -137,9 +137,8 @@ static float sinc_nopi(float x) // habdec_windows.h:27-34: sin(x)/x, no pi
 
 struct LowPass {
     std::vector<float> taps;
-    std::vector<cf32> hist;   // taps-1 samples
+    std::vector<cf32> buff;   // the work buffer itself, FirFilter.h:139-160: [T-1 history | last inputs | older leftovers]
     size_t input_size = 0;    // last setInput size (0: "No Input set")
-    size_t grown_to = 0;
 
     void design(float rel_width, float trans)
     {
@@ -167,23 +166,23 @@ struct LowPass {
         if (!T) return false;
         if (T > n + 1) return false;
         const size_t need = n + T;
-        if (grown_to < need) { // FirFilter.h:141-147: vector grows, first T entries zeroed
-            grown_to = need;
-            hist.assign(T ? T - 1 : 0, cf32(0, 0));
+        if (buff.size() < need) { // FirFilter.h:141-147: vector grows (old content kept, new tail zero), first T entries zeroed
+            buff.resize(need, cf32(0, 0));
+            std::fill(buff.begin(), buff.begin() + T, cf32(0, 0));
         }
-        if (hist.size() != T - 1) hist.resize(T - 1, cf32(0, 0)); // tap count changed without growth
-        scratch.resize(T - 1 + n);
-        std::copy(hist.begin(), hist.end(), scratch.begin());
-        std::copy(in, in + n, scratch.begin() + (T - 1));
+        // a tap count that changed without growth finds whatever the buffer holds: the head of the old history when the
+        // filter got shorter, the old history plus stale inputs of the previous call when it got longer (:149-160)
+        std::copy(in, in + n, buff.begin() + (T - 1));
+        (void)scratch;
         for (size_t i = 0; i < n; ++i) {
             float re = 0.0f, im = 0.0f;
             for (size_t t = 0; t < T; ++t) {
-                re += scratch[i + t].real() * taps[t];
-                im += scratch[i + t].imag() * taps[t];
+                re += buff[i + t].real() * taps[t];
+                im += buff[i + t].imag() * taps[t];
             }
             out[i] = cf32(re, im);
         }
-        std::copy(in + n - (T - 1), in + n, hist.begin());
+        std::copy(in + n - (T - 1), in + n, buff.begin());
         return true;
     }
 };

@@ -232,6 +232,55 @@ def test_cfg4_full_width_4096_channels(oracle_kind):
     torch.cuda.empty_cache()
 
 
+def lp_growth_schedule():
+    """(call index -> [(setter, value)]) and chunk sizes: the tap count shrinks, grows back, grows after a LARGER call has
+    enlarged the reference's work buffer, and grows past it (which zeroes the history)."""
+    marks = {5: [("lowpass_trans", 0.05)],        # 161 -> 81: the oldest 80 history samples stay (FirFilter.h:139-152)
+             9: [("lowpass_trans", 0.025)],       # 81 -> 161 inside the old buffer: history = 80 kept + 80 stale inputs of call 8
+             13: [("lowpass_trans", 0.1)],        # -> 41
+             14: [("lowpass_trans", 0.0125)],     # -> 257 taps (clipped to the 256-sample block, |1): buffer has to grow -> zeroed
+             22: [("lowpass_trans", 0.02)]}       # 257 -> 201 after the 512-sample call below: shrink again
+    sizes = {18: 131072, 19: 131072}              # two double-size calls (nf = 512): the buffer grows to 512 + 257
+    marks[24] = [("lowpass_trans", 0.01)]         # 201 -> 257 (still clipped): fits the enlarged buffer -> stale data, no zeroing
+    return marks, sizes
+
+
+def test_lowpass_grow_reads_the_stale_work_buffer(oracle_kind):
+    """FirFilter.h:139-160: the filter's work buffer is [T-1 history | inputs of the call] and is only cleared when it has to
+    GROW.  A longer filter set at run time therefore starts from the old history followed by stale inputs of the previous
+    call (or, after a shrink, by the not-yet-overwritten rest of the older history).  The queue in HBM mirrors the head of that
+    buffer, so every sequence of lowpass_trans changes gives the reference's filtered samples."""
+    fs, baud = 2.048e6, 300.0
+    iq, _ = synth.channel_iq(43, 4, fs, baud, snr_db=-15.0)
+    marks, sizes = lp_growth_schedule()
+    cfg = dict(baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
+    dec = api.BatchDecoder(1, record=True, **cfg)
+    ref = make_oracle(oracle_kind, **cfg)
+    filt, o, i, taps_seen = [], 0, 0, []
+    while o + sizes.get(i, 65536) <= len(iq):
+        for name, v in marks.get(i, []):
+            getattr(dec, name)(v, 0); ref.set_param(name, v)
+        nblk = sizes.get(i, 65536)
+        dec.pushSamples(0, iq[o:o + nblk], fs)
+        dec.process()
+        ref.push_process(iq[o:o + nblk], fs)
+        filt.append(dec.debug_stage(0, api.STAGE_FILTERED).copy())
+        taps_seen.append(len(dec.debug_stage(0, api.STAGE_LPTAPS)))
+        assert np.array_equal(dec.debug_stage(0, api.STAGE_LPTAPS), ref.stage(po.STAGE_LPTAPS)), i
+        o += nblk; i += 1
+    assert i > 26 and {161, 81, 41, 257, 201} <= set(taps_seen)
+    got, want = np.concatenate(filt), ref.stage(po.STAGE_FILTERED)
+    assert got.shape == want.shape
+    # every call on its own: a wrong history shows in the first T-1 outputs of the call after a change
+    k = 0
+    for j, f in enumerate(filt):
+        if len(f):
+            assert rel_l2(f, want[k:k + len(f)]) <= REL_L2, "call %d (taps %d)" % (j, taps_seen[j])
+        k += len(f)
+    assert dec.poll_chars(0) == ref.chars()
+    assert dec.poll_sentences(0) == ref.sentences()
+
+
 def test_setters_between_calls(oracle_kind):
     """Decoder.h:654-706: baud / rtty_bits / rtty_stops / dc_remove changed between two process() calls act on the
     samples, bits and characters already pending.  Channel 1 of a two-channel batch is re-configured twice while

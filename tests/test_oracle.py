@@ -189,3 +189,29 @@ def test_port_equals_reference_with_setters_between_calls():
     assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
     assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][3], outs[1][3])
     assert len(outs[0][1]) == 6
+
+
+@pytest.mark.skipif(not po.available("ref"), reason="oracle/_ref not built")
+def test_restatement_lowpass_work_buffer_equals_reference():
+    """The low-pass keeps its work buffer across tap-count changes (FirFilter.h:139-160): shrink, grow back, grow after a
+    larger call, grow past the buffer.  Restatement and compiled reference agree bit for bit on the filtered stream."""
+    marks = {5: 0.05, 9: 0.025, 13: 0.1, 14: 0.0125, 22: 0.02, 24: 0.01}
+    sizes = {18: 131072, 19: 131072}
+    fs, baud = 2.048e6, 300.0
+    iq, _ = synth.channel_iq(43, 2, fs, baud, snr_db=-15.0)
+    out = {}
+    for kind, cls in (("ref", po.RefDecoder), ("orc", po.PortDecoder)):
+        d = cls(po.make_config(baud=baud))
+        o = i = 0
+        taps = set()
+        while o + sizes.get(i, 65536) <= len(iq):
+            if i in marks:
+                d.set_param("lowpass_trans", marks[i])
+            n = sizes.get(i, 65536)
+            d.push_process(iq[o:o + n], fs)
+            taps.add(len(d.stage(po.STAGE_LPTAPS)))
+            o += n; i += 1
+        out[kind] = (d.stage(po.STAGE_FILTERED), d.chars(), taps)
+    assert {161, 81, 41, 257, 201, 321} <= out["ref"][2] == out["orc"][2]
+    assert np.array_equal(out["ref"][0].view(np.uint32), out["orc"][0].view(np.uint32))
+    assert out["ref"][1] == out["orc"][1]
