@@ -270,3 +270,93 @@ def test_fused_nco_equals_premix_kernel(oracle_kind, chunk):
         assert np.linalg.norm(fused.astype(np.complex128) - want) / den <= 1e-5, "channel %d fused vs reference" % c
         assert decs[0].poll_chars(c) == refs[c].chars(), "channel %d" % c
         assert decs[0].poll_sentences(c) == refs[c].sentences(), "channel %d" % c
+
+
+def _torch_fsk_into(cap, bits, fs, baud, f_c, phase0, torch):
+    """cap += exp(j phi), continuous-phase 2-FSK of `bits` at offset f_c (float64 phase on the GPU, slices of 8 M samples)."""
+    n = cap.shape[0]
+    dev = cap.device
+    bits_t = torch.from_numpy(np.asarray(bits, dtype=np.int8)).to(dev)
+    ph = float(phase0)
+    step = 1 << 23
+    for o in range(0, n, step):
+        m = min(step, n - o)
+        idx = torch.clamp((torch.arange(o, o + m, dtype=torch.float64, device=dev) * (baud / fs)).to(torch.int64), max=len(bits) - 1)
+        f = torch.where(bits_t[idx] > 0, 0.5 * 425.0, -0.5 * 425.0).to(torch.float64) + f_c
+        phi = ph + torch.cumsum(2.0 * np.pi * f / fs, dim=0)
+        ph = float(phi[-1].item()) % (2.0 * np.pi)
+        cap[o:o + m, 0] += torch.cos(phi).to(torch.float32)
+        cap[o:o + m, 1] += torch.sin(phi).to(torch.float32)
+
+
+def test_cfg5_full_width_1024_nco_channels_with_ssdv_bursts(oracle_kind):
+    """BASELINE configs[4] at full width: ONE 20 MS/s capture (5 s) channelised into 1024 frequency-offset channels on a
+    15 kHz raster through the NCO fused into K1, dec=8 (78 125 S/s per channel), SSDV packet sync on.  64 of the channels
+    carry a signal: 56 RTTY sentences at 300 baud, 8 bursts at 600 baud with an SSDV packet between junk.  Every one of the
+    64 is compared with pre-mix + reference Decoder on the same capture: characters, sentences and SSDV events exact."""
+    import concurrent.futures
+    import torch
+    import ssdv_cases
+    fs, n_ch, raster = 20e6, 1024, 15e3
+    n = 1536 * CHUNK                                       # 5.03 s
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev); gen.manual_seed(2024)
+    cap = 0.7 * torch.randn((n, 2), dtype=torch.float32, device=dev, generator=gen)
+    active = [8 + 16 * k for k in range(64)]
+    bauds, payloads = {}, {}
+    rng = np.random.default_rng(11)
+    for k, c in enumerate(active):
+        if k % 8 == 3:                                     # an SSDV burst: junk, one packet, a sentence, junk
+            bauds[c] = 600.0
+            payloads[c] = ssdv_cases.junk(rng, 20, 0.1) + ssdv_cases.random_packet(rng, ssdv_cases.CALLSIGNS[k % 4], 1 + k // 8, 0, fec=True) + \
+                short_sentence(k).encode() + ssdv_cases.junk(rng, 30, 0.0)
+        else:
+            bauds[c] = 300.0
+            payloads[c] = "".join(short_sentence(k, j) for j in range(4)).encode()
+        bits = synth.uart_bits(payloads[c], 8, 2, lead_in=30, lead_out=40)
+        assert len(bits) * fs / bauds[c] < n
+        _torch_fsk_into(cap, bits, fs, bauds[c], (c - n_ch / 2) * raster, 0.3 * k, torch)
+    torch.cuda.synchronize()
+
+    dec = api.BatchDecoder(n_ch, baud=300.0, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
+    dec.set_stream(torch.cuda.current_stream().cuda_stream)
+    for c in range(n_ch):
+        dec.set_nco((c - n_ch / 2) * raster, c)
+    for c in active:
+        dec.baud(bauds[c], c)
+    dec.set_ssdv(True)
+    events = {c: [] for c in active}
+    for i in range(n // CHUNK):
+        dec.pushWidebandDevice(cap.data_ptr() + i * CHUNK * 8, CHUNK, fs)
+        dec.process_async()
+        if (i + 1) % 8 == 0:
+            dec.collect_ready(4)
+    dec.collect()
+    for c in active:
+        events[c] = [(cs, iid, pid, w, h, size) for (cs, iid, pid, w, h, err, size, pkt) in dec.poll_ssdv_packets(c)]
+    got = {c: (dec.poll_chars(c), dec.poll_sentences(c)) for c in active}
+    noise_chars = sum(len(dec.poll_chars(c)) for c in range(0, n_ch, 16))     # channels without a signal decode noise: something, not nothing
+    host = cap.cpu().numpy().view(np.complex64).reshape(-1)
+    del cap
+    torch.cuda.empty_cache()
+
+    def oracle_for(c):
+        ref = make_oracle(oracle_kind, baud=bauds[c], rtty_bits=8, rtty_stops=2.0, dec_factor=256)
+        ph, f_c = 0.0, (c - n_ch / 2) * raster
+        for o in range(0, n, 16 * CHUNK):
+            mixed, ph = po.premix(host[o:o + 16 * CHUNK], fs, f_c, ph)
+            for q in range(0, len(mixed), CHUNK):
+                ref.push_process(mixed[q:q + CHUNK], fs)
+        ev = [(e[1], e[2], e[3], e[4], e[5], e[6]) for e in ref.ssdv_events()]
+        return c, ref.chars(), ref.sentences(), ev
+
+    bad = []
+    n_sent = n_pkt = 0
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
+        for c, chars, sents, ev in pool.map(oracle_for, active):
+            if got[c] != (chars, sents) or events[c] != ev:
+                bad.append(c)
+            n_sent += len(sents); n_pkt += len(ev)
+    assert not bad, "channels %r differ from pre-mix + %s" % (bad, oracle_kind)
+    assert n_sent >= 56 * 3 and n_pkt >= 6            # the signals really decode (sentences on the RTTY channels, packets on the bursts)
+    assert noise_chars > 0
