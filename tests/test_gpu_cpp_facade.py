@@ -57,9 +57,9 @@ def test_decoder_thread_program_matches_reference(tmp_path, oracle_kind):
     # serialiser in test_gpu_wire.py) and carrying the oracle's AFC numbers in its header
     pwr = [l.split() for l in lines if l.startswith("PWR ")]
     assert len(pwr) == 3 and all(p[4] == "same" for p in pwr), pwr
-    assert [int(p[2]) for p in pwr] == [4096 - 2 * 20, 1024, 300]          # zoom 0.01 floor / 0.5 / 0.9 and the shrink
+    assert [int(p[2]) for p in pwr] == [4075 - 20, 1024, 300]              # zoom 0.01 floor (bins [20, 4075)) / 0.5 / 0.9 and the shrink
     hdr = struct.unpack("<i4f4i2f2i", bytes.fromhex(pwr[0][5]))
-    assert hdr[0] == 52 and hdr[11] == 4 and hdr[12] == 4096 - 40
+    assert hdr[0] == 52 and hdr[11] == 4 and hdr[12] == 4055
     assert hdr[1] == pytest.approx(a.noise_floor, abs=1e-3) and hdr[3] == 8000.0 and hdr[4] == pytest.approx(a.shift_hz, abs=1e-3)
     assert hdr[5] == abs(a.peak_left) - 20 and hdr[6] == abs(a.peak_right) - 20 and hdr[7] == int(a.peak_left > 0) and hdr[8] == int(a.peak_right > 0)
 
