@@ -270,6 +270,9 @@ tail_kernel(TailArgs a)
             for (unsigned k = tid; k < nk && k0 + k < fft_take; k += kTailThreads) fb[k0 + k] = ynew[k];
         }
         have_q += nk;
+        // above 160 kS/s nothing is decoded and the whole queue is dropped (Decoder.h:522-527): the tiles of a long call must
+        // not pile up in the shared-memory queue (a factor-1 call at MS/s rates brings hundreds of them)
+        if (tick && nf == 0) have_q = 0;
 
         // ---- low-pass FIR + discriminator on one batch of 256 --------------------------------------------------
         if (produced < nf && have_q >= unsigned(kLpBatch)) {
