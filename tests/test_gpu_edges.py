@@ -420,22 +420,21 @@ def test_setup_decimation_stages_bw(oracle_kind, fs, max_rate, want):
 def test_setup_decimation_stages_bw_cascade(oracle_kind, max_rate, want, stages, baud, chunk):
     """Decoder.h:350-399: the while loop keeps appending plans of up to 256 until the rate is under the limit, so a limit far
     below the input rate cascades three or four decimators (K1, the middle-stage kernel(s), the tail kernel).  Same call
-    sequence on both sides: one process() at factor 1 (it latches the rate), then the cascade; decimated / filtered /
-    demodulated streams within 1e-5, characters and sentences exact."""
+    sequence on both sides: one one-sample process() at factor 1 (it latches the rate), then the cascade; decimated /
+    filtered / demodulated streams within 1e-5, characters, sentences and AFC peaks exact."""
     fs = 2.048e6
     iq, _ = synth.channel_iq(5, 1, fs, baud, snr_db=-20.0)
-    n = len(iq) // chunk * chunk
+    n = (len(iq) - 1) // chunk * chunk
     cfg = dict(baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=1)
     dec = api.BatchDecoder(1, record=True, **cfg)
     ref = make_oracle(oracle_kind, **cfg)
     got = {"dec": [], "filt": [], "demod": []}
-    for i, o in enumerate(range(0, n, chunk)):
-        dec.pushSamples(0, iq[o:o + chunk], fs)
+    blocks = [iq[:1]] + [iq[1 + o:1 + o + chunk] for o in range(0, n, chunk)]
+    for i, blk in enumerate(blocks):
+        dec.pushSamples(0, blk, fs)
         dec.process()
-        ref.push_process(iq[o:o + chunk], fs)
-        # (the reference harness cannot record the undecimated block of the factor-1 call: Decoder.h:522-527 clears it)
-        if i or oracle_kind != "ref":
-            got["dec"].append(dec.debug_stage(0, api.STAGE_DECIMATED).copy())
+        ref.push_process(blk, fs)
+        got["dec"].append(dec.debug_stage(0, api.STAGE_DECIMATED).copy())
         got["filt"].append(dec.debug_stage(0, api.STAGE_FILTERED).copy())
         got["demod"].append(dec.debug_stage(0, api.STAGE_DEMOD).copy())
         if i == 0:
