@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target duration of the cpu_baseline leg")
     ap.add_argument("--collect-every", type=int, default=4, help="drain finished calls every this many steps")
-    ap.add_argument("--gather-every", type=int, default=16, help="gather the result records to rank 0 every this many steps (and after the last one)")
+    ap.add_argument("--gather-every", type=int, default=0, help="gather the result records to rank 0 every this many steps; 0: once per batch, after the last step")
     ap.add_argument("--collect-lag", type=int, default=3, help="calls left in flight by the periodic drain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -293,7 +293,7 @@ def decode_leg(D: Dist, args, n_local, ch0, n_total, steps, warmup, timing=True)
         if (k + 1) % args.collect_every == 0:
             t_h = time.perf_counter()
             dec.collect_ready(args.collect_lag)   # drain finished calls; the newest few stay in flight so the GPU never idles
-            if (k + 1) % args.gather_every == 0:
+            if args.gather_every and (k + 1) % args.gather_every == 0:
                 dec.gather_results(sink)          # records of every channel -> rank 0 (NCCL send/recv)
                 gathers += 1
             t_drain += time.perf_counter() - t_h

@@ -695,6 +695,10 @@ class BatchDecoder:
     def dist_total_channels(self) -> int: return self._lib.hbd_dist_total_channels(self._h)
 
     def gather_results(self, sink: "ResultSink | None") -> int:
+        if sink is not None:
+            self._sinks = getattr(self, "_sinks", [])
+            if sink not in self._sinks:
+                self._sinks.append(sink)      # the sink borrows the handle's receive buffers: it has to outlive the handle
         rc = self._lib.hbd_gather_results(self._h, sink.handle if sink is not None else None)
         if rc < 0:
             self._chk(rc)

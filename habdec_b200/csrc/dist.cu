@@ -68,10 +68,16 @@ struct DistCtx {
     cudaStream_t stream = nullptr;
     std::vector<int> counts, offsets;          // channels per rank, first record of every rank in the gathered buffer
     int total = 0;
-    hbd_result_record* h_send = nullptr;       // pinned, counts[rank] records
-    hbd_result_record* d_send = nullptr;
+    // A gather must not stall the thread that also feeds the GPU: senders enqueue and return (their buffers rotate through
+    // a pool of kPool slots, a slot is reused once its send has completed), and rank 0 hands its pinned receive buffer to
+    // the sink WITHOUT copying (hbd::sink_feed_borrowed); the sink is flushed before that slot comes round again.
+    static constexpr int kPool = 4;
+    hbd_result_record* h_send[kPool] = {};     // pinned, counts[rank] records each
+    hbd_result_record* d_send[kPool] = {};
+    cudaEvent_t ev_sent[kPool] = {};
     hbd_result_record* d_recv = nullptr;       // rank 0: total records
-    hbd_result_record* h_recv = nullptr;       // rank 0: pinned, total records
+    hbd_result_record* h_recv[kPool] = {};     // rank 0: pinned, total records each
+    hbd_result_sink* fed[kPool] = {};          // the sink that borrowed slot k
     int* d_cnt = nullptr;
     unsigned long long gathers = 0;
 };
@@ -81,9 +87,13 @@ void free_ctx(DistCtx* c)
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->own_comm && c->comm && nccl_api()->CommDestroy) nccl_api()->CommDestroy(c->comm);
-    if (c->h_send) cudaFreeHost(c->h_send);
-    if (c->h_recv) cudaFreeHost(c->h_recv);
-    if (c->d_send) cudaFree(c->d_send);
+    for (int k = 0; k < DistCtx::kPool; ++k) {
+        if (c->fed[k]) hbd::sink_flush(c->fed[k]);
+        if (c->h_send[k]) cudaFreeHost(c->h_send[k]);
+        if (c->h_recv[k]) cudaFreeHost(c->h_recv[k]);
+        if (c->d_send[k]) cudaFree(c->d_send[k]);
+        if (c->ev_sent[k]) cudaEventDestroy(c->ev_sent[k]);
+    }
     if (c->d_recv) cudaFree(c->d_recv);
     if (c->d_cnt) cudaFree(c->d_cnt);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -115,9 +125,12 @@ int setup(hbd_decoder* h, DistCtx* c)
     c->total = 0;
     for (int r = 0; r < c->world; ++r) { c->offsets[size_t(r)] = c->total; c->total += c->counts[size_t(r)]; }
     const size_t mine = sizeof(hbd_result_record) * size_t(n_ch), all = sizeof(hbd_result_record) * size_t(c->total);
-    if (cudaHostAlloc((void**)&c->h_send, mine, cudaHostAllocDefault) != cudaSuccess || cudaMalloc((void**)&c->d_send, mine) != cudaSuccess) return fail(h, "dist: buffers");
-    if (c->rank == 0 && (cudaHostAlloc((void**)&c->h_recv, all, cudaHostAllocDefault) != cudaSuccess || cudaMalloc((void**)&c->d_recv, all) != cudaSuccess))
-        return fail(h, "dist: buffers");
+    for (int k = 0; k < DistCtx::kPool; ++k) {
+        if (cudaHostAlloc((void**)&c->h_send[k], mine, cudaHostAllocDefault) != cudaSuccess || cudaMalloc((void**)&c->d_send[k], mine) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_sent[k], cudaEventDisableTiming) != cudaSuccess) return fail(h, "dist: buffers");
+        if (c->rank == 0 && c->world > 1 && cudaHostAlloc((void**)&c->h_recv[k], all, cudaHostAllocDefault) != cudaSuccess) return fail(h, "dist: buffers");
+    }
+    if (c->rank == 0 && c->world > 1 && cudaMalloc((void**)&c->d_recv, all) != cudaSuccess) return fail(h, "dist: buffers");
     return HBD_OK;
 }
 
@@ -179,7 +192,7 @@ int hbd_dist_finalize(hbd_decoder* h)
 {
     if (!h) return HBD_ERR_ARG;
     void** slot = hbd::internal_dist_slot(h);
-    if (*slot) { cudaSetDevice(hbd::internal_device(h)); free_ctx(static_cast<DistCtx*>(*slot)); *slot = nullptr; }
+    if (*slot) { cudaSetDevice(hbd::internal_device(h)); free_ctx(static_cast<DistCtx*>(*slot)); *slot = nullptr; }   // flushes the sinks it fed
     return HBD_OK;
 }
 
@@ -202,32 +215,40 @@ int hbd_gather_results(hbd_decoder* h, hbd_result_sink* sink)
     if (cudaSetDevice(hbd::internal_device(h)) != cudaSuccess) return HBD_ERR_CUDA;
     NcclApi* n = nccl_api();
     const int mine = c->counts[size_t(c->rank)];
-    const size_t got = hbd_pack_results(h, c->offsets[size_t(c->rank)], c->h_send, size_t(mine));
+    const int k = int(c->gathers % DistCtx::kPool);
+    // slot k comes round again: its send has long completed; a sink that still borrows it takes its records in now
+    if (c->gathers >= DistCtx::kPool && cudaEventSynchronize(c->ev_sent[k]) != cudaSuccess) return fail(h, "gather: earlier send failed");
+    if (c->fed[k]) { hbd::sink_flush(c->fed[k]); c->fed[k] = nullptr; }
+    const size_t got = hbd_pack_results(h, c->offsets[size_t(c->rank)], c->h_send[k], size_t(mine));
     if (got != size_t(mine)) return HBD_ERR_STATE;
     const size_t rec = sizeof(hbd_result_record);
     if (c->world > 1) {
         if (c->rank != 0) {
-            if (cudaMemcpyAsync(c->d_send, c->h_send, rec * size_t(mine), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return fail(h, "gather: H2D");
-            const ncclResult r = n->Send(c->d_send, rec * size_t(mine), kNcclInt8, 0, c->comm, c->stream);
+            // enqueue and return: nothing here waits for rank 0 (which may be busy draining its own channels)
+            if (cudaMemcpyAsync(c->d_send[k], c->h_send[k], rec * size_t(mine), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return fail(h, "gather: H2D");
+            const ncclResult r = n->Send(c->d_send[k], rec * size_t(mine), kNcclInt8, 0, c->comm, c->stream);
             if (r) return fail(h, std::string("ncclSend: ") + n->GetErrorString(r));
+            if (cudaEventRecord(c->ev_sent[k], c->stream) != cudaSuccess) return fail(h, "gather: event");
         } else {
             ncclResult r = n->GroupStart();
             for (int p = 1; p < c->world && !r; ++p)
                 r = n->Recv(c->d_recv + c->offsets[size_t(p)], rec * size_t(c->counts[size_t(p)]), kNcclInt8, p, c->comm, c->stream);
             if (!r) r = n->GroupEnd();
             if (r) return fail(h, std::string("ncclRecv: ") + n->GetErrorString(r));
-            if (cudaMemcpyAsync(c->h_recv + mine, c->d_recv + mine, rec * size_t(c->total - mine), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+            if (cudaMemcpyAsync(c->h_recv[k] + mine, c->d_recv + mine, rec * size_t(c->total - mine), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
                 return fail(h, "gather: D2H");
+            if (cudaEventRecord(c->ev_sent[k], c->stream) != cudaSuccess) return fail(h, "gather: event");
+            if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(h, "gather: transfer failed");
         }
-        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(h, "gather: transfer failed");
     }
     ++c->gathers;
     if (c->rank != 0) {   // a sink on another rank mirrors that rank's own channels (same global numbering)
-        if (sink) { const int rc = hbd_sink_feed(sink, c->h_send, size_t(mine)); if (rc) return rc; }
+        if (sink) { const int rc = hbd::sink_feed_borrowed(sink, c->h_send[k], size_t(mine)); if (rc) return rc; c->fed[k] = sink; }
         return mine;
     }
-    int rc = hbd_sink_feed(sink, c->h_send, size_t(mine));
-    if (c->world > 1 && !rc) rc = hbd_sink_feed(sink, c->h_recv + mine, size_t(c->total - mine));
+    int rc = hbd::sink_feed_borrowed(sink, c->h_send[k], size_t(mine));
+    if (c->world > 1 && !rc) rc = hbd::sink_feed_borrowed(sink, c->h_recv[k] + mine, size_t(c->total - mine));
+    c->fed[k] = sink;
     return rc ? rc : c->total;
 }
 

@@ -7,9 +7,12 @@
 // deliver: character_callback_ / sentence_callback_ payloads (Decoder.h:135-138,604-606,625-626) and
 // getFrequencyCorrection / getShift / getNoiseFloor / getPeaks (Decoder.h:108-113).
 #include "../../include/habdec_b200.h"
+#include "api_internal.h"
 
 #include <algorithm>
+#include <cstddef>
 #include <cstring>
+#include <mutex>
 #include <sched.h>
 #include <string>
 #include <thread>
@@ -101,9 +104,17 @@ struct SinkChan {
 } // namespace
 
 struct hbd_result_sink {
+    std::mutex mtx;                          // a server thread may poll while the gather thread feeds
     std::vector<SinkChan> ch;
+    // Feeding is lazy: a fed block is only validated and copied in compact form (header + used bytes); the per-channel
+    // strings are built when somebody looks (poll / stats / totals / hash).  On rank 0 of an 8-GPU box a gather brings
+    // 28 672 records; touching that many scattered per-channel strings costs milliseconds that the caller -- the thread
+    // that also feeds the GPU -- does not have, while most channels are never polled between two gathers.
+    struct Block { std::vector<unsigned char> own; const hbd_result_record* borrowed = nullptr; size_t n = 0; };
+    std::vector<Block> pending;              // own: compact copy of a fed block; borrowed: records that stay valid until hbd::sink_flush
     unsigned long long records = 0;
     int threads = 1;
+    void materialize();
 };
 
 extern "C" {
@@ -122,59 +133,121 @@ hbd_result_sink* hbd_sink_create(int total_channels)
     return s;
 }
 void hbd_sink_destroy(hbd_result_sink* s) { delete s; }
-int hbd_sink_set_threads(hbd_result_sink* s, int n) { if (!s) return HBD_ERR_ARG; s->threads = std::max(1, std::min(n, 64)); return HBD_OK; }
+int hbd_sink_set_threads(hbd_result_sink* s, int n) { if (!s) return HBD_ERR_ARG; std::lock_guard<std::mutex> l(s->mtx); s->threads = std::max(1, std::min(n, 64)); return HBD_OK; }
 
-// Records of channels in [c_lo, c_hi) only: feeds of many thousand records are cut by channel range over a few threads
-// (the per-channel strings are scattered over the heap, the work is cache-miss bound).
-static int feed_range(hbd_result_sink* s, const hbd_result_record* recs, size_t n, size_t c_lo, size_t c_hi, unsigned long long* fed)
+} // extern "C"
+
+namespace {
+constexpr size_t kHdr = offsetof(hbd_result_record, chars);   // 40 bytes: everything in front of the text fields
+
+// compact entries [header | chars | sentence bytes] of channels in [c_lo, c_hi) into the per-channel state
+void apply_range(hbd_result_sink* s, const unsigned char* blob, size_t bytes, size_t c_lo, size_t c_hi)
 {
-    int rc = HBD_OK;
-    unsigned long long cnt = 0;
-    const bool all = c_lo == 0 && c_hi >= s->ch.size();
-    for (size_t i = 0; i < n; ++i) {
-        if (all && i + 8 < n && recs[i + 8].channel < s->ch.size()) {
-            const SinkChan& nx = s->ch[recs[i + 8].channel];
-            __builtin_prefetch(nx.chars.data() + nx.chars.size());
-            __builtin_prefetch(nx.sentences.data() + nx.sentences.size());
-        }
-        const hbd_result_record& r = recs[i];
-        if (r.channel >= s->ch.size() || r.n_chars > sizeof(r.chars) || r.sentence_bytes > sizeof(r.sentences)) { if (c_lo == 0) rc = HBD_ERR_ARG; continue; }
+    for (size_t o = 0; o + kHdr <= bytes;) {
+        hbd_result_record r;                                  // header only
+        memcpy(&r, blob + o, kHdr);
+        const unsigned char* chars = blob + o + kHdr;
+        const unsigned char* sent = chars + r.n_chars;
+        o += kHdr + r.n_chars + r.sentence_bytes;
         if (r.channel < c_lo || r.channel >= c_hi) continue;
+        SinkChan& c = s->ch[r.channel];
+        if (r.n_chars) { c.chars.append(reinterpret_cast<const char*>(chars), r.n_chars); c.h_chars = crc32c(c.h_chars, chars, r.n_chars); c.n_chars += r.n_chars; }
+        if (r.sentence_bytes) { c.sentences.append(reinterpret_cast<const char*>(sent), r.sentence_bytes); c.h_sent = crc32c(c.h_sent, sent, r.sentence_bytes); c.n_sent += r.n_sentences; }
+        c.stats[0] = r.frequency_correction; c.stats[1] = r.shift; c.stats[2] = r.noise_floor; c.stats[3] = r.noise_variance;
+        c.peaks[0] = r.peak_left; c.peaks[1] = r.peak_right; c.seen = true;
+    }
+}
+// whole records (a borrowed block, e.g. the pinned receive buffer of the NCCL gather) of channels in [c_lo, c_hi)
+void apply_records(hbd_result_sink* s, const hbd_result_record* recs, size_t n, size_t c_lo, size_t c_hi)
+{
+    for (size_t i = 0; i < n; ++i) {
+        const hbd_result_record& r = recs[i];
+        if (r.channel < c_lo || r.channel >= c_hi || r.n_chars > sizeof(r.chars) || r.sentence_bytes > sizeof(r.sentences)) continue;
         SinkChan& c = s->ch[r.channel];
         if (r.n_chars) { c.chars.append(r.chars, r.n_chars); c.h_chars = crc32c(c.h_chars, r.chars, r.n_chars); c.n_chars += r.n_chars; }
         if (r.sentence_bytes) { c.sentences.append(r.sentences, r.sentence_bytes); c.h_sent = crc32c(c.h_sent, r.sentences, r.sentence_bytes); c.n_sent += r.n_sentences; }
         c.stats[0] = r.frequency_correction; c.stats[1] = r.shift; c.stats[2] = r.noise_floor; c.stats[3] = r.noise_variance;
         c.peaks[0] = r.peak_left; c.peaks[1] = r.peak_right; c.seen = true;
-        ++cnt;
     }
-    *fed = cnt;
-    return rc;
 }
+} // namespace
+
+namespace hbd {
+// Library-internal (dist.cu): feed without copying.  `recs` must stay valid and unchanged until sink_flush(s) returns.
+int sink_feed_borrowed(hbd_result_sink* s, const hbd_result_record* recs, size_t n)
+{
+    if (!s || (!recs && n)) return HBD_ERR_ARG;
+    std::lock_guard<std::mutex> l(s->mtx);
+    hbd_result_sink::Block b;
+    b.borrowed = recs; b.n = n;
+    s->pending.push_back(std::move(b));
+    s->records += n;
+    return HBD_OK;
+}
+void sink_flush(hbd_result_sink* s)
+{
+    if (!s) return;
+    std::lock_guard<std::mutex> l(s->mtx);
+    s->materialize();
+}
+} // namespace hbd
+
+void hbd_result_sink::materialize()
+{
+    if (pending.empty()) return;
+    size_t total = 0;
+    for (const auto& b : pending) total += b.own.size() + b.n * 64;
+    const int n_thr = std::max(1, std::min(threads, int(total / (256 * 1024))));
+    auto run = [&](int t) {
+        const size_t c_lo = ch.size() * size_t(t) / size_t(n_thr), c_hi = ch.size() * size_t(t + 1) / size_t(n_thr);
+        for (const auto& b : pending) {      // blocks in feed order: streams stay in order
+            if (b.borrowed) apply_records(this, b.borrowed, b.n, c_lo, c_hi);
+            else apply_range(this, b.own.data(), b.own.size(), c_lo, c_hi);
+        }
+    };
+    if (n_thr == 1) run(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < n_thr; ++t) th.emplace_back(run, t);
+        run(0);
+        for (auto& x : th) x.join();
+    }
+    pending.clear();
+}
+
+extern "C" {
 
 int hbd_sink_feed(hbd_result_sink* s, const hbd_result_record* recs, size_t n)
 {
     if (!s || (!recs && n)) return HBD_ERR_ARG;
-    const int n_thr = std::max(1, std::min(s->threads, int(n / 4096)));
-    if (n_thr == 1) {
-        unsigned long long fed = 0;
-        const int rc = feed_range(s, recs, n, 0, s->ch.size(), &fed);
-        s->records += fed;
-        return rc;
-    }
-    std::vector<unsigned long long> fed(size_t(n_thr), 0);
-    std::vector<int> rcs(size_t(n_thr), HBD_OK);
-    // the records arrive in channel order: ranges of the channels present, so the threads get equal shares
-    uint32_t lo = ~0u, hi = 0;
-    for (size_t i = 0; i < n; ++i) { lo = std::min(lo, recs[i].channel); hi = std::max(hi, recs[i].channel); }
-    hi = std::min<uint64_t>(uint64_t(hi) + 1, s->ch.size());
-    lo = std::min(lo, hi);
-    auto bound = [&](int t) { return t == 0 ? size_t(0) : t == n_thr ? s->ch.size() : size_t(lo + (uint64_t(hi - lo) * t) / n_thr); };
-    std::vector<std::thread> th;
-    for (int t = 1; t < n_thr; ++t) th.emplace_back([&, t] { rcs[size_t(t)] = feed_range(s, recs, n, bound(t), bound(t + 1), &fed[size_t(t)]); });
-    rcs[0] = feed_range(s, recs, n, bound(0), bound(1), &fed[0]);
-    for (auto& x : th) x.join();
+    if (!n) return HBD_OK;
     int rc = HBD_OK;
-    for (int t = 0; t < n_thr; ++t) { s->records += fed[size_t(t)]; if (rcs[size_t(t)]) rc = rcs[size_t(t)]; }
+    std::vector<unsigned char> blob;
+    blob.resize(n * (kHdr + 48));                 // grows below if the records are fuller than that on average
+    size_t o = 0, kept = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const hbd_result_record& r = recs[i];
+        if (r.n_chars > sizeof(r.chars) || r.sentence_bytes > sizeof(r.sentences)) { rc = HBD_ERR_ARG; continue; }
+        const size_t need = kHdr + r.n_chars + r.sentence_bytes;
+        if (o + need > blob.size()) blob.resize(std::max(blob.size() * 2, o + need));
+        memcpy(blob.data() + o, &r, kHdr);
+        memcpy(blob.data() + o + kHdr, r.chars, r.n_chars);
+        memcpy(blob.data() + o + kHdr + r.n_chars, r.sentences, r.sentence_bytes);
+        o += need; ++kept;
+    }
+    blob.resize(o);
+    std::lock_guard<std::mutex> l(s->mtx);
+    // the channel numbers are checked against THIS sink here, so that a bad block is reported by the feed that brought it
+    for (size_t q = 0; q + kHdr <= blob.size();) {
+        hbd_result_record r; memcpy(&r, blob.data() + q, kHdr);
+        if (r.channel >= s->ch.size()) { rc = HBD_ERR_ARG; uint32_t bad = ~0u; memcpy(blob.data() + q, &bad, 4); --kept; }
+        q += kHdr + r.n_chars + r.sentence_bytes;
+    }
+    s->records += kept;
+    hbd_result_sink::Block b;
+    b.own = std::move(blob);
+    s->pending.push_back(std::move(b));
+    if (s->pending.size() > 64) s->materialize();   // bound the backlog of a sink nobody reads
     return rc;
 }
 
@@ -188,17 +261,23 @@ static size_t sink_take(std::string& src, char* out, size_t cap)
 size_t hbd_sink_poll_chars(hbd_result_sink* s, int ch, char* out, size_t cap)
 {
     if (!s || ch < 0 || size_t(ch) >= s->ch.size()) return 0;
+    std::lock_guard<std::mutex> l(s->mtx);
+    s->materialize();
     return sink_take(s->ch[size_t(ch)].chars, out, cap);
 }
 size_t hbd_sink_poll_sentences(hbd_result_sink* s, int ch, char* out, size_t cap)
 {
     if (!s || ch < 0 || size_t(ch) >= s->ch.size()) return 0;
+    std::lock_guard<std::mutex> l(s->mtx);
+    s->materialize();
     return sink_take(s->ch[size_t(ch)].sentences, out, cap);
 }
 // the newest record's scalars: out[0..5] = frequency correction, shift, noise floor, noise variance, peak left, peak right
 int hbd_sink_stats(hbd_result_sink* s, int ch, double out[6])
 {
     if (!s || !out || ch < 0 || size_t(ch) >= s->ch.size()) return HBD_ERR_ARG;
+    std::lock_guard<std::mutex> l(s->mtx);
+    s->materialize();
     const SinkChan& c = s->ch[size_t(ch)];
     if (!c.seen) return HBD_ERR_STATE;
     for (int i = 0; i < 4; ++i) out[i] = c.stats[i];
@@ -209,6 +288,8 @@ int hbd_sink_stats(hbd_result_sink* s, int ch, double out[6])
 void hbd_sink_totals(hbd_result_sink* s, unsigned long long* chars, unsigned long long* sentences, unsigned long long* min_sentences, unsigned long long* records)
 {
     unsigned long long nc = 0, ns = 0, mn = ~0ull;
+    std::unique_lock<std::mutex> l;
+    if (s) { l = std::unique_lock<std::mutex>(s->mtx); s->materialize(); }
     if (s) for (const SinkChan& c : s->ch) { nc += c.n_chars; ns += c.n_sent; mn = std::min<unsigned long long>(mn, c.n_sent); }
     if (chars) *chars = nc;
     if (sentences) *sentences = ns;
@@ -221,6 +302,8 @@ uint64_t hbd_sink_hash(hbd_result_sink* s)
 {
     uint64_t h = kFnvInit;
     if (!s) return h;
+    std::lock_guard<std::mutex> l(s->mtx);
+    s->materialize();
     for (size_t c = 0; c < s->ch.size(); ++c) {
         const SinkChan& x = s->ch[c];
         const uint64_t rec[5] = {uint64_t(c), uint64_t(x.h_chars), uint64_t(x.h_sent), x.n_chars, x.n_sent};

@@ -246,7 +246,10 @@ int    hbd_dist_finalize(hbd_decoder* h);
 int    hbd_dist_total_channels(hbd_decoder* h);
 /* every rank, at the same points of its call sequence: pack, ncclSend to rank 0 / ncclRecv there, feed `sink`: on rank 0
  * (required) with the records of ALL channels; on other ranks (optional, may be NULL) with the rank's own records, a local
- * mirror.  Global channel = channels of the lower ranks + local index.  Returns the records moved, < 0 on error */
+ * mirror.  Global channel = channels of the lower ranks + local index.  Returns the records moved, < 0 on error.
+ * Ranks > 0 only enqueue their send and return.  The sink takes the records in lazily (when it is polled, or a few gathers
+ * later) and reads them from the handle's buffers until then: destroy a sink AFTER hbd_dist_finalize() / hbd_destroy() of
+ * every handle that fed it. */
 int    hbd_gather_results(hbd_decoder* h, hbd_result_sink* sink);
 
 /* ---- websocket wire formats, produced on the GPU (the step after the path) -----------------------------------
