@@ -1229,7 +1229,10 @@ size_t hbd_pack_results(hbd_decoder* h, int ch_offset, hbd_result_record* out, s
     for (size_t c = 0; c < n; ++c) {
         hbd_result_record& pr = h->pend[c];
         hbd_result_record& o = out[c];
-        o = pr;
+        // header + the bytes in use only (the rest of a record is not read by anybody)
+        o.n_chars = pr.n_chars; o.sentence_bytes = pr.sentence_bytes; o.reserved = 0;
+        if (pr.n_chars) memcpy(o.chars, pr.chars, pr.n_chars);
+        if (pr.sentence_bytes) memcpy(o.sentences, pr.sentences, pr.sentence_bytes);
         o.channel = uint32_t(ch_offset + int(c));
         const double* sc = st.data() + 6 * c;
         o.frequency_correction = float(sc[0]); o.shift = float(sc[1]); o.noise_floor = float(sc[2]); o.noise_variance = float(sc[3]);
