@@ -101,7 +101,7 @@ __device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src
 #ifndef HBD_K1_PSB_MIN
 #define HBD_K1_PSB_MIN 12
 #endif
-template <int M, int T>
+template <int M, int T, int PSBMIN = HBD_K1_PSB_MIN>
 struct Geo {
     static constexpr int SB    = 64;                   // samples per superblock
     static constexpr int NOUT  = SB / M;               // outputs ending inside one superblock
@@ -110,7 +110,7 @@ struct Geo {
     static constexpr int gcd_(int a, int b) { return b ? gcd_(b, a % b) : a; }
     static constexpr int U     = NLIVE / gcd_(NLIVE, NOUT);       // accumulator rotation period (superblocks)
     static constexpr int RAMP_GROUPS = (RAMP + U - 1) / U;        // ramp-in walked as whole groups of U
-    static constexpr int PSB   = U * ((HBD_K1_PSB_MIN + U - 1) / U); // superblocks per ring piece (multiple of U)
+    static constexpr int PSB   = U * ((PSBMIN + U - 1) / U); // superblocks per ring piece (multiple of U)
     static constexpr int GROUPS_PER_PIECE = PSB / U;
     static constexpr int PIECE_SAMPLES = PSB * SB;
     static constexpr int PIECE_BYTES   = (PIECE_SAMPLES + 2) * 8; // +2: 16-byte alignment slack on both sides
@@ -131,13 +131,17 @@ constexpr int kRedPitch = 36;            // float2 per row: 16-byte aligned rows
 // (288 B) is written after superblock b (512 B) of the slot has been read, so it only ever covers consumed samples, and
 // the tile is summed before the slot is handed back to the TMA.  That takes 27 KB per CTA off K1's footprint, which is
 // what lets a third tail CTA (or a second FFT CTA) co-reside with K1 on an SM.
-template <int M, int T>
+template <int M, int T, int PSBMIN = HBD_K1_PSB_MIN>
 struct WarpSmem {
-    static constexpr bool kRedInRing = HBD_K1_RED_IN_RING && Geo<M, T>::NOUT == 1 && Geo<M, T>::PSB * kRedPitch * 8 <= Geo<M, T>::PSB * 64 * 8;
-    alignas(16) unsigned char ring[kStages][Geo<M, T>::PIECE_BYTES];
-    alignas(16) float2 red[kRedInRing ? 1 : Geo<M, T>::RED_ROWS][kRedPitch];
+    using G = Geo<M, T, PSBMIN>;
+    static constexpr bool kRedInRing = HBD_K1_RED_IN_RING && G::NOUT == 1 && G::PSB * kRedPitch * 8 <= G::PSB * 64 * 8;
+    alignas(16) unsigned char ring[kStages][G::PIECE_BYTES];
+    alignas(16) float2 red[kRedInRing ? 1 : G::RED_ROWS][kRedPitch];
     alignas(8) uint64_t full[kStages];
 };
+// The NCO variant is bound by instruction issue, not by bytes in flight (a wideband capture row is re-read from L2 by every
+// channel): twice the warps with half-size ring pieces hide the latency of its longer dependent chains.
+template <bool NCO> struct K1Cfg { static constexpr int kWarps = NCO ? 16 : kDecimWarps; static constexpr int kPsbMin = NCO ? 6 : HBD_K1_PSB_MIN; };
 
 // taps for lane position P (0..63) and live output j (1..NLIVE): t = T - M*j + P
 template <int M, int T>
@@ -181,9 +185,10 @@ __device__ __forceinline__ void reduce_rows(const float2 (*red)[kRedPitch], int 
 // ~1.5e-7 relative -- the size of the FIR's own float rounding, two orders below the 1e-5 stage tolerance.  (A float64
 // product per sample costs 4 FP64 operations + 2 conversions and made this kernel 2.3x slower than the plain K1.)
 struct NcoWarpSmem {
-    double2 s1[64], s2[64];
+    double2 s1[64];       // S1[a] = cis(64 a inc)
+    float2 s2[64];        // cf32(S2[b]), S2[b] = cis(b inc)
     double2 e[32];        // E[ebase .. ebase+31]
-    float2 pq[16];        // cf32(E * S1) for the 64-sample groups a ring piece touches
+    float4 pq[16];        // cf32(E * S1) of the 64-sample groups a ring piece touches, as (re, re, im, im): both packed operands of a product
 };
 __device__ __forceinline__ double2 nco_cis(double ph)
 {
@@ -197,17 +202,31 @@ __device__ __forceinline__ double2 nco_cmul(double2 a, double2 b)
     return make_double2(__fma_rn(a.x, b.x, -__dmul_rn(a.y, b.y)), __fma_rn(a.x, b.y, __dmul_rn(a.y, b.x)));
 }
 __device__ __forceinline__ float2 nco_f(double2 p) { return make_float2(float(p.x), float(p.y)); }
-__device__ __forceinline__ float2 nco_phasor(float2 p, float2 s) // cf32(E*S1) (x) cf32(S2), fixed operation order
+__device__ __forceinline__ float4 nco_f4(double2 p) { const float2 f = nco_f(p); return make_float4(f.x, f.x, f.y, f.y); }
+__device__ __forceinline__ float2 cmul2(float2 a, float2 b)   // packed FMUL2
 {
-    return make_float2(__fmaf_rn(p.x, s.x, -__fmul_rn(p.y, s.y)), __fmaf_rn(p.x, s.y, __fmul_rn(p.y, s.x)));
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
 }
-__device__ __forceinline__ float2 nco_apply(float2 x, float2 ph) // std::complex<float> product, no FMA (like nco.cu)
+__device__ __forceinline__ float2 cfma2(float2 a, float2 b, float2 c)   // packed FFMA2, per-component operands
 {
-    const float pr = ph.x, pi = ph.y;
-    float2 y;
-    y.x = __fsub_rn(__fmul_rn(x.x, pr), __fmul_rn(x.y, pi));
-    y.y = __fadd_rn(__fmul_rn(x.x, pi), __fmul_rn(x.y, pr));
-    return y;
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+// phasor(j) = cf32(E * S1) (x) cf32(S2):  (a + ib)(c + id) = (a, a) * (c, d) + (b, b) * (-d, c), two packed operations;
+// s2r = (-d, c) is a lane constant.  One fixed operation order everywhere (FIR loop, boundary pieces, carry): the value
+// depends on j only.
+__device__ __forceinline__ float2 nco_phasor(float4 pq, float2 s2, float2 s2r)
+{
+    return cfma2(make_float2(pq.z, pq.w), s2r, cmul2(make_float2(pq.x, pq.y), s2));
+}
+// y = x * phasor:  (xr + i xi)(pr + i pi) = (xr, xi) * (pr, pr) + (-xi, xr) * (pi, pi)
+__device__ __forceinline__ float2 nco_apply(float2 x, float2 ph)
+{
+    return cfma2(make_float2(-x.y, x.x), make_float2(ph.y, ph.y), cmul2(x, make_float2(ph.x, ph.x)));
 }
 __device__ __forceinline__ void nco_fill_e(NcoWarpSmem& ns, const NcoChan& nc, int ebase, int lane)
 {
@@ -217,14 +236,16 @@ __device__ __forceinline__ void nco_fill_e(NcoWarpSmem& ns, const NcoChan& nc, i
 }
 
 template <int M, int T, bool NCO>
-__global__ void __launch_bounds__(kDecimWarps * 32, 1)
+__global__ void __launch_bounds__(K1Cfg<NCO>::kWarps * 32, 1)
 decim1_kernel(DecimArgs a)
 {
-    using G = Geo<M, T>;
+    constexpr int kWarps = K1Cfg<NCO>::kWarps;
+    using G = Geo<M, T, K1Cfg<NCO>::kPsbMin>;
+    using WS = WarpSmem<M, T, K1Cfg<NCO>::kPsbMin>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem<M, T>& sm = reinterpret_cast<WarpSmem<M, T>*>(smem_raw)[warp];
-    NcoWarpSmem& ns = reinterpret_cast<NcoWarpSmem*>(smem_raw + sizeof(WarpSmem<M, T>) * kDecimWarps)[NCO ? warp : 0];
+    WS& sm = reinterpret_cast<WS*>(smem_raw)[warp];
+    NcoWarpSmem& ns = reinterpret_cast<NcoWarpSmem*>(smem_raw + sizeof(WS) * kWarps)[NCO ? warp : 0];
 
     if (lane == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
@@ -248,7 +269,7 @@ decim1_kernel(DecimArgs a)
     // ramp-in (RAMP superblocks whose outputs are discarded) is paid once per span and once per channel start
     // instead of once per 128 superblocks, and all warps finish together (no wave quantisation).
     const long long total_sb = (long long)a.n_channels * a.sb_per_channel;
-    long long g = (long long)(blockIdx.x * kDecimWarps + warp) * a.span;
+    long long g = (long long)(blockIdx.x * kWarps + warp) * a.span;
     const long long g_end = g + a.span < total_sb ? g + a.span : total_sb;
 
     while (g < g_end) {
@@ -274,7 +295,7 @@ decim1_kernel(DecimArgs a)
                 __syncwarp();
                 for (int k = lane; k < 64; k += 32) {
                     ns.s1[k] = nco_cis(__dmul_rn(double(64 * k), nc.inc));
-                    ns.s2[k] = nco_cis(__dmul_rn(double(k), nc.inc));
+                    ns.s2[k] = nco_f(nco_cis(__dmul_rn(double(k), nc.inc)));
                 }
                 nco_fill_e(ns, nc, ebase, lane);
             }
@@ -305,7 +326,7 @@ decim1_kernel(DecimArgs a)
             if (lane == 0) {
                 if (hi2 > lo) {
                     const int c_hi = min(hi2, 0), d_lo = max(lo, 0);
-                    if (WarpSmem<M, T>::kRedInRing) fence_proxy_async();   // the slot last held generic-proxy stores (reduction rows)
+                    if (WS::kRedInRing) fence_proxy_async();   // the slot last held generic-proxy stores (reduction rows)
                     mbar_expect_tx(&sm.full[slot], uint32_t(hi2 - lo) * 8u);
                     if (c_hi > lo) tma_load_1d(dst + (lo - A) * 8, carry + lo, uint32_t(c_hi - lo) * 8u, &sm.full[slot]);
                     if (hi2 > d_lo) {
@@ -347,54 +368,58 @@ decim1_kernel(DecimArgs a)
             mbar_wait(&sm.full[slot], (phase_bits >> slot) & 1u);
             phase_bits ^= 1u << slot;
             __syncwarp();
+            // ---- fused NCO: samples 0 <= j < n of the raw chunk get their phasor; j < 0 is the already mixed carry ----------
+            // A piece that lies completely inside [0, n) (all but the first and last of a channel) is mixed in REGISTERS on
+            // its way into the FIR; a boundary piece is mixed in place first.  Same phasor, same operation order either way.
+            bool mix_in_loop = false;
+            float2 s2a = make_float2(1.f, 0.f), s2ar = make_float2(0.f, 1.f), s2b = s2a, s2br = s2ar;
+            int w0 = 0, w1 = 0;
             if (NCO && mixing) {
-                // mix the piece in place (samples with 0 <= j < n come from the raw chunk; j < 0 is the already mixed carry)
                 const int jp = j0 + p * G::PIECE_SAMPLES;                    // j of this lane-0 sample of superblock 0
                 const int j_last = min(jp + G::PIECE_SAMPLES - 1, j_end - 1);
                 if (j_last >= 0) {
                     const int b_min = max(jp, 0) >> 12, b_max = j_last >> 12;
                     if (b_min < ebase || b_max >= ebase + 32) { ebase = b_min; nco_fill_e(ns, nc, ebase, lane); }
                     const int q0 = jp >> 6;                                   // floor: jp may be negative
+                    __syncwarp();
                     if (lane <= G::PSB) {
                         const int q = q0 + lane;
-                        if (q >= 0 && (q >> 6) < ebase + 32) ns.pq[lane] = nco_f(nco_cmul(ns.e[(q >> 6) - ebase], ns.s1[q & 63]));
+                        if (q >= 0 && (q >> 6) < ebase + 32) ns.pq[lane] = nco_f4(nco_cmul(ns.e[(q >> 6) - ebase], ns.s1[q & 63]));
                     }
                     __syncwarp();
                     const int c0 = jp & 63;
-                    const int w0 = (c0 + lane) >> 6, w1 = (c0 + lane + 32) >> 6;
-                    const float2 s2a = nco_f(ns.s2[(c0 + lane) & 63]), s2b = nco_f(ns.s2[(c0 + lane + 32) & 63]);
-                    float2* px = reinterpret_cast<float2*>(sm.ring[slot]) + odd + lane;
-                    // batches of 4 superblocks: all loads first, then the arithmetic, then the stores -- a load-mix-store
-                    // loop serialises on shared-memory ordering (each LDS behind the previous STS, ~100 cycles a round)
-                    static_assert(!NCO || G::PSB % 4 == 0, "pre-pass batches");
+                    w0 = (c0 + lane) >> 6; w1 = (c0 + lane + 32) >> 6;
+                    s2a = ns.s2[(c0 + lane) & 63]; s2b = ns.s2[(c0 + lane + 32) & 63];
+                    s2ar = make_float2(-s2a.y, s2a.x); s2br = make_float2(-s2b.y, s2b.x);
+                    mix_in_loop = jp >= 0 && jp + G::PIECE_SAMPLES <= j_end;
+                    if (!mix_in_loop) {
+                        float2* px = reinterpret_cast<float2*>(sm.ring[slot]) + odd + lane;
 #pragma unroll 1
-                    for (int sb0 = 0; sb0 < G::PSB; sb0 += 4) {
-                        float2 xa[4], xb[4], pa[4], pb[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            xa[u] = px[(sb0 + u) * 64]; xb[u] = px[(sb0 + u) * 64 + 32];
-                            pa[u] = ns.pq[sb0 + u + w0]; pb[u] = ns.pq[sb0 + u + w1];
+                        for (int sb = 0; sb < G::PSB; ++sb) {
+                            const int j = jp + sb * 64 + lane;
+                            const float2 xa = px[sb * 64], xb = px[sb * 64 + 32];
+                            const float2 ya = nco_apply(xa, nco_phasor(ns.pq[sb + w0], s2a, s2ar)), yb = nco_apply(xb, nco_phasor(ns.pq[sb + w1], s2b, s2br));
+                            __syncwarp();
+                            if (j >= 0 && j < j_end) px[sb * 64] = ya;
+                            if (j + 32 >= 0 && j + 32 < j_end) px[sb * 64 + 32] = yb;
                         }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int j = jp + (sb0 + u) * 64 + lane;
-                            const float2 ya = nco_apply(xa[u], nco_phasor(pa[u], s2a)), yb = nco_apply(xb[u], nco_phasor(pb[u], s2b));
-                            if (j >= 0 && j < j_end) px[(sb0 + u) * 64] = ya;
-                            if (j + 32 >= 0 && j + 32 < j_end) px[(sb0 + u) * 64 + 32] = yb;
-                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
             const float2* src = reinterpret_cast<const float2*>(sm.ring[slot]) + odd + lane;
-            float2 (*red)[kRedPitch] = WarpSmem<M, T>::kRedInRing ? reinterpret_cast<float2 (*)[kRedPitch]>(sm.ring[slot]) : sm.red;
+            float2 (*red)[kRedPitch] = WS::kRedInRing ? reinterpret_cast<float2 (*)[kRedPitch]>(sm.ring[slot]) : sm.red;
 
 #pragma unroll 1
             for (int g = 0; g < G::GROUPS_PER_PIECE; ++g) {
 #pragma unroll
                 for (int u = 0; u < G::U; ++u) {
-                    const float2 x0 = src[(g * G::U + u) * 64];
-                    const float2 x1 = src[(g * G::U + u) * 64 + 32];
+                    float2 x0 = src[(g * G::U + u) * 64];
+                    float2 x1 = src[(g * G::U + u) * 64 + 32];
+                    if (NCO && mix_in_loop) {
+                        x0 = nco_apply(x0, nco_phasor(ns.pq[g * G::U + u + w0], s2a, s2ar));
+                        x1 = nco_apply(x1, nco_phasor(ns.pq[g * G::U + u + w1], s2b, s2br));
+                    }
 #pragma unroll
                     for (int j = 0; j < G::NLIVE; ++j) {
                         const int r = (j + u * G::NOUT) % G::NLIVE; // register holding live output j
@@ -408,7 +433,7 @@ decim1_kernel(DecimArgs a)
                     for (int j = 0; j < G::NOUT; ++j) {
                         const int r = (j + u * G::NOUT) % G::NLIVE;
                         if (G::NOUT == 1) {
-                            if (WarpSmem<M, T>::kRedInRing) __syncwarp();     // every lane has read superblock (g*U+u) of the slot
+                            if (WS::kRedInRing) __syncwarp();     // every lane has read superblock (g*U+u) of the slot
                             red[g * G::U + u][lane] = acc[r];               // row = superblock within the piece
                         } else {
                             sm.red[staged][lane] = acc[r];
@@ -442,8 +467,10 @@ decim1_kernel(DecimArgs a)
             for (int i = lane; i < keep; i += 32) {
                 const int j = jn - keep + i;
                 float2 v = (j < 0) ? carry[j] : chunk[j];
-                if (NCO && mixing && j >= 0)   // the carry holds MIXED samples: same phasor as the in-ring mix above
-                    v = nco_apply(v, nco_phasor(nco_f(nco_cmul(ns.e[(j >> 12) - ebase], ns.s1[(j >> 6) & 63])), nco_f(ns.s2[j & 63])));
+                if (NCO && mixing && j >= 0) { // the carry holds MIXED samples: same phasor as above
+                    const float2 s2 = ns.s2[j & 63];
+                    v = nco_apply(v, nco_phasor(nco_f4(nco_cmul(ns.e[(j >> 12) - ebase], ns.s1[(j >> 6) & 63])), s2, make_float2(-s2.y, s2.x)));
+                }
                 next[i - keep] = v;
             }
         }
@@ -515,8 +542,9 @@ constexpr int kMinSpan = 48; // superblocks: keeps the ramp-in below ~12 % when 
 template <int M, int T, bool NCO = false>
 static cudaError_t launch_fast(DecimArgs a, unsigned max_n1, int n_sms, cudaStream_t stream, int* launches)
 {
-    using G = Geo<M, T>;
-    const size_t smem = sizeof(WarpSmem<M, T>) * kDecimWarps + (NCO ? sizeof(NcoWarpSmem) * kDecimWarps : 0);
+    constexpr int kWarps = K1Cfg<NCO>::kWarps;
+    using G = Geo<M, T, K1Cfg<NCO>::kPsbMin>;
+    const size_t smem = sizeof(WarpSmem<M, T, K1Cfg<NCO>::kPsbMin>) * kWarps + (NCO ? sizeof(NcoWarpSmem) * kWarps : 0);
     static bool configured = false; // one device per process (one process per GPU)
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(decim1_kernel<M, T, NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -528,14 +556,14 @@ static cudaError_t launch_fast(DecimArgs a, unsigned max_n1, int n_sms, cudaStre
     }
     a.sb_per_channel = max_n1 ? int((max_n1 - 1 + G::NOUT - 1) / G::NOUT + 1) : 1;
     const long long total_sb = (long long)a.n_channels * a.sb_per_channel;
-    const long long warps_max = (long long)n_sms * kDecimWarps;
+    const long long warps_max = (long long)n_sms * kWarps;
     long long span = (total_sb + warps_max - 1) / warps_max;
     if (span < kMinSpan) span = kMinSpan;
     a.span = (int)span;
     const long long n_spans = (total_sb + span - 1) / span;
-    int grid = (int)std::min<long long>(n_sms, (n_spans + kDecimWarps - 1) / kDecimWarps);
+    int grid = (int)std::min<long long>(n_sms, (n_spans + kWarps - 1) / kWarps);
     if (grid < 1) grid = 1;
-    decim1_kernel<M, T, NCO><<<grid, kDecimWarps * 32, smem, stream>>>(a);
+    decim1_kernel<M, T, NCO><<<grid, kWarps * 32, smem, stream>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
