@@ -131,17 +131,32 @@ constexpr int kRedPitch = 36;            // float2 per row: 16-byte aligned rows
 // (288 B) is written after superblock b (512 B) of the slot has been read, so it only ever covers consumed samples, and
 // the tile is summed before the slot is handed back to the TMA.  That takes 27 KB per CTA off K1's footprint, which is
 // what lets a third tail CTA (or a second FFT CTA) co-reside with K1 on an SM.
-template <int M, int T, int PSBMIN = HBD_K1_PSB_MIN>
+template <int M, int T, int PSBMIN = HBD_K1_PSB_MIN, int STAGES = kStages>
 struct WarpSmem {
     using G = Geo<M, T, PSBMIN>;
     static constexpr bool kRedInRing = HBD_K1_RED_IN_RING && G::NOUT == 1 && G::PSB * kRedPitch * 8 <= G::PSB * 64 * 8;
-    alignas(16) unsigned char ring[kStages][G::PIECE_BYTES];
+    alignas(16) unsigned char ring[STAGES][G::PIECE_BYTES];
     alignas(16) float2 red[kRedInRing ? 1 : G::RED_ROWS][kRedPitch];
-    alignas(8) uint64_t full[kStages];
+    alignas(8) uint64_t full[STAGES];
 };
 // The NCO variant is bound by instruction issue, not by bytes in flight (a wideband capture row is re-read from L2 by every
-// channel): twice the warps with half-size ring pieces hide the latency of its longer dependent chains.
-template <bool NCO> struct K1Cfg { static constexpr int kWarps = NCO ? 16 : kDecimWarps; static constexpr int kPsbMin = NCO ? 6 : HBD_K1_PSB_MIN; };
+// channel): more warps (14 instead of 8) with a two-deep ring hide the latency of its longer dependent chains.  Measured on
+// 4096 channels of one 20 MS/s capture (tools/bench_wideband.py): 8 warps x 3 stages (round 1) 0.560 ms, 16 warps x 3 stages of
+// half-size pieces 0.448 ms (the per-piece overhead doubles), 12 x 2 0.424 ms, 14 x 2 0.384 ms.
+#ifndef HBD_NCO_WARPS
+#define HBD_NCO_WARPS 14
+#endif
+#ifndef HBD_NCO_PSB
+#define HBD_NCO_PSB 12
+#endif
+#ifndef HBD_NCO_STAGES
+#define HBD_NCO_STAGES 2
+#endif
+template <bool NCO> struct K1Cfg {
+    static constexpr int kWarps = NCO ? HBD_NCO_WARPS : kDecimWarps;
+    static constexpr int kPsbMin = NCO ? HBD_NCO_PSB : HBD_K1_PSB_MIN;
+    static constexpr int kSt = NCO ? HBD_NCO_STAGES : kStages;
+};
 
 // taps for lane position P (0..63) and live output j (1..NLIVE): t = T - M*j + P
 template <int M, int T>
@@ -241,14 +256,15 @@ decim1_kernel(DecimArgs a)
 {
     constexpr int kWarps = K1Cfg<NCO>::kWarps;
     using G = Geo<M, T, K1Cfg<NCO>::kPsbMin>;
-    using WS = WarpSmem<M, T, K1Cfg<NCO>::kPsbMin>;
+    using WS = WarpSmem<M, T, K1Cfg<NCO>::kPsbMin, K1Cfg<NCO>::kSt>;
+    constexpr int kSt = K1Cfg<NCO>::kSt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WS& sm = reinterpret_cast<WS*>(smem_raw)[warp];
     NcoWarpSmem& ns = reinterpret_cast<NcoWarpSmem*>(smem_raw + sizeof(WS) * kWarps)[NCO ? warp : 0];
 
     if (lane == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < kSt; ++s) mbar_init(&sm.full[s], 1);
         fence_mbar_init();
     }
     __syncwarp();
@@ -316,7 +332,7 @@ decim1_kernel(DecimArgs a)
 
         // ---- producer: copy piece p into its ring slot ----------------------------------------------------
         auto issue_piece = [&](int p) {
-            const int slot = p % kStages;
+            const int slot = p % kSt;
             unsigned char* dst = sm.ring[slot];
             const int A = j0 - odd + p * G::PIECE_SAMPLES;          // j of ring sample 0 (even)
             const int want_lo = A + odd, want_hi = want_lo + G::PIECE_SAMPLES;
@@ -351,7 +367,7 @@ decim1_kernel(DecimArgs a)
         // WAR note: a ring slot is only re-filled by the warp that has finished reading it
         // (program order + __syncwarp), so no "empty" barrier is needed.
         __syncwarp();
-        for (int p = 0; p < min(kStages - 1, n_pieces); ++p) issue_piece(p);
+        for (int p = 0; p < min(kSt - 1, n_pieces); ++p) issue_piece(p);
 
         float2 acc[G::NLIVE];
 #pragma unroll
@@ -362,9 +378,9 @@ decim1_kernel(DecimArgs a)
         int staged = 0;                              // NOUT > 1 only: rows waiting in sm.red
 
         for (int p = 0; p < n_pieces; ++p) {
-            const int slot = p % kStages;
+            const int slot = p % kSt;
             __syncwarp(); // every lane is done reading the slot that is about to be refilled
-            if (p + kStages - 1 < n_pieces) issue_piece(p + kStages - 1);
+            if (p + kSt - 1 < n_pieces) issue_piece(p + kSt - 1);
             mbar_wait(&sm.full[slot], (phase_bits >> slot) & 1u);
             phase_bits ^= 1u << slot;
             __syncwarp();
@@ -544,7 +560,7 @@ static cudaError_t launch_fast(DecimArgs a, unsigned max_n1, int n_sms, cudaStre
 {
     constexpr int kWarps = K1Cfg<NCO>::kWarps;
     using G = Geo<M, T, K1Cfg<NCO>::kPsbMin>;
-    const size_t smem = sizeof(WarpSmem<M, T, K1Cfg<NCO>::kPsbMin>) * kWarps + (NCO ? sizeof(NcoWarpSmem) * kWarps : 0);
+    const size_t smem = sizeof(WarpSmem<M, T, K1Cfg<NCO>::kPsbMin, K1Cfg<NCO>::kSt>) * kWarps + (NCO ? sizeof(NcoWarpSmem) * kWarps : 0);
     static bool configured = false; // one device per process (one process per GPU)
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(decim1_kernel<M, T, NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
