@@ -533,7 +533,7 @@ class BatchDecoder:
     def collect_ready(self, lag: int): self._chk(self._lib.hbd_collect_ready(self._h, int(lag)))
     def synchronize(self): self._chk(self._lib.hbd_synchronize(self._h))
     def kernel_launches(self) -> int: return int(self._lib.hbd_kernel_launches(self._h))
-    def set_kernel_timing(self, on: bool): self._chk(self._lib.hbd_set_kernel_timing(self._h, int(on)))
+    def set_kernel_timing(self, on): self._chk(self._lib.hbd_set_kernel_timing(self._h, int(on)))   # 0 off, 1 K1 only, 2 K1 + rest of step
     def kernel_timing(self, which: int):
         """(total_ms, launches) of K1 (which=0) or of the rest of the step (which=1) since set_kernel_timing."""
         ms, cnt = C.c_double(0), C.c_uint(0)

@@ -272,7 +272,7 @@ struct hbd_decoder {
     int pending_marks = 0;   // async calls since the last collect
     int sv_override = -1;
     // optional per-kernel CUDA-event timing (bench roofline): one event pair per K1 launch / per rest-of-step
-    bool timing = false;
+    int timing = 0;          // 0 off, 1: events around K1 only (what the roofline needs), 2: also around the rest of the step (pipeline diagnostics)
     std::vector<cudaEvent_t> ev_k1, ev_rest; // pairs: [2i] start, [2i+1] stop
     size_t ev_used_k1 = 0, ev_used_rest = 0;
     cudaEvent_t next_event(std::vector<cudaEvent_t>& pool, size_t& used)
@@ -857,7 +857,7 @@ int hbd_decoder::process_async_locked()
     }
     HBD_CUDA_CHECK(cudaEventRecord(ev_consumed, hi)); // input no longer needed; stage-1 output ready
     HBD_CUDA_CHECK(cudaStreamWaitEvent(lo, ev_consumed, 0));
-    if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
+    if (timing > 1) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
     if (any_work) {
         // cascaded plan: the stages between K1's and the tail kernel's (1/64 of the input rate or less)
         for (size_t k = 0; k < mids.size(); ++k) {
@@ -905,7 +905,7 @@ int hbd_decoder::process_async_locked()
         aa.fs_dec = fs_dec; aa.ch0 = 0;
         HBD_CUDA_CHECK(launch_demod_accumulate(aa, n_ch, lo, &nl));
     }
-    if (timing) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
+    if (timing > 1) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
     if (!tail_recorded) HBD_CUDA_CHECK(cudaEventRecord(ev_tail[s1_cur], lo));
     tail_pending[s1_cur] = true;
     // the caller's stream resumes once the input has been consumed (it does not wait for the tail kernels)
@@ -1687,7 +1687,7 @@ int hbd_set_kernel_timing(hbd_decoder* h, int on)
 {
     HBD_CHECK_H(h);
     std::lock_guard<std::mutex> l(h->mtx);
-    h->timing = on != 0;
+    h->timing = on < 0 ? 0 : on;
     h->ev_used_k1 = h->ev_used_rest = 0;
     h->drain_host_ms = 0; h->drain_calls = 0;
     if (on) {   // events are created here, not on the issue path of the calls being measured

@@ -96,7 +96,7 @@ __device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src
 
 // ---- compile-time geometry of one (M, T) decimator ---------------------------------------------------------
 #ifndef HBD_K1_STAGES
-#define HBD_K1_STAGES 3
+#define HBD_K1_STAGES 2
 #endif
 #ifndef HBD_K1_PSB_MIN
 #define HBD_K1_PSB_MIN 12

@@ -6,7 +6,7 @@
 namespace hbd {
 
 #ifndef HBD_K1_WARPS
-#define HBD_K1_WARPS 8
+#define HBD_K1_WARPS 10
 #endif
 constexpr int kDecimWarps = HBD_K1_WARPS; // warps per CTA; each warp runs its own TMA ring
 

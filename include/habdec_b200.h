@@ -120,8 +120,8 @@ int hbd_collect_ready(hbd_decoder* h, unsigned lag);
 int hbd_synchronize(hbd_decoder* h);
 /* number of CUDA kernels this handle has launched so far */
 unsigned long long hbd_kernel_launches(hbd_decoder* h);
-/* measurement hook: record CUDA events around every K1 (stage-1 decimator) launch and around the rest of the
- * step; `which` 0 = K1, 1 = rest; 2..4 = signed pipeline gaps (K1 end -> next K1 start, K1 end -> own tail start,
+/* measurement hook: on = 1 records CUDA events around every K1 (stage-1 decimator) launch, on = 2 also around the rest of
+ * the step (two more event records per call on the low-priority stream); `which` 0 = K1, 1 = rest; 2..4 = signed pipeline gaps (K1 end -> next K1 start, K1 end -> own tail start,
  * tail end -> K1 start two calls later); 5 = host time of the drains' sentence-layer replay (count = calls drained).
  * Calling set (on or off) clears the accumulated samples. */
 int hbd_set_kernel_timing(hbd_decoder* h, int on);

@@ -24,7 +24,7 @@ def run(n, timing):
     return e0.elapsed_time(e1) / n
 run(30, False)
 ms_plain = run(steps, False)
-ms_timed = run(steps, True)
+ms_timed = run(steps, 2)
 k1, n1 = dec.kernel_timing(0); rest, n2 = dec.kernel_timing(1)
 try:
     dr, n3 = dec.kernel_timing(5)
