@@ -280,24 +280,28 @@ def decode_leg(D: Dist, args, n_local, ch0, n_total, steps, warmup, timing=True)
     launches0 = dec.kernel_launches()
     dec.set_kernel_timing((2 if args.pipeline_diagnostics else 1) if timing else 0)
     sampler = ClockSampler(D.local_rank)
-    if D.rank == 0:
-        sampler.start()
+    sampler.start()                      # every rank watches its own GPU (a throttled GPU shows up as a slow rank)
     D.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     t_issue = t_drain = 0.0
+    issue_max = drain_max = 0.0
     gathers = 0
     for k in range(steps):
         t_h = time.perf_counter()
         step()
-        t_issue += time.perf_counter() - t_h
+        dt_h = time.perf_counter() - t_h
+        t_issue += dt_h
+        issue_max = max(issue_max, dt_h)
         if (k + 1) % args.collect_every == 0:
             t_h = time.perf_counter()
             dec.collect_ready(args.collect_lag)   # drain finished calls; the newest few stay in flight so the GPU never idles
             if args.gather_every and (k + 1) % args.gather_every == 0:
                 dec.gather_results(sink)          # records of every channel -> rank 0 (NCCL send/recv)
                 gathers += 1
-            t_drain += time.perf_counter() - t_h
+            dt_h = time.perf_counter() - t_h
+            t_drain += dt_h
+            drain_max = max(drain_max, dt_h)
     t_fc = time.perf_counter()
     dec.collect()                       # results drained (D2H + sentence layer) inside the timed region
     dec.gather_results(sink)
@@ -305,7 +309,7 @@ def decode_leg(D: Dist, args, n_local, ch0, n_total, steps, warmup, timing=True)
     final_ms = (time.perf_counter() - t_fc) * 1e3
     ev1.record(stream)
     D.barrier()
-    clocks = sampler.stop() if D.rank == 0 else None
+    clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     k1_ms, k1_cnt = dec.kernel_timing(0) if timing else (0.0, 0)
     rest_ms, rest_cnt = dec.kernel_timing(1) if timing else (0.0, 0)
@@ -314,6 +318,7 @@ def decode_leg(D: Dist, args, n_local, ch0, n_total, steps, warmup, timing=True)
         for name, w in (("k1_end_to_next_k1_start_ms", 2), ("k1_end_to_tail_start_ms", 3), ("tail_end_to_k1_plus2_start_ms", 4)):
             g_ms, g_cnt = dec.kernel_timing(w)
             gaps[name] = g_ms / g_cnt if g_cnt else None
+    replay_ms, replay_calls = dec.kernel_timing(5) if timing else (0.0, 0)
     dec.set_kernel_timing(False)
     launches = dec.kernel_launches() - launches0
     # characters that did not fit the last records (more than 256 pending in one channel): flush them, untimed
@@ -321,11 +326,14 @@ def decode_leg(D: Dist, args, n_local, ch0, n_total, steps, warmup, timing=True)
         if not any(dec.poll_chars(c) for c in (0, n_local // 2, n_local - 1)):
             break
         dec.gather_results(sink)
+    per_rank_diag = {"k1_avg_ms": D.all_values(k1_ms / max(k1_cnt, 1)), "host_replay_ms_total": D.all_values(replay_ms),
+                     "issue_max_ms": D.all_values(issue_max * 1e3), "drain_max_ms": D.all_values(drain_max * 1e3), "final_ms": D.all_values(final_ms),
+                     "sm_mhz": D.all_values(float(clocks["sm_mhz"] or 0)), "throttle_reasons": D.all_values(float(len(clocks["reasons"])))}
     per_rank_ms = D.all_values(ms)
     per_rank_issue = D.all_values(t_issue * 1e3 / max(steps, 1))
     per_rank_drain = D.all_values((t_drain * 1e3 + final_ms) / max(steps, 1))
     return {"dec": dec, "sink": sink, "ring": ring, "ms": ms, "ms_max": max(per_rank_ms), "per_rank_ms": per_rank_ms,
-            "per_rank_issue_ms": per_rank_issue, "per_rank_drain_ms": per_rank_drain, "k1_ms": k1_ms, "k1_cnt": k1_cnt,
+            "per_rank_issue_ms": per_rank_issue, "per_rank_drain_ms": per_rank_drain, "per_rank_diag": per_rank_diag, "k1_ms": k1_ms, "k1_cnt": k1_cnt,
             "rest_ms": rest_ms, "rest_cnt": rest_cnt, "gaps": gaps, "launches": launches, "clocks": clocks, "final_ms": final_ms,
             "chunks_decoded": n_done, "preroll": preroll, "gathers": gathers, "L": L}
 
@@ -569,7 +577,7 @@ def run_ours(args):
                                         "note": "whole step (all kernels, drains and gathers of the timed region) against the same HBM peak, SURVEY 8(d)"}},
             "e2e": e2e, "gpu_launches": int(leg["launches"]), "clocks": leg["clocks"],
             "per_rank": {"ms": leg["per_rank_ms"], "host_issue_ms_per_step": leg["per_rank_issue_ms"], "host_drain_ms_per_step": leg["per_rank_drain_ms"],
-                         "spread": (max(leg["per_rank_ms"]) - min(leg["per_rank_ms"])) / max(leg["per_rank_ms"])},
+                         "spread": (max(leg["per_rank_ms"]) - min(leg["per_rank_ms"])) / max(leg["per_rank_ms"]), **leg["per_rank_diag"]},
             "host_issue_ms_per_step": leg["per_rank_issue_ms"][0], "final_collect_ms": leg["final_ms"],
             "results": {"channels_gathered": args.channels, "gathers_in_timed_region": leg["gathers"], "transport": "hbd_gather_results (NCCL send/recv to rank 0)" if world > 1 else "hbd_gather_results (one rank)",
                         "chars": totals["chars"], "sentences": totals["sentences"], "sentences_min": totals["sentences_min"], "records": totals["records"],
