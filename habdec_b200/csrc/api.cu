@@ -1274,6 +1274,7 @@ int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
     if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) h->n_sms = prop.multiProcessorCount;
     h->hc.resize(size_t(n_channels));
     h->text.resize(size_t(n_channels));
+    for (auto& tc : h->text) { tc.text_stream.reserve(120); tc.last_sentence.reserve(96); }   // no allocation on the drain path in steady state
     { hbd_result_record z; memset(&z, 0, sizeof(z)); h->pend.assign(size_t(n_channels), z); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return HBD_ERR_CUDA; }
     h->own_stream = true;
