@@ -181,9 +181,8 @@ void TextChannel::feed(const unsigned char* raw, size_t n, int ch, const Sentenc
             latent = !memchr(text_stream.data(), '*', text_stream.size());   // the scan below gives up at once: the groups seen so far stay latent
             SentenceMatch m;
             while (extract_sentence(text_stream, m)) {
-                std::string rest = text_stream.substr(m.rest_offset);
-                std::replace(rest.begin(), rest.end(), '\n', ' ');    // the reference keeps the space-substituted copy (:599)
-                text_stream.swap(rest);
+                text_stream.erase(0, m.rest_offset);                   // in place: the buffer keeps its capacity
+                std::replace(text_stream.begin(), text_stream.end(), '\n', ' ');    // the reference keeps the space-substituted copy (:599)
                 last_sentence.clear();
                 last_sentence.reserve(m.callsign.size() + m.data.size() + 7);
                 last_sentence += m.callsign; last_sentence += ','; last_sentence += m.data;
