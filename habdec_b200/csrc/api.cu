@@ -233,7 +233,7 @@ struct hbd_decoder {
     std::vector<unsigned> seg_start;     // collect_locked: first log entry of every (call, channel) segment
     static constexpr int kCharBufHost = 64;   // == kCharBuf (slicer_dev.cuh): characters per device-side flush
     double drain_host_ms = 0; unsigned drain_calls = 0;   // host time of the replay part of the drains (hbd_get_kernel_timing which = 5)
-    int host_threads = 1;                // threads the drain may use (hbd_set_host_threads; default: min(4, cores this process may run on))
+    int host_threads = 1;                // threads the drain may use (hbd_set_host_threads; default: min(4, half the cores this process may run on))
     bool keep_raw = true;                // hbd_set_raw_chars: retain the raw (unfiltered) characters for hbd_poll_raw_chars
     float* d_taps1 = nullptr; float* d_taps2 = nullptr;
     float2* d_twiddle = nullptr;
@@ -1286,7 +1286,7 @@ int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
             cpu_set_t set;
             int cores = int(std::thread::hardware_concurrency());
             if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
-            h->host_threads = std::max(1, std::min(4, cores));
+            h->host_threads = std::max(1, std::min(4, cores / 2));   // measured on 8 ranks x 4 cores: 2 threads 0.44 ms/step, 4 threads 0.51 (stalls)
             if (const char* ht = getenv("HBD_HOST_THREADS")) h->host_threads = std::max(1, atoi(ht));
         }
         int prio_lo = 0, prio_hi = 0;

@@ -128,7 +128,7 @@ hbd_result_sink* hbd_sink_create(int total_channels)
         cpu_set_t set;
         int cores = int(std::thread::hardware_concurrency());
         if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
-        s->threads = std::max(1, std::min(4, cores));
+        s->threads = std::max(1, std::min(4, cores / 2));
     }
     return s;
 }

@@ -139,8 +139,8 @@ size_t hbd_poll_raw_chars(hbd_decoder* h, int ch, unsigned char* out, size_t cap
 /* retain raw characters for hbd_poll_raw_chars (default on; the reference itself keeps none, a caller that never polls
  * them switches it off) */
 int    hbd_set_raw_chars(hbd_decoder* h, int on);
-/* host threads hbd_collect* may use for the sentence layer of many channels (the caller's included); default min(4, cores
- * the process may run on).  Results and callback order do not depend on it. */
+/* host threads hbd_collect* may use for the sentence layer of many channels (the caller's included); default min(4, half
+ * the cores the process may run on).  Results and callback order do not depend on it. */
 int    hbd_set_host_threads(hbd_decoder* h, int n);
 int    hbd_set_sentence_callback(hbd_decoder* h, hbd_sentence_cb cb, void* user);
 int    hbd_set_chars_callback(hbd_decoder* h, hbd_chars_cb cb, void* user);
