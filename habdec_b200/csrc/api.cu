@@ -1907,12 +1907,12 @@ size_t hbd_ssdv_host_replay(const unsigned char* chars, const size_t* chunk_size
     return n_ev;
 }
 
-int hbd_get_decimation_factor(hbd_decoder* h) { return h ? h->factor : 0; }
-double hbd_get_input_sampling_rate(hbd_decoder* h) { return h ? h->fs_in : 0; }
-double hbd_get_decimated_sampling_rate(hbd_decoder* h) { return h ? h->fs_in / h->factor : 0; }
+int hbd_get_decimation_factor(hbd_decoder* h) { if (!h) return 0; std::lock_guard<std::mutex> l(h->mtx); return h->factor; }
+double hbd_get_input_sampling_rate(hbd_decoder* h) { if (!h) return 0; std::lock_guard<std::mutex> l(h->mtx); return h->fs_in; }
+double hbd_get_decimated_sampling_rate(hbd_decoder* h) { if (!h) return 0; std::lock_guard<std::mutex> l(h->mtx); return h->fs_in / h->factor; }
 double hbd_get_symbol_rate(hbd_decoder* h, int ch) { return hbd_get_baud(h, ch); }
 int hbd_n_channels(hbd_decoder* h) { return h ? h->n_ch : 0; }
-size_t hbd_get_bins_count(hbd_decoder* h) { return h ? size_t(h->fft_n) : size_t(kFftN); }
+size_t hbd_get_bins_count(hbd_decoder* h) { if (!h) return size_t(kFftN); std::lock_guard<std::mutex> l(h->mtx); return size_t(h->fft_n); }
 
 static int fetch_state(hbd_decoder* h, int ch, ChanState* st)
 {
