@@ -209,6 +209,7 @@ struct hbd_decoder {
     float* d_lptaps = nullptr;
     float* d_slicer = nullptr;   size_t slicer_pitch = 0;
     float* d_demod = nullptr;    size_t demod_pitch = 0;
+    unsigned* d_maskc = nullptr;             // cached slicer position masks [n][2][kMaskWords] (tail.cu)
     unsigned short* d_uart_runs = nullptr;   // UART backlog [n][kUartRunsCap] (slicer_dev.cuh)
     // Decoded-character log: ring of log_cap entries appended by the tail kernels (monotonic head in d_log_ctl[0]).
     // After the kernels of a call the control words are copied to that call's slot of h_heads (pinned), in stream order:
@@ -234,6 +235,7 @@ struct hbd_decoder {
     static constexpr int kCharBufHost = 64;   // == kCharBuf (slicer_dev.cuh): characters per device-side flush
     double drain_host_ms = 0; unsigned drain_calls = 0;   // host time of the replay part of the drains (hbd_get_kernel_timing which = 5)
     int host_threads = 1;                // threads the drain may use (hbd_set_host_threads; default: min(4, half the cores this process may run on))
+    bool input_fence = true;             // hbd_set_input_fence: the caller's stream waits until a pushed DEVICE buffer has been consumed
     bool keep_raw = true;                // hbd_set_raw_chars: retain the raw (unfiltered) characters for hbd_poll_raw_chars
     float* d_taps1 = nullptr; float* d_taps2 = nullptr;
     float2* d_twiddle = nullptr;
@@ -271,6 +273,7 @@ struct hbd_decoder {
     int mix_into_stage(const float2* src, size_t src_pitch, int c0, int nc, size_t dst_off, size_t n);
     int pending_marks = 0;   // async calls since the last collect
     int sv_override = -1;
+    bool mask_cache = true;      // HBD_MASK_CACHE=0 (test hook): the slicer's position masks are rebuilt from scratch in every call
     // optional per-kernel CUDA-event timing (bench roofline): one event pair per K1 launch / per rest-of-step
     int timing = 0;          // 0 off, 1: events around K1 only (what the roofline needs), 2: also around the rest of the step (pipeline diagnostics)
     std::vector<cudaEvent_t> ev_k1, ev_rest; // pairs: [2i] start, [2i+1] stop
@@ -407,6 +410,7 @@ int hbd_decoder::alloc_fixed()
     }
     { const int rc = alloc_fft(); if (rc) return rc; }
     HBD_CUDA_CHECK(dalloc(&d_uart_runs, n * size_t(kUartRunsCap)));
+    HBD_CUDA_CHECK(dalloc(&d_maskc, n * size_t(2 * kMaskWords)));
     HBD_CUDA_CHECK(dalloc(&d_lptaps, n * kLpMaxTaps));
     HBD_CUDA_CHECK(cudaMemset(d_lptaps, 0, n * kLpMaxTaps * sizeof(float)));
     // character log: at least 512 entries per channel (a 600 baud channel decodes ~2 characters per 65 536-sample call,
@@ -528,7 +532,7 @@ void hbd_decoder::free_all()
     if (ev_consumed) cudaEventDestroy(ev_consumed);
     for (cudaEvent_t e : ev_tail) if (e) cudaEventDestroy(e);
     if (ev_in) cudaEventDestroy(ev_in);
-    void* ptrs[] = {d_state, d_plan, d_carry2[0], d_carry2[1], d_s1x[0], d_s1x[1], d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_uart_runs, d_log, d_log_ctl,
+    void* ptrs[] = {d_state, d_plan, d_carry2[0], d_carry2[1], d_s1x[0], d_s1x[1], d_decq, d_fftbuf, d_spectrum, d_power, d_lptaps, d_slicer, d_demod, d_uart_runs, d_maskc, d_log, d_log_ctl,
                     d_taps1, d_taps2, d_twiddle, d_cfg_baud, d_cfg_stops, d_cfg_bits, d_cfg_dc, d_cfg_ntaps,
                     d_cfg_dirty, d_rec_dec, d_rec_filt, d_rec_bits, d_rec_bits_n, d_stage, d_nco, d_wide, d_dacc, d_dacc_n, d_frames, d_frame_sizes,
                     d_ssdv_ring, d_ssdv_total, d_ssdv_scanned, d_ssdv_log};
@@ -880,6 +884,7 @@ int hbd_decoder::process_async_locked()
         ta.slicer = d_slicer; ta.slicer_pitch = slicer_pitch; ta.sv_want = sv_want;
         ta.log = d_log; ta.log_ctl = d_log_ctl; ta.log_mask = log_cap - 1u; ta.call_seq = call_seq & 0xffffffu;
         ta.uart_runs = d_uart_runs;
+        ta.maskc = mask_cache ? d_maskc : nullptr;
         ta.ssdv_ring = ssdv_on ? d_ssdv_ring : nullptr; ta.ssdv_total = d_ssdv_total;
         ta.demod_last = d_demod; ta.demod_pitch = demod_pitch;
         ta.rec_decimated = record ? d_rec_dec : nullptr; ta.rec_filtered = record ? d_rec_filt : nullptr; ta.rec_pitch = rec_pitch;
@@ -908,8 +913,11 @@ int hbd_decoder::process_async_locked()
     if (timing > 1) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
     if (!tail_recorded) HBD_CUDA_CHECK(cudaEventRecord(ev_tail[s1_cur], lo));
     tail_pending[s1_cur] = true;
-    // the caller's stream resumes once the input has been consumed (it does not wait for the tail kernels)
-    HBD_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_consumed, 0));
+    // the caller's stream resumes once the input has been consumed (it does not wait for the tail kernels).  A caller that
+    // keeps its device buffers untouched until the call is collected (hbd_set_input_fence(h, 0)) spares the pipeline the
+    // round trip this wait puts between two calls: K1 -> ev_consumed -> caller's stream -> ev_in -> next K1.  The staging
+    // buffer of host pushes is the library's own and is always fenced.
+    if (input_fence || !ext) HBD_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_consumed, 0));
     carry_cur ^= 1;
     if (any_work) s1_cur ^= 1; // the tail (which moves the stage-2 history to the other buffer) ran
     launches += unsigned(nl);
@@ -1280,6 +1288,7 @@ int hbd_create(int n_channels, int cuda_device, hbd_decoder** out)
     h->own_stream = true;
     {
         if (const char* sv = getenv("HBD_SV_WANT")) h->sv_override = atoi(sv);
+        if (const char* mc = getenv("HBD_MASK_CACHE")) h->mask_cache = atoi(mc) != 0;
         if (const char* tl = getenv("HBD_TAIL_EV_LATE")) h->tail_ev_late = atoi(tl) != 0;
         if (const char* nf = getenv("HBD_NCO_FUSED")) h->nco_fused = atoi(nf) != 0;
         {
@@ -1796,6 +1805,10 @@ int hbd_set_host_threads(hbd_decoder* h, int n)
 int hbd_set_raw_chars(hbd_decoder* h, int on)
 {
     HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); h->keep_raw = on != 0; return HBD_OK;
+}
+int hbd_set_input_fence(hbd_decoder* h, int on)
+{
+    HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); h->input_fence = on != 0; return HBD_OK;
 }
 int hbd_attach_tracker(hbd_decoder* h, hbd_tracker* t, int ch_offset)
 {

@@ -26,6 +26,7 @@ constexpr int kFftN         = 4096;   // Decoder.h:163 fft_bins_cnt_ (default; h
 constexpr int kFftNMax      = 16384;
 constexpr int kSlicerVent   = 30000;  // SymbolExtractor.h:116 safety vent (3e4)
 constexpr int kBitsCap      = 16384;  // bits the slicer may emit in one call (+ pending UART bits)
+constexpr unsigned kMaskWords = 192;    // cached slicer mask words per channel and mask (6144 positions, the most the tail kernel stages)
 constexpr unsigned kUartRunsCap = 2048; // UART backlog entries per channel (slicer runs since the last decoded character)
 constexpr unsigned kLogCapMin = 1u << 20; // decoded-character log entries (ring) between host drains: max(this, 512 per channel)
 
@@ -66,6 +67,8 @@ struct ChanState {
     unsigned uart_runs_n;   // entries of the channel's UART backlog (slicer_dev.cuh: bits since the last decoded character)
     unsigned uart_ovf;      // the backlog outgrew its buffer
     unsigned uart_rescan;   // rtty_bits / rtty_stops changed: the backlog is re-evaluated when the next bit arrives
+    unsigned mask_valid;    // slicer positions [0, mask_valid) whose flip-search mask bits are cached in HBM (tail.cu), for radius mask_R
+    int      mask_R;
     unsigned pad0_;
 
     // AFC (AFC.h:72-90): two Average<double>(100), two Average<int>(4)

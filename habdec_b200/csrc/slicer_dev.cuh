@@ -143,11 +143,12 @@ __device__ __noinline__ int next_flip(const float* __restrict__ v, int n, int st
 // sequential flip search becomes find-first-set / find-first-clear on bit masks:
 //   A[q]  = sgn(mean_l(q)) != sgn(mean_r(q))
 //   NZ[q] = the arg-max weight |(int)(mean_r - mean_l)| may be non-zero (exact weights are then recomputed)
+// Words below w_begin are already in place (the tail kernel's cache of earlier calls).
 __device__ __forceinline__ void slicer_build_masks(const float* __restrict__ v, int n, int R, unsigned* maskA, unsigned* maskN,
-                                                   int warp, int n_warps, int lane)
+                                                   int w_begin, int warp, int n_warps, int lane)
 {
     const int n_words = (n + 31) >> 5;
-    for (int w = warp; w < n_words; w += n_warps) {
+    for (int w = w_begin + warp; w < n_words; w += n_warps) {
         const int q = w * 32 + lane;
         bool a = false, nz = false;
         if (q >= R && q < n) {

@@ -79,7 +79,9 @@ tail_kernel(TailArgs a)
     float*  s_h2 = reinterpret_cast<float*>(s_f + kTile + 2);     // stage-2 taps (shifted, zero padded)
     float*  s_hl = s_h2 + a.h2cap;                                // low-pass taps (shifted, zero padded)
     float*  s_v  = s_hl + a.hlcap;                                // slicer samples: [old pending | this call's]
-    unsigned char* s_chars = reinterpret_cast<unsigned char*>(s_v + a.sv_cap);
+    unsigned* s_maskA = reinterpret_cast<unsigned*>(s_v + a.sv_cap);   // flip-search position masks over s_v (slicer_dev.cuh)
+    unsigned* s_maskN = s_maskA + a.mask_words;
+    unsigned char* s_chars = reinterpret_cast<unsigned char*>(s_maskN + a.mask_words);
     __shared__ ChanState s_st;
     __shared__ float2 sh_dc_wp;
 
@@ -170,8 +172,23 @@ tail_kernel(TailArgs a)
     if (nf && n_old > unsigned(kSlicerVent)) n_old = 0; // checked before the append, only when there is something to append
     const bool smem_mode = nf && (n_old + nf <= unsigned(a.sv_cap));
     float* v_g = a.slicer + (size_t)ch * a.slicer_pitch;
-    // ---- round trip 2: pending slicer samples (consumed after the FIRs) ------------------------------------
-    if (smem_mode) for (unsigned i = tid; i < n_old; i += kTailThreads) cp_async4(&s_v[i], &v_g[i]);
+    // Position masks of the pending samples.  A position's two bits depend on v[q-R, q+R) only, so the bits of every
+    // position whose right window was complete in the call that built them stay true while the samples stay; the kernel
+    // keeps them in HBM (shifted by what the slicer erased) and a call evaluates only the positions behind them -- the
+    // appended samples plus one radius -- instead of all n_old + nf.  Whole words are reused; the build restarts at the
+    // word that holds the first unknown position.
+    unsigned* mask_g = a.maskc ? a.maskc + (size_t)ch * (2 * kMaskWords) : nullptr;
+    unsigned m_words = 0;
+    if (smem_mode && mask_g && n_old == s_st.slicer_n) {
+        int spb0 = 0, R0 = 0;
+        if (slicer_geometry(int(n_old + nf), a.fs_dec, s_st.baud, spb0, R0) && R0 == s_st.mask_R && n_old > unsigned(R0))
+            m_words = hbd_min_u(hbd_min_u(s_st.mask_valid, n_old - unsigned(R0)) >> 5, kMaskWords);
+    }
+    // ---- round trip 2: pending slicer samples and their cached masks (consumed after the FIRs) ---------------
+    if (smem_mode) {
+        for (unsigned i = tid; i < n_old; i += kTailThreads) cp_async4(&s_v[i], &v_g[i]);
+        for (unsigned i = tid; i < m_words; i += kTailThreads) { cp_async4(&s_maskA[i], &mask_g[i]); cp_async4(&s_maskN[i], &mask_g[kMaskWords + i]); }
+    }
     cp_async_commit();
 
     const unsigned fft_have0 = s_st.fft_have;
@@ -366,14 +383,14 @@ tail_kernel(TailArgs a)
     int spb = 0, R = 0;
     const int n_sl = int(n_old + nf);
     const bool slicing = nf && slicer_geometry(n_sl, a.fs_dec, s_st.baud, spb, R);
-    unsigned* s_maskA = reinterpret_cast<unsigned*>(s_x);           // the stage-2 window is dead by now
-    unsigned* s_maskN = s_maskA + ((a.sv_cap + 31) >> 5);
     if (slicing && smem_mode) {
-        slicer_build_masks(s_v, n_sl, R, s_maskA, s_maskN, tid >> 5, kTailThreads / 32, lane);
+        slicer_build_masks(s_v, n_sl, R, s_maskA, s_maskN, int(m_words), tid >> 5, kTailThreads / 32, lane);
         __syncthreads();
     }
     if (tid < 32) {
         unsigned slicer_n = s_st.slicer_n;
+        unsigned mask_valid = s_st.mask_valid;
+        int mask_R = s_st.mask_R;
         UartState us{s_st.uart_win, int(s_st.uart_n), a.uart_runs + (size_t)ch * kUartRunsCap, s_st.uart_runs_n, s_st.uart_ovf};
         bool rescan = s_st.uart_rescan != 0;
         if (nf) {
@@ -392,6 +409,22 @@ tail_kernel(TailArgs a)
             if (a.rec_bits && lane == 0) a.rec_bits_n[ch] = rec_n;
             // erase consumed samples (SymbolExtractor.h:156-157) / write the queue back
             const int keep = n - erase;
+            if (n_old != s_st.slicer_n) mask_valid = 0;     // vented: the cached masks describe samples that are gone
+            if (slicing) {
+                // masks of the positions that keep their value, moved down by the erased samples: [0, keep - R) of the new queue
+                const int nv = keep - R;
+                if (smem_mode && mask_g && nv > 0 && n <= int(kMaskWords * 32u)) {
+                    const int nvw = (nv + 31) >> 5, nw = (n + 31) >> 5, ws = erase >> 5;
+                    const unsigned bs = unsigned(erase) & 31u;
+                    for (int w = (erase ? 0 : int(m_words)) + lane; w < nvw; w += 32) {
+                        const unsigned la = s_maskA[w + ws], ln = s_maskN[w + ws];
+                        const unsigned ha = (w + ws + 1 < nw) ? s_maskA[w + ws + 1] : 0u, hn = (w + ws + 1 < nw) ? s_maskN[w + ws + 1] : 0u;
+                        mask_g[w] = __funnelshift_r(la, ha, bs);
+                        mask_g[kMaskWords + w] = __funnelshift_r(ln, hn, bs);
+                    }
+                    mask_valid = unsigned(nv); mask_R = R;
+                } else mask_valid = 0;
+            }
             if (smem_mode) {
                 const int from = erase ? 0 : int(n_old);    // nothing erased: only the new samples are missing in HBM
                 for (int k = from + lane; k < keep; k += 32) v_g[k] = s_v[erase + k];
@@ -421,6 +454,8 @@ tail_kernel(TailArgs a)
                 gst.demod_primed = 1;
                 gst.demod_n = nf;
                 gst.slicer_n = slicer_n;
+                gst.mask_valid = mask_valid;
+                gst.mask_R = mask_R;
                 gst.uart_win = us.win;
                 gst.uart_n = unsigned(us.have);
                 gst.uart_runs_n = us.n_runs;
@@ -441,9 +476,8 @@ static void tail_layout(TailArgs& a, size_t* bytes)
     a.h2cap = (a.T2 + 8 + 3) & ~3;
     a.hlcap = (Tm + 8 + 3) & ~3;
     a.sv_cap = (a.sv_want + 3) & ~3;
-    const int mask_f2 = ((a.sv_cap + 31) >> 5) + 1;  // two bit masks over the staged slicer samples alias the window
-    if (a.xw < mask_f2) a.xw = (mask_f2 + 3) & ~3;
-    *bytes = size_t(a.xw + a.qcap + kTile + 2) * 8 + size_t(a.h2cap + a.hlcap + a.sv_cap) * 4 + kCharBuf;
+    a.mask_words = ((a.sv_cap + 31) >> 5) + 1;       // per mask: one bit per staged slicer sample
+    *bytes = size_t(a.xw + a.qcap + kTile + 2) * 8 + size_t(a.h2cap + a.hlcap + a.sv_cap + 2 * a.mask_words) * 4 + kCharBuf;
 }
 
 cudaError_t launch_tail(TailArgs a, int n_channels, cudaStream_t stream, int* launches)

@@ -29,6 +29,7 @@ struct TailArgs {
     // log_ctl[kCtlCharHead]): entry = (channel, call_seq << 8 | char).  Kernels of successive calls run in stream order,
     // so the log is sorted by call and, per channel, by time.
     uint2* log; unsigned* log_ctl; unsigned log_mask; unsigned call_seq;
+    unsigned* maskc;             // cached slicer position masks [channel][2][kMaskWords] (null: rebuilt every call)
     unsigned short* uart_runs;   // UART backlog [channel][kUartRunsCap] (slicer_dev.cuh)
     // SSDV packet sync (ssdv.cu): per-channel raw-character ring [channel][kSsdvRing] + append counts; null = off
     unsigned char* ssdv_ring; unsigned* ssdv_total;
@@ -38,7 +39,7 @@ struct TailArgs {
     float2* rec_decimated; float2* rec_filtered; size_t rec_pitch;
     unsigned char* rec_bits; unsigned* rec_bits_n; unsigned rec_bits_pitch;  // every emitted bit [channel][rec_bits_pitch]
     // shared-memory layout, filled by launch_tail
-    int xw, qcap, h2cap, hlcap, sv_cap;
+    int xw, qcap, h2cap, hlcap, sv_cap, mask_words;
 };
 
 cudaError_t launch_tail(TailArgs a, int n_channels, cudaStream_t stream, int* launches);

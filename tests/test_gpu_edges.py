@@ -477,3 +477,79 @@ def test_lowpass_setters_between_calls(oracle_kind):
     assert np.array_equal(dec.debug_stage(0, api.STAGE_LPTAPS), ref.stage(po.STAGE_LPTAPS)) and len(ref.stage(po.STAGE_LPTAPS)) == 81
     assert dec.poll_chars(0) == ref.chars()
     assert dec.poll_sentences(0) == ref.sentences()
+
+
+@pytest.mark.parametrize("baud0", [300.0, 50.0])
+def test_slicer_mask_cache_large_window_with_baud_changes(oracle_kind, monkeypatch, baud0):
+    """SymbolExtractor.h:162-224 at fs_dec = 78 125 Hz (window radius 65 at 300 baud, 390 at 50 baud): the tail kernel keeps
+    the flip-search masks of the pending samples across calls (tail.cu).  Irregular chunks -- calls that only append, calls
+    that erase, empty pushes -- and baud changes between calls (another radius: the cache has to be dropped) must give the
+    reference's characters and leave the reference's pending samples behind; HBD_MASK_CACHE=0 (masks rebuilt from scratch
+    in every call) is run beside it as a second witness."""
+    fs, factor = 312500.0, 4
+    a, _ = synth.channel_iq(41, 2, fs, baud0, snr_db=-3.0)
+    b, _ = synth.channel_iq(42, 2, fs, 100.0, nbits=7, nstops=1, snr_db=-3.0)
+    rng = np.random.default_rng(5)
+    noise = (0.7 * (rng.standard_normal(150000) + 1j * rng.standard_normal(150000))).astype(np.complex64)
+    iq = np.concatenate([a, noise, b, a[:len(a) // 2]])
+    pattern = [1024, 2048, 0, 1031, 4096, 16384, 1024, 1024, 9500, 0, 32768, 1500, 65536, 1024]
+    sizes, left, k = [], len(iq), 0
+    while left > 0:
+        n = min(pattern[k % len(pattern)], left)
+        if 0 < left - n < 1024:
+            n = left
+        sizes.append(n); left -= n; k += 1
+    switch = {len(a) + len(noise): [("baud", 100.0), ("rtty_bits", 7), ("rtty_stops", 1.0)],
+              len(a) + len(noise) + len(b): [("baud", baud0), ("rtty_bits", 8), ("rtty_stops", 2.0)]}
+    cfg = dict(baud=baud0, rtty_bits=8, rtty_stops=2.0, dec_factor=factor)
+    monkeypatch.setenv("HBD_MASK_CACHE", "0")
+    plain = api.BatchDecoder(1, **cfg)
+    monkeypatch.delenv("HBD_MASK_CACHE")
+    dec = api.BatchDecoder(1, **cfg)
+    ref = make_oracle(oracle_kind, **cfg)
+    o, done = 0, set()
+    for n in sizes:
+        for at, sets in switch.items():
+            if o >= at and at not in done:
+                done.add(at)
+                for name, v in sets:
+                    for d in (dec, plain):
+                        getattr(d, name)(v, 0)
+                    ref.set_param(name, v)
+        blk = iq[o:o + n]
+        o += n
+        for d in (dec, plain):
+            d.pushSamples(0, blk, fs)
+            d.process()
+        ref.push_process(blk, fs)
+        got_p, want_p = dec.debug_stage(0, api.STAGE_PENDING), ref.stage(po.STAGE_PENDING)
+        assert got_p.shape == want_p.shape, "pending samples after %d input samples" % o
+        assert plain.debug_stage(0, api.STAGE_PENDING).shape == want_p.shape
+    assert len(done) == 2
+    assert dec.poll_chars(0) == ref.chars()
+    assert plain.poll_chars(0) == ref.chars()
+    assert dec.poll_sentences(0) == ref.sentences()
+    assert len(ref.sentences()) >= 3
+
+
+def test_input_fence_off_on_a_read_only_ring():
+    """hbd_set_input_fence(h, 0): the caller keeps the pushed device buffer unchanged, the library drops the stream wait
+    between calls.  Same characters, sentences and AFC state as the fenced run, call for call (64 channels, two ring passes,
+    the queue never drained in between so that consecutive calls really overlap)."""
+    import torch
+    fs, baud, chunk, n = 2.048e6, 300.0, 65536, 64
+    L = synth.ring_length(fs, baud)
+    ring = synth.ring_iq_torch(0, n, torch.device("cuda", 0), fs, baud, snr_db=-15.0)
+    torch.cuda.synchronize()
+    out = []
+    for fence in (True, False):
+        dec = api.BatchDecoder(n, baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
+        dec.set_input_fence(fence)
+        for k in range(2 * (L // chunk)):
+            dec.pushSamplesDevice(ring.data_ptr() + (k % (L // chunk)) * chunk * 8, chunk, L, fs)
+            dec.process_async()
+        dec.collect()
+        out.append([(dec.poll_chars(c), dec.poll_sentences(c), dec.getPeaks(c), dec.getFrequencyCorrection(c)) for c in range(n)])
+        dec.close()
+    assert out[0] == out[1]
+    assert all(len(s) >= 1 for _, s, _, _ in out[0])
