@@ -69,8 +69,6 @@ def parse():
     ap.add_argument("--no-wideband", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true", help="diagnostic: no CUDA events around K1 (no roofline numbers)")
     ap.add_argument("--pipeline-diagnostics", action="store_true", help="also time the rest of the step (two more event records per call): rest_of_step_ms, pipeline_gaps")
-    ap.add_argument("--input-fence", action="store_true", help="diagnostic: keep the library's default input fence (the caller's stream waits for K1 "
-                    "after every call); the bench's ring is read-only, so it runs without")
     ap.add_argument("--no-pin", action="store_true", help="diagnostic: leave the CPU affinity alone")
     ap.add_argument("--ref-passes", type=int, default=8, help="reference arm: ring passes per host thread per step")
     a = ap.parse_args()
@@ -142,9 +140,7 @@ def workload_config(args, world):
                         "dec=8 (factor 256), lowpass 1500 Hz, chunk %d samples/channel/step" % (args.channels // world, args.channels, args.chunk),
             "channels_total": args.channels, "channels_per_gpu": args.channels // world, "chunk": args.chunk,
             "snr_db_fullband": SNR_DB, "l2_policy": "inputs larger than L2: every step reads a different %.2f GiB slice of a ring resident in HBM"
-            % (args.channels // world * args.chunk * 8 / 2**30), "parallelism": "channels block-partitioned, %d rank(s)" % world,
-            "input_fence": "on (library default)" if getattr(args, "input_fence", False) else
-            "off (hbd_set_input_fence(h, 0): the ring is read-only, so the caller's stream does not wait for K1 between calls)"}
+            % (args.channels // world * args.chunk * 8 / 2**30), "parallelism": "channels block-partitioned, %d rank(s)" % world}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -260,7 +256,6 @@ def decode_leg(D: Dist, args, n_local, ch0, n_total, steps, warmup, timing=True)
                            dec_factor=FACTOR)
     dec.set_stream(stream.cuda_stream)
     dec.set_raw_chars(False)            # nobody polls the unfiltered characters here (the reference keeps none either)
-    dec.set_input_fence(args.input_fence)   # default off: the ring is never rewritten, the caller's stream need not wait for K1
     uid = D.share_bytes(api.dist_unique_id() if (D.rank == 0 and D.world > 1) else None, 128) if D.world > 1 else None
     dec.dist_init(D.rank, D.world, uid)                     # NCCL communicator owned by the library (csrc/dist.cu)
     sink = api.ResultSink(n_total)                          # rank 0: every channel; other ranks: a mirror of their own block
@@ -462,7 +457,6 @@ def run_wideband(D: Dist, args):
     stream = torch.cuda.current_stream()
     dec.set_stream(stream.cuda_stream)
     dec.set_raw_chars(False)
-    dec.set_input_fence(args.input_fence)
     for c in range(n_ch):
         dec.set_nco((c - n_ch / 2) * 15e3, c)                    # 15 kHz raster over the capture
     done = 0

@@ -103,7 +103,6 @@ SIGNATURES = {
     "hbd_poll_sentences": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_poll_raw_chars": (C.c_size_t, [_H, C.c_int, C.c_void_p, C.c_size_t]),
     "hbd_set_raw_chars": (C.c_int, [_H, C.c_int]),
-    "hbd_set_input_fence": (C.c_int, [_H, C.c_int]),
     "hbd_set_host_threads": (C.c_int, [_H, C.c_int]),
     "hbd_set_sentence_callback": (C.c_int, [_H, SENTENCE_CB, C.c_void_p]),
     "hbd_set_chars_callback": (C.c_int, [_H, CHARS_CB, C.c_void_p]),
@@ -556,9 +555,6 @@ class BatchDecoder:
     def poll_raw_chars(self, ch=0) -> bytes: return self._bytes(self._lib.hbd_poll_raw_chars, ch)
     def set_host_threads(self, n: int): self._chk(self._lib.hbd_set_host_threads(self._h, int(n)))
     def set_raw_chars(self, on: bool): self._chk(self._lib.hbd_set_raw_chars(self._h, int(on)))
-    def set_input_fence(self, on: bool):
-        """hbd_set_input_fence: off = the caller leaves pushed DEVICE buffers alone until their call is collected."""
-        self._chk(self._lib.hbd_set_input_fence(self._h, int(on)))
     def poll_sentences(self, ch=0) -> list[bytes]:
         return [s for s in self._bytes(self._lib.hbd_poll_sentences, ch).split(b"\n") if s]
 

@@ -235,7 +235,6 @@ struct hbd_decoder {
     static constexpr int kCharBufHost = 64;   // == kCharBuf (slicer_dev.cuh): characters per device-side flush
     double drain_host_ms = 0; unsigned drain_calls = 0;   // host time of the replay part of the drains (hbd_get_kernel_timing which = 5)
     int host_threads = 1;                // threads the drain may use (hbd_set_host_threads; default: min(4, half the cores this process may run on))
-    bool input_fence = true;             // hbd_set_input_fence: the caller's stream waits until a pushed DEVICE buffer has been consumed
     bool keep_raw = true;                // hbd_set_raw_chars: retain the raw (unfiltered) characters for hbd_poll_raw_chars
     float* d_taps1 = nullptr; float* d_taps2 = nullptr;
     float2* d_twiddle = nullptr;
@@ -913,11 +912,8 @@ int hbd_decoder::process_async_locked()
     if (timing > 1) HBD_CUDA_CHECK(cudaEventRecord(next_event(ev_rest, ev_used_rest), lo));
     if (!tail_recorded) HBD_CUDA_CHECK(cudaEventRecord(ev_tail[s1_cur], lo));
     tail_pending[s1_cur] = true;
-    // the caller's stream resumes once the input has been consumed (it does not wait for the tail kernels).  A caller that
-    // keeps its device buffers untouched until the call is collected (hbd_set_input_fence(h, 0)) spares the pipeline the
-    // round trip this wait puts between two calls: K1 -> ev_consumed -> caller's stream -> ev_in -> next K1.  The staging
-    // buffer of host pushes is the library's own and is always fenced.
-    if (input_fence || !ext) HBD_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_consumed, 0));
+    // the caller's stream resumes once the input has been consumed (it does not wait for the tail kernels)
+    HBD_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_consumed, 0));
     carry_cur ^= 1;
     if (any_work) s1_cur ^= 1; // the tail (which moves the stage-2 history to the other buffer) ran
     launches += unsigned(nl);
@@ -1805,10 +1801,6 @@ int hbd_set_host_threads(hbd_decoder* h, int n)
 int hbd_set_raw_chars(hbd_decoder* h, int on)
 {
     HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); h->keep_raw = on != 0; return HBD_OK;
-}
-int hbd_set_input_fence(hbd_decoder* h, int on)
-{
-    HBD_CHECK_H(h); std::lock_guard<std::mutex> l(h->mtx); h->input_fence = on != 0; return HBD_OK;
 }
 int hbd_attach_tracker(hbd_decoder* h, hbd_tracker* t, int ch_offset)
 {

@@ -90,14 +90,6 @@ int hbd_push_samples_batch(hbd_decoder* h, const float* iq, size_t n_complex, si
 /* zero copy: DEVICE matrix [n_channels][pitch_complex], 16-byte aligned rows; it must stay valid and
  * unchanged until the next hbd_process()/hbd_process_async() has completed (hbd_synchronize) */
 int hbd_push_samples_device(hbd_decoder* h, const float* d_iq, size_t n_complex, size_t pitch_complex, double sampling_rate);
-/* Input fence of the zero-copy pushes (default on): after hbd_process_async the handle's stream waits until the kernels
- * have read the pushed DEVICE buffer, so whatever the caller enqueues on that stream afterwards may overwrite it.  Off: the
- * caller promises to leave buffers given to hbd_push_samples_device / hbd_push_wideband_device unchanged until their call
- * has been collected (hbd_collect, or hbd_collect_ready reaching it) -- e.g. a capture ring that is only rewritten behind
- * the drain.  That takes a cross-stream round trip (~8 us) out of the gap between two calls' decimator kernels.  Work the
- * caller enqueued on the stream BEFORE the push is waited for in both modes; host pushes (library-owned staging buffer) are
- * always fenced.  There is no counterpart in the reference (its pushSamples copies, Decoder.h:206-219). */
-int hbd_set_input_fence(hbd_decoder* h, int on);
 
 /* ---- NCO pre-mixer (new; the reference retunes the SDR instead: websocketServer/main.cpp:247-265) -----------
  * Channel `ch` (-1: all) is mixed down by freq_hz before the decimator: x[i] * exp(-2 pi i f t), phase kept in

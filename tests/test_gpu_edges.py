@@ -531,25 +531,3 @@ def test_slicer_mask_cache_large_window_with_baud_changes(oracle_kind, monkeypat
     assert dec.poll_sentences(0) == ref.sentences()
     assert len(ref.sentences()) >= 3
 
-
-def test_input_fence_off_on_a_read_only_ring():
-    """hbd_set_input_fence(h, 0): the caller keeps the pushed device buffer unchanged, the library drops the stream wait
-    between calls.  Same characters, sentences and AFC state as the fenced run, call for call (64 channels, two ring passes,
-    the queue never drained in between so that consecutive calls really overlap)."""
-    import torch
-    fs, baud, chunk, n = 2.048e6, 300.0, 65536, 64
-    L = synth.ring_length(fs, baud)
-    ring = synth.ring_iq_torch(0, n, torch.device("cuda", 0), fs, baud, snr_db=-15.0)
-    torch.cuda.synchronize()
-    out = []
-    for fence in (True, False):
-        dec = api.BatchDecoder(n, baud=baud, rtty_bits=8, rtty_stops=2.0, dec_factor=256)
-        dec.set_input_fence(fence)
-        for k in range(2 * (L // chunk)):
-            dec.pushSamplesDevice(ring.data_ptr() + (k % (L // chunk)) * chunk * 8, chunk, L, fs)
-            dec.process_async()
-        dec.collect()
-        out.append([(dec.poll_chars(c), dec.poll_sentences(c), dec.getPeaks(c), dec.getFrequencyCorrection(c)) for c in range(n)])
-        dec.close()
-    assert out[0] == out[1]
-    assert all(len(s) >= 1 for _, s, _, _ in out[0])
