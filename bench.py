@@ -306,9 +306,11 @@ def decode_leg(D: Dist, args, n_local, ch0, n_total, steps, warmup, timing=True)
             drain_max = max(drain_max, dt_h)
     t_fc = time.perf_counter()
     dec.collect()                       # results drained (D2H + sentence layer) inside the timed region
+    t_fg = time.perf_counter()
     dec.gather_results(sink)
     gathers += 1
     final_ms = (time.perf_counter() - t_fc) * 1e3
+    final_gather_ms = (time.perf_counter() - t_fg) * 1e3
     ev1.record(stream)
     D.barrier()
     clocks = sampler.stop()
@@ -329,7 +331,7 @@ def decode_leg(D: Dist, args, n_local, ch0, n_total, steps, warmup, timing=True)
             break
         dec.gather_results(sink)
     per_rank_diag = {"k1_avg_ms": D.all_values(k1_ms / max(k1_cnt, 1)), "host_replay_ms_total": D.all_values(replay_ms),
-                     "issue_max_ms": D.all_values(issue_max * 1e3), "drain_max_ms": D.all_values(drain_max * 1e3), "final_ms": D.all_values(final_ms),
+                     "issue_max_ms": D.all_values(issue_max * 1e3), "drain_max_ms": D.all_values(drain_max * 1e3), "final_ms": D.all_values(final_ms), "final_gather_ms": D.all_values(final_gather_ms),
                      "sm_mhz": D.all_values(float(clocks["sm_mhz"] or 0)), "throttle_reasons": D.all_values(float(len(clocks["reasons"])))}
     per_rank_ms = D.all_values(ms)
     per_rank_issue = D.all_values(t_issue * 1e3 / max(steps, 1))

@@ -23,6 +23,7 @@
 #include "fft_afc.cuh"
 #include "hbd_common.cuh"
 #include "host_tail.h"
+#include "range_pool.h"
 #include "telemetry_abi.h"
 #include "api_internal.h"
 #include "nco.cuh"
@@ -234,6 +235,7 @@ struct hbd_decoder {
     std::vector<unsigned> seg_start;     // collect_locked: first log entry of every (call, channel) segment
     static constexpr int kCharBufHost = 64;   // == kCharBuf (slicer_dev.cuh): characters per device-side flush
     double drain_host_ms = 0; unsigned drain_calls = 0;   // host time of the replay part of the drains (hbd_get_kernel_timing which = 5)
+    hbd::RangePool pool;                 // the drain's worker threads (part t of a drain / a pack always runs on the same thread)
     int host_threads = 1;                // threads the drain may use (hbd_set_host_threads; default: min(4, half the cores this process may run on))
     bool keep_raw = true;                // hbd_set_raw_chars: retain the raw (unfiltered) characters for hbd_poll_raw_chars
     float* d_taps1 = nullptr; float* d_taps2 = nullptr;
@@ -1128,13 +1130,7 @@ int hbd_decoder::collect_locked(unsigned lag)
             }
         }
     };
-    if (n_thr == 1) replay(0);
-    else {
-        std::vector<std::thread> workers;
-        for (int t = 1; t < n_thr; ++t) workers.emplace_back(replay, t);
-        replay(0);
-        for (auto& w : workers) w.join();
-    }
+    pool.run(n_thr, replay);
     {   // callbacks back into log order (stable: a channel's events keep the order they were recorded in)
         size_t total = 0;
         for (const ReplayPart& pt : parts) { total += pt.events.size(); if (pt.spilled) spill_free = false; }
@@ -1213,46 +1209,55 @@ size_t hbd_pack_results(hbd_decoder* h, int ch_offset, hbd_result_record* out, s
     std::lock_guard<std::mutex> l(h->mtx);
     const size_t n = size_t(h->n_ch);
     if (!out || cap_records < n) return n;
-    std::vector<double> st(6 * n, 0.0);
-    if (h->snap_on && h->h_snap_valid) {
-        for (size_t i = 0; i < 6 * n; ++i) st[i] = h->h_snap[i];
-    } else {   // no snapshot yet: read the live state (waits for the calls in flight)
+    std::vector<float> live;     // AFC scalars when no snapshot has been taken yet
+    const float* st = h->h_snap;
+    if (!(h->snap_on && h->h_snap_valid)) {   // read the live state (waits for the calls in flight)
         if (h->enable_snap() != HBD_OK) return 0;
         cudaSetDevice(h->device);
         h->sync_groups();
         cudaStreamSynchronize(h->stream);
         std::vector<ChanState> cs(n);
         if (cudaMemcpy(cs.data(), h->d_state, n * sizeof(ChanState), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+        live.resize(6 * n);
         for (size_t c = 0; c < n; ++c) {
-            st[6 * c + 0] = cs[c].afc_correction; st[6 * c + 1] = cs[c].afc_shift_hz; st[6 * c + 2] = cs[c].afc_noise_floor;
-            st[6 * c + 3] = cs[c].afc_noise_var; st[6 * c + 4] = cs[c].gui_left; st[6 * c + 5] = cs[c].gui_right;
+            live[6 * c + 0] = float(cs[c].afc_correction); live[6 * c + 1] = float(cs[c].afc_shift_hz); live[6 * c + 2] = float(cs[c].afc_noise_floor);
+            live[6 * c + 3] = float(cs[c].afc_noise_var); live[6 * c + 4] = float(cs[c].gui_left); live[6 * c + 5] = float(cs[c].gui_right);
         }
+        st = live.data();
     }
-    // the pending slots ARE the records: copy, stamp, reset (and move spilled bytes up)
-    bool any_left = false;
-    for (size_t c = 0; c < n; ++c) {
-        hbd_result_record& pr = h->pend[c];
-        hbd_result_record& o = out[c];
-        // header + the bytes in use only (the rest of a record is not read by anybody)
-        o.n_chars = pr.n_chars; o.sentence_bytes = pr.sentence_bytes; o.reserved = 0;
-        if (pr.n_chars) memcpy(o.chars, pr.chars, pr.n_chars);
-        if (pr.sentence_bytes) memcpy(o.sentences, pr.sentences, pr.sentence_bytes);
-        o.channel = uint32_t(ch_offset + int(c));
-        const double* sc = st.data() + 6 * c;
-        o.frequency_correction = float(sc[0]); o.shift = float(sc[1]); o.noise_floor = float(sc[2]); o.noise_variance = float(sc[3]);
-        o.peak_left = int32_t(sc[4]); o.peak_right = int32_t(sc[5]);
-        o.n_sentences = pr.sentence_bytes ? uint16_t(std::count(pr.sentences, pr.sentences + pr.sentence_bytes, '\n')) : uint16_t(0);
-        pr.n_chars = 0; pr.sentence_bytes = 0;
-        uint16_t fl = 0;
-        if (__builtin_expect(!h->spill_free, 0)) {
-            TextChannel& tc = h->text[c];
-            if (!tc.chars_spill.empty()) { fl |= 1u; TextChannel::refill(pr.chars, pr.n_chars, sizeof(pr.chars), tc.chars_spill); }
-            if (!tc.sent_spill.empty()) { fl |= 2u; TextChannel::refill(pr.sentences, pr.sentence_bytes, sizeof(pr.sentences), tc.sent_spill); }
-            any_left = any_left || !tc.chars_spill.empty() || !tc.sent_spill.empty();
+    // the pending slots ARE the records: copy, stamp, reset (and move spilled bytes up).  Cut by channel range like the
+    // replay of the drain, so that a range is packed by the thread that filled it.
+    const bool spill_free = h->spill_free;
+    const int n_thr = int(std::max<size_t>(1, std::min<size_t>(size_t(h->host_threads), n / 1024)));
+    std::vector<unsigned char> left(size_t(n_thr), 0);
+    h->pool.run(n_thr, [&](int t) {
+        const size_t c_lo = n * size_t(t) / size_t(n_thr), c_hi = n * size_t(t + 1) / size_t(n_thr);
+        bool any_left = false;
+        for (size_t c = c_lo; c < c_hi; ++c) {
+            hbd_result_record& pr = h->pend[c];
+            hbd_result_record& o = out[c];
+            // header + the bytes in use only (the rest of a record is not read by anybody)
+            o.n_chars = pr.n_chars; o.sentence_bytes = pr.sentence_bytes; o.reserved = 0;
+            if (pr.n_chars) memcpy(o.chars, pr.chars, pr.n_chars);
+            if (pr.sentence_bytes) memcpy(o.sentences, pr.sentences, pr.sentence_bytes);
+            o.channel = uint32_t(ch_offset + int(c));
+            const float* sc = st + 6 * c;
+            o.frequency_correction = sc[0]; o.shift = sc[1]; o.noise_floor = sc[2]; o.noise_variance = sc[3];
+            o.peak_left = int32_t(sc[4]); o.peak_right = int32_t(sc[5]);
+            o.n_sentences = pr.sentence_bytes ? uint16_t(std::count(pr.sentences, pr.sentences + pr.sentence_bytes, '\n')) : uint16_t(0);
+            pr.n_chars = 0; pr.sentence_bytes = 0;
+            uint16_t fl = 0;
+            if (__builtin_expect(!spill_free, 0)) {
+                TextChannel& tc = h->text[c];
+                if (!tc.chars_spill.empty()) { fl |= 1u; TextChannel::refill(pr.chars, pr.n_chars, sizeof(pr.chars), tc.chars_spill); }
+                if (!tc.sent_spill.empty()) { fl |= 2u; TextChannel::refill(pr.sentences, pr.sentence_bytes, sizeof(pr.sentences), tc.sent_spill); }
+                any_left = any_left || !tc.chars_spill.empty() || !tc.sent_spill.empty();
+            }
+            o.flags = fl;
         }
-        o.flags = fl;
-    }
-    if (!h->spill_free) h->spill_free = !any_left;
+        left[size_t(t)] = any_left;
+    });
+    if (!h->spill_free) h->spill_free = std::find(left.begin(), left.end(), 1) == left.end();
     return n;
 }
 int hbd_set_stats_snapshot(hbd_decoder* h, int on)

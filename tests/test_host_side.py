@@ -185,3 +185,25 @@ def test_cpp_facade_builds_links_and_fails_loudly_without_a_gpu(tmp_path):
     r = subprocess.run([exe, path, "2048000", "300", "8", "2", "256"], capture_output=True)
     assert r.returncode != 0
     assert b"no usable CUDA device" in r.stderr and b"CHARS" not in r.stdout
+
+
+def test_range_pool_runs_every_part_once_on_a_stable_thread(tmp_path):
+    """habdec_b200/csrc/range_pool.h (the drain's persistent worker threads): tests/cpp/range_pool_test.cpp under the thread
+    sanitizer where gcc has it, plain otherwise."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "cpp", "range_pool_test.cpp")
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "range_pool_test")
+    built = False
+    for extra in (["-fsanitize=thread"], []):
+        r = subprocess.run([gxx, "-std=c++17", "-O2", "-pthread", *extra, src, "-o", exe], capture_output=True, text=True)
+        if r.returncode == 0:
+            built = True
+            break
+    assert built, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
