@@ -235,7 +235,7 @@ struct hbd_decoder {
     std::vector<unsigned> seg_start;     // collect_locked: first log entry of every (call, channel) segment
     static constexpr int kCharBufHost = 64;   // == kCharBuf (slicer_dev.cuh): characters per device-side flush
     double drain_host_ms = 0; unsigned drain_calls = 0;   // host time of the replay part of the drains (hbd_get_kernel_timing which = 5)
-    hbd::RangePool pool;                 // worker threads of hbd_pack_results (part t always runs on the same thread)
+    hbd::RangePool pool;                 // the drain's worker threads (part t of a drain / a pack runs on the same thread every time)
     int host_threads = 1;                // threads the drain may use (hbd_set_host_threads; default: min(4, half the cores this process may run on))
     bool keep_raw = true;                // hbd_set_raw_chars: retain the raw (unfiltered) characters for hbd_poll_raw_chars
     float* d_taps1 = nullptr; float* d_taps2 = nullptr;
@@ -1130,15 +1130,7 @@ int hbd_decoder::collect_locked(unsigned lag)
             }
         }
     };
-    // fresh threads per drain on purpose: on hosts where a rank has few cores (8 ranks x 4) the wake-up of sleeping pool
-    // workers was the slower start (strong-scaling leg, host bound: 0.135 -> 0.19 ms/step at N = 4 with the pool here)
-    if (n_thr == 1) replay(0);
-    else {
-        std::vector<std::thread> workers;
-        for (int t = 1; t < n_thr; ++t) workers.emplace_back(replay, t);
-        replay(0);
-        for (auto& w : workers) w.join();
-    }
+    pool.run(n_thr, replay);     // part t on worker t (it finds its channels' text state in its cache), late workers' parts on this thread
     {   // callbacks back into log order (stable: a channel's events keep the order they were recorded in)
         size_t total = 0;
         for (const ReplayPart& pt : parts) { total += pt.events.size(); if (pt.spilled) spill_free = false; }

@@ -1,8 +1,9 @@
-// A few persistent host threads for per-channel-range work on the result path (record packing in hbd_pack_results).
-// Creating std::threads for ~100 us of work costs about as much again, and a worker that keeps "its" channel range
-// finds the records in its own cache.  A worker that is slow to wake up (a busy core) never holds the caller up: the
-// calling thread takes every part nobody has started by the time it gets there, so the worst case is the single-threaded
-// loop.  Host side only (the reference's counterpart is the tail of Decoder::process, Decoder.h:572-632), no device code.
+// A few persistent host threads for the per-channel-range work of the result path (sentence-layer replay in
+// hbd_collect*, record packing in hbd_pack_results).  One small drain is ~100 us of work; creating std::threads for it
+// costs about as much again, and a worker that keeps "its" channel range from drain to drain finds the channels' text
+// state in its own cache.  A worker that is slow to wake up (a busy core) never holds the drain up: the calling thread
+// takes every part nobody has started by the time it gets there, so the worst case is the single-threaded drain.
+// Host side only (the reference's counterpart is the tail of Decoder::process, Decoder.h:572-632), no device code.
 #pragma once
 #include <algorithm>
 #include <atomic>
