@@ -1,13 +1,15 @@
-// The reference's caller code with habdec_b200's types swapped in -- nothing else changed:
-//   DECODER_THREAD                     code/websocketServer/main.cpp:203-283
-//       IQSource::get() -> IQVector -> Decoder::pushSamples -> Decoder::operator() -> callbacks / getters
-//   the three callback installs        code/websocketServer/main.cpp:573-604
-//       sentence_callback_, character_callback_, ssdv_callback_ (messages are printed instead of sent to websocket sessions)
-//   SpectrumToStream                   code/websocketServer/habdec_ws_protocol.cpp:355-405 (+ ShrinkVector :338-351)
-//       Decoder::getSpectrumInfo() -> zoom / peak shift / ShrinkVector -> SerializeSpectrum (NetTransport.h:61-85)
-// It prints what callbacks, getters and the spectrum stream deliver so that tests/test_gpu_cpp_facade.py can hold it
-// against the oracle and against the library's own PWR_ frames (which are pinned to the reference's serialiser).
+// A small server-less client of the C++ facade (include/habdec_b200/Decoder.hpp), written the way the reference's
+// websocket server drives its habdec::Decoder -- the SAME member calls in the same order, in this repo's own code:
+//   feed loop            IQSource::get() -> IQVector -> pushSamples() -> operator()      (what DECODER_THREAD does,
+//                                                                                          code/websocketServer/main.cpp:233-245)
+//   three callbacks      sentence_callback_, character_callback_, ssdv_callback_ assigned as std::function members
+//                        (main.cpp:573-604); the messages the server would send are only measured and printed here
+//   spectrum for a GUI   getSpectrumInfo() -> centre zoom -> peak re-indexing -> nearest-bin decimation -> PWR_ header + floats
+//                        (the contract of habdec_ws_protocol.cpp:338-405 with NetTransport.h:29-85; the byte layout is the
+//                        wire format, tests/test_gpu_wire.py pins the library's own frames to it)
+// tests/test_gpu_cpp_facade.py compares what is printed with the oracle and with the library's hbd_get_spectrum_frame().
 //   decoder_thread file.cf32 fs baud bits stops factor
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -15,182 +17,179 @@
 #include <iostream>
 #include <memory>
 #include <sstream>
-#include <utility>
+#include <string>
+#include <vector>
 #include "habdec_b200/Decoder.hpp"
 #include "habdec_b200/IQSource.hpp"
 
-typedef habdec_b200::Decoder TDecoder;                     // typedef habdec::Decoder<TReal> TDecoder (GLOBALS.h:36-37)
-static std::unique_ptr<TDecoder> g_decoder;                // GLOBALS::get().decoder_
-#define DECODER (*g_decoder)
+using Decoder = habdec_b200::Decoder;
+static std::unique_ptr<Decoder> decoder;      // the server keeps one decoder in its globals; so does this client
 
-// ---- NetTransport.h:29-47,61-85 for TTransport = float (CompressedVector<float> keeps the values, min/max of the data)
-struct SpectrumInfoHeader {
-    int32_t header_size_ = (int32_t)sizeof(SpectrumInfoHeader);
-    float noise_floor_ = 0, noise_variance_ = 0, sampling_rate_ = 0, shift_ = 0;
-    int32_t peak_left_ = 0, peak_right_ = 0, peak_left_valid_ = 0, peak_right_valid_ = 0;
-    float min_ = 0, max_ = 0;
-    int32_t type_size_ = 0, size_ = 0;
+// ---- the PWR_ payload: 13 little-endian 4-byte fields, then the bins as float ------------------------------------
+#pragma pack(push, 1)
+struct PwrHeader {
+    int32_t bytes;
+    float noise_floor, noise_variance, sampling_rate, shift;
+    int32_t peak_left, peak_right, peak_left_valid, peak_right_valid;
+    float lowest, highest;
+    int32_t bytes_per_bin, bins;
 };
-template <typename TSpectrumInfo>
-void SerializeSpectrum(const TSpectrumInfo& spectrum_info, std::stringstream& ostr, float*)
+#pragma pack(pop)
+static_assert(sizeof(PwrHeader) == 52, "PWR_ header is 52 bytes");
+
+// One "cmd::power:res=R,zoom=Z" request: what a client asks for and what goes back to it.  Returns the bins sent.
+// Every step goes through the container interface of SpectrumInfo (a vector of bins with the AFC scalars as members),
+// i.e. the operations the reference's server performs on its own SpectrumInfo.
+static size_t power_frame(std::string& frame, float zoom, int resolution)
 {
-    SpectrumInfoHeader header;
-    header.noise_floor_ = spectrum_info.noise_floor_;
-    header.noise_variance_ = spectrum_info.noise_variance_;
-    header.sampling_rate_ = spectrum_info.sampling_rate_;
-    header.shift_ = spectrum_info.shift_;
-    header.peak_left_ = spectrum_info.peak_left_;
-    header.peak_right_ = spectrum_info.peak_right_;
-    header.peak_left_valid_ = spectrum_info.peak_left_valid_;
-    header.peak_right_valid_ = spectrum_info.peak_right_valid_;
-    header.size_ = spectrum_info.size();
-    header.min_ = *std::min_element(spectrum_info.begin(), spectrum_info.end());
-    header.max_ = *std::max_element(spectrum_info.begin(), spectrum_info.end());
-    header.type_size_ = sizeof(float);
-    ostr.write(reinterpret_cast<char*>(&header), sizeof(header));
-    ostr.write(reinterpret_cast<const char*>(spectrum_info.data()), spectrum_info.size() * sizeof(float));
+    auto info = decoder->getSpectrumInfo();
+    frame.clear();
+    if (info.size() == 0) return 0;
+
+    // centre zoom: drop zoom/2 of the bins at either end (the zoom factor is kept inside [0.01, 0.99])
+    const float z = std::max(0.01f, std::min(zoom, 0.99f));
+    const size_t all = info.size();
+    const size_t first = size_t(z / 2 * all), last = size_t((1.0f - z / 2) * all);
+    info.erase(info.begin() + last, info.end());
+    info.erase(info.begin(), info.begin() + first);
+
+    // the two FSK peaks follow the slice; one that falls outside is reported as absent
+    auto reindex = [&](int& peak, bool& valid) {
+        peak -= int(first);
+        if (peak < 0 || size_t(peak) > info.size()) { peak = 0; valid = false; }
+    };
+    reindex(info.peak_left_, info.peak_left_valid_);
+    reindex(info.peak_right_, info.peak_right_valid_);
+
+    // fewer bins than the slice holds: bin i of the reply is bin floor(i/resolution * size) of the slice (float ratio)
+    if (resolution >= 0 && size_t(resolution) < info.size()) {
+        const size_t before = info.size();
+        info.peak_left_ = int(double(info.peak_left_) * resolution / before);
+        info.peak_right_ = int(double(info.peak_right_) * resolution / before);
+        for (size_t i = 0; i < size_t(resolution); ++i) {
+            const float ratio = float(i) / resolution;
+            info[i] = info[size_t(ratio * before)];
+        }
+        info.resize(size_t(resolution));
+    }
+
+    PwrHeader h{};
+    h.bytes = int32_t(sizeof(h));
+    h.noise_floor = float(info.noise_floor_); h.noise_variance = float(info.noise_variance_);
+    h.sampling_rate = float(info.sampling_rate_); h.shift = float(info.shift_);
+    h.peak_left = info.peak_left_; h.peak_right = info.peak_right_;
+    h.peak_left_valid = info.peak_left_valid_; h.peak_right_valid = info.peak_right_valid_;
+    const auto range = std::minmax_element(info.begin(), info.end());
+    h.lowest = *range.first; h.highest = *range.second;
+    h.bytes_per_bin = 4; h.bins = int32_t(info.size());
+    frame.assign(reinterpret_cast<const char*>(&h), sizeof(h));
+    frame.append(reinterpret_cast<const char*>(info.data()), info.size() * sizeof(float));
+    return info.size();
 }
 
-// ---- habdec_ws_protocol.cpp:338-351
-template <typename T>
-void ShrinkVector(T& vec, size_t new_size)
+static std::string to_hex(const std::string& bytes)
 {
-    if (new_size >= vec.size()) return;
-    for (size_t i = 0; i < new_size; ++i) {
-        float i_0_1 = float(i) / new_size;
-        size_t I = i_0_1 * vec.size();
-        vec[i] = vec[I];
-    }
-    vec.resize(new_size);
+    std::string out;
+    char two[3];
+    for (unsigned char b : bytes) { std::snprintf(two, sizeof(two), "%02x", b); out += two; }
+    return out;
 }
 
-// ---- habdec_ws_protocol.cpp:355-405
-size_t SpectrumToStream(std::stringstream& res_stream, float zoom, int resolution)
+// zlib's CRC-32: the checksum the oracle's SSDV transcript carries for an image's packet set
+static uint32_t crc32_of(const std::vector<uint8_t>& bytes)
 {
-    using namespace std;
-    auto spectrum_info = DECODER.getSpectrumInfo();
-    if (!spectrum_info.size()) return 0;
-    zoom = min(max(zoom, 0.01f), 0.99f);
-    const size_t zoom_slice_begin = zoom / 2 * spectrum_info.size();
-    const size_t zoom_slice_end = (1.0f - zoom / 2) * spectrum_info.size();
-    spectrum_info.erase(spectrum_info.begin() + zoom_slice_end, spectrum_info.end());
-    spectrum_info.erase(spectrum_info.begin(), spectrum_info.begin() + zoom_slice_begin);
-    spectrum_info.peak_left_ -= zoom_slice_begin;
-    if (spectrum_info.peak_left_ < 0 || spectrum_info.peak_left_ > spectrum_info.size()) {
-        spectrum_info.peak_left_ = 0;
-        spectrum_info.peak_left_valid_ = false;
+    uint32_t crc = ~0u;
+    for (uint8_t b : bytes) {
+        crc ^= b;
+        for (int bit = 0; bit < 8; ++bit) crc = (crc >> 1) ^ (0xEDB88320u & (0u - (crc & 1u)));
     }
-    spectrum_info.peak_right_ -= zoom_slice_begin;
-    if (spectrum_info.peak_right_ < 0 || spectrum_info.peak_right_ > spectrum_info.size()) {
-        spectrum_info.peak_right_ = 0;
-        spectrum_info.peak_right_valid_ = false;
-    }
-    if (resolution < spectrum_info.size()) {
-        spectrum_info.peak_left_ = double(spectrum_info.peak_left_) * resolution / spectrum_info.size();
-        spectrum_info.peak_right_ = double(spectrum_info.peak_right_) * resolution / spectrum_info.size();
-        ShrinkVector(spectrum_info, resolution);
-    }
-    SerializeSpectrum(spectrum_info, res_stream, (float*)0);      // TransportDataType::kFloat
-    return spectrum_info.size();
-}
-
-static std::string hex(const std::string& s)
-{
-    static const char d[] = "0123456789abcdef";
-    std::string r;
-    for (unsigned char c : s) { r.push_back(d[c >> 4]); r.push_back(d[c & 15]); }
-    return r;
-}
-static uint32_t crc32_zlib(const uint8_t* p, size_t n)   // the checksum the oracle's SSDV transcript carries for an image's packet set
-{
-    uint32_t c = 0xffffffffu;
-    for (size_t i = 0; i < n; ++i) { c ^= p[i]; for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1; }
-    return ~c;
+    return ~crc;
 }
 
 int main(int argc, char** argv)
 {
-    using namespace std;
-    if (argc < 7) return 2;
-    const std::string path = argv[1];
-    double fs = atof(argv[2]);
-    bool no = false;
-    habdec_b200::IQSourceFile src;
-    src.quiet = true;
-    src.setOption("file_string", &path);                 // IQSource_File.h:205-232 option names
-    src.setOption("sampling_rate_double", &fs);
-    src.setOption("realtime_bool", &no);
-    src.setOption("loop_bool", &no);
-    if (!src.init() || !src.start()) { std::cerr << "source\n"; return 1; }
+    if (argc < 7) { std::fprintf(stderr, "usage: decoder_thread file.cf32 fs baud bits stops factor\n"); return 2; }
+    const std::string file = argv[1];
+    double rate = std::atof(argv[2]);
+    bool off = false;
 
-    g_decoder.reset(new TDecoder());
-    DECODER.livePrint(false);
-    DECODER.baud(atof(argv[3])); DECODER.rtty_bits(atoi(argv[4])); DECODER.rtty_stops(float(atof(argv[5])));   // main.cpp:544-553
-    DECODER.dc_remove(false);
-    DECODER.lowpass_bw(1500); DECODER.lowpass_trans(0.025f);
-    DECODER.setupDecimationStagesFactor(atoi(argv[6]));
-    DECODER.ssdvBaseFile("ssdv_");
+    habdec_b200::IQSourceFile source;                 // option names: IQSource_File.h:205-232
+    source.quiet = true;
+    source.setOption("file_string", &file);
+    source.setOption("sampling_rate_double", &rate);
+    source.setOption("realtime_bool", &off);
+    source.setOption("loop_bool", &off);
+    if (!source.init() || !source.start()) { std::fprintf(stderr, "cannot open %s\n", file.c_str()); return 1; }
 
-    std::string chars;
-    size_t n_sent = 0, n_ssdv = 0;
-    // ---- main.cpp:573-604 ------------------------------------------------------------------------------------
-    DECODER.sentence_callback_ =
-        [&n_sent](string callsign, string data, string crc)
-        {
-            ++n_sent;
-            // a callback may use the decoder (the reference's SentenceCallback reads GLOBALS state under its own locks)
-            cout << "SENT " << callsign << "," << data << "*" << crc << " last=" << (DECODER.getLastSentence() == callsign + "," + data + "*" + crc) << "\n";
-        };
-    DECODER.character_callback_ =
-        [&chars](string rtty_characters)
-        {
-            stringstream data_stream_;
-            data_stream_ << "cmd::info:liveprint=" << rtty_characters;
-            chars += data_stream_.str().substr(20);
-        };
-    DECODER.ssdv_callback_ =
-        [&n_ssdv](string callsign, int image_id, std::vector<uint8_t> jpeg)
-        {
-            stringstream data_stream_;
-            pair<int, int> ssdv_header{(int)callsign.size(), (int)image_id};
-            data_stream_ << "SDV_";
-            data_stream_.write(reinterpret_cast<char*>(&ssdv_header), sizeof(ssdv_header));
-            data_stream_ << callsign;
-            ++n_ssdv;
-            cout << "SSDV " << callsign << " " << image_id << " " << jpeg.size() << " " << crc32_zlib(jpeg.data(), jpeg.size()) << " hdr=" << data_stream_.str().size() << "\n";
-        };
+    decoder.reset(new Decoder());
+    Decoder& dec = *decoder;
+    dec.livePrint(false);
+    dec.baud(std::atof(argv[3]));                     // the setters a server applies from its command line (main.cpp:544-553)
+    dec.rtty_bits(std::atoi(argv[4]));
+    dec.rtty_stops(float(std::atof(argv[5])));
+    dec.dc_remove(false);
+    dec.lowpass_bw(1500);
+    dec.lowpass_trans(0.025f);
+    dec.setupDecimationStagesFactor(std::atoi(argv[6]));
+    dec.ssdvBaseFile("ssdv_");
 
-    // ---- main.cpp:233-245 --------------------------------------------------------------------------------------
-    habdec_b200::IQVector samples;                        // TIQVector
-    samples.resize(256 * 256);
-    samples.samplingRate(src.samplingRate());
-    for (;;) {
-        const size_t count = src.get(samples.data(), samples.size());   // main.cpp:238
-        if (!count) break;
-        samples.resize(count);
-        DECODER.pushSamples(samples);                     // main.cpp:243
-        DECODER();                                        // main.cpp:245
-        samples.resize(256 * 256);
-        if (count < samples.size()) break;
+    std::string live_print;       // what the "cmd::info:liveprint=" messages would carry, concatenated
+    size_t sentences = 0, ssdv_packets = 0;
+    const std::string live_tag = "cmd::info:liveprint=";
+
+    dec.sentence_callback_ = [&](std::string callsign, std::string data, std::string crc) {
+        ++sentences;
+        const std::string whole = callsign + "," + data + "*" + crc;
+        // a callback may call back into the decoder (the server's SentenceCallback does, under its own locks)
+        std::cout << "SENT " << whole << " last=" << (dec.getLastSentence() == whole) << "\n";
+    };
+    dec.character_callback_ = [&](std::string rtty_characters) {
+        std::ostringstream message;
+        message << live_tag << rtty_characters;
+        live_print += message.str().substr(live_tag.size());
+    };
+    dec.ssdv_callback_ = [&](std::string callsign, int image_id, std::vector<uint8_t> jpeg) {
+        // binary "SDV_" message: tag, two ints (callsign length, image id), callsign; the JPEG would follow base64 coded
+        std::ostringstream message;
+        const int32_t lengths[2] = {int32_t(callsign.size()), int32_t(image_id)};
+        message << "SDV_";
+        message.write(reinterpret_cast<const char*>(lengths), sizeof(lengths));
+        message << callsign;
+        ++ssdv_packets;
+        std::cout << "SSDV " << callsign << " " << image_id << " " << jpeg.size() << " " << crc32_of(jpeg) << " hdr=" << message.str().size() << "\n";
+    };
+
+    // the feed loop: blocks of 65 536 samples from the source, one process() per block
+    const size_t block = 256 * 256;
+    habdec_b200::IQVector samples;
+    samples.samplingRate(source.samplingRate());
+    for (bool more = true; more;) {
+        samples.resize(block);
+        const size_t got = source.get(samples.data(), samples.size());
+        if (got == 0) break;
+        samples.resize(got);
+        dec.pushSamples(samples);
+        dec();
+        more = got == block;
     }
-    cout << "NSENT " << n_sent << "\n";
-    cout << "NSSDV " << n_ssdv << "\n";
-    cout << "LAST " << DECODER.getLastSentence() << "\n";
-    cout << "RATE " << DECODER.getDecimatedSamplingRate() << " " << DECODER.getDecimationFactor() << " " << DECODER.getBinsCount() << "\n";
-    int pl = 0, pr = 0; DECODER.getPeaks(pl, pr);
-    cout << "PEAKS " << pl << " " << pr << "\n";
-    // ---- the "cmd::power:res=R,zoom=Z" requests of a client (habdec_ws_protocol.cpp:92-124 -> SpectrumToStream) --------
-    const float zooms[] = {0.0f, 0.5f, 0.9f};
-    const int ress[] = {100000, 1024, 300};
-    for (int k = 0; k < 3; ++k) {
-        stringstream s;
-        const size_t n = SpectrumToStream(s, zooms[k], ress[k]);
-        // the same frame from the library (PWR_ payload produced on the GPU, type_size 4)
-        std::string lib(s.str().size() + 64, '\0');
-        const size_t ln = hbd_get_spectrum_frame(DECODER.batch().handle(), 0, zooms[k], ress[k], 4, reinterpret_cast<unsigned char*>(&lib[0]), lib.size());
-        lib.resize(std::min(ln, lib.size()));
-        cout << "PWR " << k << " " << n << " " << s.str().size() << " " << (lib == s.str() ? "same" : "DIFFERENT") << " " << hex(s.str().substr(0, 52)) << "\n";
+
+    std::cout << "NSENT " << sentences << "\n" << "NSSDV " << ssdv_packets << "\n" << "LAST " << dec.getLastSentence() << "\n";
+    std::cout << "RATE " << dec.getDecimatedSamplingRate() << " " << dec.getDecimationFactor() << " " << dec.getBinsCount() << "\n";
+    int left = 0, right = 0;
+    dec.getPeaks(left, right);
+    std::cout << "PEAKS " << left << " " << right << "\n";
+
+    // three spectrum requests of a GUI client; each frame is held against the library's own (GPU-built) PWR_ payload
+    const struct { float zoom; int resolution; } requests[] = {{0.0f, 100000}, {0.5f, 1024}, {0.9f, 300}};
+    int k = 0;
+    for (const auto& rq : requests) {
+        std::string mine;
+        const size_t bins = power_frame(mine, rq.zoom, rq.resolution);
+        std::string theirs(mine.size() + 64, '\0');
+        const size_t n = hbd_get_spectrum_frame(dec.batch().handle(), 0, rq.zoom, rq.resolution, 4, reinterpret_cast<unsigned char*>(&theirs[0]), theirs.size());
+        theirs.resize(std::min(n, theirs.size()));
+        std::cout << "PWR " << k++ << " " << bins << " " << mine.size() << " " << (theirs == mine ? "same" : "DIFFERENT") << " " << to_hex(mine.substr(0, sizeof(PwrHeader))) << "\n";
     }
-    cout << "CHARS " << chars.size() << "\n" << chars << "\nEND\n";
+    std::cout << "CHARS " << live_print.size() << "\n" << live_print << "\nEND\n";
     return 0;
 }

@@ -34,7 +34,8 @@ def _run(exe, path, fs, baud, bits, stops, factor):
 
 
 def test_decoder_thread_program_matches_reference(tmp_path, oracle_kind):
-    """DECODER_THREAD + the callback installs + SpectrumToStream of the reference, compiled against the facade."""
+    """tests/cpp/decoder_thread.cpp: a client of the C++ facade that makes the member calls the reference's server makes
+    (feed loop, the three callback members, getSpectrumInfo() -> zoom / peak re-indexing / decimation -> PWR_ payload)."""
     import struct
     fs, baud = 2.048e6, 300.0
     iq, _ = synth.channel_iq(9, 3, fs, baud, snr_db=-15.0)
