@@ -24,6 +24,7 @@ Legs of one invocation (all on the same JSON line):
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -283,6 +284,8 @@ def decode_leg(D: Dist, args, n_local, ch0, n_total, steps, warmup, timing=True)
     dec.set_kernel_timing((2 if args.pipeline_diagnostics else 1) if timing else 0)
     sampler = ClockSampler(D.local_rank)
     sampler.start()                      # every rank watches its own GPU (a throttled GPU shows up as a slow rank)
+    gc.collect()
+    gc.disable()                         # no collector pause of the Python harness inside a 2..8 ms timed region
     D.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -312,6 +315,7 @@ def decode_leg(D: Dist, args, n_local, ch0, n_total, steps, warmup, timing=True)
     final_ms = (time.perf_counter() - t_fc) * 1e3
     final_gather_ms = (time.perf_counter() - t_fg) * 1e3
     ev1.record(stream)
+    gc.enable()
     D.barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
