@@ -207,3 +207,54 @@ def test_range_pool_runs_every_part_once_on_a_stable_thread(tmp_path):
     assert built, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+
+
+def _slicer_masks_full(v, R):
+    """slicer_build_masks (slicer_dev.cuh) for every position: bit q of A = the window means left and right of q differ in
+    sign, windows clipped to the buffer like window_sums; positions below R are not evaluated."""
+    n = len(v)
+    words = [0] * ((n + 31) // 32)
+    for q in range(R, n):
+        sl = float(np.sum(v[max(q - R, 0):q], dtype=np.float64))
+        sr = float(np.sum(v[q:min(q + R, n)], dtype=np.float64))
+        if (sl > 0) - (sl < 0) != (sr > 0) - (sr < 0):
+            words[q >> 5] |= 1 << (q & 31)
+    return words
+
+
+def test_slicer_mask_cache_model_equals_full_rebuild():
+    """The bookkeeping of the tail kernel's mask cache (tail.cu), modelled word for word on the host: whole cached words are
+    reused, the build restarts at the word holding the first unknown position, and after the slicer erased `erase` samples the
+    words move down by a funnel shift with `keep - R` positions staying valid.  Over random append / erase sequences every
+    position the flip search may consult (q >= R) has the bit a from-scratch build gives."""
+    rng = random.Random(11)
+    nrng = np.random.default_rng(11)
+    for R in (4, 7, 33, 65):
+        v = np.zeros(0, dtype=np.float32)
+        cached, valid = [], 0                       # HBM words and ChanState::mask_valid
+        for step in range(60):
+            v = np.concatenate([v, nrng.standard_normal(rng.choice([32, 256, 257, 300])).astype(np.float32)])
+            n = len(v)
+            full = _slicer_masks_full(v, R)
+            # load: whole words below `valid` (= pending length before this append, minus R)
+            m_words = valid >> 5
+            work = list(cached[:m_words]) + [0] * (len(full) - m_words)
+            for w in range(m_words, len(full)):      # rebuild from the first unknown word on
+                work[w] = full[w]
+            for q in range(R, n):
+                assert (work[q >> 5] >> (q & 31)) & 1 == (full[q >> 5] >> (q & 31)) & 1, (R, step, q)
+            # the slicer erases up to some flip point (or nothing)
+            erase = rng.choice([0, 0, rng.randrange(0, n), max(0, n - R - rng.randrange(0, 40))])
+            keep = n - erase
+            nv = keep - R
+            if nv > 0:
+                nvw, nw, ws, bs = (nv + 31) >> 5, (n + 31) >> 5, erase >> 5, erase & 31
+                new = list(cached) + [0] * max(0, nvw - len(cached))
+                for w in range(m_words if erase == 0 else 0, nvw):
+                    lo = work[w + ws]
+                    hi = work[w + ws + 1] if w + ws + 1 < nw else 0
+                    new[w] = ((lo | (hi << 32)) >> bs) & 0xffffffff
+                cached, valid = new, nv
+            else:
+                valid = 0
+            v = v[erase:]
