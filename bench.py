@@ -44,8 +44,9 @@ SNR_DB = -15.0
 ALGO_BYTES_PER_SAMPLE_K1 = 8.0 + 8.0 / 64.0   # cf32 read + stage-1 output write
 ALGO_BYTES_PER_SAMPLE_STEP = 8.0 + 12.0 / 256.0  # cf32 read + (demod 4 + decimated IQ 8) / 256
 # DRAM bytes per input sample that K1 really moved in the ncu --set full capture of this exact workload
-# (profiles/r1c_k1_ncu_full_raw.csv: dram__bytes_read.sum 2.170465 GB + dram__bytes_write.sum 0.046897 GB per 2^28 samples)
-NCU_TRAFFIC_BYTES_PER_SAMPLE_K1 = (2.170465e9 + 0.046897e9) / 268435456.0
+# (profiles/r2_k1_ncu_full_raw.csv: dram__bytes_read.sum 2.172891 GB + dram__bytes_write.sum 0.009870 GB per 2^28 samples;
+# round 1, before the L2 evict-first hint on the input stream: 2.170465 + 0.046897 GB)
+NCU_TRAFFIC_BYTES_PER_SAMPLE_K1 = (2.172891e9 + 0.009870e9) / 268435456.0
 FP32_PEAK_TFLOPS = 73.8                        # measured with tools/micro/ffma2_bench.cu on this pool's B200
 METRIC = "aggregate IQ MSamples/s decoded (chars bit-exact)"
 
@@ -576,7 +577,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "decim1_kernel<64,348> (K1, stage-1 FIR decimator)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": (NCU_TRAFFIC_BYTES_PER_SAMPLE_K1 * C * args.chunk * args.steps / max(k1_cnt, 1)) if (C == 4096 and args.chunk == 65536) else None,
-                         "traffic_source": "ncu --set full capture of this workload, profiles/r1c_k1_ncu_full_raw.csv (bytes per launch)",
+                         "traffic_source": "ncu --set full capture of this workload, profiles/r2_k1_ncu_full_raw.csv (bytes per launch)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_ms, "launches_timed": k1_cnt,
                          "k1_share_of_step": (k1_ms / leg["ms"]) if leg["ms"] else None, "rest_of_step_ms": (leg["rest_ms"] / leg["rest_cnt"]) if leg["rest_cnt"] else None,
